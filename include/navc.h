@@ -1,0 +1,227 @@
+/*
+ * navc.h -- C ABI of libnavc.so: hand-written sm_100a kernels for the hot path of
+ * yangbang18/Non-Autoregressive-Video-Captioning (encoder, BERT-style decoder, vocabulary
+ * projection, iterative-refinement decode step).
+ *
+ * The reference has no FFI layer: its boundary is the Python object API
+ * (models.get_model -> Seq2Seq, models.Translator, decoding.generate).  The Python host package
+ * mirrors that API and calls these entry points through ctypes; each entry point names the
+ * reference code (file:line under the reference repo) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; plain C types only.
+ *   - the callee never allocates, frees or synchronises; the caller owns all buffers.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - return value: 0 = ok, non-zero = error; navc_last_error() returns a message (thread local).
+ *   - row-major everywhere; "ld" = leading dimension in elements.
+ *   - token ids / categories are int64 (torch.long), as in the reference.
+ *   - bf16 "hi/lo" pairs: hi = bf16_rn(x), lo = bf16_rn(x - hi); x ~= hi + lo to ~2^-17 relative.
+ */
+#ifndef NAVC_H
+#define NAVC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAVC_VERSION 1
+
+/* token ids, config/Constants.py:1-6 */
+#define NAVC_PAD 0
+#define NAVC_UNK 1
+#define NAVC_BOS 2
+#define NAVC_EOS 3
+#define NAVC_MASK 4
+#define NAVC_VIS 5
+
+/* activation codes (models/bert.py:9-19 ACT2FN, plus tanh/sigmoid for the highway gate) */
+enum { NAVC_ACT_NONE = 0, NAVC_ACT_GELU_NEW = 1, NAVC_ACT_GELU = 2, NAVC_ACT_RELU = 3, NAVC_ACT_SWISH = 4 };
+
+/* self-attention mask kinds, models/Decoder.py:105-124 */
+enum { NAVC_MASK_KEYPAD = 0 /* NARFormer */, NAVC_MASK_CAUSAL = 1 /* ARFormer */, NAVC_MASK_SELF = 2 /* SelfMask */ };
+
+/* tensor-core operand modes of the tcgen05 GEMMs */
+enum { NAVC_TC_BF16 = 1 /* one product: hi*hi */, NAVC_TC_BF16X3 = 3 /* hi*hi + hi*lo + lo*hi */ };
+
+/* Epilogue applied to a GEMM tile before it is stored:
+ *   v = acc + bias[col]; v = act(v); v += residual[row,col]; if (row_tokens[row]==PAD) v = 0;
+ * (bias / activation: nn.Linear + ACT2FN, models/bert.py:227-230; residual: bert.py:196-197, 243;
+ *  row mask: `* non_pad_mask`, bert.py:271-272, 293-294, 298-299).  Any output may be NULL. */
+typedef struct {
+    const float* bias;          /* [N] or NULL */
+    const float* residual;      /* [M, ld_res] or NULL */
+    const int64_t* row_tokens;  /* [M] or NULL */
+    int32_t act;                /* NAVC_ACT_* */
+    int32_t ld_res;
+    float* out_f32;             /* [M, ld_out] or NULL */
+    uint16_t* out_hi;           /* bf16 bits [M, ld_out] or NULL */
+    uint16_t* out_lo;           /* bf16 bits [M, ld_out] or NULL */
+    int32_t ld_out;
+    int32_t reserved;
+} navc_epilogue_t;
+
+int navc_version(void);
+const char* navc_last_error(void);
+/* One-time per-process setup for `device`: opt-in shared memory sizes, driver entry points. */
+int navc_init(int device);
+/* Number of SMs of the current device (grid sizing of the persistent kernels). */
+int navc_sm_count(void);
+
+/* ---- dense layers -------------------------------------------------------------------------- */
+/* Y[M,N] = epilogue(X[M,K] * W[N,K]^T), fp32 CUDA-core path (reference-exact mode).
+ * Replaces nn.Linear call sites: models/bert.py:146-152,193,228,241; models/Encoder.py:13-24;
+ * models/Predictor.py:16-21; models/__init__.py:83.  K % 4 == 0, ldx % 4 == 0, ldw % 4 == 0. */
+int navc_linear_f32(const float* x, int ldx, const float* w, int ldw, int M, int N, int K,
+                    const navc_epilogue_t* epi, void* stream);
+
+/* Same contract on the tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue).
+ * Operands are bf16 (hi) or split bf16 (hi+lo); accumulation fp32.  K % 64 == 0, ld % 8 == 0.
+ * x_lo / w_lo may be NULL when mode == NAVC_TC_BF16. */
+int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx,
+                   const uint16_t* w_hi, const uint16_t* w_lo, int ldw, int M, int N, int K,
+                   const navc_epilogue_t* epi, void* stream);
+
+/* fp32 -> bf16 hi/lo split of a contiguous buffer (weights are split once when packed). */
+int navc_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int64_t n, void* stream);
+
+/* ---- vocabulary projection with on-the-fly softmax statistics ------------------------------- */
+/* For logits[M,V] = H[M,K] * Wv[V,K]^T (+bias), never written to memory, emit per row and per
+ * column tile t (tile width = navc_vocab_tile(tc)) the partial triple
+ *   part_max[row,t] = max_c logit, part_sum[row,t] = sum_c exp(logit - max), part_idx[row,t] = argmax
+ * (lowest column on ties) and, if `target` != NULL, target_logit[row] = logit[row, target[row]].
+ * Replaces model.tgt_word_prj + F.softmax + max (decoding/algorithms.py:7-15, 149, 197-200). */
+int navc_vocab_tile(int tc);
+int navc_vocab_partials_f32(const float* h, int ldh, const float* w, int ldw, const float* bias,
+                            int M, int V, int K, float* part_max, float* part_sum, int32_t* part_idx,
+                            const int64_t* target, float* target_logit, void* stream);
+int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,
+                           const uint16_t* w_hi, const uint16_t* w_lo, int ldw, const float* bias,
+                           int M, int V, int K, float* part_max, float* part_sum, int32_t* part_idx,
+                           const int64_t* target, float* target_logit, void* stream);
+/* log_softmax over rows of a materialised logits matrix, in place allowed (seq2seq.py:102-103). */
+int navc_log_softmax(const float* logits, float* out, int M, int V, int ld, void* stream);
+
+/* ---- encoder ------------------------------------------------------------------------------- */
+/* Highway gate + frame mean + (eval) BatchNorm + temporal concat for one modality
+ * (models/Encoder.py:19-25; models/joint_representation.py:27, 43-51).
+ *   x  [B*F, D]  = Linear0(feats) ;  yg [B*F, 2D] = [w1 x + b1 | w2 x + b2] (pre-activation)
+ *   o = sigmoid(g)*x + (1-sigmoid(g))*tanh(y)        (gate==0: o = x + tanh(y), yg is [B*F, D])
+ *   enc_hidden[b,:] (+)= mean_f(o) / n_modalities    (accumulate != 0 adds to the existing value)
+ *   enc_out[b, slot*F + f, :] = bn ? (o - rm) / sqrt(rv + eps) * bw + bb : o
+ * enc_out has E rows per video (ld = D); optional bf16 hi/lo copies of enc_out. */
+int navc_highway_bn(const float* x, const float* yg, int gate, int B, int F, int D, int E, int slot,
+                    int n_modalities, int accumulate, const float* bn_rm, const float* bn_rv,
+                    const float* bn_w, const float* bn_b, float bn_eps, float* enc_hidden,
+                    float* enc_out, uint16_t* enc_hi, uint16_t* enc_lo, void* stream);
+
+/* Length head (models/Predictor.py:23-30) + the frame mean reused by enhance_input=2
+ * (models/Decoder.py:137): enc_mean[b,:] = mean_e enc_out[b,e,:];
+ * pred_length[b,:] = log_softmax(W2 relu(W1 enc_mean + b1) + b2).  w1 may be NULL (mean only). */
+int navc_length_head(const float* enc_out, int B, int E, int D, const float* w1, const float* b1,
+                     const float* w2, const float* b2, int max_len, float* enc_mean,
+                     float* pred_length, void* stream);
+
+/* ---- decoder ------------------------------------------------------------------------------- */
+/* BertEmbeddings (models/bert.py:70-96): out[n,s,:] = LayerNorm(word[tok] + pos[s] +
+ * cat[category[n / group]] + extra[n / group]); cat_emb / extra may be NULL.  `group` = decoder rows
+ * per video (length candidates); category and extra are per video.  tokens [N,S]; outputs [N*S, D]. */
+int navc_embed_ln(const int64_t* tokens, const int64_t* category, const float* word_emb,
+                  const float* pos_emb, const float* cat_emb, const float* extra, int group,
+                  const float* ln_w, const float* ln_b, float eps, int N, int S, int D,
+                  float* out_f32, uint16_t* out_hi, uint16_t* out_lo, void* stream);
+
+/* LayerNorm over rows (+ optional `* non_pad_mask`): with_layernorm=True variant of
+ * BertSelfOutput / BertOutput (models/bert.py:198-199, 244-245).  In place allowed. */
+int navc_layernorm(const float* x, const float* w, const float* b, float eps, const int64_t* row_tokens,
+                   int M, int D, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, void* stream);
+
+/* Token self-attention core (models/bert.py:154-176): per (row n, head h)
+ * softmax(mask_fill(Q K^T / sqrt(dk), -1e7)) V with the mask derived in-kernel from the tokens
+ * (key j masked iff tokens[n,j]==PAD; + causal / diagonal per mask_kind; `watch` as
+ * models/Decoder.py:23-39).  qkv [N*S, ld] holds Q | K | V at column offsets 0, D, 2D.
+ * ctx outputs [N*S, D] (merged heads).  probs (optional) is [H, N, S, S]. */
+int navc_self_attention(const float* qkv, int ld, const int64_t* tokens, int N, int S, int D, int H,
+                        int mask_kind, int watch, float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo,
+                        float* probs, void* stream);
+
+/* Text-to-video cross-attention core (models/bert.py:282-290 with the all-False mask of
+ * models/Decoder.py:127-128).  q [N*S, ldq]; kv [(N/group)*E, ldkv] holds K | V at column offsets
+ * 0 and D for this layer (computed once per video, shared by its `group` length candidates --
+ * replaces the physical x lbs repeat of misc/utils.py:205-213).  probs (optional) [H, N, S, E]. */
+int navc_cross_attention(const float* q, int ldq, const float* kv, int ldkv, int N, int S, int E,
+                         int D, int H, int group, float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo,
+                         float* probs, void* stream);
+
+/* ---- iterative refinement (decoding/na_generate.py, decoding/algorithms.py) ----------------- */
+/* Length beam + canvas (na_generate.py:33-50, 116-135): beam[b,:] = clamp(top-lbs indices of
+ * pred_length[b,:] + length_bias, 4, max_len-1) (descending value, lowest index on ties);
+ * smax[0] = max over the batch (int32, atomicMax; caller zeroes it).  */
+int navc_length_beam(const float* pred_length, int B, int max_len, int lbs, int length_bias,
+                     int32_t* beam, int32_t* smax, void* stream);
+/* canvas[n,s] = tokens[n,s] = s < beam[n] ? fill : PAD ; probs[n,s] = s < beam[n] ? 0 : 1
+ * (algorithms.py:291-292, 363-364).  tokens / probs may be NULL. */
+int navc_init_canvas(const int32_t* beam, int N, int S, int64_t fill, int64_t* canvas, int64_t* tokens,
+                     float* probs, void* stream);
+
+/* How the step kernel merges the pass result into the state and which positions it re-masks. */
+enum {
+    NAVC_MERGE_NONE = 0,     /* no pass result */
+    NAVC_MERGE_ALL = 1,      /* first pass: take every position (algorithms.py:238-241) */
+    NAVC_MERGE_MASKED = 2,   /* only where upd_mask (algorithms.py:264-265) */
+    NAVC_MERGE_EF = 3,       /* easy-first commit: min(q, remaining) most confident masked (297-309) */
+};
+enum {
+    NAVC_SELECT_NONE = 0,    /* last step: no re-mask, emit lprobs = log(prob * teacher) */
+    NAVC_SELECT_WORST = 1,   /* k = max(1, trunc(float(len)*ratio)) smallest prob*teacher (206-215) */
+    NAVC_SELECT_MASKTOK = 2, /* positions whose token is MASK (algorithms.py:253-254) */
+    NAVC_SELECT_GIVEN = 3,   /* caller-provided mask `given` (visual_mask, algorithms.py:327, 399) */
+    NAVC_SELECT_KEEP = 4,    /* no re-mask, canvas = tokens (easy-first growth loop, 381-396) */
+    NAVC_SELECT_WINDOW = 5,  /* left-to-right: the win_lo..win_hi-th set positions of `given` (297-316) */
+};
+typedef struct {
+    /* pass result (NULL when merge == NONE) */
+    const float* part_max; const float* part_sum; const int32_t* part_idx; int32_t n_tiles;
+    int32_t is_ct;             /* coarse-grained template pass: prob = 0 where prediction == MASK */
+    int32_t merge;             /* NAVC_MERGE_* */
+    int32_t select;            /* NAVC_SELECT_* */
+    int32_t q;                 /* easy-first commit width */
+    float ratio;               /* NAVC_SELECT_WORST */
+    int32_t win_lo, win_hi;    /* NAVC_SELECT_WINDOW */
+    const int32_t* lens;       /* [N] candidate lengths (positions >= len are PAD) */
+    const float* teacher;      /* [N,S] teacher probabilities or NULL (= ones) */
+    const uint8_t* given;      /* [N,S] for NAVC_SELECT_GIVEN / NAVC_SELECT_WINDOW */
+    int64_t* tokens;           /* [N,S] state: current hypothesis */
+    float* probs;              /* [N,S] state: its probabilities */
+    uint8_t* upd_mask;         /* [N,S] in: positions masked for the pass just run; out: next */
+    int64_t* canvas;           /* [N,S] out: decoder input of the next pass */
+    float* lprobs;             /* [N,S] out (NAVC_SELECT_NONE): log(prob * teacher) */
+    int32_t* counters;         /* [2] out, atomicAdd (caller zeroes): [0] MASK tokens left in `tokens`
+                                  after the merge, [1] positions selected for re-masking */
+    uint8_t* visual;           /* [N,S] out or NULL: token != MASK && != PAD after the merge */
+    uint8_t* masked0;          /* [N,S] out or NULL: token == MASK && s < len after the merge */
+} navc_step_t;
+/* One launch per refinement iteration: combine the vocabulary partials into (argmax, max prob),
+ * apply the pad rules, merge into the state, choose the next positions to re-mask, write the next
+ * canvas.  N rows of S positions. */
+int navc_refine_step(const navc_step_t* p, int N, int S, void* stream);
+
+/* Teacher re-scoring tail (algorithms.py:197-203): teacher[n,s] = exp(target_logit - max)/sum from
+ * combined partials; 1.0 at pads (s >= lens[n]). */
+int navc_teacher_probs(const float* part_max, const float* part_sum, int n_tiles, const float* target_logit,
+                       const int32_t* lens, int N, int S, float* teacher, void* stream);
+/* Shifted teacher input (algorithms.py:189-190, optional id remap 169-173):
+ * out[n,0] = BOS, out[n,s] = map(tokens[n,s-1]); mapped[n,s] = map(tokens[n,s]). map may be NULL. */
+int navc_teacher_inputs(const int64_t* tokens, const int64_t* map, int N, int S, int64_t* shifted,
+                        int64_t* mapped, void* stream);
+
+/* Candidate selection (na_generate.py:66-77): score[b,j] = sum_s lprobs / len^alpha; first argmax
+ * over j; hyp[b,:] = tokens[b*lbs + j*, :]. */
+int navc_select_best(const int64_t* tokens, const float* lprobs, const int32_t* lens, int B, int lbs,
+                     int S, float alpha, int64_t* hyp, float* score, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAVC_H */

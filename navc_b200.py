@@ -1,0 +1,13 @@
+"""Import alias: the package directory is named after the reference repo
+(`non-autoregressive-video-captioning_b200/`, not a valid Python identifier); `import navc_b200`
+loads it under an importable name."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "non-autoregressive-video-captioning_b200")
+_spec = importlib.util.spec_from_file_location("navc_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["navc_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,150 @@
+// Shared device/host helpers for libnavc (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/navc.h"
+
+namespace navc {
+
+// ---- error reporting (thread local message, C ABI returns int) ---------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define NAVC_REQUIRE(cond, ...)            \
+    do {                                   \
+        if (!(cond)) {                     \
+            navc::set_error(__VA_ARGS__);  \
+            return 1;                      \
+        }                                  \
+    } while (0)
+
+#define NAVC_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            navc::set_error("%s failed: %s", #call, cudaGetErrorString(e__));            \
+            return 2;                                                                    \
+        }                                                                                \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- bf16 split ------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t bf16_bits(float x) {
+    return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ float bf16_to_f32(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+    hi = bf16_bits(x);
+    lo = bf16_bits(x - bf16_to_f32(hi));
+}
+
+// ---- activations (models/bert.py:9-19) ----------------------------------------------------------
+__device__ __forceinline__ float act_apply(float x, int act) {
+    switch (act) {
+        case NAVC_ACT_GELU_NEW: {
+            const float c = 0.7978845608028654f;  // sqrt(2/pi)
+            float x3 = x * x * x;
+            return 0.5f * x * (1.0f + tanhf(c * (x + 0.044715f * x3)));
+        }
+        case NAVC_ACT_GELU: return x * 0.5f * (1.0f + erff(x * 0.7071067811865475f));
+        case NAVC_ACT_RELU: return fmaxf(x, 0.0f);
+        case NAVC_ACT_SWISH: return x / (1.0f + expf(-x));
+        default: return x;
+    }
+}
+
+// Epilogue for `n` consecutive columns of one row (n <= 8 typical); col0 multiple of 4 when n>=4.
+struct EpiParams {
+    const float* bias;
+    const float* residual;
+    const int64_t* row_tokens;
+    int act;
+    int ld_res;
+    float* out_f32;
+    uint16_t* out_hi;
+    uint16_t* out_lo;
+    int ld_out;
+};
+static inline EpiParams to_params(const navc_epilogue_t* e) {
+    EpiParams p;
+    p.bias = e->bias; p.residual = e->residual; p.row_tokens = e->row_tokens; p.act = e->act;
+    p.ld_res = e->ld_res; p.out_f32 = e->out_f32; p.out_hi = e->out_hi; p.out_lo = e->out_lo;
+    p.ld_out = e->ld_out;
+    return p;
+}
+
+// store 4 consecutive columns [col, col+4) of `row`; caller guarantees col+4 <= N or uses the tail path
+__device__ __forceinline__ void epi_store4(const EpiParams& p, int row, int col, float4 v, bool row_zero) {
+    if (p.bias) {
+        float4 b = *reinterpret_cast<const float4*>(p.bias + col);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (p.act) {
+        v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act);
+        v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act);
+    }
+    if (p.residual) {
+        float4 r = *reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + col);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (row_zero) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    size_t o = (size_t)row * p.ld_out + col;
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+    if (p.out_hi) {
+        uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+        uint2 hv = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+        *reinterpret_cast<uint2*>(p.out_hi + o) = hv;
+        if (p.out_lo) {
+            uint2 lv = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+            *reinterpret_cast<uint2*>(p.out_lo + o) = lv;
+        }
+    }
+}
+__device__ __forceinline__ void epi_store1(const EpiParams& p, int row, int col, float v, bool row_zero) {
+    if (p.bias) v += p.bias[col];
+    if (p.act) v = act_apply(v, p.act);
+    if (p.residual) v += p.residual[(size_t)row * p.ld_res + col];
+    if (row_zero) v = 0.f;
+    size_t o = (size_t)row * p.ld_out + col;
+    if (p.out_f32) p.out_f32[o] = v;
+    if (p.out_hi) {
+        uint16_t h, l;
+        split_bf16(v, h, l);
+        p.out_hi[o] = h;
+        if (p.out_lo) p.out_lo[o] = l;
+    }
+}
+
+// ---- warp helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// online-softmax partial (max, sum of exp(x-max), argmax with lowest index on ties)
+struct SoftPart {
+    float m, s;
+    int i;
+};
+__device__ __forceinline__ SoftPart soft_combine(SoftPart a, SoftPart b) {
+    SoftPart r;
+    if (b.m > a.m || (b.m == a.m && b.i < a.i)) { r.m = b.m; r.i = b.i; } else { r.m = a.m; r.i = a.i; }
+    float sa = (a.s == 0.f) ? 0.f : a.s * expf(a.m - r.m);
+    float sb = (b.s == 0.f) ? 0.f : b.s * expf(b.m - r.m);
+    r.s = sa + sb;
+    return r;
+}
+
+}  // namespace navc

@@ -1,0 +1,280 @@
+// Iterative-refinement decode kernels: length beam, canvas init, the fused per-iteration step
+// (combine vocabulary partials -> argmax/prob -> pad rules -> merge -> re-mask selection -> next
+// canvas), teacher probabilities and candidate selection.  All tiny, latency-bound, int/float work.
+#include "common.cuh"
+
+namespace navc {
+
+// one warp per video: top-`lbs` of max_len values (descending, lowest index first on ties)
+__global__ void length_beam_kernel(const float* __restrict__ pred, int B, int max_len, int lbs, int bias,
+                                   int32_t* __restrict__ beam, int32_t* __restrict__ smax) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= B) return;
+    float* vals = sm + (size_t)warp * max_len;
+    for (int i = lane; i < max_len; i += 32) vals[i] = pred[(size_t)b * max_len + i];
+    __syncwarp();
+    int local_max = 0;
+    for (int r = 0; r < lbs; ++r) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < max_len; i += 32) {
+            float v = vals[i];
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        int len = bi + bias;
+        len = len < 4 ? 4 : len;
+        len = len > max_len - 1 ? max_len - 1 : len;
+        if (lane == 0) {
+            beam[(size_t)b * lbs + r] = len;
+            vals[bi] = -INFINITY;  // NaN-free inputs assumed (log-probabilities)
+        }
+        local_max = max(local_max, len);
+        __syncwarp();
+    }
+    if (lane == 0) atomicMax(smax, local_max);
+}
+
+__global__ void init_canvas_kernel(const int32_t* __restrict__ beam, int N, int S, int64_t fill,
+                                   int64_t* canvas, int64_t* tokens, float* probs) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * S) return;
+    int n = idx / S, s = idx - n * S;
+    bool inside = s < beam[n];
+    int64_t t = inside ? fill : (int64_t)NAVC_PAD;
+    if (canvas) canvas[idx] = t;
+    if (tokens) tokens[idx] = t;
+    if (probs) probs[idx] = inside ? 0.f : 1.f;
+}
+
+struct StepArgs {
+    navc_step_t p;
+};
+
+// one block per candidate row; thread i owns position i.
+__global__ void refine_step_kernel(StepArgs a, int S) {
+    extern __shared__ float sm[];
+    float* key = sm;                                   // [S] ranking keys
+    int* flag = reinterpret_cast<int*>(sm + S);        // [S] 0/1 flags
+    const navc_step_t& p = a.p;
+    const int n = blockIdx.x, i = threadIdx.x;
+    const bool active = i < S;
+    const size_t o = (size_t)n * S + (active ? i : 0);
+    const int len = p.lens[n];
+    const bool pad = active && i >= len;
+
+    int64_t tok = active ? p.tokens[o] : (int64_t)NAVC_PAD;
+    float prob = active ? p.probs[o] : 1.f;
+
+    if (p.merge != NAVC_MERGE_NONE) {
+        int64_t ntok = NAVC_PAD;
+        float nprob = 1.f;
+        if (active) {
+            const size_t pr = o * p.n_tiles;
+            SoftPart acc;
+            acc.m = -INFINITY; acc.s = 0.f; acc.i = 0x7fffffff;
+            for (int t = 0; t < p.n_tiles; ++t) {
+                SoftPart q;
+                q.m = p.part_max[pr + t]; q.s = p.part_sum[pr + t]; q.i = p.part_idx[pr + t];
+                acc = soft_combine(acc, q);
+            }
+            ntok = acc.i;
+            nprob = 1.0f / acc.s;
+            if (pad) { ntok = NAVC_PAD; nprob = 1.0f; }
+            if (p.is_ct && ntok == NAVC_MASK) nprob = 0.0f;
+        }
+        if (p.merge == NAVC_MERGE_ALL) {
+            tok = ntok; prob = nprob;
+        } else if (p.merge == NAVC_MERGE_MASKED) {
+            if (active && p.upd_mask[o]) { tok = ntok; prob = nprob; }
+        } else {  // NAVC_MERGE_EF
+            const bool is_masked = active && tok == NAVC_MASK;
+            const float cand = is_masked ? nprob : 0.f;
+            if (active) key[i] = cand;
+            const int remaining = __syncthreads_count(is_masked);
+            const int k = remaining < p.q ? remaining : p.q;
+            if (active) {
+                int rank = 0;
+                for (int j = 0; j < S; ++j) {
+                    float kj = key[j];
+                    rank += (kj > cand) || (kj == cand && j < i);
+                }
+                if (rank < k) { tok = ntok; prob = cand; }
+            }
+            __syncthreads();
+        }
+    }
+
+    const int left = __syncthreads_count(active && tok == NAVC_MASK);
+    if (active) {
+        if (p.visual) p.visual[o] = (tok != NAVC_MASK && tok != NAVC_PAD) ? 1 : 0;
+        if (p.masked0) p.masked0[o] = (tok == NAVC_MASK && i < len) ? 1 : 0;
+    }
+
+    const float tprob = (active && p.teacher) ? p.teacher[o] : 1.f;
+    bool sel = false;
+    if (p.select == NAVC_SELECT_WORST) {
+        int k = (int)((float)len * p.ratio);
+        k = k < 1 ? 1 : k;
+        const float mykey = prob * tprob;
+        if (active) key[i] = mykey;
+        __syncthreads();
+        if (active) {
+            int rank = 0;
+            for (int j = 0; j < S; ++j) {
+                float kj = key[j];
+                rank += (kj < mykey) || (kj == mykey && j < i);
+            }
+            sel = rank < k;
+        }
+    } else if (p.select == NAVC_SELECT_MASKTOK) {
+        sel = active && tok == NAVC_MASK;
+    } else if (p.select == NAVC_SELECT_GIVEN) {
+        sel = active && p.given[o] != 0;
+    } else if (p.select == NAVC_SELECT_WINDOW) {
+        const int g = (active && p.given[o] != 0) ? 1 : 0;
+        if (active) flag[i] = g;
+        __syncthreads();
+        if (g) {
+            int ord = 0;
+            for (int j = 0; j < i; ++j) ord += flag[j];
+            sel = ord >= p.win_lo && ord < p.win_hi;
+        }
+    }
+    const int nsel = __syncthreads_count(sel);
+    if (active) {
+        p.tokens[o] = tok;
+        p.probs[o] = prob;
+        if (p.upd_mask) p.upd_mask[o] = sel ? 1 : 0;
+        if (p.canvas) p.canvas[o] = sel ? (int64_t)NAVC_MASK : tok;
+        if (p.select == NAVC_SELECT_NONE && p.lprobs) p.lprobs[o] = logf(prob * tprob);
+    }
+    if (i == 0 && p.counters) {
+        if (left) atomicAdd(p.counters + 0, left);
+        if (nsel) atomicAdd(p.counters + 1, nsel);
+    }
+}
+
+__global__ void teacher_probs_kernel(const float* __restrict__ pm, const float* __restrict__ ps, int n_tiles,
+                                     const float* __restrict__ tl, const int32_t* __restrict__ lens, int N, int S,
+                                     float* __restrict__ out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * S) return;
+    int n = idx / S, s = idx - n * S;
+    if (s >= lens[n]) { out[idx] = 1.0f; return; }
+    SoftPart acc;
+    acc.m = -INFINITY; acc.s = 0.f; acc.i = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        SoftPart q;
+        q.m = pm[(size_t)idx * n_tiles + t]; q.s = ps[(size_t)idx * n_tiles + t]; q.i = 0;
+        acc = soft_combine(acc, q);
+    }
+    out[idx] = expf(tl[idx] - acc.m) / acc.s;
+}
+
+__global__ void teacher_inputs_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ map, int N,
+                                      int S, int64_t* __restrict__ shifted, int64_t* __restrict__ mapped) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * S) return;
+    int s = idx % S;
+    int64_t t = tokens[idx];
+    if (map) t = map[t];
+    mapped[idx] = t;
+    if (s == 0) shifted[idx] = NAVC_BOS;
+    if (s + 1 < S) shifted[idx + 1] = t;
+}
+
+// one warp per video
+__global__ void select_best_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ lprobs,
+                                   const int32_t* __restrict__ lens, int B, int lbs, int S, float alpha,
+                                   int64_t* __restrict__ hyp, float* __restrict__ score) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= B) return;
+    float best = -INFINITY;
+    int bj = 0;
+    for (int j = 0; j < lbs; ++j) {
+        const size_t row = (size_t)b * lbs + j;
+        // sequential sum in position order (matches a left-to-right fp32 reduction closely; the
+        // comparison between candidates only needs to be stable, ties resolve to the lowest j)
+        float s = 0.f;
+        for (int t = lane; t < S; t += 32) s += lprobs[row * S + t];
+        s = warp_sum(s);
+        float sc = s / powf((float)lens[row], alpha);
+        if (score && lane == 0) score[row] = sc;
+        if (sc > best) { best = sc; bj = j; }
+    }
+    const size_t row = (size_t)b * lbs + bj;
+    for (int t = lane; t < S; t += 32) hyp[(size_t)b * S + t] = tokens[row * S + t];
+}
+
+}  // namespace navc
+
+using namespace navc;
+
+extern "C" int navc_length_beam(const float* pred_length, int B, int max_len, int lbs, int length_bias,
+                                int32_t* beam, int32_t* smax, void* stream) {
+    NAVC_REQUIRE(pred_length && beam && smax, "navc_length_beam: null pointer");
+    NAVC_REQUIRE(B > 0 && max_len > 4 && lbs > 0 && lbs <= max_len, "navc_length_beam: bad shape");
+    const int wpb = 4;
+    size_t smem = (size_t)wpb * max_len * sizeof(float);
+    length_beam_kernel<<<(B + wpb - 1) / wpb, wpb * 32, smem, as_stream(stream)>>>(pred_length, B, max_len, lbs,
+                                                                                  length_bias, beam, smax);
+    return check_launch("navc_length_beam");
+}
+
+extern "C" int navc_init_canvas(const int32_t* beam, int N, int S, int64_t fill, int64_t* canvas, int64_t* tokens,
+                                float* probs, void* stream) {
+    NAVC_REQUIRE(beam && N > 0 && S > 0, "navc_init_canvas: bad arguments");
+    init_canvas_kernel<<<(N * S + 255) / 256, 256, 0, as_stream(stream)>>>(beam, N, S, fill, canvas, tokens, probs);
+    return check_launch("navc_init_canvas");
+}
+
+extern "C" int navc_refine_step(const navc_step_t* p, int N, int S, void* stream) {
+    NAVC_REQUIRE(p && p->lens && p->tokens && p->probs, "navc_refine_step: null pointer");
+    NAVC_REQUIRE(N > 0 && S > 0 && S <= 1024, "navc_refine_step: bad shape");
+    NAVC_REQUIRE(p->merge == NAVC_MERGE_NONE || (p->part_max && p->part_sum && p->part_idx && p->n_tiles > 0),
+                 "navc_refine_step: merge requested without partials");
+    NAVC_REQUIRE(p->merge != NAVC_MERGE_MASKED || p->upd_mask, "navc_refine_step: MERGE_MASKED needs upd_mask");
+    NAVC_REQUIRE((p->select != NAVC_SELECT_GIVEN && p->select != NAVC_SELECT_WINDOW) || p->given,
+                 "navc_refine_step: selection needs `given`");
+    StepArgs a;
+    a.p = *p;
+    int threads = ((S + 31) / 32) * 32;
+    size_t smem = (size_t)S * (sizeof(float) + sizeof(int));
+    refine_step_kernel<<<N, threads, smem, as_stream(stream)>>>(a, S);
+    return check_launch("navc_refine_step");
+}
+
+extern "C" int navc_teacher_probs(const float* part_max, const float* part_sum, int n_tiles,
+                                  const float* target_logit, const int32_t* lens, int N, int S, float* teacher,
+                                  void* stream) {
+    NAVC_REQUIRE(part_max && part_sum && target_logit && lens && teacher && n_tiles > 0,
+                 "navc_teacher_probs: bad arguments");
+    teacher_probs_kernel<<<(N * S + 255) / 256, 256, 0, as_stream(stream)>>>(part_max, part_sum, n_tiles,
+                                                                            target_logit, lens, N, S, teacher);
+    return check_launch("navc_teacher_probs");
+}
+
+extern "C" int navc_teacher_inputs(const int64_t* tokens, const int64_t* map, int N, int S, int64_t* shifted,
+                                   int64_t* mapped, void* stream) {
+    NAVC_REQUIRE(tokens && shifted && mapped, "navc_teacher_inputs: null pointer");
+    teacher_inputs_kernel<<<(N * S + 255) / 256, 256, 0, as_stream(stream)>>>(tokens, map, N, S, shifted, mapped);
+    return check_launch("navc_teacher_inputs");
+}
+
+extern "C" int navc_select_best(const int64_t* tokens, const float* lprobs, const int32_t* lens, int B, int lbs,
+                                int S, float alpha, int64_t* hyp, float* score, void* stream) {
+    NAVC_REQUIRE(tokens && lprobs && lens && hyp, "navc_select_best: null pointer");
+    const int wpb = 4;
+    select_best_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, as_stream(stream)>>>(tokens, lprobs, lens, B, lbs, S,
+                                                                               alpha, hyp, score);
+    return check_launch("navc_select_best");
+}

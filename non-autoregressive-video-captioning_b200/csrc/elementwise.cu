@@ -1,0 +1,330 @@
+// HBM-bound vectorised kernels: bf16 split, highway gate + BatchNorm + concat, length head,
+// embedding gather + LayerNorm, LayerNorm, log-softmax.
+#include "common.cuh"
+
+namespace navc {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi,
+                                  uint16_t* __restrict__ lo, int64_t n) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += stride) {
+        if (i + 4 <= n) {
+            float4 v = *reinterpret_cast<const float4*>(x + i);
+            uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+            split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+            *reinterpret_cast<uint2*>(hi + i) =
+                make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+            if (lo)
+                *reinterpret_cast<uint2*>(lo + i) =
+                    make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+        } else {
+            for (int64_t j = i; j < n; ++j) {
+                uint16_t h, l;
+                split_bf16(x[j], h, l);
+                hi[j] = h;
+                if (lo) lo[j] = l;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one block per video; thread d owns column d (strided), loops over the F frames.
+__global__ void highway_bn_kernel(const float* __restrict__ x, const float* __restrict__ yg, int gate, int F,
+                                  int D, int E, int slot, float inv_fm, int accumulate,
+                                  const float* __restrict__ rm, const float* __restrict__ rv,
+                                  const float* __restrict__ bw, const float* __restrict__ bb, float eps,
+                                  float* __restrict__ enc_hidden, float* __restrict__ enc_out,
+                                  uint16_t* __restrict__ enc_hi, uint16_t* __restrict__ enc_lo) {
+    const int b = blockIdx.x;
+    const int ldy = gate ? 2 * D : D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float mean = 0.f, istd = 1.f, w = 1.f, bias = 0.f;
+        if (rm) {
+            mean = rm[d];
+            istd = 1.0f / sqrtf(rv[d] + eps);
+            w = bw ? bw[d] : 1.f;
+            bias = bb ? bb[d] : 0.f;
+        }
+        float hsum = 0.f;
+        for (int f = 0; f < F; ++f) {
+            size_t r = (size_t)b * F + f;
+            float xv = x[r * D + d];
+            float y = tanhf(yg[r * ldy + d]);
+            float o;
+            if (gate) {
+                float g = 1.0f / (1.0f + expf(-yg[r * ldy + D + d]));
+                o = g * xv + (1.0f - g) * y;
+            } else {
+                o = xv + y;
+            }
+            hsum += o;
+            float v = rm ? ((o - mean) * istd * w + bias) : o;
+            size_t oi = ((size_t)b * E + (size_t)slot * F + f) * D + d;
+            enc_out[oi] = v;
+            if (enc_hi) {
+                uint16_t h, l;
+                split_bf16(v, h, l);
+                enc_hi[oi] = h;
+                if (enc_lo) enc_lo[oi] = l;
+            }
+        }
+        if (enc_hidden) {
+            float hv = hsum * inv_fm;
+            size_t hi_ = (size_t)b * D + d;
+            enc_hidden[hi_] = accumulate ? enc_hidden[hi_] + hv : hv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one block (256 threads) per video.  dynamic smem: mean[D] + h1[D] + logits[max_len]
+__global__ void length_head_kernel(const float* __restrict__ enc_out, int E, int D,
+                                   const float* __restrict__ w1, const float* __restrict__ b1,
+                                   const float* __restrict__ w2, const float* __restrict__ b2, int max_len,
+                                   float* __restrict__ enc_mean, float* __restrict__ pred_length) {
+    extern __shared__ float sm[];
+    float* mean = sm;
+    float* h1 = sm + D;
+    float* logit = sm + 2 * D;
+    const int b = blockIdx.x;
+    const float* src = enc_out + (size_t)b * E * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.f;
+        for (int e = 0; e < E; ++e) s += src[(size_t)e * D + d];
+        float m = s / (float)E;
+        mean[d] = m;
+        if (enc_mean) enc_mean[(size_t)b * D + d] = m;
+    }
+    if (!w1) return;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < D; j += nw) {
+        const float* wr = w1 + (size_t)j * D;
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) s = fmaf(wr[d], mean[d], s);
+        s = warp_sum(s);
+        if (lane == 0) h1[j] = fmaxf(s + b1[j], 0.f);
+    }
+    __syncthreads();
+    for (int j = warp; j < max_len; j += nw) {
+        const float* wr = w2 + (size_t)j * D;
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) s = fmaf(wr[d], h1[d], s);
+        s = warp_sum(s);
+        if (lane == 0) logit[j] = s + b2[j];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float m = -INFINITY;
+        for (int j = lane; j < max_len; j += 32) m = fmaxf(m, logit[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < max_len; j += 32) s += expf(logit[j] - m);
+        s = warp_sum(s);
+        float lse = m + logf(s);
+        for (int j = lane; j < max_len; j += 32) pred_length[(size_t)b * max_len + j] = logit[j] - lse;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm of one row held in registers by one warp: lane owns float4 chunks c = lane + 32*t.
+constexpr int kMaxChunks = 8;  // D <= 1024
+
+__device__ __forceinline__ void warp_ln_store(float4 (&v)[kMaxChunks], int nchunk, int D, int lane,
+                                              const float* __restrict__ w, const float* __restrict__ b,
+                                              float eps, bool zero, size_t row, float* out_f32,
+                                              uint16_t* out_hi, uint16_t* out_lo) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < kMaxChunks; ++t)
+        if (t < nchunk && lane + 32 * t < D / 4) s += v[t].x + v[t].y + v[t].z + v[t].w;
+    float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int t = 0; t < kMaxChunks; ++t)
+        if (t < nchunk && lane + 32 * t < D / 4) {
+            float a = v[t].x - mean, bq = v[t].y - mean, c = v[t].z - mean, d = v[t].w - mean;
+            q += a * a + bq * bq + c * c + d * d;
+        }
+    float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int t = 0; t < kMaxChunks; ++t) {
+        int c = lane + 32 * t;
+        if (t < nchunk && c < D / 4) {
+            float4 ww = *reinterpret_cast<const float4*>(w + c * 4);
+            float4 bv = *reinterpret_cast<const float4*>(b + c * 4);
+            float4 o;
+            o.x = (v[t].x - mean) * rstd * ww.x + bv.x;
+            o.y = (v[t].y - mean) * rstd * ww.y + bv.y;
+            o.z = (v[t].z - mean) * rstd * ww.z + bv.z;
+            o.w = (v[t].w - mean) * rstd * ww.w + bv.w;
+            if (zero) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            size_t oi = row * D + (size_t)c * 4;
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = o;
+            if (out_hi) {
+                uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+                split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
+                *reinterpret_cast<uint2*>(out_hi + oi) =
+                    make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+                if (out_lo)
+                    *reinterpret_cast<uint2*>(out_lo + oi) =
+                        make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+            }
+        }
+    }
+}
+
+__global__ void embed_ln_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ category,
+                                const float* __restrict__ word, const float* __restrict__ pos,
+                                const float* __restrict__ cat, const float* __restrict__ extra, int group,
+                                const float* __restrict__ lw, const float* __restrict__ lb, float eps, int R,
+                                int S, int D, float* out_f32, uint16_t* out_hi, uint16_t* out_lo) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= R) return;
+    const int n = row / S, s = row % S;
+    const int64_t tok = tokens[row];
+    const float* wr = word + (size_t)tok * D;
+    const float* pr = pos + (size_t)s * D;
+    const float* cr = cat ? cat + (size_t)category[n / group] * D : nullptr;
+    const float* er = extra ? extra + (size_t)(n / group) * D : nullptr;
+    const int nchunk = (D / 4 + 31) / 32;
+    float4 v[kMaxChunks];
+#pragma unroll
+    for (int t = 0; t < kMaxChunks; ++t) {
+        int c = lane + 32 * t;
+        if (t < nchunk && c < D / 4) {
+            float4 a = *reinterpret_cast<const float4*>(wr + c * 4);
+            float4 p = *reinterpret_cast<const float4*>(pr + c * 4);
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+            if (cr) {
+                float4 q = *reinterpret_cast<const float4*>(cr + c * 4);
+                a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+            }
+            if (er) {
+                float4 q = *reinterpret_cast<const float4*>(er + c * 4);
+                a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+            }
+            v[t] = a;
+        }
+    }
+    warp_ln_store(v, nchunk, D, lane, lw, lb, eps, false, (size_t)row, out_f32, out_hi, out_lo);
+}
+
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ lw,
+                                 const float* __restrict__ lb, float eps, const int64_t* __restrict__ row_tokens,
+                                 int R, int D, float* out_f32, uint16_t* out_hi, uint16_t* out_lo) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= R) return;
+    const int nchunk = (D / 4 + 31) / 32;
+    float4 v[kMaxChunks];
+#pragma unroll
+    for (int t = 0; t < kMaxChunks; ++t) {
+        int c = lane + 32 * t;
+        if (t < nchunk && c < D / 4) v[t] = *reinterpret_cast<const float4*>(x + (size_t)row * D + c * 4);
+    }
+    bool zero = row_tokens ? (row_tokens[row] == NAVC_PAD) : false;
+    warp_ln_store(v, nchunk, D, lane, lw, lb, eps, zero, (size_t)row, out_f32, out_hi, out_lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one block per row: log_softmax over V columns
+__global__ void log_softmax_kernel(const float* __restrict__ x, float* __restrict__ out, int V, int ld) {
+    __shared__ float red[32];
+    const float* r = x + (size_t)blockIdx.x * ld;
+    float* o = out + (size_t)blockIdx.x * ld;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, r[i]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = (lane < nw) ? red[lane] : -INFINITY;
+    m = warp_max(m);
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(r[i] - m);
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = (lane < nw) ? red[lane] : 0.f;
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    for (int i = threadIdx.x; i < V; i += blockDim.x) o[i] = r[i] - lse;
+}
+
+}  // namespace navc
+
+using namespace navc;
+
+extern "C" int navc_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int64_t n, void* stream) {
+    NAVC_REQUIRE(x && hi && n >= 0, "navc_split_bf16: bad arguments");
+    if (n == 0) return 0;
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    split_bf16_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, hi, lo, n);
+    return check_launch("navc_split_bf16");
+}
+
+extern "C" int navc_highway_bn(const float* x, const float* yg, int gate, int B, int F, int D, int E, int slot,
+                               int n_modalities, int accumulate, const float* bn_rm, const float* bn_rv,
+                               const float* bn_w, const float* bn_b, float bn_eps, float* enc_hidden,
+                               float* enc_out, uint16_t* enc_hi, uint16_t* enc_lo, void* stream) {
+    NAVC_REQUIRE(x && yg && enc_out, "navc_highway_bn: null pointer");
+    NAVC_REQUIRE(B > 0 && F > 0 && D > 0 && (slot + 1) * F <= E, "navc_highway_bn: bad shape");
+    NAVC_REQUIRE((bn_rm == nullptr) == (bn_rv == nullptr), "navc_highway_bn: need both running stats");
+    int threads = D >= 512 ? 512 : ((D + 31) / 32) * 32;
+    highway_bn_kernel<<<B, threads, 0, as_stream(stream)>>>(x, yg, gate, F, D, E, slot,
+                                                            1.0f / ((float)F * (float)n_modalities), accumulate,
+                                                            bn_rm, bn_rv, bn_w, bn_b, bn_eps, enc_hidden, enc_out,
+                                                            enc_hi, enc_lo);
+    return check_launch("navc_highway_bn");
+}
+
+extern "C" int navc_length_head(const float* enc_out, int B, int E, int D, const float* w1, const float* b1,
+                                const float* w2, const float* b2, int max_len, float* enc_mean,
+                                float* pred_length, void* stream) {
+    NAVC_REQUIRE(enc_out && B > 0 && E > 0 && D > 0, "navc_length_head: bad arguments");
+    NAVC_REQUIRE(!w1 || (b1 && w2 && b2 && pred_length && max_len > 0), "navc_length_head: missing head weights");
+    size_t smem = (size_t)(2 * D + (max_len > 0 ? max_len : 0)) * sizeof(float);
+    length_head_kernel<<<B, 256, smem, as_stream(stream)>>>(enc_out, E, D, w1, b1, w2, b2, max_len, enc_mean,
+                                                           pred_length);
+    return check_launch("navc_length_head");
+}
+
+extern "C" int navc_embed_ln(const int64_t* tokens, const int64_t* category, const float* word_emb,
+                             const float* pos_emb, const float* cat_emb, const float* extra, int group,
+                             const float* ln_w, const float* ln_b, float eps, int N, int S, int D, float* out_f32,
+                             uint16_t* out_hi, uint16_t* out_lo, void* stream) {
+    NAVC_REQUIRE(tokens && word_emb && pos_emb && ln_w && ln_b, "navc_embed_ln: null pointer");
+    NAVC_REQUIRE(!cat_emb || category, "navc_embed_ln: category embeddings without category ids");
+    NAVC_REQUIRE(D % 4 == 0 && D <= 4 * 32 * kMaxChunks, "navc_embed_ln: D must be a multiple of 4 and <= 1024");
+    NAVC_REQUIRE(group >= 1, "navc_embed_ln: group must be >= 1");
+    int R = N * S;
+    int wpb = 8;
+    embed_ln_kernel<<<(R + wpb - 1) / wpb, wpb * 32, 0, as_stream(stream)>>>(
+        tokens, category, word_emb, pos_emb, cat_emb, extra, group, ln_w, ln_b, eps, R, S, D, out_f32, out_hi,
+        out_lo);
+    return check_launch("navc_embed_ln");
+}
+
+extern "C" int navc_layernorm(const float* x, const float* w, const float* b, float eps, const int64_t* row_tokens,
+                              int M, int D, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, void* stream) {
+    NAVC_REQUIRE(x && w && b, "navc_layernorm: null pointer");
+    NAVC_REQUIRE(D % 4 == 0 && D <= 4 * 32 * kMaxChunks, "navc_layernorm: D must be a multiple of 4 and <= 1024");
+    int wpb = 8;
+    layernorm_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, as_stream(stream)>>>(x, w, b, eps, row_tokens, M, D,
+                                                                             out_f32, out_hi, out_lo);
+    return check_launch("navc_layernorm");
+}
+
+extern "C" int navc_log_softmax(const float* logits, float* out, int M, int V, int ld, void* stream) {
+    NAVC_REQUIRE(logits && out && M > 0 && V > 0 && ld >= V, "navc_log_softmax: bad arguments");
+    log_softmax_kernel<<<M, 256, 0, as_stream(stream)>>>(logits, out, V, ld);
+    return check_launch("navc_log_softmax");
+}

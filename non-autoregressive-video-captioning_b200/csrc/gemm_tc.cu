@@ -1,0 +1,403 @@
+// tcgen05 GEMM for sm_100a:  Y = epilogue(X[M,K] * W[N,K]^T)
+//
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (UMMA 128x256x16,
+//   kind::f16, bf16 operands, fp32 accumulators in TMEM, double buffered) -> tcgen05.ld -> fused
+//   epilogue (bias / activation / residual / non-pad row mask / bf16 hi-lo split, or on-the-fly
+//   softmax statistics for the vocabulary projection).
+//
+// Warp roles (192 threads, persistent, one CTA per SM):
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + MMA issuer (one elected lane)
+//   warps 2..5  epilogue, one TMEM lane quarter each (row = TMEM lane)
+//
+// Operand modes: NAVC_TC_BF16 issues one product per k-step (hi*hi); NAVC_TC_BF16X3 issues three
+// (hi*hi + hi*lo + lo*hi) which recovers ~fp32 accuracy from bf16 tensor cores.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace navc {
+
+constexpr int TBM = 128, TBN = 256, TBK = 64;        // CTA tile; TBK bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kTcThreads = 192;
+constexpr int kTileABytes = TBM * TBK * 2;           // 16 KB
+constexpr int kTileBBytes = TBN * TBK * 2;           // 32 KB
+constexpr int kAccStages = 2;                        // 2 x 256 TMEM columns
+constexpr int kTmemCols = 512;
+
+template <bool kX3> struct TcCfg {
+    static constexpr int kStages = kX3 ? 2 : 4;
+    static constexpr int kStageBytes = (kX3 ? 2 : 1) * (kTileABytes + kTileBBytes);
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzled operand tile (rows x 64 bf16): 8-row atoms of 1024 B.
+// cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcVocab {
+    const float* bias;
+    float* part_max;
+    float* part_sum;
+    int32_t* part_idx;
+    const int64_t* target;
+    float* target_logit;
+    int n_tiles;
+};
+
+template <bool kX3, bool kVocab>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               int M, int N, int K, EpiParams epi, TcVocab vep) {
+    using Cfg = TcCfg<kX3>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    // barriers live after the tile ring
+    const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + kAccStages + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 2 * kAccStages));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blocks = (M + TBM - 1) / TBM, n_blocks = (N + TBN - 1) / TBN;
+    const int n_tiles = m_blocks * n_blocks;
+    const int k_blocks = K / TBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int mb = tile / n_blocks, nb = tile % n_blocks;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                    mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * TBK, mb * TBM);
+                    tma_load_2d(sa + kTileABytes, &map_b_hi, full_bar(stage), kb * TBK, nb * TBN);
+                    if (kX3) {
+                        tma_load_2d(sa + kTileABytes + kTileBBytes, &map_a_lo, full_bar(stage), kb * TBK, mb * TBM);
+                        tma_load_2d(sa + 2 * kTileABytes + kTileBBytes, &map_b_lo, full_bar(stage), kb * TBK, nb * TBN);
+                    }
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TBM, TBN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TBN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                    const uint64_t da_hi = make_smem_desc(sa);
+                    const uint64_t db_hi = make_smem_desc(sa + kTileABytes);
+                    const uint64_t da_lo = make_smem_desc(sa + kTileABytes + kTileBBytes);
+                    const uint64_t db_lo = make_smem_desc(sa + 2 * kTileABytes + kTileBBytes);
+#pragma unroll
+                    for (int k = 0; k < TBK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // 32 bytes per k-step
+                        if (kX3) {
+                            // small cross terms first, the dominant hi*hi product last
+                            tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
+                        } else {
+                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(empty_bar(stage));                       // frees the smem slot when the MMAs retire
+                    if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int mb = tile / n_blocks, nb = tile % n_blocks;
+            const int row = mb * TBM + quarter * 32 + lane;
+            const int n0 = nb * TBN;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN);
+
+            if constexpr (!kVocab) {
+                const bool row_ok = row < M;
+                const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[row] == NAVC_PAD) : false;
+                const bool vec = (epi.ld_out % 4 == 0) && (N % 4 == 0) && (!epi.residual || epi.ld_res % 4 == 0);
+#pragma unroll 1
+                for (int c = 0; c < TBN / 32; ++c) {
+                    if (n0 + c * 32 >= N) break;  // warp-uniform
+                    uint32_t r[32];
+                    tc_ld32(t_row + (uint32_t)(c * 32), r);
+                    tc_wait_ld();
+                    if (row_ok) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const int col = n0 + c * 32 + g * 4;
+                            if (col >= N) break;
+                            if (vec) {
+                                epi_store4(epi, row, col,
+                                           make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                                       __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])), rz);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (col + j < N) epi_store1(epi, row, col + j, __uint_as_float(r[g * 4 + j]), rz);
+                            }
+                        }
+                    }
+                }
+            } else {
+                const int64_t tgt = (vep.target && row < M) ? vep.target[row] : -1;
+                float run_m = -INFINITY, run_s = 0.f;
+                int run_i = 0x7fffffff;
+#pragma unroll 1
+                for (int c = 0; c < TBN / 32; ++c) {
+                    if (n0 + c * 32 >= N) break;
+                    uint32_t r[32];
+                    tc_ld32(t_row + (uint32_t)(c * 32), r);
+                    tc_wait_ld();
+                    float cm = -INFINITY;
+                    int ci = 0x7fffffff;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = n0 + c * 32 + j;
+                        float v = __uint_as_float(r[j]);
+                        if (col < N) {
+                            if (vep.bias) v += vep.bias[col];
+                            if (v > cm) { cm = v; ci = col; }
+                            if ((int64_t)col == tgt) vep.target_logit[row] = v;
+                        } else {
+                            v = -INFINITY;
+                        }
+                        r[j] = __float_as_uint(v);
+                    }
+                    const float nm = fmaxf(run_m, cm);
+                    float s = (run_s == 0.f) ? 0.f : run_s * expf(run_m - nm);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]);
+                        if (v != -INFINITY) s += expf(v - nm);
+                    }
+                    if (cm > run_m) run_i = ci;  // strict: earlier chunk keeps ties (lowest column)
+                    run_m = nm;
+                    run_s = s;
+                }
+                if (row < M) {
+                    const size_t o = (size_t)row * vep.n_tiles + nb;
+                    vep.part_max[o] = run_m; vep.part_sum[o] = run_s; vep.part_idx[o] = run_i;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static bool g_tc_ready = false;
+
+int tc_init() {
+    if (g_tc_ready) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    NAVC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    NAVC_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "navc_init: cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
+    g_tc_ready = true;
+    return 0;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, K] matrix with leading dimension ld, box = [box_rows, 64].
+static int make_map(CUtensorMap* map, const uint16_t* ptr, int rows, int K, int ld, int box_rows) {
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ptr), gdim, gstride, box,
+                          estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NAVC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+    return 0;
+}
+
+template <bool kVocab>
+static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi,
+                     const uint16_t* w_lo, int ldw, int M, int N, int K, const EpiParams& epi, const TcVocab& vep,
+                     cudaStream_t st, const char* what) {
+    NAVC_REQUIRE(g_tc_ready, "%s: navc_init() has not been called", what);
+    NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "%s: bad mode %d", what, mode);
+    NAVC_REQUIRE(x_hi && w_hi && (mode == NAVC_TC_BF16 || (x_lo && w_lo)), "%s: null operand", what);
+    NAVC_REQUIRE(M > 0 && N > 0 && K > 0 && K % TBK == 0 && ldx % 8 == 0 && ldw % 8 == 0,
+                 "%s: need K%%64==0 and ld%%8==0 (M=%d N=%d K=%d ldx=%d ldw=%d)", what, M, N, K, ldx, ldw);
+    NAVC_REQUIRE((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0,
+                 "%s: operands must be 16-byte aligned", what);
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    if (make_map(&ma_hi, x_hi, M, K, ldx, TBM)) return 1;
+    if (make_map(&mb_hi, w_hi, N, K, ldw, TBN)) return 1;
+    if (mode == NAVC_TC_BF16X3) {
+        if (make_map(&ma_lo, x_lo, M, K, ldx, TBM)) return 1;
+        if (make_map(&mb_lo, w_lo, N, K, ldw, TBN)) return 1;
+    } else {
+        ma_lo = ma_hi;
+        mb_lo = mb_hi;
+    }
+    const int tiles = ((M + TBM - 1) / TBM) * ((N + TBN - 1) / TBN);
+    int sms = navc_sm_count();
+    if (sms <= 0) sms = 148;
+    const int grid = tiles < sms ? tiles : sms;
+    if (mode == NAVC_TC_BF16X3) {
+        gemm_tc_kernel<true, kVocab><<<grid, kTcThreads, TcCfg<true>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, epi, vep);
+    } else {
+        gemm_tc_kernel<false, kVocab><<<grid, kTcThreads, TcCfg<false>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, epi, vep);
+    }
+    return check_launch(what);
+}
+
+}  // namespace navc
+
+using namespace navc;
+
+extern "C" int navc_vocab_tile(int tc) { return tc ? TBN : 128; }
+
+extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi,
+                              const uint16_t* w_lo, int ldw, int M, int N, int K, const navc_epilogue_t* e,
+                              void* stream) {
+    NAVC_REQUIRE(e && (e->out_f32 || e->out_hi), "navc_linear_tc: no output");
+    TcVocab v = {};
+    return launch_tc<false>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, to_params(e), v, as_stream(stream),
+                            "navc_linear_tc");
+}
+
+extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,
+                                      const uint16_t* w_hi, const uint16_t* w_lo, int ldw, const float* bias, int M,
+                                      int V, int K, float* part_max, float* part_sum, int32_t* part_idx,
+                                      const int64_t* target, float* target_logit, void* stream) {
+    NAVC_REQUIRE(part_max && part_sum && part_idx, "navc_vocab_partials_tc: null output");
+    NAVC_REQUIRE(!target || target_logit, "navc_vocab_partials_tc: target without target_logit");
+    TcVocab v = {bias, part_max, part_sum, part_idx, target, target_logit, (V + TBN - 1) / TBN};
+    EpiParams e = {};
+    return launch_tc<true>(mode, h_hi, h_lo, ldh, w_hi, w_lo, ldw, M, V, K, e, v, as_stream(stream),
+                           "navc_vocab_partials_tc");
+}

@@ -1,0 +1,360 @@
+"""Host-side orchestration of the sm_100a kernels behind the reference's model API.
+
+``Engine`` owns the packed weights of one ``Seq2Seq`` model (concatenated QKV / cross K|V of all
+layers, bf16 hi/lo copies for the tensor-core modes) and issues the C-ABI calls of
+``include/navc.h`` on torch-owned device buffers.  PyTorch is used for memory, streams and module
+plumbing only; every arithmetic step of the hot path is one of our kernels.
+
+Precision modes (``opt['navc_precision']`` or ``$NAVC_PRECISION``):
+  ``fp32``    CUDA-core fp32 GEMMs: reference-exact mode used for bit-exact token parity.
+  ``bf16x3``  tcgen05 GEMMs on split-bf16 operands (3 MMAs / product): ~fp32 accuracy.
+  ``bf16``    tcgen05 GEMMs on bf16 operands: fastest, ~3e-3 relative logit error.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from .config import Constants
+
+PRECISIONS = ("fp32", "bf16x3", "bf16")
+
+
+def default_precision(opt=None) -> str:
+    p = (opt or {}).get("navc_precision") or os.environ.get("NAVC_PRECISION") or "bf16x3"
+    if p not in PRECISIONS:
+        raise ValueError("navc precision must be one of %s, got %r" % (PRECISIONS, p))
+    return p
+
+
+class Act:
+    """An activation matrix [M, N]: fp32 copy and/or bf16 hi(/lo) copies."""
+    __slots__ = ("f32", "hi", "lo", "M", "N")
+
+    def __init__(self, M, N, f32=None, hi=None, lo=None):
+        self.M, self.N, self.f32, self.hi, self.lo = M, N, f32, hi, lo
+
+
+class PackedLinear:
+    __slots__ = ("w", "b", "w_hi", "w_lo", "N", "K")
+
+    def __init__(self, w, b):
+        self.w = w.detach().contiguous().float()
+        self.b = None if b is None else b.detach().contiguous().float()
+        self.N, self.K = self.w.shape
+        self.w_hi = self.w_lo = None
+
+
+class Engine:
+    def __init__(self, model, precision: Optional[str] = None):
+        self.model = model
+        self.opt = model.opt
+        self.precision = precision or default_precision(self.opt)
+        self.tc = self.precision != "fp32"
+        self.tc_mode = {"bf16": L.TC_BF16, "bf16x3": L.TC_BF16X3}.get(self.precision, 0)
+        self._sig = None
+        self.device = None
+        self.P: Dict[str, object] = {}
+
+    # ------------------------------------------------------------------------------------------
+    # weight packing
+    # ------------------------------------------------------------------------------------------
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in self.model.buffers())
+
+    def sync_weights(self):
+        """(Re)pack weights if any parameter changed (optimizer step, load_state_dict, .to())."""
+        dev = next(self.model.parameters()).device
+        L.ensure_init(dev)
+        sig = self._signature()
+        if sig == self._sig and dev == self.device:
+            return
+        self.device = dev
+        self._pack()
+        self._sig = sig
+
+    def _lin(self, w, b=None) -> PackedLinear:
+        pl = PackedLinear(w, b)
+        if self.tc:
+            pl.w_hi = torch.empty(pl.w.shape, dtype=torch.bfloat16, device=pl.w.device)
+            pl.w_lo = torch.empty_like(pl.w_hi) if self.precision == "bf16x3" else None
+            L.call("navc_split_bf16", L.ptr(pl.w), L.ptr(pl.w_hi), L.ptr(pl.w_lo), pl.w.numel(), L.stream())
+        return pl
+
+    def _pack(self):
+        m, opt = self.model, self.opt
+        sd = {k: v for k, v in m.state_dict().items()}
+        P = {}
+        with torch.no_grad():
+            # encoder streams (models/Encoder.py)
+            P["streams"] = []
+            for ch in opt["modality"].lower():
+                pre = "encoder.Encoder_%s" % ch.upper()
+                gate = (pre + ".1.w2.weight") in sd
+                w12 = torch.cat([sd[pre + ".1.w1.weight"]] + ([sd[pre + ".1.w2.weight"]] if gate else []), 0)
+                b12 = torch.cat([sd[pre + ".1.w1.bias"]] + ([sd[pre + ".1.w2.bias"]] if gate else []), 0)
+                P["streams"].append(dict(l0=self._lin(sd[pre + ".0.weight"], sd[pre + ".0.bias"]),
+                                         l12=self._lin(w12, b12), gate=int(gate)))
+            # joint representation norms
+            P["norms"] = []
+            jr = "joint_representation_learner."
+            for i in range(len(opt["modality"])):
+                if (jr + "bn%d.weight" % i) in sd:
+                    P["norms"].append(("bn", sd[jr + "bn%d.running_mean" % i].float(), sd[jr + "bn%d.running_var" % i].float(),
+                                       sd[jr + "bn%d.weight" % i].float(), sd[jr + "bn%d.bias" % i].float()))
+                elif (jr + "ln%d.weight" % i) in sd:
+                    P["norms"].append(("ln", sd[jr + "ln%d.weight" % i].float(), sd[jr + "ln%d.bias" % i].float()))
+                else:
+                    P["norms"].append(None)
+            # length head
+            ap = "auxiliary_task_predictor.layers.0.net."
+            P["len_head"] = None
+            if (ap + "0.weight") in sd:
+                P["len_head"] = tuple(sd[ap + k].float().contiguous() for k in ("0.weight", "0.bias", "3.weight", "3.bias"))
+            # decoder
+            dp = "decoder.bert." if ("decoder.bert.embedding.LayerNorm.weight" in sd) else "decoder."
+            e = dp + "embedding."
+            P["emb"] = dict(word=sd[e + "word_embeddings.weight"].float().contiguous(),
+                            pos=sd[e + "position_embeddings.weight"].float().contiguous(),
+                            cat=sd[e + "category_embeddings.weight"].float().contiguous() if (e + "category_embeddings.weight") in sd else None,
+                            ln_w=sd[e + "LayerNorm.weight"].float().contiguous(), ln_b=sd[e + "LayerNorm.bias"].float().contiguous())
+            layers, kv_w, kv_b = [], [], []
+            for l in range(opt["num_hidden_layers_decoder"]):
+                lp = "%slayer.%d." % (dp, l)
+                sa, ca = lp + "attention.", lp + "attend_to_enc_output."
+                qkv_w = torch.cat([sd[sa + "self.%s.weight" % n] for n in ("query", "key", "value")], 0)
+                qkv_b = torch.cat([sd[sa + "self.%s.bias" % n] for n in ("query", "key", "value")], 0)
+                kv_w.append(torch.cat([sd[ca + "self.key.weight"], sd[ca + "self.value.weight"]], 0))
+                kv_b.append(torch.cat([sd[ca + "self.key.bias"], sd[ca + "self.value.bias"]], 0))
+
+                def ln(prefix):
+                    k = prefix + "LayerNorm.weight"
+                    return (sd[k].float().contiguous(), sd[prefix + "LayerNorm.bias"].float().contiguous()) if k in sd else None
+                layers.append(dict(
+                    qkv=self._lin(qkv_w, qkv_b), so=self._lin(sd[sa + "output.dense.weight"], sd[sa + "output.dense.bias"]),
+                    so_ln=ln(sa + "output."),
+                    cq=self._lin(sd[ca + "self.query.weight"], sd[ca + "self.query.bias"]),
+                    co=self._lin(sd[ca + "output.dense.weight"], sd[ca + "output.dense.bias"]), co_ln=ln(ca + "output."),
+                    f1=self._lin(sd[lp + "intermediate.dense.weight"], sd[lp + "intermediate.dense.bias"]),
+                    f2=self._lin(sd[lp + "output.dense.weight"], sd[lp + "output.dense.bias"]), f2_ln=ln(lp + "output.")))
+            P["layers"] = layers
+            P["kv_all"] = self._lin(torch.cat(kv_w, 0), torch.cat(kv_b, 0))  # [L*2D, D]
+            P["vocab"] = self._lin(sd["tgt_word_prj.weight"], sd.get("tgt_word_prj.bias"))
+        self.P = P
+        self.D = opt["dim_hidden"]
+        self.H = opt["num_attention_heads"]
+        self.nl = opt["num_hidden_layers_decoder"]
+        self.act = L.ACT[opt["hidden_act"]]
+        self.eps = float(opt["layer_norm_eps"])
+
+    # ------------------------------------------------------------------------------------------
+    # primitive wrappers
+    # ------------------------------------------------------------------------------------------
+    def _new(self, M, N, f32, bf):
+        dev = self.device
+        a = Act(M, N)
+        if f32:
+            a.f32 = torch.empty((M, N), dtype=torch.float32, device=dev)
+        if bf and self.tc:
+            a.hi = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+            if self.precision == "bf16x3":
+                a.lo = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+        return a
+
+    def from_f32(self, x2d: torch.Tensor, need_bf=True) -> Act:
+        x2d = x2d.contiguous().float()
+        a = Act(x2d.shape[0], x2d.shape[1], f32=x2d)
+        if self.tc and need_bf:
+            a.hi = torch.empty(x2d.shape, dtype=torch.bfloat16, device=x2d.device)
+            a.lo = torch.empty_like(a.hi) if self.precision == "bf16x3" else None
+            L.call("navc_split_bf16", L.ptr(x2d), L.ptr(a.hi), L.ptr(a.lo), x2d.numel(), L.stream())
+        return a
+
+    def linear(self, x: Act, lin: PackedLinear, act=0, residual: Optional[torch.Tensor] = None,
+               row_tokens: Optional[torch.Tensor] = None, f32=True, bf=True) -> Act:
+        """nn.Linear + fused epilogue (include/navc.h navc_epilogue_t)."""
+        M, N, K = x.M, lin.N, lin.K
+        assert x.N == K, (x.N, K)
+        use_tc = self.tc and (K % 64 == 0) and x.hi is not None
+        out = self._new(M, N, f32 or not self.tc, bf)
+        ep = L.Epilogue(L.ptr(lin.b), L.ptr(residual), L.ptr(row_tokens), act,
+                        residual.shape[-1] if residual is not None else 0,
+                        L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), N, 0)
+        if use_tc:
+            L.call("navc_linear_tc", self.tc_mode, L.ptr(x.hi), L.ptr(x.lo), K, L.ptr(lin.w_hi), L.ptr(lin.w_lo), K,
+                   M, N, K, ep, L.stream())
+        else:
+            if x.f32 is None:
+                raise L.NavcError("fp32 GEMM path needs an fp32 activation (K=%d not a multiple of 64?)" % K)
+            L.call("navc_linear_f32", L.ptr(x.f32), K, L.ptr(lin.w), K, M, N, K, ep, L.stream())
+        return out
+
+    def layernorm(self, x: Act, ln, row_tokens, f32=True, bf=True) -> Act:
+        out = self._new(x.M, x.N, f32 or not self.tc, bf)
+        L.call("navc_layernorm", L.ptr(x.f32), L.ptr(ln[0]), L.ptr(ln[1]), self.eps, L.ptr(row_tokens), x.M, x.N,
+               L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), L.stream())
+        return out
+
+    def _proj_res(self, x: Act, lin, ln, residual, row_tokens) -> Act:
+        """dense -> (+residual) -> [LayerNorm] -> * non_pad_mask   (models/bert.py:192-200, 240-247, 271-299)"""
+        if ln is None:
+            return self.linear(x, lin, residual=residual, row_tokens=row_tokens)
+        y = self.linear(x, lin, residual=residual, row_tokens=None, f32=True, bf=False)
+        return self.layernorm(y, ln, row_tokens)
+
+    # ------------------------------------------------------------------------------------------
+    # encoder  (models/seq2seq.py:35-63)
+    # ------------------------------------------------------------------------------------------
+    def encode(self, feats: List[torch.Tensor]):
+        self.sync_weights()
+        opt, P, D = self.opt, self.P, self.D
+        assert len(feats) == len(P["streams"])
+        if opt.get("fusion", "temporal_concat") not in ("temporal_concat", "none"):
+            raise NotImplementedError("fusion=%r (broken in the reference, joint_representation.py:41)" % opt["fusion"])
+        B = feats[0].shape[0]
+        frames = [f.shape[1] for f in feats]
+        assert len(set(frames)) == 1 or True
+        E = sum(frames)
+        dev = self.device
+        enc = Act(B * E, D, f32=torch.empty((B, E, D), dtype=torch.float32, device=dev))
+        if self.tc:
+            enc.hi = torch.empty((B * E, D), dtype=torch.bfloat16, device=dev)
+            enc.lo = torch.empty_like(enc.hi) if self.precision == "bf16x3" else None
+        enc_hidden = torch.empty((B, D), dtype=torch.float32, device=dev)
+        no_norm = opt.get("fusion", "temporal_concat") == "none" or opt.get("no_encoder_bn", False)
+        row0 = 0
+        for i, (f, st) in enumerate(zip(feats, P["streams"])):
+            F_ = f.shape[1]
+            if len(set(frames)) != 1:
+                raise NotImplementedError("modalities with different frame counts")
+            x_in = self.from_f32(f.reshape(B * F_, f.shape[2]).to(dev))
+            x = self.linear(x_in, st["l0"], f32=True, bf=True)
+            yg = self.linear(x, st["l12"], f32=True, bf=False)
+            norm = None if no_norm else P["norms"][i]
+            if norm is not None and norm[0] == "ln":
+                raise NotImplementedError("norm_type='ln' encoder norm")
+            rm = rv = bw = bb = None
+            if norm is not None:
+                _, rm, rv, bw, bb = norm
+            L.call("navc_highway_bn", L.ptr(x.f32), L.ptr(yg.f32), st["gate"], B, F_, D, E, i, len(feats), int(i > 0),
+                   L.ptr(rm), L.ptr(rv), L.ptr(bw), L.ptr(bb), 1e-5, L.ptr(enc_hidden), L.ptr(enc.f32),
+                   L.ptr(enc.hi), L.ptr(enc.lo), L.stream())
+            row0 += F_
+        results = {}
+        enc_mean = torch.empty((B, D), dtype=torch.float32, device=dev)
+        if P["len_head"] is not None:
+            w1, b1, w2, b2 = P["len_head"]
+            max_len = w2.shape[0]
+            pred = torch.empty((B, max_len), dtype=torch.float32, device=dev)
+            L.call("navc_length_head", L.ptr(enc.f32), B, E, D, L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), max_len,
+                   L.ptr(enc_mean), L.ptr(pred), L.stream())
+            results["pred_length"] = pred
+        else:
+            L.call("navc_length_head", L.ptr(enc.f32), B, E, D, None, None, None, None, 0, L.ptr(enc_mean), None, L.stream())
+        results["enc_output"] = enc.f32
+        results["enc_hidden"] = enc_hidden
+        results["_navc"] = dict(enc=enc, enc_mean=enc_mean, B=B, E=E, owner=id(self))
+        return results
+
+    # ------------------------------------------------------------------------------------------
+    # decoder
+    # ------------------------------------------------------------------------------------------
+    def memory(self, enc_output: torch.Tensor, cache: Optional[dict] = None):
+        """Per-video decoder memory: cross-attention K|V of every layer (computed once)
+        and the frame mean used by enhance_input=2."""
+        self.sync_weights()
+        if cache is not None and cache.get("owner") == id(self) and cache["enc"].f32.data_ptr() == enc_output.data_ptr():
+            if "kv" in cache:
+                return cache
+            enc, enc_mean = cache["enc"], cache["enc_mean"]
+        else:
+            Bv, E, D = enc_output.shape
+            enc = self.from_f32(enc_output.reshape(Bv * E, D))
+            enc_mean = torch.empty((Bv, D), dtype=torch.float32, device=self.device)
+            L.call("navc_length_head", L.ptr(enc.f32), Bv, E, D, None, None, None, None, 0, L.ptr(enc_mean), None, L.stream())
+            cache = dict(enc=enc, enc_mean=enc_mean, B=Bv, E=E, owner=id(self))
+        cache["kv"] = self.linear(enc, self.P["kv_all"], f32=True, bf=False)  # [Bv*E, L*2D]
+        return cache
+
+    def decoder_pass(self, tokens: torch.Tensor, mem: dict, group: int, category: Optional[torch.Tensor],
+                     decoding_type: str, want_attn=False):
+        """One BertDecoder forward (models/Decoder.py:96-178) -> hidden Act [N*S, D] (+ attention probs)."""
+        P, D, H = self.P, self.D, self.H
+        N, S = tokens.shape
+        R = N * S
+        E = mem["E"]
+        assert N == mem["B"] * group, (N, mem["B"], group)
+        tok_flat = tokens.reshape(R)
+        emb = P["emb"]
+        extra = None
+        if decoding_type == "NARFormer":
+            ei = self.opt.get("enhance_input", 2)
+            if ei == 2:
+                extra = mem["enc_mean"]
+            elif ei != 0:
+                raise NotImplementedError("enhance_input=1 fails in the reference itself (SURVEY 8c)")
+        x = self._new(R, D, True, True)
+        L.call("navc_embed_ln", L.ptr(tokens), L.ptr(category), L.ptr(emb["word"]), L.ptr(emb["pos"]), L.ptr(emb["cat"]),
+               L.ptr(extra), group, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), self.eps, N, S, D,
+               L.ptr(x.f32), L.ptr(x.hi), L.ptr(x.lo), L.stream())
+        kv = mem["kv"]
+        attns = []
+        mask_kind = L.MASK_KIND[decoding_type]
+        for l, lw in enumerate(P["layers"]):
+            qkv = self.linear(x, lw["qkv"], f32=True, bf=False)
+            ctx = self._new(R, D, not self.tc, True)
+            p_self = torch.empty((H, N, S, S), dtype=torch.float32, device=self.device) if want_attn else None
+            L.call("navc_self_attention", L.ptr(qkv.f32), 3 * D, L.ptr(tokens), N, S, D, H, mask_kind,
+                   int(self.opt.get("watch", 0)), L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.ptr(p_self), L.stream())
+            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x.f32, tok_flat)
+            q = self.linear(a, lw["cq"], f32=True, bf=False)
+            ctx2 = self._new(R, D, not self.tc, True)
+            p_cross = torch.empty((H, N, S, E), dtype=torch.float32, device=self.device) if want_attn else None
+            kv_l = kv.f32[:, l * 2 * D:]
+            L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, S, E, D, H, group,
+                   L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
+            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a.f32, tok_flat)
+            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True)
+            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c.f32, tok_flat)
+            if want_attn:
+                attns.append((p_self, p_cross))
+        return x, attns
+
+    # ------------------------------------------------------------------------------------------
+    # vocabulary projection
+    # ------------------------------------------------------------------------------------------
+    def vocab_partials(self, hidden: Act, target: Optional[torch.Tensor] = None):
+        """tgt_word_prj + softmax statistics without materialising logits (algorithms.py:7-15)."""
+        lin = self.P["vocab"]
+        R, V, K = hidden.M, lin.N, lin.K
+        use_tc = self.tc and K % 64 == 0 and hidden.hi is not None
+        tile = L._lib.navc_vocab_tile(1 if use_tc else 0)
+        nt = (V + tile - 1) // tile
+        dev = self.device
+        pm = torch.empty((R, nt), dtype=torch.float32, device=dev)
+        ps = torch.empty((R, nt), dtype=torch.float32, device=dev)
+        pi = torch.empty((R, nt), dtype=torch.int32, device=dev)
+        tl = torch.empty((R,), dtype=torch.float32, device=dev) if target is not None else None
+        if use_tc:
+            L.call("navc_vocab_partials_tc", self.tc_mode, L.ptr(hidden.hi), L.ptr(hidden.lo), K, L.ptr(lin.w_hi),
+                   L.ptr(lin.w_lo), K, L.ptr(lin.b), R, V, K, L.ptr(pm), L.ptr(ps), L.ptr(pi), L.ptr(target), L.ptr(tl),
+                   L.stream())
+        else:
+            L.call("navc_vocab_partials_f32", L.ptr(hidden.f32), K, L.ptr(lin.w), K, L.ptr(lin.b), R, V, K,
+                   L.ptr(pm), L.ptr(ps), L.ptr(pi), L.ptr(target), L.ptr(tl), L.stream())
+        return pm, ps, pi, nt, tl
+
+    def logits(self, hidden2d: torch.Tensor) -> torch.Tensor:
+        """Materialised tgt_word_prj(hidden) for callers that use the attribute directly."""
+        self.sync_weights()
+        x = self.from_f32(hidden2d)
+        return self.linear(x, self.P["vocab"], f32=True, bf=False).f32
+
+    def log_softmax_(self, logits2d: torch.Tensor) -> torch.Tensor:
+        M, V = logits2d.shape
+        L.call("navc_log_softmax", L.ptr(logits2d), L.ptr(logits2d), M, V, V, L.stream())
+        return logits2d
