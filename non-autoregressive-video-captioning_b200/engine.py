@@ -58,6 +58,10 @@ class Engine:
         self._sig = None
         self.device = None
         self.P: Dict[str, object] = {}
+        # optional live timing of one class of launches (bench.py roofline): CUDA events recorded on
+        # the launching stream around every `linear(..., tag=profile_tag)` call
+        self.profile_tag = None
+        self.profile_events = []
 
     # ------------------------------------------------------------------------------------------
     # weight packing
@@ -175,7 +179,7 @@ class Engine:
         return a
 
     def linear(self, x: Act, lin: PackedLinear, act=0, residual: Optional[torch.Tensor] = None,
-               row_tokens: Optional[torch.Tensor] = None, f32=True, bf=True) -> Act:
+               row_tokens: Optional[torch.Tensor] = None, f32=True, bf=True, tag=None) -> Act:
         """nn.Linear + fused epilogue (include/navc.h navc_epilogue_t)."""
         M, N, K = x.M, lin.N, lin.K
         assert x.N == K, (x.N, K)
@@ -184,6 +188,10 @@ class Engine:
         ep = L.Epilogue(L.ptr(lin.b), L.ptr(residual), L.ptr(row_tokens), act,
                         residual.shape[-1] if residual is not None else 0,
                         L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), N, 0)
+        timed = tag is not None and tag == self.profile_tag
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         if use_tc:
             L.call("navc_linear_tc", self.tc_mode, L.ptr(x.hi), L.ptr(x.lo), K, L.ptr(lin.w_hi), L.ptr(lin.w_lo), K,
                    M, N, K, ep, L.stream())
@@ -191,6 +199,9 @@ class Engine:
             if x.f32 is None:
                 raise L.NavcError("fp32 GEMM path needs an fp32 activation (K=%d not a multiple of 64?)" % K)
             L.call("navc_linear_f32", L.ptr(x.f32), K, L.ptr(lin.w), K, M, N, K, ep, L.stream())
+        if timed:
+            e1.record()
+            self.profile_events.append((e0, e1))
         return out
 
     def layernorm(self, x: Act, ln, row_tokens, f32=True, bf=True) -> Act:
@@ -318,7 +329,7 @@ class Engine:
             L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, S, E, D, H, group,
                    L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
             c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a.f32, tok_flat)
-            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True)
+            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1")
             x = self._proj_res(h, lw["f2"], lw["f2_ln"], c.f32, tok_flat)
             if want_attn:
                 attns.append((p_self, p_cross))

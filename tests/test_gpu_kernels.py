@@ -161,7 +161,8 @@ def test_self_attention(N, S, D, H, kind, watch):
     toks[0, 2] = 0  # an interior PAD (predicted <pad>)
     ctx = torch.empty(N * S, D, device=DEV)
     probs = torch.empty(H, N, S, S, device=DEV)
-    L.call("navc_self_attention", L.ptr(qkv.to(DEV)), 3 * D, L.ptr(toks.to(DEV)), N, S, D, H, L.MASK_KIND[kind], watch,
+    qkv_d, toks_d = qkv.to(DEV), toks.to(DEV)  # keep device copies alive across the async launch
+    L.call("navc_self_attention", L.ptr(qkv_d), 3 * D, L.ptr(toks_d), N, S, D, H, L.MASK_KIND[kind], watch,
            L.ptr(ctx), None, None, L.ptr(probs), L.stream())
     torch.cuda.synchronize()
     dk = D // H
@@ -185,8 +186,8 @@ def test_cross_attention(B, group, S, E, D, H):
     layer = 1
     ctx = torch.empty(N * S, D, device=DEV)
     probs = torch.empty(H, N, S, E, device=DEV)
-    kvd = kv.to(DEV)
-    L.call("navc_cross_attention", L.ptr(q.to(DEV)), D, kvd[:, layer * 2 * D:].data_ptr(), L_ * 2 * D, N, S, E, D, H, group,
+    kvd, q_d = kv.to(DEV), q.to(DEV)
+    L.call("navc_cross_attention", L.ptr(q_d), D, kvd[:, layer * 2 * D:].data_ptr(), L_ * 2 * D, N, S, E, D, H, group,
            L.ptr(ctx), None, None, L.ptr(probs), L.stream())
     torch.cuda.synchronize()
     dk = D // H
@@ -212,9 +213,9 @@ def test_embed_ln_and_layernorm():
     category = torch.randint(0, 20, (N // group, 1), generator=gen)
     out = torch.empty(N * S, D, device=DEV)
     hi = torch.empty(N * S, D, dtype=torch.bfloat16, device=DEV); lo = torch.empty_like(hi)
-    d = lambda t: t.to(DEV)
-    L.call("navc_embed_ln", L.ptr(d(toks)), L.ptr(d(category)), L.ptr(d(word)), L.ptr(d(pos)), L.ptr(d(cat)), L.ptr(d(extra)),
-           group, L.ptr(d(lw)), L.ptr(d(lb)), 1e-5, N, S, D, L.ptr(out), L.ptr(hi), L.ptr(lo), L.stream())
+    dv = [t.to(DEV) for t in (toks, category, word, pos, cat, extra, lw, lb)]  # kept alive
+    L.call("navc_embed_ln", L.ptr(dv[0]), L.ptr(dv[1]), L.ptr(dv[2]), L.ptr(dv[3]), L.ptr(dv[4]), L.ptr(dv[5]),
+           group, L.ptr(dv[6]), L.ptr(dv[7]), 1e-5, N, S, D, L.ptr(out), L.ptr(hi), L.ptr(lo), L.stream())
     torch.cuda.synchronize()
     e = word[toks] + pos[:S].unsqueeze(0) + O.enlarge(cat[category.squeeze(1)], group).unsqueeze(1) + O.enlarge(extra, group).unsqueeze(1)
     ref = torch.nn.functional.layer_norm(e, (D,), lw, lb, 1e-5).view(N * S, D)
@@ -225,7 +226,8 @@ def test_embed_ln_and_layernorm():
     rt = torch.randint(0, 2, (50,), generator=gen)
     lw5 = torch.randn(512, generator=gen); lb5 = torch.randn(512, generator=gen)
     o2 = torch.empty(50, 512, device=DEV)
-    L.call("navc_layernorm", L.ptr(d(x)), L.ptr(d(lw5)), L.ptr(d(lb5)), 1e-5, L.ptr(d(rt)), 50, 512, L.ptr(o2), None, None, L.stream())
+    dv2 = [t.to(DEV) for t in (x, lw5, lb5, rt)]
+    L.call("navc_layernorm", L.ptr(dv2[0]), L.ptr(dv2[1]), L.ptr(dv2[2]), 1e-5, L.ptr(dv2[3]), 50, 512, L.ptr(o2), None, None, L.stream())
     torch.cuda.synchronize()
     ref2 = torch.nn.functional.layer_norm(x, (512,), lw5, lb5, 1e-5) * rt.ne(0).float().unsqueeze(1)
     assert (o2.cpu() - ref2).abs().max().item() < 1e-5
@@ -237,7 +239,8 @@ def test_length_beam_canvas_and_select_best():
     pred = torch.log_softmax(torch.randn(B, max_len, generator=gen), -1)
     beam = torch.empty(B, lbs, dtype=torch.int32, device=DEV)
     smax = torch.zeros(1, dtype=torch.int32, device=DEV)
-    L.call("navc_length_beam", L.ptr(pred.to(DEV)), B, max_len, lbs, 0, L.ptr(beam), L.ptr(smax), L.stream())
+    pred_d = pred.to(DEV)
+    L.call("navc_length_beam", L.ptr(pred_d), B, max_len, lbs, 0, L.ptr(beam), L.ptr(smax), L.stream())
     ref = O.length_beam(pred, lbs, 0, max_len)
     assert torch.equal(beam.cpu().long(), ref)
     S = int(smax.item())
@@ -253,7 +256,8 @@ def test_length_beam_canvas_and_select_best():
     tk = torch.randint(6, 99, (N, S), generator=gen)
     hyp = torch.empty(B, S, dtype=torch.int64, device=DEV)
     score = torch.empty(N, device=DEV)
-    L.call("navc_select_best", L.ptr(tk.to(DEV)), L.ptr(lprobs.to(DEV)), L.ptr(beam), B, lbs, S, 1.35, L.ptr(hyp), L.ptr(score), L.stream())
+    tk_d, lprobs_d = tk.to(DEV), lprobs.to(DEV)
+    L.call("navc_select_best", L.ptr(tk_d), L.ptr(lprobs_d), L.ptr(beam), B, lbs, S, 1.35, L.ptr(hyp), L.ptr(score), L.stream())
     sc = lprobs.view(B, lbs, S).sum(-1) / (ref.float() ** 1.35)
     best = sc.max(-1)[1]
     ref_hyp = tk.view(B, lbs, S)[torch.arange(B), best]
@@ -379,7 +383,8 @@ def test_refine_step_easy_first_and_window():
 def test_split_and_log_softmax():
     x = torch.randn(1000, 333, generator=g(19))
     hi = torch.empty(x.shape, dtype=torch.bfloat16, device=DEV); lo = torch.empty_like(hi)
-    L.call("navc_split_bf16", L.ptr(x.to(DEV)), L.ptr(hi), L.ptr(lo), x.numel(), L.stream())
+    x_d = x.to(DEV)
+    L.call("navc_split_bf16", L.ptr(x_d), L.ptr(hi), L.ptr(lo), x.numel(), L.stream())
     h, l = split(x)
     assert torch.equal(hi.cpu(), h) and torch.equal(lo.cpu(), l)
     xd = x.to(DEV).contiguous()
