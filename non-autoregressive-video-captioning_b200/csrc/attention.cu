@@ -1,7 +1,13 @@
-// Attention cores (fp32 CUDA-core version): token self-attention and text->video cross-attention.
-// The projections around them are GEMMs (gemm_simt.cu / gemm_tc.cu); these kernels do
-// softmax(mask_fill(Q K^T / sqrt(dk), -1e7)) V per (sequence, head) with K/V staged in shared
-// memory and one warp per query row.  Masks are derived from the token ids in-kernel.
+// Attention cores (fp32 CUDA cores, exact in every precision mode): token self-attention and
+// text->video cross-attention.  The projections around them are GEMMs (gemm_simt.cu / gemm_tc.cu);
+// these kernels do softmax(mask_fill(Q K^T / sqrt(dk), -1e7)) V per (key/value owner, head).
+// Masks are derived from the token ids in-kernel.
+//
+// Fast path `attn_tile_kernel`: one block per (K/V owner, head, query chunk).  K is staged
+// TRANSPOSED in shared memory ([dk][keys]) and V row-major, so the inner loops are one broadcast
+// LDS.128 per four FMAs; every query is owned by TPQ threads that keep its KH scores in registers
+// (softmax needs no shuffles beyond the TPQ pair) and then accumulate dk/TPQ output columns each.
+// The warp-per-query kernels below remain as the generic fallback (any dk, S <= 128, E <= 256).
 #include "common.cuh"
 
 namespace navc {
@@ -171,6 +177,190 @@ __global__ void cross_attention_kernel(const float* __restrict__ q, int ldq, con
     }
 }
 
+
+// ---- register-tiled fast path ---------------------------------------------------------------------
+// q      [.., ldq]   query rows; block (g, h, z) owns query rows g*NQ + z*QB + [0, QB) (clipped to NQ)
+// k, v   [.., ldkv]  key/value rows g*Sk + [0, Sk)
+// tokens [.., S]     self-attention only (NQ == Sk == S, g = sequence): key-pad / causal / diagonal masks
+template <int DK, int KH, int TPQ>
+__global__ void __launch_bounds__(384) attn_tile_kernel(
+    const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v, int ldkv,
+    const int64_t* __restrict__ tokens, int NQ, int QB, int S, int Sk, int D, int H, int mask_kind, int watch,
+    float* __restrict__ ctx_f32, uint16_t* __restrict__ ctx_hi, uint16_t* __restrict__ ctx_lo,
+    float* __restrict__ probs, int n_seq_total) {
+    constexpr int KP = KH * TPQ;   // padded key count
+    constexpr int DT = DK / TPQ;   // output columns per thread
+    extern __shared__ __align__(16) float sm[];
+    float* Kt = sm;                      // [DK][KP]
+    float* Vs = Kt + DK * KP;            // [Sk][DK]
+    float* QP = Vs + (size_t)Sk * DK;    // Q rows [QB][DK+1] during QK^T, then P rows [QB][KP+1]
+    const int g = blockIdx.x, h = blockIdx.y;
+    const int q_lo = blockIdx.z * QB;
+    const int nq = min(QB, NQ - q_lo);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    // ---- stage K (transposed), V, Q ----
+    const float* kb = k + (size_t)g * Sk * ldkv + h * DK;
+    const float* vb = v + (size_t)g * Sk * ldkv + h * DK;
+    for (int idx = tid; idx < KP * (DK / 4); idx += nthr) {
+        const int j = idx % KP, d4 = idx / KP;
+        float4 kv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < Sk) kv4 = *reinterpret_cast<const float4*>(kb + (size_t)j * ldkv + d4 * 4);
+        Kt[(d4 * 4 + 0) * KP + j] = kv4.x; Kt[(d4 * 4 + 1) * KP + j] = kv4.y;
+        Kt[(d4 * 4 + 2) * KP + j] = kv4.z; Kt[(d4 * 4 + 3) * KP + j] = kv4.w;
+    }
+    for (int idx = tid; idx < Sk * (DK / 4); idx += nthr) {
+        const int j = idx / (DK / 4), d4 = idx % (DK / 4);
+        *reinterpret_cast<float4*>(Vs + j * DK + d4 * 4) = *reinterpret_cast<const float4*>(vb + (size_t)j * ldkv + d4 * 4);
+    }
+    const float* qb = q + ((size_t)g * NQ + q_lo) * ldq + h * DK;
+    for (int idx = tid; idx < nq * (DK / 4); idx += nthr) {
+        const int i = idx / (DK / 4), d4 = idx % (DK / 4);
+        const float4 qv = *reinterpret_cast<const float4*>(qb + (size_t)i * ldq + d4 * 4);
+        float* dst = QP + i * (DK + 1) + d4 * 4;
+        dst[0] = qv.x; dst[1] = qv.y; dst[2] = qv.z; dst[3] = qv.w;
+    }
+    __syncthreads();
+
+    const int qi = tid / TPQ, t = tid % TPQ;
+    const bool live = qi < nq;
+    const int qs = live ? qi : 0;
+
+    // ---- scores: KH keys per thread in registers ----
+    float sc[KH];
+#pragma unroll
+    for (int i = 0; i < KH; ++i) sc[i] = 0.f;
+    {
+        const float* qrow = QP + qs * (DK + 1);
+        const float* kt = Kt + t * KH;
+#pragma unroll 2
+        for (int d = 0; d < DK; ++d) {
+            const float qd = qrow[d];
+#pragma unroll
+            for (int i4 = 0; i4 < KH / 4; ++i4) {
+                const float4 kk = *reinterpret_cast<const float4*>(kt + d * KP + i4 * 4);
+                sc[i4 * 4 + 0] = fmaf(qd, kk.x, sc[i4 * 4 + 0]);
+                sc[i4 * 4 + 1] = fmaf(qd, kk.y, sc[i4 * 4 + 1]);
+                sc[i4 * 4 + 2] = fmaf(qd, kk.z, sc[i4 * 4 + 2]);
+                sc[i4 * 4 + 3] = fmaf(qd, kk.w, sc[i4 * 4 + 3]);
+            }
+        }
+    }
+    __syncthreads();  // all Q rows consumed: the region is reused for P
+
+    // ---- mask + softmax (models/bert.py:157-164) ----
+    const float sqrt_dk = sqrtf((float)DK);
+    const int ipos = (q_lo + qs) % S;  // position of this query inside its sequence
+    const bool use_watch = (mask_kind == NAVC_MASK_CAUSAL) && watch != 0 && S >= watch;
+    const int64_t* trow = tokens ? tokens + (size_t)g * S : nullptr;
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+        const int j = t * KH + i;
+        float sv = -INFINITY;
+        if (j < Sk) {
+            sv = sc[i] / sqrt_dk;
+            if (trow) {
+                bool masked = trow[j] == NAVC_PAD;
+                if (mask_kind == NAVC_MASK_CAUSAL) masked = masked || (j > ipos) || (use_watch && j <= ipos - watch);
+                if (mask_kind == NAVC_MASK_SELF) masked = masked || (j == ipos);
+                if (masked) sv = kMaskFill;
+            }
+        }
+        sc[i] = sv;
+        m = fmaxf(m, sv);
+    }
+    if (TPQ == 2) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+        sc[i] = expf(sc[i] - m);  // exp(-inf) = 0 for the padded keys
+        sum += sc[i];
+    }
+    if (TPQ == 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    {
+        float* prow = QP + qs * (KP + 1) + t * KH;
+        const int n_glob = g * (NQ / S) + (q_lo + qs) / S;  // sequence index for the probs output
+        float* pg = (probs && live) ? probs + (((size_t)h * n_seq_total + n_glob) * S + ipos) * Sk : nullptr;
+#pragma unroll
+        for (int i = 0; i < KH; ++i) {
+            const float pv = sc[i] / sum;
+            if (live) prow[i] = pv;
+            if (pg && t * KH + i < Sk) pg[t * KH + i] = pv;
+        }
+    }
+    __syncwarp();
+
+    // ---- context: DT output columns per thread ----
+    float out[DT];
+#pragma unroll
+    for (int i = 0; i < DT; ++i) out[i] = 0.f;
+    {
+        const float* prow = QP + qs * (KP + 1);
+        const float* vcol = Vs + t * DT;
+#pragma unroll 4
+        for (int j = 0; j < Sk; ++j) {
+            const float pj = prow[j];
+#pragma unroll
+            for (int mm = 0; mm < DT / 4; ++mm) {
+                const float4 vv = *reinterpret_cast<const float4*>(vcol + j * DK + mm * 4);
+                out[mm * 4 + 0] = fmaf(pj, vv.x, out[mm * 4 + 0]);
+                out[mm * 4 + 1] = fmaf(pj, vv.y, out[mm * 4 + 1]);
+                out[mm * 4 + 2] = fmaf(pj, vv.z, out[mm * 4 + 2]);
+                out[mm * 4 + 3] = fmaf(pj, vv.w, out[mm * 4 + 3]);
+            }
+        }
+    }
+    if (live) {
+        const size_t o = ((size_t)g * NQ + q_lo + qi) * D + h * DK + t * DT;
+#pragma unroll
+        for (int mm = 0; mm < DT / 4; ++mm) {
+            const float4 vv = make_float4(out[mm * 4], out[mm * 4 + 1], out[mm * 4 + 2], out[mm * 4 + 3]);
+            if (ctx_f32) *reinterpret_cast<float4*>(ctx_f32 + o + mm * 4) = vv;
+            if (ctx_hi) {
+                uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+                split_bf16(vv.x, h0, l0); split_bf16(vv.y, h1, l1); split_bf16(vv.z, h2, l2); split_bf16(vv.w, h3, l3);
+                *reinterpret_cast<uint2*>(ctx_hi + o + mm * 4) =
+                    make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+                if (ctx_lo)
+                    *reinterpret_cast<uint2*>(ctx_lo + o + mm * 4) =
+                        make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+            }
+        }
+    }
+}
+
+// Returns 0 = launched, -1 = shape not covered by the fast path (caller falls back), >0 = error.
+template <int DK, int KH, int TPQ>
+static int launch_tile(const float* q, int ldq, const float* k, const float* v, int ldkv, const int64_t* tokens,
+                       int G, int NQ, int S, int Sk, int D, int H, int mask_kind, int watch, float* f32,
+                       uint16_t* hi, uint16_t* lo, float* probs, int n_seq_total, cudaStream_t st, const char* what) {
+    constexpr int KP = KH * TPQ;
+    const int qb_max = 384 / TPQ;
+    const int QB = NQ < qb_max ? NQ : qb_max;
+    const int threads = ((QB * TPQ + 31) / 32) * 32;
+    const size_t qp = (size_t)QB * ((KP + 1) > (DK + 1) ? (KP + 1) : (DK + 1));
+    const size_t smem = ((size_t)DK * KP + (size_t)Sk * DK + qp) * sizeof(float);
+    if (smem > 220 * 1024) return -1;
+    auto kern = attn_tile_kernel<DK, KH, TPQ>;
+    if (smem > 48 * 1024) NAVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(G, H, (NQ + QB - 1) / QB);
+    kern<<<grid, threads, smem, st>>>(q, ldq, k, v, ldkv, tokens, NQ, QB, S, Sk, D, H, mask_kind, watch, f32, hi, lo,
+                                      probs, n_seq_total);
+    return check_launch(what);
+}
+
+template <int KH, int TPQ>
+static int dispatch_tile(int dk, const float* q, int ldq, const float* k, const float* v, int ldkv,
+                         const int64_t* tokens, int G, int NQ, int S, int Sk, int D, int H, int mask_kind, int watch,
+                         float* f32, uint16_t* hi, uint16_t* lo, float* probs, int n_seq_total, cudaStream_t st,
+                         const char* what) {
+    if (dk == 64) return launch_tile<64, KH, TPQ>(q, ldq, k, v, ldkv, tokens, G, NQ, S, Sk, D, H, mask_kind, watch, f32, hi, lo, probs, n_seq_total, st, what);
+    if (dk == 32) return launch_tile<32, KH, TPQ>(q, ldq, k, v, ldkv, tokens, G, NQ, S, Sk, D, H, mask_kind, watch, f32, hi, lo, probs, n_seq_total, st, what);
+    if (dk == 16) return launch_tile<16, KH, TPQ>(q, ldq, k, v, ldkv, tokens, G, NQ, S, Sk, D, H, mask_kind, watch, f32, hi, lo, probs, n_seq_total, st, what);
+    return -1;
+}
+
 template <int KPL>
 static int launch_self(const float* qkv, int ld, const int64_t* tokens, int N, int S, int D, int H, int mask_kind,
                        int watch, float* f32, uint16_t* hi, uint16_t* lo, float* probs, cudaStream_t st) {
@@ -213,6 +403,13 @@ extern "C" int navc_self_attention(const float* qkv, int ld, const int64_t* toke
     NAVC_REQUIRE(S <= 128, "navc_self_attention: S > 128 unsupported (max_len is 30 in the reference)");
     NAVC_REQUIRE(mask_kind >= 0 && mask_kind <= 2, "navc_self_attention: bad mask kind");
     cudaStream_t st = as_stream(stream);
+    if (ld % 4 == 0 && D % 4 == 0 && (((uintptr_t)qkv) & 15) == 0 && S <= 64) {
+        const int dk = D / H;
+        int rc = (S <= 32)
+            ? dispatch_tile<32, 1>(dk, qkv, ld, qkv + D, qkv + 2 * D, ld, tokens, N, S, S, S, D, H, mask_kind, watch, ctx_f32, ctx_hi, ctx_lo, probs, N, st, "navc_self_attention")
+            : dispatch_tile<64, 1>(dk, qkv, ld, qkv + D, qkv + 2 * D, ld, tokens, N, S, S, S, D, H, mask_kind, watch, ctx_f32, ctx_hi, ctx_lo, probs, N, st, "navc_self_attention");
+        if (rc >= 0) return rc;
+    }
     if (S <= 32) return launch_self<1>(qkv, ld, tokens, N, S, D, H, mask_kind, watch, ctx_f32, ctx_hi, ctx_lo, probs, st);
     if (S <= 64) return launch_self<2>(qkv, ld, tokens, N, S, D, H, mask_kind, watch, ctx_f32, ctx_hi, ctx_lo, probs, st);
     return launch_self<4>(qkv, ld, tokens, N, S, D, H, mask_kind, watch, ctx_f32, ctx_hi, ctx_lo, probs, st);
@@ -226,6 +423,14 @@ extern "C" int navc_cross_attention(const float* q, int ldq, const float* kv, in
                  "navc_cross_attention: bad shape");
     NAVC_REQUIRE(E <= 256, "navc_cross_attention: E > 256 unsupported");
     cudaStream_t st = as_stream(stream);
+    if (ldq % 4 == 0 && ldkv % 4 == 0 && D % 4 == 0 && ((((uintptr_t)q) | ((uintptr_t)kv)) & 15) == 0 && E <= 128) {
+        const int dk = D / H;
+        const int G = N / group;
+        int rc = (E <= 64)
+            ? dispatch_tile<32, 2>(dk, q, ldq, kv, kv + D, ldkv, nullptr, G, group * S, S, E, D, H, 0, 0, ctx_f32, ctx_hi, ctx_lo, probs, N, st, "navc_cross_attention")
+            : dispatch_tile<64, 2>(dk, q, ldq, kv, kv + D, ldkv, nullptr, G, group * S, S, E, D, H, 0, 0, ctx_f32, ctx_hi, ctx_lo, probs, N, st, "navc_cross_attention");
+        if (rc >= 0) return rc;
+    }
     if (E <= 32) return launch_cross<1>(q, ldq, kv, ldkv, N, S, E, D, H, group, ctx_f32, ctx_hi, ctx_lo, probs, st);
     if (E <= 64) return launch_cross<2>(q, ldq, kv, ldkv, N, S, E, D, H, group, ctx_f32, ctx_hi, ctx_lo, probs, st);
     if (E <= 128) return launch_cross<4>(q, ldq, kv, ldkv, N, S, E, D, H, group, ctx_f32, ctx_hi, ctx_lo, probs, st);

@@ -58,6 +58,28 @@ __device__ __forceinline__ float act_apply(float x, int act) {
     }
 }
 
+// ex2.approx (MUFU): 2 ulp, exp2(-inf) = 0
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Tensor-core GEMM epilogues: gelu_new / swish through one MUFU exp + one MUFU rcp.
+// 0.5*x*(1+tanh(u)) == x*sigmoid(2u) == x / (1 + exp(-2u)) exactly; this form has no cancellation
+// for u << 0 (where the reference's own 1+tanh(u) loses digits), abs error <~ 2e-7*|x|.
+__device__ __forceinline__ float act_apply_fast(float x, int act) {
+    switch (act) {
+        case NAVC_ACT_GELU_NEW: {
+            const float k = -2.0f * 0.7978845608028654f * 1.4426950408889634f;  // -2*sqrt(2/pi)*log2(e)
+            const float u = x * fmaf(0.044715f * x, x, 1.0f);
+            return __fdividef(x, 1.0f + fast_exp2(k * u));
+        }
+        case NAVC_ACT_SWISH: return __fdividef(x, 1.0f + fast_exp2(-1.4426950408889634f * x));
+        case NAVC_ACT_RELU: return fmaxf(x, 0.0f);
+        default: return act_apply(x, act);
+    }
+}
+
 // Epilogue for `n` consecutive columns of one row (n <= 8 typical); col0 multiple of 4 when n>=4.
 struct EpiParams {
     const float* bias;

@@ -5,10 +5,13 @@
 //   epilogue (bias / activation / residual / non-pad row mask / bf16 hi-lo split, or on-the-fly
 //   softmax statistics for the vocabulary projection).
 //
-// Warp roles (192 threads, persistent, one CTA per SM):
+// Warp roles (320 threads, persistent, one CTA per SM):
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  epilogue, one TMEM lane quarter each (row = TMEM lane)
+//   warps 2..9  epilogue: warp w reads TMEM lane quarter w%4 (row = TMEM lane) and column half
+//               (w-2)/4 of the 256-column accumulator; 32x32 chunks are transposed through a
+//               swizzled shared-memory staging buffer so that every global load/store of the
+//               epilogue (residual, fp32 / bf16 hi / bf16 lo outputs) is a coalesced row segment.
 //
 // Operand modes: NAVC_TC_BF16 issues one product per k-step (hi*hi); NAVC_TC_BF16X3 issues three
 // (hi*hi + hi*lo + lo*hi) which recovers ~fp32 accuracy from bf16 tensor cores.
@@ -20,7 +23,9 @@ namespace navc {
 
 constexpr int TBM = 128, TBN = 256, TBK = 64;        // CTA tile; TBK bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+constexpr int kStageFloats = 32 * 32;                // per-epilogue-warp transpose buffer (4 KB)
 constexpr int kTileABytes = TBM * TBK * 2;           // 16 KB
 constexpr int kTileBBytes = TBN * TBK * 2;           // 32 KB
 constexpr int kAccStages = 2;                        // 2 x 256 TMEM columns
@@ -29,7 +34,8 @@ constexpr int kTmemCols = 512;
 template <bool kX3> struct TcCfg {
     static constexpr int kStages = kX3 ? 2 : 4;
     static constexpr int kStageBytes = (kX3 ? 2 : 1) * (kTileABytes + kTileBBytes);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kRingBytes = kStages * kStageBytes;
+    static constexpr int kSmemBytes = kRingBytes + kEpiWarps * kStageFloats * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -125,12 +131,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     // barriers live after the tile ring
-    const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    float* stage_all = reinterpret_cast<float*>(smem_gen + Cfg::kRingBytes);
+    const uint32_t bar_off = Cfg::kRingBytes + kEpiWarps * kStageFloats * 4;
+    const uint32_t bar_base = smem_base + bar_off;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + kAccStages + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 2 * kAccStages));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + bar_off + 8 * (2 * Cfg::kStages + 2 * kAccStages));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + TBM - 1) / TBM, n_blocks = (N + TBN - 1) / TBN;
@@ -139,7 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -212,52 +220,103 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
+        const int ew = warp - 2;
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int half = ew >> 2;      // column half [half*128, half*128+128) of the accumulator
+        float* stage = stage_all + ew * kStageFloats;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int mb = tile / n_blocks, nb = tile % n_blocks;
-            const int row = mb * TBM + quarter * 32 + lane;
-            const int n0 = nb * TBN;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN);
+            const int row0 = mb * TBM + quarter * 32;
+            const int row = row0 + lane;
+            const int n0 = nb * TBN + half * (TBN / 2);
 
             if constexpr (!kVocab) {
                 const bool row_ok = row < M;
-                const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[row] == NAVC_PAD) : false;
+                const bool my_rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[row] == NAVC_PAD) : false;
+                const uint32_t rz_mask = __ballot_sync(0xffffffffu, my_rz);
                 const bool vec = (epi.ld_out % 4 == 0) && (N % 4 == 0) && (!epi.residual || epi.ld_res % 4 == 0);
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + half * (TBN / 2));
 #pragma unroll 1
-                for (int c = 0; c < TBN / 32; ++c) {
-                    if (n0 + c * 32 >= N) break;  // warp-uniform
+                for (int c = 0; c < TBN / 64; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= N) break;  // warp-uniform
                     uint32_t r[32];
                     tc_ld32(t_row + (uint32_t)(c * 32), r);
                     tc_wait_ld();
-                    if (row_ok) {
+                    if (vec) {
+                        // phase 1 (lane = row): bias + activation, park the 32x32 chunk in shared memory.
+                        // float4 slot g of row `lane` lives at slot g ^ (lane & 7): conflict-free both ways.
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
-                            const int col = n0 + c * 32 + g * 4;
-                            if (col >= N) break;
-                            if (vec) {
-                                epi_store4(epi, row, col,
-                                           make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                                                       __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])), rz);
-                            } else {
+                            float4 v = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                                   __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+                            const int col = col0 + g * 4;
+                            if (col < N) {
+                                if (epi.bias) {
+                                    const float4 bv = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+                                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                                }
+                                if (epi.act) {
+                                    v.x = act_apply_fast(v.x, epi.act); v.y = act_apply_fast(v.y, epi.act);
+                                    v.z = act_apply_fast(v.z, epi.act); v.w = act_apply_fast(v.w, epi.act);
+                                }
+                            }
+                            *reinterpret_cast<float4*>(stage + lane * 32 + ((g ^ (lane & 7)) << 2)) = v;
+                        }
+                        __syncwarp();
+                        // phase 2 (8 lanes per row, 4 rows per step): residual, row mask, coalesced stores
+                        const int cc = lane & 7, rr = lane >> 3;
+                        const int col = col0 + cc * 4;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    if (col + j < N) epi_store1(epi, row, col + j, __uint_as_float(r[g * 4 + j]), rz);
+                        for (int it = 0; it < 8; ++it) {
+                            const int rl = it * 4 + rr;
+                            const int grow = row0 + rl;
+                            float4 v = *reinterpret_cast<const float4*>(stage + rl * 32 + ((cc ^ (rl & 7)) << 2));
+                            if (grow < M && col < N) {
+                                if (epi.residual) {
+                                    const float4 q = *reinterpret_cast<const float4*>(epi.residual + (size_t)grow * epi.ld_res + col);
+                                    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                                }
+                                if ((rz_mask >> rl) & 1u) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                const size_t o = (size_t)grow * epi.ld_out + col;
+                                if (epi.out_f32) *reinterpret_cast<float4*>(epi.out_f32 + o) = v;
+                                if (epi.out_hi) {
+                                    uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+                                    split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
+                                    split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+                                    *reinterpret_cast<uint2*>(epi.out_hi + o) =
+                                        make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+                                    if (epi.out_lo)
+                                        *reinterpret_cast<uint2*>(epi.out_lo + o) =
+                                            make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+                                }
                             }
                         }
+                        __syncwarp();
+                    } else if (row_ok) {
+                        // odd leading dimensions / N: scalar fallback (lane = row)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < N) epi_store1(epi, row, col0 + j, __uint_as_float(r[j]), my_rz);
                     }
                 }
             } else {
                 const int64_t tgt = (vep.target && row < M) ? vep.target[row] : -1;
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + half * (TBN / 2));
                 float run_m = -INFINITY, run_s = 0.f;
                 int run_i = 0x7fffffff;
+                constexpr float kLog2e = 1.4426950408889634f;
 #pragma unroll 1
-                for (int c = 0; c < TBN / 32; ++c) {
-                    if (n0 + c * 32 >= N) break;
+                for (int c = 0; c < TBN / 64; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= N) break;
                     uint32_t r[32];
                     tc_ld32(t_row + (uint32_t)(c * 32), r);
                     tc_wait_ld();
@@ -265,10 +324,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     int ci = 0x7fffffff;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int col = n0 + c * 32 + j;
+                        const int col = col0 + j;
                         float v = __uint_as_float(r[j]);
                         if (col < N) {
-                            if (vep.bias) v += vep.bias[col];
+                            if (vep.bias) v += __ldg(vep.bias + col);
                             if (v > cm) { cm = v; ci = col; }
                             if ((int64_t)col == tgt) vep.target_logit[row] = v;
                         } else {
@@ -277,18 +336,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         r[j] = __float_as_uint(v);
                     }
                     const float nm = fmaxf(run_m, cm);
-                    float s = (run_s == 0.f) ? 0.f : run_s * expf(run_m - nm);
+                    float s = (run_s == 0.f) ? 0.f : run_s * fast_exp2((run_m - nm) * kLog2e);
+                    const float nm2 = nm * kLog2e;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float v = __uint_as_float(r[j]);
-                        if (v != -INFINITY) s += expf(v - nm);
+                        s += fast_exp2(fmaf(v, kLog2e, -nm2));  // exp2(-inf) = 0 for the padded columns
                     }
                     if (cm > run_m) run_i = ci;  // strict: earlier chunk keeps ties (lowest column)
                     run_m = nm;
                     run_s = s;
                 }
-                if (row < M) {
-                    const size_t o = (size_t)row * vep.n_tiles + nb;
+                if (row < M && n0 < N) {
+                    const size_t o = (size_t)row * vep.n_tiles + (nb * 2 + half);
                     vep.part_max[o] = run_m; vep.part_sum[o] = run_s; vep.part_idx[o] = run_i;
                 }
             }
@@ -379,7 +439,7 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
 
 using namespace navc;
 
-extern "C" int navc_vocab_tile(int tc) { return tc ? TBN : 128; }
+extern "C" int navc_vocab_tile(int tc) { return tc ? TBN / 2 : 128; }
 
 extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi,
                               const uint16_t* w_lo, int ldw, int M, int N, int K, const navc_epilogue_t* e,
@@ -396,7 +456,7 @@ extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint
                                       const int64_t* target, float* target_logit, void* stream) {
     NAVC_REQUIRE(part_max && part_sum && part_idx, "navc_vocab_partials_tc: null output");
     NAVC_REQUIRE(!target || target_logit, "navc_vocab_partials_tc: target without target_logit");
-    TcVocab v = {bias, part_max, part_sum, part_idx, target, target_logit, (V + TBN - 1) / TBN};
+    TcVocab v = {bias, part_max, part_sum, part_idx, target, target_logit, (V + TBN / 2 - 1) / (TBN / 2)};
     EpiParams e = {};
     return launch_tc<true>(mode, h_hi, h_lo, ldh, w_hi, w_lo, ldw, M, V, K, e, v, as_stream(stream),
                            "navc_vocab_partials_tc");
