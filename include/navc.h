@@ -154,6 +154,18 @@ int navc_cross_attention(const float* q, int ldq, const float* kv, int ldkv, int
                          int D, int H, int group, float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo,
                          float* probs, void* stream);
 
+/* tcgen05 versions of the two attention cores (dk == 64; S <= 32 / E <= 128), same arithmetic and
+ * masks; operands are the bf16 hi (+lo when mode == NAVC_TC_BF16X3) copies written by the
+ * projection GEMMs: qkv_* [N*S, ld] = Q | K | V at column offsets 0, D, 2D; kv_* [(N/group)*E, ldkv]
+ * = K | V at 0, D.  Attention probabilities are not materialised (use the fp32 cores for those). */
+int navc_self_attention_tc(int mode, const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld,
+                           const int64_t* tokens, int N, int S, int D, int H, int mask_kind, int watch,
+                           float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream);
+int navc_cross_attention_tc(int mode, const uint16_t* q_hi, const uint16_t* q_lo, int ldq,
+                            const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv, int N, int S, int E,
+                            int D, int H, int group, float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo,
+                            void* stream);
+
 /* ---- iterative refinement (decoding/na_generate.py, decoding/algorithms.py) ----------------- */
 /* Length beam + canvas (na_generate.py:33-50, 116-135): beam[b,:] = clamp(top-lbs indices of
  * pred_length[b,:] + length_bias, 4, max_len-1) (descending value, lowest index on ties);

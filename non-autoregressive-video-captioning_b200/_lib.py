@@ -54,6 +54,8 @@ _PROTOS = {
     "navc_layernorm": [vp, vp, vp, f32, vp, i32, i32, vp, vp, vp, vp],
     "navc_self_attention": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "navc_cross_attention": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+    "navc_self_attention_tc": [i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_cross_attention_tc": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
     "navc_length_beam": [vp, i32, i32, i32, i32, vp, vp, vp],
     "navc_init_canvas": [vp, i32, i32, i64, vp, vp, vp, vp],
     "navc_refine_step": [C.POINTER(Step), i32, i32, vp],

@@ -15,14 +15,11 @@
 //
 // Operand modes: NAVC_TC_BF16 issues one product per k-step (hi*hi); NAVC_TC_BF16X3 issues three
 // (hi*hi + hi*lo + lo*hi) which recovers ~fp32 accuracy from bf16 tensor cores.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace navc {
 
 constexpr int TBM = 128, TBN = 256, TBK = 64;        // CTA tile; TBK bf16 = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kStageFloats = 32 * 32;                // per-epilogue-warp transpose buffer (4 KB)
@@ -37,79 +34,6 @@ template <bool kX3> struct TcCfg {
     static constexpr int kRingBytes = kStages * kStageBytes;
     static constexpr int kSmemBytes = kRingBytes + kEpiWarps * kStageFloats * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte swizzled operand tile (rows x 64 bf16): 8-row atoms of 1024 B.
-// cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
-// layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
 
 struct TcVocab {
     const float* bias;
@@ -373,6 +297,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static bool g_tc_ready = false;
+bool tc_ready() { return g_tc_ready; }
 
 int tc_init() {
     if (g_tc_ready) return 0;
@@ -390,7 +315,7 @@ int tc_init() {
 }
 
 // 2-D bf16 tensor map over a row-major [rows, K] matrix with leading dimension ld, box = [box_rows, 64].
-static int make_map(CUtensorMap* map, const uint16_t* ptr, int rows, int K, int ld, int box_rows) {
+int tc_make_map(CUtensorMap* map, const uint16_t* ptr, int rows, int K, int ld, int box_rows) {
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
@@ -414,11 +339,11 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
     NAVC_REQUIRE((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0,
                  "%s: operands must be 16-byte aligned", what);
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    if (make_map(&ma_hi, x_hi, M, K, ldx, TBM)) return 1;
-    if (make_map(&mb_hi, w_hi, N, K, ldw, TBN)) return 1;
+    if (tc_make_map(&ma_hi, x_hi, M, K, ldx, TBM)) return 1;
+    if (tc_make_map(&mb_hi, w_hi, N, K, ldw, TBN)) return 1;
     if (mode == NAVC_TC_BF16X3) {
-        if (make_map(&ma_lo, x_lo, M, K, ldx, TBM)) return 1;
-        if (make_map(&mb_lo, w_lo, N, K, ldw, TBN)) return 1;
+        if (tc_make_map(&ma_lo, x_lo, M, K, ldx, TBM)) return 1;
+        if (tc_make_map(&mb_lo, w_lo, N, K, ldw, TBN)) return 1;
     } else {
         ma_lo = ma_hi;
         mb_lo = mb_hi;

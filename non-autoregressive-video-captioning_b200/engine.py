@@ -288,8 +288,18 @@ class Engine:
             enc_mean = torch.empty((Bv, D), dtype=torch.float32, device=self.device)
             L.call("navc_length_head", L.ptr(enc.f32), Bv, E, D, None, None, None, None, 0, L.ptr(enc_mean), None, L.stream())
             cache = dict(enc=enc, enc_mean=enc_mean, B=Bv, E=E, owner=id(self))
-        cache["kv"] = self.linear(enc, self.P["kv_all"], f32=True, bf=False)  # [Bv*E, L*2D]
+        tc_attn = self.tc_attention_ok(32, cache["E"])
+        cache["kv"] = self.linear(enc, self.P["kv_all"], f32=not tc_attn, bf=tc_attn)  # [Bv*E, L*2D]
         return cache
+
+    def tc_attention_ok(self, S, E):
+        """tcgen05 attention cores need dk == 64, S <= 32 and E <= 128 (navc.h)."""
+        return self.tc and self.D == self.H * 64 and S <= 32 and E <= 128
+
+    def _kv_f32(self, mem):
+        if mem["kv"].f32 is None:  # fp32 cores requested (attention probabilities) after a tensor-core cache
+            mem["kv"].f32 = self.linear(mem["enc"], self.P["kv_all"], f32=True, bf=False).f32
+        return mem["kv"].f32
 
     def decoder_pass(self, tokens: torch.Tensor, mem: dict, group: int, category: Optional[torch.Tensor],
                      decoding_type: str, want_attn=False):
@@ -315,19 +325,32 @@ class Engine:
         kv = mem["kv"]
         attns = []
         mask_kind = L.MASK_KIND[decoding_type]
+        tc_attn = self.tc_attention_ok(S, E) and not want_attn and kv.hi is not None
+        watch = int(self.opt.get("watch", 0))
         for l, lw in enumerate(P["layers"]):
-            qkv = self.linear(x, lw["qkv"], f32=True, bf=False)
+            qkv = self.linear(x, lw["qkv"], f32=not tc_attn, bf=tc_attn)
             ctx = self._new(R, D, not self.tc, True)
-            p_self = torch.empty((H, N, S, S), dtype=torch.float32, device=self.device) if want_attn else None
-            L.call("navc_self_attention", L.ptr(qkv.f32), 3 * D, L.ptr(tokens), N, S, D, H, mask_kind,
-                   int(self.opt.get("watch", 0)), L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.ptr(p_self), L.stream())
+            p_self = p_cross = None
+            if tc_attn:
+                L.call("navc_self_attention_tc", self.tc_mode, L.ptr(qkv.hi), L.ptr(qkv.lo), 3 * D, L.ptr(tokens), N, S,
+                       D, H, mask_kind, watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.stream())
+            else:
+                p_self = torch.empty((H, N, S, S), dtype=torch.float32, device=self.device) if want_attn else None
+                L.call("navc_self_attention", L.ptr(qkv.f32), 3 * D, L.ptr(tokens), N, S, D, H, mask_kind,
+                       watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.ptr(p_self), L.stream())
             a = self._proj_res(ctx, lw["so"], lw["so_ln"], x.f32, tok_flat)
-            q = self.linear(a, lw["cq"], f32=True, bf=False)
+            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn)
             ctx2 = self._new(R, D, not self.tc, True)
-            p_cross = torch.empty((H, N, S, E), dtype=torch.float32, device=self.device) if want_attn else None
-            kv_l = kv.f32[:, l * 2 * D:]
-            L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, S, E, D, H, group,
-                   L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
+            if tc_attn:
+                off = l * 2 * D
+                L.call("navc_cross_attention_tc", self.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D,
+                       kv.hi[:, off:].data_ptr(), kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N,
+                       N, S, E, D, H, group, L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.stream())
+            else:
+                p_cross = torch.empty((H, N, S, E), dtype=torch.float32, device=self.device) if want_attn else None
+                kv_l = self._kv_f32(mem)[:, l * 2 * D:]
+                L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, S, E, D, H, group,
+                       L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
             c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a.f32, tok_flat)
             h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1")
             x = self._proj_res(h, lw["f2"], lw["f2_ln"], c.f32, tok_flat)

@@ -202,6 +202,68 @@ def test_cross_attention(B, group, S, E, D, H):
     assert (ctx.cpu() - ref).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("N,S,D,H,kind,watch", [(7, 9, 512, 8, "NARFormer", 0), (768, 28, 512, 8, "NARFormer", 0),
+                                              (6, 15, 256, 4, "ARFormer", 0), (9, 15, 128, 2, "ARFormer", 3),
+                                              (5, 32, 128, 2, "SelfMask", 0), (3, 1, 64, 1, "NARFormer", 0)])
+def test_self_attention_tc(mode, tol, N, S, D, H, kind, watch):
+    """tcgen05 self-attention core vs plain torch fp32 on the same (unsplit) inputs."""
+    gen = g(15)
+    qkv = torch.randn(N * S, 3 * D, generator=gen)
+    toks = torch.randint(1, 50, (N, S), generator=gen)
+    for n in range(N):
+        if n % 4 and S > 4:
+            toks[n, S - (n % 4):] = 0
+    if S > 4:
+        toks[0, 2] = 0
+    hi, lo = split(qkv)
+    ctx = torch.empty(N * S, D, device=DEV)
+    chi = torch.empty(N * S, D, dtype=torch.bfloat16, device=DEV)
+    clo = torch.empty(N * S, D, dtype=torch.bfloat16, device=DEV)
+    hi_d, lo_d, toks_d = hi.to(DEV), lo.to(DEV), toks.to(DEV)
+    L.call("navc_self_attention_tc", L.TC_BF16X3 if mode == "bf16x3" else L.TC_BF16, L.ptr(hi_d), L.ptr(lo_d), 3 * D,
+           L.ptr(toks_d), N, S, D, H, L.MASK_KIND[kind], watch, L.ptr(ctx), L.ptr(chi), L.ptr(clo), L.stream())
+    torch.cuda.synchronize()
+    dk = D // H
+    q, k, v = [t.view(N, S, H, dk).permute(2, 0, 1, 3) for t in qkv.split(D, dim=1)]
+    mask = O.self_attention_mask(toks, kind, watch)
+    sc = ((q @ k.transpose(-1, -2)) / math.sqrt(dk)).masked_fill(mask.unsqueeze(0), O.MASK_FILL)
+    ref = (torch.softmax(sc, -1) @ v).permute(1, 2, 0, 3).reshape(N * S, D)
+    err = (ctx.cpu() - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), err
+    assert (chi.float().cpu() + clo.float().cpu() - ctx.cpu()).abs().max().item() < 1e-5 * max(4.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("B,group,S,E,D,H", [(3, 1, 9, 16, 128, 2), (4, 3, 15, 12, 256, 4), (2, 6, 29, 120, 512, 8),
+                                             (128, 6, 28, 120, 512, 8), (2, 10, 30, 128, 64, 1)])
+def test_cross_attention_tc(mode, tol, B, group, S, E, D, H):
+    gen = g(16)
+    N = B * group
+    L_ = 2
+    q = torch.randn(N * S, D, generator=gen)
+    kv = torch.randn(B * E, L_ * 2 * D, generator=gen)
+    layer = 1
+    qh, ql = split(q)
+    kh, kl_ = split(kv)
+    ctx = torch.empty(N * S, D, device=DEV)
+    qh, ql, kh, kl_ = qh.to(DEV), ql.to(DEV), kh.to(DEV), kl_.to(DEV)
+    L.call("navc_cross_attention_tc", L.TC_BF16X3 if mode == "bf16x3" else L.TC_BF16, L.ptr(qh), L.ptr(ql), D,
+           kh[:, layer * 2 * D:].data_ptr(), kl_[:, layer * 2 * D:].data_ptr(), L_ * 2 * D, N, S, E, D, H, group,
+           L.ptr(ctx), None, None, L.stream())
+    torch.cuda.synchronize()
+    dk = D // H
+    kl = kv[:, layer * 2 * D: layer * 2 * D + D].view(B, E, H, dk)
+    vl = kv[:, layer * 2 * D + D: (layer + 1) * 2 * D].view(B, E, H, dk)
+    kl = O.enlarge(kl, group).permute(2, 0, 1, 3)
+    vl = O.enlarge(vl, group).permute(2, 0, 1, 3)
+    qq = q.view(N, S, H, dk).permute(2, 0, 1, 3)
+    p = torch.softmax((qq @ kl.transpose(-1, -2)) / math.sqrt(dk), -1)
+    ref = (p @ vl).permute(1, 2, 0, 3).reshape(N * S, D)
+    err = (ctx.cpu() - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), err
+
+
 def test_embed_ln_and_layernorm():
     gen = g(15)
     N, S, D, V, group = 12, 11, 128, 60, 3
