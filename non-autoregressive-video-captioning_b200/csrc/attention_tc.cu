@@ -7,7 +7,7 @@
 //     (-1e7 fill as models/bert.py:157-161; keys of other sequences / beyond E excluded),
 //     e = exp(s - max) split to bf16 hi/lo and written to shared memory in the canonical
 //     K-major 128B-swizzle layout (the A operand of the second MMA; aliases the Q/K buffers)
-//   tcgen05.mma  O[128,64] = P V             (V consumed MN-major, as TMA loaded it) -> TMEM [128,192)
+//   tcgen05.mma  O[128,64] = P V             (V consumed MN-major, as TMA loaded it) -> TMEM [0,64) (reuses S)
 //   epilogue: tcgen05.ld O row per thread, * 1/sum, bf16 hi/lo (+fp32) context rows.
 // Split mode issues hi*hi + hi*lo + lo*hi for both products (fp32-like accuracy).
 //
@@ -28,8 +28,8 @@ template <bool kX3> struct AtCfg {
     static constexpr int kQKBytes = 2 * kParts * kAtTile;
     static constexpr int kVBytes = kParts * kAtTile;
     static constexpr int kUsedBytes = kQKBytes + kVBytes + 1024 /*align*/ + 256 /*barriers, flags*/;
-    // at most 2 CTAs per SM (2 x 256 TMEM columns): keep the footprint above a third of shared memory
-    static constexpr int kSmemBytes = kUsedBytes > 80 * 1024 ? kUsedBytes : 80 * 1024;
+    // at most 4 CTAs per SM (4 x 128 TMEM columns): keep the footprint above a fifth of shared memory
+    static constexpr int kSmemBytes = kUsedBytes > 48 * 1024 ? kUsedBytes : 48 * 1024;
 };
 
 struct AtParams {
@@ -47,7 +47,7 @@ struct AtParams {
 };
 
 template <bool kX3>
-__global__ void __launch_bounds__(kAtThreads, 2)
+__global__ void __launch_bounds__(kAtThreads, kX3 ? 2 : 4)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
                AtParams p) {
@@ -92,7 +92,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
@@ -105,7 +105,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+    const uint32_t tS = tmem_base, tO = tmem_base;  // O reuses the S columns (S is dead once P is in smem)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -230,11 +230,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     e2[u] = visible ? fast_exp2((s - m) * kLog2e) : 0.f;
                     sum += e2[u];
                 }
-                uint16_t h0, h1, l0, l1;
-                split_bf16(e2[0], h0, l0);
-                split_bf16(e2[1], h1, l1);
-                hi_w[j >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                lo_w[j >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                split_bf16x2(e2[0], e2[1], hi_w[j >> 1], lo_w[j >> 1]);
             }
             // 32 keys = 64 B = four 16-byte chunks of panel c/2, chunk index (c%2)*4 + i
             uint8_t* panel_hi = gP + (c >> 1) * kAtTile + row_off;
@@ -270,13 +266,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     const size_t oo = o + c * 32 + g4 * 4;
                     if (p.ctx_f32) *reinterpret_cast<float4*>(p.ctx_f32 + oo) = f;
                     if (p.ctx_hi) {
-                        uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-                        split_bf16(f.x, h0, l0); split_bf16(f.y, h1, l1); split_bf16(f.z, h2, l2); split_bf16(f.w, h3, l3);
-                        *reinterpret_cast<uint2*>(p.ctx_hi + oo) =
-                            make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-                        if (p.ctx_lo)
-                            *reinterpret_cast<uint2*>(p.ctx_lo + oo) =
-                                make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+                        uint2 hv, lv;
+                        split_bf16x4(f, hv, lv);
+                        *reinterpret_cast<uint2*>(p.ctx_hi + oo) = hv;
+                        if (p.ctx_lo) *reinterpret_cast<uint2*>(p.ctx_lo + oo) = lv;
                     }
                 }
             }
@@ -287,7 +280,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
     }
 }
 

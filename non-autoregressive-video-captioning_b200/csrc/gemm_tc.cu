@@ -161,72 +161,110 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const bool row_ok = row < M;
                 const bool my_rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[row] == NAVC_PAD) : false;
                 const uint32_t rz_mask = __ballot_sync(0xffffffffu, my_rz);
-                const bool vec = (epi.ld_out % 4 == 0) && (N % 4 == 0) && (!epi.residual || epi.ld_res % 4 == 0);
+                const bool vec = (epi.ld_out % 4 == 0) && (N % 4 == 0) && (!epi.residual || epi.ld_res % 4 == 0) &&
+                                 ((((uintptr_t)epi.bias) & 15) == 0) &&
+                                 (epi.act == NAVC_ACT_NONE || epi.act == NAVC_ACT_GELU_NEW);  // other activations: scalar path
+                const int cc = lane & 7, rr = lane >> 3;  // phase-2 mapping: 8 lanes per row, 4 rows per step
+                // number of 32-column chunks of this warp's half that exist (warp-uniform)
+                int n_chunks = (N - n0 + 31) / 32;
+                n_chunks = n_chunks < 0 ? 0 : (n_chunks > TBN / 64 ? TBN / 64 : n_chunks);
+                if (epi.dbg == 1) n_chunks = 0;
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + half * (TBN / 2));
+                uint32_t r[32];
+                if (n_chunks > 0) tc_ld32(t_row, r);
 #pragma unroll 1
-                for (int c = 0; c < TBN / 64; ++c) {
+                for (int c = 0; c < n_chunks; ++c) {
                     const int col0 = n0 + c * 32;
-                    if (col0 >= N) break;  // warp-uniform
-                    uint32_t r[32];
-                    tc_ld32(t_row + (uint32_t)(c * 32), r);
+                    const int col2 = col0 + cc * 4;
+                    // global operands of this chunk are requested before the TMEM wait so their latency overlaps
+                    float4 q[8], bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (vec) {
+                        if (epi.bias && col2 < N) bv = __ldg(reinterpret_cast<const float4*>(epi.bias + col2));
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int grow = row0 + it * 4 + rr;
+                            q[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (epi.residual && grow < M && col2 < N)
+                                q[it] = __ldg(reinterpret_cast<const float4*>(epi.residual + (size_t)grow * epi.ld_res + col2));
+                        }
+                    }
                     tc_wait_ld();
                     if (vec) {
-                        // phase 1 (lane = row): bias + activation, park the 32x32 chunk in shared memory.
+                        // phase 1 (lane = row): park the raw 32x32 accumulator chunk in shared memory.
                         // float4 slot g of row `lane` lives at slot g ^ (lane & 7): conflict-free both ways.
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            float4 v = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                                                   __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
-                            const int col = col0 + g * 4;
-                            if (col < N) {
-                                if (epi.bias) {
-                                    const float4 bv = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
-                                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                                }
-                                if (epi.act) {
-                                    v.x = act_apply_fast(v.x, epi.act); v.y = act_apply_fast(v.y, epi.act);
-                                    v.z = act_apply_fast(v.z, epi.act); v.w = act_apply_fast(v.w, epi.act);
-                                }
-                            }
-                            *reinterpret_cast<float4*>(stage + lane * 32 + ((g ^ (lane & 7)) << 2)) = v;
-                        }
+                        for (int g = 0; g < 8; ++g)
+                            *reinterpret_cast<uint4*>(stage + lane * 32 + ((g ^ (lane & 7)) << 2)) =
+                                make_uint4(r[g * 4 + 0], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]);
                         __syncwarp();
-                        // phase 2 (8 lanes per row, 4 rows per step): residual, row mask, coalesced stores
-                        const int cc = lane & 7, rr = lane >> 3;
-                        const int col = col0 + cc * 4;
+                        if (c + 1 < n_chunks) tc_ld32(t_row + (uint32_t)((c + 1) * 32), r);  // overlaps phase 2
+                        // phase 2: residual, row mask, coalesced stores.  Branch-free so the eight row
+                        // groups overlap: all shared loads first, then the math, then predicated stores.
+                        if (epi.dbg == 2) continue;
+                        float4 v[8];
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
                             const int rl = it * 4 + rr;
-                            const int grow = row0 + rl;
-                            float4 v = *reinterpret_cast<const float4*>(stage + rl * 32 + ((cc ^ (rl & 7)) << 2));
-                            if (grow < M && col < N) {
-                                if (epi.residual) {
-                                    const float4 q = *reinterpret_cast<const float4*>(epi.residual + (size_t)grow * epi.ld_res + col);
-                                    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-                                }
-                                if ((rz_mask >> rl) & 1u) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                                const size_t o = (size_t)grow * epi.ld_out + col;
-                                if (epi.out_f32) *reinterpret_cast<float4*>(epi.out_f32 + o) = v;
-                                if (epi.out_hi) {
-                                    uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-                                    split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
-                                    split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-                                    *reinterpret_cast<uint2*>(epi.out_hi + o) =
-                                        make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-                                    if (epi.out_lo)
-                                        *reinterpret_cast<uint2*>(epi.out_lo + o) =
-                                            make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+                            v[it] = *reinterpret_cast<const float4*>(stage + rl * 32 + ((cc ^ (rl & 7)) << 2));
+                        }
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            v[it].x += bv.x; v[it].y += bv.y; v[it].z += bv.z; v[it].w += bv.w;
+                        }
+                        if (epi.act == NAVC_ACT_GELU_NEW) {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                v[it].x = act_apply_fast(v[it].x, NAVC_ACT_GELU_NEW); v[it].y = act_apply_fast(v[it].y, NAVC_ACT_GELU_NEW);
+                                v[it].z = act_apply_fast(v[it].z, NAVC_ACT_GELU_NEW); v[it].w = act_apply_fast(v[it].w, NAVC_ACT_GELU_NEW);
+                            }
+                        }
+                        const bool col_ok = col2 < N && epi.dbg != 3;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rl = it * 4 + rr;
+                            const float keep = ((rz_mask >> rl) & 1u) ? 0.f : 1.f;
+                            v[it].x = (v[it].x + q[it].x) * keep; v[it].y = (v[it].y + q[it].y) * keep;
+                            v[it].z = (v[it].z + q[it].z) * keep; v[it].w = (v[it].w + q[it].w) * keep;
+                        }
+                        if (epi.out_f32) {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int grow = row0 + it * 4 + rr;
+                                if (grow < M && col_ok) *reinterpret_cast<float4*>(epi.out_f32 + (size_t)grow * epi.ld_out + col2) = v[it];
+                            }
+                        }
+                        if (epi.out_hi) {
+                            uint2 hv[8], lv[8];
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) split_bf16x4(v[it], hv[it], lv[it]);
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int grow = row0 + it * 4 + rr;
+                                if (grow < M && col_ok) *reinterpret_cast<uint2*>(epi.out_hi + (size_t)grow * epi.ld_out + col2) = hv[it];
+                            }
+                            if (epi.out_lo) {
+#pragma unroll
+                                for (int it = 0; it < 8; ++it) {
+                                    const int grow = row0 + it * 4 + rr;
+                                    if (grow < M && col_ok) *reinterpret_cast<uint2*>(epi.out_lo + (size_t)grow * epi.ld_out + col2) = lv[it];
                                 }
                             }
                         }
                         __syncwarp();
-                    } else if (row_ok) {
-                        // odd leading dimensions / N: scalar fallback (lane = row)
+                    } else {
+                        // odd leading dimensions / N: scalar fallback through the staging buffer (lane = row)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < N) epi_store1(epi, row, col0 + j, __uint_as_float(r[j]), my_rz);
+                        for (int j = 0; j < 32; ++j) stage[lane * 32 + ((j + lane) & 31)] = __uint_as_float(r[j]);
+                        __syncwarp();
+                        if (c + 1 < n_chunks) tc_ld32(t_row + (uint32_t)((c + 1) * 32), r);
+                        if (row_ok) {
+#pragma unroll 1
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < N) epi_store1(epi, row, col0 + j, stage[lane * 32 + ((j + lane) & 31)], my_rz);
+                        }
+                        __syncwarp();
                     }
                 }
             } else {

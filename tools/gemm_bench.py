@@ -10,6 +10,7 @@ from navc_b200 import _lib as L
 dev = torch.device("cuda", 0)
 L.ensure_init(dev)
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 21504
+DBG = int(os.environ.get("NAVC_DBG", "0"))
 shapes = [("qkv", 1536, 512, 0, False), ("so", 512, 512, 0, True), ("f1", 2048, 512, 1, False), ("f2", 512, 2048, 0, True),
           ("enc0", 512, 2048, 0, False)]
 for mode, mname in ((L.TC_BF16X3, "bf16x3"), (L.TC_BF16, "bf16")):
@@ -25,7 +26,7 @@ for mode, mname in ((L.TC_BF16X3, "bf16x3"), (L.TC_BF16, "bf16")):
         of = torch.empty(m, N, device=dev) if res else None
         oh = torch.empty(m, N, dtype=torch.bfloat16, device=dev)
         ol = torch.empty(m, N, dtype=torch.bfloat16, device=dev) if mode == L.TC_BF16X3 else None
-        ep = L.Epilogue(L.ptr(b), L.ptr(r), L.ptr(toks) if res else None, act, N if res else 0, L.ptr(of), L.ptr(oh), L.ptr(ol), N, 0)
+        ep = L.Epilogue(L.ptr(b), L.ptr(r), L.ptr(toks) if res else None, act, N if res else 0, L.ptr(of), L.ptr(oh), L.ptr(ol), N, DBG)
         def run(i):
             L.call("navc_linear_tc", mode, L.ptr(xs[i % nb]), L.ptr(xl[i % nb]), K, L.ptr(wh), L.ptr(wl), K, m, N, K, ep, L.stream())
         for i in range(3):
