@@ -25,7 +25,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -50,35 +49,46 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+class ClockSampler:
+    """One `nvidia-smi -lms` process sampling clocks / throttle reasons during the timed regions."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.proc = index, [], None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 7 and f[0].replace(".", "", 1).isdigit():
+                self.samples.append(f)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        mhz = sorted(int(float(s[0])) for s in self.samples)
+        busy = [s for s in self.samples if float(s[2]) > 250.0] or self.samples  # samples taken under load
+        mhz = sorted(int(float(s[0])) for s in busy)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
-                "samples": len(mhz), "power_w_max": max(float(s[2]) for s in self.samples)}
+                "samples": len(self.samples), "samples_under_load": len(busy),
+                "power_w_max": max(float(s[2]) for s in self.samples)}
 
 
 def cpu_oracle_run(opt, batch, steps, warmup):
@@ -201,24 +211,31 @@ def main():
         return ms, out
 
     with torch.no_grad():
-        for i in range(args.warmup):
+        # every rotated batch once eagerly and once more (first call per (B, Smax) shape runs eagerly,
+        # the second captures the CUDA graph of the refinement loop), then the counted warm-up
+        for i in range(2 * n_rot + args.warmup):
             step_resident(i)
             step_e2e(i)
         torch.cuda.synchronize()
-        # ---- timed region 1: resident inputs (kernel-side throughput) + live per-kernel events ----
         sampler = ClockSampler(local_rank)
         sampler.start()
-        model.engine.profile_tag, model.engine.profile_events = "f1", []
+        # ---- timed region 1: resident inputs (kernel-side throughput) ----
         launches0 = L.launches
         ms, hyp = timed(step_resident, args.steps)
         launches = L.launches - launches0
-        events = model.engine.profile_events
-        model.engine.profile_tag = None
+        stats = dict(navc_b200.generate.last_stats)
         # ---- timed region 2: end to end from host buffers ----
         ms_e2e, hyp_host = timed(step_e2e, args.steps)
-        sampler.stop_flag = True
-        sampler.join(timeout=2)
-    stats = dict(navc_b200.generate.last_stats)
+        # ---- region 3: the same steps launched eagerly (graph replay off) with CUDA events around
+        # every FFN up-projection GEMM launch: per-launch duration of the dominant kernel ----
+        tr.opt = dict(opt, navc_graphs=False)
+        step_resident(0)
+        model.engine.profile_tag, model.engine.profile_events = "f1", []
+        timed(step_resident, min(args.steps, 5))
+        events = model.engine.profile_events
+        model.engine.profile_tag = None
+        tr.opt = opt
+        sampler.stop()
     d2h = hyp_host.numel() * 8
 
     value = world * B * args.steps / (ms / 1e3)
@@ -237,7 +254,7 @@ def main():
         mma_mult = {"bf16x3": 3.0, "bf16": 1.0}.get(args.precision, 0.0)
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "gemm_tc_kernel (FFN up-projection, M=%d N=%d K=%d)" % (R, opt["intermediate_size"], opt["dim_hidden"]),
-                "launches_timed": len(durs), "mean_us": mean_ms * 1e3, "peak_source": pk_src + " (sustained cuBLAS bf16)",
+                "launches_timed": len(durs), "timed_in": "eager re-run of the same steps (graph replay off), CUDA events on the launching stream", "mean_us": mean_ms * 1e3, "peak_source": pk_src + " (sustained cuBLAS bf16)",
                 "algorithmic_flops_per_launch": flops,
                 "issued_mma_frac": achieved * mma_mult / peak if mma_mult else None,
                 "note": "achieved counts useful (fp32-equivalent) FLOPs; %s mode issues %.0fx as many bf16 MMAs" % (args.precision, mma_mult or 0)}
@@ -256,7 +273,7 @@ def main():
                           "bf16": "bf16", "fp32": "f32"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "precision": args.precision, "passes": stats.get("passes"),
-                           "S": stats.get("S"), "rows": stats.get("N"),
+                           "S": stats.get("S"), "rows": stats.get("N"), "cuda_graph": bool(stats.get("graph")),
                            "l2": "inputs rotate over %d distinct batches (%d MB of features > 126 MB L2)" % (n_rot, n_rot * h2d >> 20)},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},

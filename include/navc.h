@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NAVC_VERSION 1
+#define NAVC_VERSION 2
 
 /* token ids, config/Constants.py:1-6 */
 #define NAVC_PAD 0
@@ -60,6 +60,9 @@ typedef struct {
     uint16_t* out_lo;           /* bf16 bits [M, ld_out] or NULL */
     int32_t ld_out;
     int32_t reserved;
+    int32_t split_k;            /* tcgen05 path: > 1 splits the K loop over that many CTAs per output tile;
+                                   implies accumulate (out_f32 only, no bias/act/residual/mask) */
+    int32_t accumulate;         /* != 0: out_f32 += tile (atomic float adds; caller zero-fills first) */
 } navc_epilogue_t;
 
 int navc_version(void);
@@ -77,8 +80,10 @@ int navc_linear_f32(const float* x, int ldx, const float* w, int ldw, int M, int
                     const navc_epilogue_t* epi, void* stream);
 
 /* Same contract on the tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue).
- * Operands are bf16 (hi) or split bf16 (hi+lo); accumulation fp32.  K % 64 == 0, ld % 8 == 0.
- * x_lo / w_lo may be NULL when mode == NAVC_TC_BF16. */
+ * Operands are bf16 (hi) or split bf16 (hi+lo); accumulation fp32.  K % 8 == 0, ld % 8 == 0 (the
+ * K tail of the last 64-wide block is zero-filled by TMA).  x_lo / w_lo may be NULL when
+ * mode == NAVC_TC_BF16.  Gradient GEMMs of the training path are this same entry point on
+ * transposed operands (navc_transpose_pack) with split_k / accumulate. */
 int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx,
                    const uint16_t* w_hi, const uint16_t* w_lo, int ldw, int M, int N, int K,
                    const navc_epilogue_t* epi, void* stream);
@@ -232,6 +237,89 @@ int navc_teacher_inputs(const int64_t* tokens, const int64_t* map, int N, int S,
  * over j; hyp[b,:] = tokens[b*lbs + j*, :]. */
 int navc_select_best(const int64_t* tokens, const float* lprobs, const int32_t* lens, int B, int lbs,
                      int S, float alpha, int64_t* hyp, float* score, void* stream);
+
+
+/* ==== training path (forward in train mode + hand-written backward; misc/run.py:254-261) ======
+ * Dropout masks are never stored: keep(seed, i) is a counter-based hash of the element index, so
+ * the backward kernels regenerate the forward mask from the same seed.  Scale 1/(1-p), p in [0,1). */
+
+/* out = rowmask( drop(seed2,p2)( drop(seed1,p1)(y) + res ) ) over [M, D] (ld = D):
+ * BertSelfOutput dense->dropout->+residual (models/bert.py:193-197), BertOutput
+ * dense->dropout->+input->dropout (bert.py:241-247), `* non_pad_mask` (bert.py:271-299), and the
+ * embedding dropout (bert.py:96) with res == NULL.  res / row_tokens may be NULL. */
+int navc_drop_add(const float* y, const float* res, uint64_t seed1, float p1, uint64_t seed2, float p2,
+                  const int64_t* row_tokens, int M, int D, float* out_f32, uint16_t* out_hi,
+                  uint16_t* out_lo, void* stream);
+/* g = dout * rowmask * m2/(1-p2);  d_res = g (may be NULL);  d_y = g * m1/(1-p1). */
+int navc_drop_add_bwd(const float* dout, uint64_t seed1, float p1, uint64_t seed2, float p2,
+                      const int64_t* row_tokens, int M, int D, float* d_y, float* d_res, void* stream);
+
+/* out = drop(seed,p)(act(u)) elementwise over n values (BertIntermediate gelu, bert.py:227-230;
+ * length head ReLU->Dropout, models/Predictor.py:16-21).  du = dout * m/(1-p) * act'(u). */
+int navc_act_drop(const float* u, int act, uint64_t seed, float p, int64_t n, float* out_f32,
+                  uint16_t* out_hi, uint16_t* out_lo, void* stream);
+int navc_act_drop_bwd(const float* dout, const float* u, int act, uint64_t seed, float p, int64_t n,
+                      float* du, void* stream);
+
+/* x [M,N] (ld) fp32 -> any of: bf16 hi/lo copy [M, ld_s]; transposed fp32 / bf16 hi/lo [N, ld_t]
+ * (columns M..ld_t-1 zero-filled); colsum[n] += sum_m x[m,n] (atomic; caller zero-fills).  Feeds
+ * the gradient GEMMs dX = dY W and dW = dY^T X and the bias gradients. */
+int navc_transpose_pack(const float* x, int M, int N, int ld, uint16_t* hi, uint16_t* lo, int ld_s,
+                        float* t_f32, uint16_t* t_hi, uint16_t* t_lo, int ld_t, float* colsum,
+                        void* stream);
+
+/* Encoder, train mode (models/Encoder.py:19-25, 62-66): o = drop(seed,p)(highway(x, yg)) [BF, D]. */
+int navc_highway_fwd_train(const float* x, const float* yg, int gate, int BF, int D, uint64_t seed,
+                           float p, float* o, void* stream);
+/* d_x (direct term) [BF,D] and d_yg [BF, gate?2D:D] from d_o. */
+int navc_highway_bwd(const float* d_o, const float* x, const float* yg, int gate, int BF, int D,
+                     uint64_t seed, float p, float* d_x, float* d_yg, void* stream);
+/* BatchNorm1d batch statistics over the M rows of o [M,D] (joint_representation.py:43-45):
+ * mean[d], var[d] (biased); if running_mean != NULL the running statistics are updated in place
+ * with `momentum` and the unbiased variance, as nn.BatchNorm1d does in train mode. */
+int navc_bn_stats(const float* o, int M, int D, float* mean, float* var, float momentum,
+                  float* running_mean, float* running_var, void* stream);
+/* enc_out[b, slot*F+f, :] = mean ? (o - mean)*rsqrt(var+eps)*w + b : o ; enc_hidden as navc_highway_bn. */
+int navc_bn_apply_concat(const float* o, const float* mean, const float* var, const float* w,
+                         const float* b, float eps, int B, int F, int D, int E, int slot, int n_modalities,
+                         int accumulate, float* enc_hidden, float* enc_out, uint16_t* enc_hi,
+                         uint16_t* enc_lo, void* stream);
+/* Backward of the above for one modality slot: d_o [B*F, D]; d_w, d_b [D] (overwritten; NULL when
+ * mean == NULL i.e. no norm); d_enc_hidden may be NULL. */
+int navc_bn_bwd(const float* d_enc_out, const float* d_enc_hidden, const float* o, const float* mean,
+                const float* var, const float* w, float eps, int B, int F, int D, int E, int slot,
+                int n_modalities, float* d_w, float* d_b, float* d_o, void* stream);
+/* d_enc_out[b,e,:] += d_mean[b,:] / E  (backward of enc_output.mean(1): Predictor.py:29,
+ * Decoder.py:137). */
+int navc_mean_bwd(const float* d_mean, int B, int E, int D, float* d_enc_out, void* stream);
+
+/* log_softmax backward over rows: dlogits = g - exp(logp) * sum(g); columns V..ld_out-1 of the
+ * output are zero-filled (seq2seq.py:102-103 under autograd). */
+int navc_log_softmax_bwd(const float* g, const float* logp, int M, int V, int ld_in, float* dlogits,
+                         int ld_out, void* stream);
+
+/* LayerNorm backward (rows whose token is PAD were zeroed by the forward -> zero gradient):
+ * dx [M,D]; dw[d] += , db[d] += (atomic; caller zero-fills). */
+int navc_layernorm_bwd(const float* dy, const float* x, const float* w, float eps,
+                       const int64_t* row_tokens, int M, int D, float* dx, float* dw, float* db,
+                       void* stream);
+/* Backward of navc_embed_ln given d(out) [N*S, D]: LayerNorm backward (d_ln_w, d_ln_b += ) and
+ * scatter-add of the embedding-sum gradient into d_word[tok] (not for PAD: padding_idx),
+ * d_pos[s], d_cat[category[n/group]], d_extra[n/group] (all atomic; caller zero-fills). */
+int navc_embed_ln_bwd(const float* dout, const int64_t* tokens, const int64_t* category,
+                      const float* word_emb, const float* pos_emb, const float* cat_emb,
+                      const float* extra, int group, const float* ln_w, const float* ln_b, float eps,
+                      int N, int S, int D, float* d_word, float* d_pos, float* d_cat, float* d_extra,
+                      float* d_ln_w, float* d_ln_b, void* stream);
+
+/* Attention backward (softmax recomputed from Q, K; masks as the forward).  Self: d_qkv [N*S, ld]
+ * receives dQ | dK | dV at column offsets 0, D, 2D.  Cross: d_q [N*S, ld_dq]; d_kv [(N/group)*E,
+ * ld_dkv] receives dK | dV at 0, D summed over the `group` rows of each video. */
+int navc_self_attention_bwd(const float* qkv, int ld, const int64_t* tokens, int N, int S, int D, int H,
+                            int mask_kind, int watch, const float* d_ctx, float* d_qkv, void* stream);
+int navc_cross_attention_bwd(const float* q, int ldq, const float* kv, int ldkv, int N, int S, int E,
+                             int D, int H, int group, const float* d_ctx, float* d_q, int ld_dq,
+                             float* d_kv, int ld_dkv, void* stream);
 
 #ifdef __cplusplus
 }

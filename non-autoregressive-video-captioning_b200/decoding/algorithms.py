@@ -42,13 +42,7 @@ class Refiner:
         self.use_ct = bool(opt.get("use_ct", False))
         self.masking_decision = bool(opt.get("masking_decision", False)) and teacher_model is not None
         self.final_teacher = teacher_model is not None and not opt.get("no_candidate_decision", False)
-        self.map = None
-        if dict_mapping:
-            size = max(dict_mapping) + 1
-            m = torch.arange(size, dtype=torch.int64)
-            for k, v in dict_mapping.items():
-                m[k] = v
-            self.map = m.to(dev)
+        self.map = dict_mapping if isinstance(dict_mapping, torch.Tensor) else None  # id remap table (na_generate.py)
 
     # -- building blocks ---------------------------------------------------------------------
     def init_canvas(self, fill):

@@ -62,6 +62,8 @@ class Engine:
         # the launching stream around every `linear(..., tag=profile_tag)` call
         self.profile_tag = None
         self.profile_events = []
+        self.pack_id = 0
+        self.graphs: Dict[tuple, object] = {}  # CUDA graphs of the decode loop (decoding/na_generate.py)
 
     # ------------------------------------------------------------------------------------------
     # weight packing
@@ -80,6 +82,8 @@ class Engine:
         self.device = dev
         self._pack()
         self._sig = sig
+        self.pack_id += 1
+        self.graphs.clear()  # captured graphs hold pointers into the previous packed weights
 
     def _lin(self, w, b=None) -> PackedLinear:
         pl = PackedLinear(w, b)
@@ -274,22 +278,25 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # decoder
     # ------------------------------------------------------------------------------------------
+    def enc_inputs(self, enc_output: torch.Tensor, cache: Optional[dict] = None):
+        """Encoder memory in the operand formats of this engine (fp32 + bf16 hi/lo copies) and the
+        frame mean used by enhance_input=2; reuses what ``encode`` already produced."""
+        self.sync_weights()
+        if cache is not None and cache.get("owner") == id(self) and cache["enc"].f32.data_ptr() == enc_output.data_ptr():
+            return cache
+        Bv, E, D = enc_output.shape
+        enc = self.from_f32(enc_output.reshape(Bv * E, D))
+        enc_mean = torch.empty((Bv, D), dtype=torch.float32, device=self.device)
+        L.call("navc_length_head", L.ptr(enc.f32), Bv, E, D, None, None, None, None, 0, L.ptr(enc_mean), None, L.stream())
+        return dict(enc=enc, enc_mean=enc_mean, B=Bv, E=E, owner=id(self))
+
     def memory(self, enc_output: torch.Tensor, cache: Optional[dict] = None):
         """Per-video decoder memory: cross-attention K|V of every layer (computed once)
         and the frame mean used by enhance_input=2."""
-        self.sync_weights()
-        if cache is not None and cache.get("owner") == id(self) and cache["enc"].f32.data_ptr() == enc_output.data_ptr():
-            if "kv" in cache:
-                return cache
-            enc, enc_mean = cache["enc"], cache["enc_mean"]
-        else:
-            Bv, E, D = enc_output.shape
-            enc = self.from_f32(enc_output.reshape(Bv * E, D))
-            enc_mean = torch.empty((Bv, D), dtype=torch.float32, device=self.device)
-            L.call("navc_length_head", L.ptr(enc.f32), Bv, E, D, None, None, None, None, 0, L.ptr(enc_mean), None, L.stream())
-            cache = dict(enc=enc, enc_mean=enc_mean, B=Bv, E=E, owner=id(self))
-        tc_attn = self.tc_attention_ok(32, cache["E"])
-        cache["kv"] = self.linear(enc, self.P["kv_all"], f32=not tc_attn, bf=tc_attn)  # [Bv*E, L*2D]
+        cache = self.enc_inputs(enc_output, cache)
+        if "kv" not in cache:
+            tc_attn = self.tc_attention_ok(32, cache["E"])
+            cache["kv"] = self.linear(cache["enc"], self.P["kv_all"], f32=not tc_attn, bf=tc_attn)  # [Bv*E, L*2D]
         return cache
 
     def tc_attention_ok(self, S, E):

@@ -175,3 +175,35 @@ def test_full_size_properties():
     assert (a == b).float().mean().item() >= 0.99
     # PAD is a suffix or an interior predicted <pad>; every row has at least 4 non-pad positions
     assert ((a != 0).sum(1) >= 1).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_graph_replay_matches_eager(precision):
+    """The CUDA-graph replay of the mask-predict loop (decoding/na_generate.py) returns the same ids
+    as the eager launches, also when the replayed graph is fed a different batch, and is dropped
+    when the weights change."""
+    opt = cases.small("NACF", use_ct=True)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt).to(DEV).eval()
+    model.set_precision(precision)
+    outs, replayed = {}, False
+    for graphs in (False, True):
+        o = dict(opt, navc_graphs=graphs)
+        tr = navc_b200.Translator(model, o, device=DEV)
+        for rep in range(4):
+            feats, category = cases.synth_inputs(opt, 6, seed=100 + rep % 2)
+            with torch.no_grad():
+                enc = model.encode(feats=to_dev(feats))
+                hyp, _ = tr.translate_batch(enc, category.to(DEV), None, {})
+            st = navc_b200.generate.last_stats
+            if not graphs or rep == 0:
+                assert not st["graph"]  # first call per (batch, Smax) shape is eager
+            replayed = replayed or st["graph"]
+            outs[(graphs, rep)] = hyp.cpu()
+    for rep in range(4):
+        assert torch.equal(outs[(False, rep)], outs[(True, rep)]), rep
+    assert replayed and any(v != "warm" for v in model.engine.graphs.values())
+    with torch.no_grad():
+        model.tgt_word_prj.weight.mul_(1.0)  # bumps the version -> repack -> graphs dropped
+    model.engine.sync_weights()
+    assert not model.engine.graphs
