@@ -107,6 +107,8 @@ int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint16_t* h_lo,
                            const int64_t* target, float* target_logit, void* stream);
 /* log_softmax over rows of a materialised logits matrix, in place allowed (seq2seq.py:102-103). */
 int navc_log_softmax(const float* logits, float* out, int M, int V, int ld, void* stream);
+/* Same with separate leading dimensions (training: logits come from a GEMM with a padded ld). */
+int navc_log_softmax_ld(const float* logits, int ld_in, float* out, int ld_out, int M, int V, void* stream);
 
 /* ---- encoder ------------------------------------------------------------------------------- */
 /* Highway gate + frame mean + (eval) BatchNorm + temporal concat for one modality

@@ -15,12 +15,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnavc.so")
 
 c_f32p = C.c_void_p
-i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+i32, i64, u64, f32, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
 
 
 class Epilogue(C.Structure):
     _fields_ = [("bias", vp), ("residual", vp), ("row_tokens", vp), ("act", i32), ("ld_res", i32),
-                ("out_f32", vp), ("out_hi", vp), ("out_lo", vp), ("ld_out", i32), ("reserved", i32)]
+                ("out_f32", vp), ("out_hi", vp), ("out_lo", vp), ("ld_out", i32), ("reserved", i32),
+                ("split_k", i32), ("accumulate", i32)]
 
 
 class Step(C.Structure):
@@ -48,6 +49,7 @@ _PROTOS = {
     "navc_vocab_partials_f32": [vp, i32, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "navc_vocab_partials_tc": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "navc_log_softmax": [vp, vp, i32, i32, i32, vp],
+    "navc_log_softmax_ld": [vp, i32, vp, i32, i32, i32, vp],
     "navc_highway_bn": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp],
     "navc_length_head": [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp],
     "navc_embed_ln": [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp],
@@ -62,6 +64,23 @@ _PROTOS = {
     "navc_teacher_probs": [vp, vp, i32, vp, vp, i32, i32, vp, vp],
     "navc_teacher_inputs": [vp, vp, i32, i32, vp, vp, vp],
     "navc_select_best": [vp, vp, vp, i32, i32, i32, f32, vp, vp, vp],
+    # training path
+    "navc_drop_add": [vp, vp, u64, f32, u64, f32, vp, i32, i32, vp, vp, vp, vp],
+    "navc_drop_add_bwd": [vp, u64, f32, u64, f32, vp, i32, i32, vp, vp, vp],
+    "navc_act_drop": [vp, i32, u64, f32, i64, vp, vp, vp, vp],
+    "navc_act_drop_bwd": [vp, vp, i32, u64, f32, i64, vp, vp],
+    "navc_transpose_pack": [vp, i32, i32, i32, vp, vp, i32, vp, vp, vp, i32, vp, vp],
+    "navc_highway_fwd_train": [vp, vp, i32, i32, i32, u64, f32, vp, vp],
+    "navc_highway_bwd": [vp, vp, vp, i32, i32, i32, u64, f32, vp, vp, vp],
+    "navc_bn_stats": [vp, i32, i32, vp, vp, f32, vp, vp, vp],
+    "navc_bn_apply_concat": [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+    "navc_bn_bwd": [vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_mean_bwd": [vp, i32, i32, i32, vp, vp],
+    "navc_log_softmax_bwd": [vp, vp, i32, i32, i32, vp, i32, vp],
+    "navc_layernorm_bwd": [vp, vp, vp, f32, vp, i32, i32, vp, vp, vp, vp],
+    "navc_embed_ln_bwd": [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+    "navc_self_attention_bwd": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
+    "navc_cross_attention_bwd": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, vp],
 }
 EXPORTS = ["navc_version", "navc_last_error", "navc_sm_count"] + list(_PROTOS)
 

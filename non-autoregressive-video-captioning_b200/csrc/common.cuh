@@ -108,6 +108,8 @@ struct EpiParams {
     uint16_t* out_lo;
     int ld_out;
     int dbg;  // profiling aid (navc_epilogue_t.reserved): 1 = skip epilogue, 2 = no phase 2, 3 = no global stores
+    int split_k;     // tcgen05 path only
+    int accumulate;  // out_f32 += (atomic)
 };
 static inline EpiParams to_params(const navc_epilogue_t* e) {
     EpiParams p;
@@ -115,6 +117,8 @@ static inline EpiParams to_params(const navc_epilogue_t* e) {
     p.ld_res = e->ld_res; p.out_f32 = e->out_f32; p.out_hi = e->out_hi; p.out_lo = e->out_lo;
     p.ld_out = e->ld_out;
     p.dbg = e->reserved;
+    p.split_k = e->split_k > 1 ? e->split_k : 1;
+    p.accumulate = (e->accumulate != 0 || p.split_k > 1) ? 1 : 0;
     return p;
 }
 
@@ -134,6 +138,10 @@ __device__ __forceinline__ void epi_store4(const EpiParams& p, int row, int col,
     }
     if (row_zero) v = make_float4(0.f, 0.f, 0.f, 0.f);
     size_t o = (size_t)row * p.ld_out + col;
+    if (p.accumulate) {
+        atomicAdd(reinterpret_cast<float4*>(p.out_f32 + o), v);
+        return;
+    }
     if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
     if (p.out_hi) {
         uint2 hv, lv;
@@ -148,6 +156,10 @@ __device__ __forceinline__ void epi_store1(const EpiParams& p, int row, int col,
     if (p.residual) v += p.residual[(size_t)row * p.ld_res + col];
     if (row_zero) v = 0.f;
     size_t o = (size_t)row * p.ld_out + col;
+    if (p.accumulate) {
+        atomicAdd(p.out_f32 + o, v);
+        return;
+    }
     if (p.out_f32) p.out_f32[o] = v;
     if (p.out_hi) {
         uint16_t h, l;

@@ -154,10 +154,13 @@ extern "C" int navc_linear_f32(const float* x, int ldx, const float* w, int ldw,
     NAVC_REQUIRE(K % BK == 0 && ldx % 4 == 0 && ldw % 4 == 0,
                  "navc_linear_f32: need K%%16==0, ldx%%4==0, ldw%%4==0 (K=%d ldx=%d ldw=%d)", K, ldx, ldw);
     NAVC_REQUIRE(e->out_f32 || e->out_hi, "navc_linear_f32: no output");
+    NAVC_REQUIRE(!(e->accumulate || e->split_k > 1) || e->out_f32, "navc_linear_f32: accumulate needs out_f32");
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     NAVC_REQUIRE(grid.y <= 65535, "navc_linear_f32: M too large");
     VocabEpi v = {};
-    gemm_f32_kernel<false><<<grid, NT, 0, as_stream(stream)>>>(x, ldx, w, ldw, M, N, K, to_params(e), v);
+    EpiParams p = to_params(e);
+    p.split_k = 1;  // the CUDA-core path runs the whole K loop per tile (accumulate still honoured)
+    gemm_f32_kernel<false><<<grid, NT, 0, as_stream(stream)>>>(x, ldx, w, ldw, M, N, K, p, v);
     return check_launch("navc_linear_f32");
 }
 

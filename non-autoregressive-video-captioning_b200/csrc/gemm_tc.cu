@@ -66,8 +66,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + TBM - 1) / TBM, n_blocks = (N + TBN - 1) / TBN;
-    const int n_tiles = m_blocks * n_blocks;
-    const int k_blocks = K / TBK;
+    const int k_blocks = (K + TBK - 1) / TBK;  // TMA zero-fills the K tail of the last block
+    const int split = kVocab ? 1 : epi.split_k;
+    const int kpb = (k_blocks + split - 1) / split;  // k-blocks per split (host guarantees every split is non-empty)
+    const int n_tiles = m_blocks * n_blocks * split;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -89,8 +91,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int mb = tile / n_blocks, nb = tile % n_blocks;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                const int ks = tile % split, mn = tile / split;
+                const int mb = mn / n_blocks, nb = mn % n_blocks;
+                const int kb0 = ks * kpb, kb1 = min(k_blocks, kb0 + kpb);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
@@ -116,7 +120,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TBN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                const int kb0 = (tile % split) * kpb, kb1 = min(k_blocks, kb0 + kpb);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -129,15 +134,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // 32 bytes per k-step
                         if (kX3) {
                             // small cross terms first, the dominant hi*hi product last
-                            tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, ((kb - kb0) | k) ? 1u : 0u);
                             tc_mma_bf16(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
                             tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
                         } else {
-                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, ((kb - kb0) | k) ? 1u : 0u);
                         }
                     }
                     tc_commit(empty_bar(stage));                       // frees the smem slot when the MMAs retire
-                    if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+                    if (kb == kb1 - 1) tc_commit(tfull_bar(acc));  // accumulator ready for the epilogue
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                 }
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
@@ -152,7 +157,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int mb = tile / n_blocks, nb = tile % n_blocks;
+            const int mn = tile / split;
+            const int mb = mn / n_blocks, nb = mn % n_blocks;
             const int row0 = mb * TBM + quarter * 32;
             const int row = row0 + lane;
             const int n0 = nb * TBN + half * (TBN / 2);
@@ -228,14 +234,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             v[it].x = (v[it].x + q[it].x) * keep; v[it].y = (v[it].y + q[it].y) * keep;
                             v[it].z = (v[it].z + q[it].z) * keep; v[it].w = (v[it].w + q[it].w) * keep;
                         }
-                        if (epi.out_f32) {
+                        if (epi.accumulate) {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int grow = row0 + it * 4 + rr;
+                                if (grow < M && col_ok) atomicAdd(reinterpret_cast<float4*>(epi.out_f32 + (size_t)grow * epi.ld_out + col2), v[it]);
+                            }
+                        } else if (epi.out_f32) {
 #pragma unroll
                             for (int it = 0; it < 8; ++it) {
                                 const int grow = row0 + it * 4 + rr;
                                 if (grow < M && col_ok) *reinterpret_cast<float4*>(epi.out_f32 + (size_t)grow * epi.ld_out + col2) = v[it];
                             }
                         }
-                        if (epi.out_hi) {
+                        if (epi.out_hi && !epi.accumulate) {
                             uint2 hv[8], lv[8];
 #pragma unroll
                             for (int it = 0; it < 8; ++it) split_bf16x4(v[it], hv[it], lv[it]);
@@ -372,8 +384,8 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
     NAVC_REQUIRE(g_tc_ready, "%s: navc_init() has not been called", what);
     NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "%s: bad mode %d", what, mode);
     NAVC_REQUIRE(x_hi && w_hi && (mode == NAVC_TC_BF16 || (x_lo && w_lo)), "%s: null operand", what);
-    NAVC_REQUIRE(M > 0 && N > 0 && K > 0 && K % TBK == 0 && ldx % 8 == 0 && ldw % 8 == 0,
-                 "%s: need K%%64==0 and ld%%8==0 (M=%d N=%d K=%d ldx=%d ldw=%d)", what, M, N, K, ldx, ldw);
+    NAVC_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0,
+                 "%s: need K%%8==0 and ld%%8==0 (M=%d N=%d K=%d ldx=%d ldw=%d)", what, M, N, K, ldx, ldw);
     NAVC_REQUIRE((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0,
                  "%s: operands must be 16-byte aligned", what);
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -386,7 +398,7 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
-    const int tiles = ((M + TBM - 1) / TBM) * ((N + TBN - 1) / TBN);
+    const int tiles = ((M + TBM - 1) / TBM) * ((N + TBN - 1) / TBN) * epi.split_k;
     int sms = navc_sm_count();
     if (sms <= 0) sms = 148;
     const int grid = tiles < sms ? tiles : sms;
@@ -408,9 +420,18 @@ extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_
                               const uint16_t* w_lo, int ldw, int M, int N, int K, const navc_epilogue_t* e,
                               void* stream) {
     NAVC_REQUIRE(e && (e->out_f32 || e->out_hi), "navc_linear_tc: no output");
+    EpiParams p = to_params(e);
+    if (p.accumulate) {
+        NAVC_REQUIRE(p.out_f32 && !p.bias && !p.residual && !p.row_tokens && p.act == NAVC_ACT_NONE,
+                     "navc_linear_tc: accumulate / split_k outputs take no bias, activation, residual or row mask");
+        // every split must own at least one 64-wide k-block
+        const int k_blocks = (K + TBK - 1) / TBK;
+        if (p.split_k > k_blocks) p.split_k = k_blocks;
+        const int kpb = (k_blocks + p.split_k - 1) / p.split_k;
+        p.split_k = (k_blocks + kpb - 1) / kpb;
+    }
     TcVocab v = {};
-    return launch_tc<false>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, to_params(e), v, as_stream(stream),
-                            "navc_linear_tc");
+    return launch_tc<false>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
 }
 
 extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,
@@ -421,6 +442,7 @@ extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint
     NAVC_REQUIRE(!target || target_logit, "navc_vocab_partials_tc: target without target_logit");
     TcVocab v = {bias, part_max, part_sum, part_idx, target, target_logit, (V + TBN / 2 - 1) / (TBN / 2)};
     EpiParams e = {};
+    e.split_k = 1;
     return launch_tc<true>(mode, h_hi, h_lo, ldh, w_hi, w_lo, ldw, M, V, K, e, v, as_stream(stream),
                            "navc_vocab_partials_tc");
 }

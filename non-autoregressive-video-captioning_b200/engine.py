@@ -39,13 +39,19 @@ class Act:
 
 
 class PackedLinear:
-    __slots__ = ("w", "b", "w_hi", "w_lo", "N", "K")
+    """One (possibly concatenated) nn.Linear in kernel operand formats.  ``src`` lists the
+    state_dict entries the rows came from: (weight key, bias key or None, row0, row1) -- the training
+    path uses it to hand gradients of the packed matrix back to the individual parameters."""
+    __slots__ = ("w", "b", "w_hi", "w_lo", "N", "K", "src", "T", "pad")
 
-    def __init__(self, w, b):
+    def __init__(self, w, b, src=()):
         self.w = w.detach().contiguous().float()
         self.b = None if b is None else b.detach().contiguous().float()
         self.N, self.K = self.w.shape
         self.w_hi = self.w_lo = None
+        self.src = tuple(src)
+        self.T = None  # transposed operand copy for dgrad GEMMs (training.py), built on first use
+        self.pad = None  # row-padded operand copy (vocabulary projection in training), built on first use
 
 
 class Engine:
@@ -69,8 +75,10 @@ class Engine:
     # weight packing
     # ------------------------------------------------------------------------------------------
     def _signature(self):
+        # num_batches_tracked is bookkeeping only (BatchNorm momentum is fixed); the running statistics
+        # are referenced in place, so train-mode updates need no repack
         return tuple((p.data_ptr(), p._version) for p in self.model.parameters()) + \
-            tuple((b.data_ptr(), b._version) for b in self.model.buffers())
+            tuple((b.data_ptr(), b._version) for n, b in self.model.named_buffers() if not n.endswith("num_batches_tracked"))
 
     def sync_weights(self):
         """(Re)pack weights if any parameter changed (optimizer step, load_state_dict, .to())."""
@@ -85,8 +93,8 @@ class Engine:
         self.pack_id += 1
         self.graphs.clear()  # captured graphs hold pointers into the previous packed weights
 
-    def _lin(self, w, b=None) -> PackedLinear:
-        pl = PackedLinear(w, b)
+    def _lin(self, w, b=None, src=()) -> PackedLinear:
+        pl = PackedLinear(w, b, src)
         if self.tc:
             pl.w_hi = torch.empty(pl.w.shape, dtype=torch.bfloat16, device=pl.w.device)
             pl.w_lo = torch.empty_like(pl.w_hi) if self.precision == "bf16x3" else None
@@ -105,8 +113,12 @@ class Engine:
                 gate = (pre + ".1.w2.weight") in sd
                 w12 = torch.cat([sd[pre + ".1.w1.weight"]] + ([sd[pre + ".1.w2.weight"]] if gate else []), 0)
                 b12 = torch.cat([sd[pre + ".1.w1.bias"]] + ([sd[pre + ".1.w2.bias"]] if gate else []), 0)
-                P["streams"].append(dict(l0=self._lin(sd[pre + ".0.weight"], sd[pre + ".0.bias"]),
-                                         l12=self._lin(w12, b12), gate=int(gate)))
+                D_ = sd[pre + ".0.weight"].shape[0]
+                src12 = [(pre + ".1.w1.weight", pre + ".1.w1.bias", 0, D_)] + \
+                    ([(pre + ".1.w2.weight", pre + ".1.w2.bias", D_, 2 * D_)] if gate else [])
+                P["streams"].append(dict(l0=self._lin(sd[pre + ".0.weight"], sd[pre + ".0.bias"],
+                                                      [(pre + ".0.weight", pre + ".0.bias", 0, D_)]),
+                                         l12=self._lin(w12, b12, src12), gate=int(gate)))
             # joint representation norms
             P["norms"] = []
             jr = "joint_representation_learner."
@@ -121,37 +133,51 @@ class Engine:
             # length head
             ap = "auxiliary_task_predictor.layers.0.net."
             P["len_head"] = None
+            P["norm_keys"] = [jr + ("bn%d" if (jr + "bn%d.weight" % i) in sd else "ln%d") % i for i in range(len(opt["modality"]))]
             if (ap + "0.weight") in sd:
                 P["len_head"] = tuple(sd[ap + k].float().contiguous() for k in ("0.weight", "0.bias", "3.weight", "3.bias"))
+                P["len_head_keys"] = tuple(ap + k for k in ("0.weight", "0.bias", "3.weight", "3.bias"))
             # decoder
             dp = "decoder.bert." if ("decoder.bert.embedding.LayerNorm.weight" in sd) else "decoder."
             e = dp + "embedding."
+            P["emb_prefix"] = e
             P["emb"] = dict(word=sd[e + "word_embeddings.weight"].float().contiguous(),
                             pos=sd[e + "position_embeddings.weight"].float().contiguous(),
                             cat=sd[e + "category_embeddings.weight"].float().contiguous() if (e + "category_embeddings.weight") in sd else None,
                             ln_w=sd[e + "LayerNorm.weight"].float().contiguous(), ln_b=sd[e + "LayerNorm.bias"].float().contiguous())
-            layers, kv_w, kv_b = [], [], []
+            layers, kv_w, kv_b, kv_src = [], [], [], []
+            D_ = opt["dim_hidden"]
             for l in range(opt["num_hidden_layers_decoder"]):
                 lp = "%slayer.%d." % (dp, l)
                 sa, ca = lp + "attention.", lp + "attend_to_enc_output."
                 qkv_w = torch.cat([sd[sa + "self.%s.weight" % n] for n in ("query", "key", "value")], 0)
                 qkv_b = torch.cat([sd[sa + "self.%s.bias" % n] for n in ("query", "key", "value")], 0)
+                qkv_src = [(sa + "self.%s.weight" % n, sa + "self.%s.bias" % n, i * D_, (i + 1) * D_)
+                           for i, n in enumerate(("query", "key", "value"))]
                 kv_w.append(torch.cat([sd[ca + "self.key.weight"], sd[ca + "self.value.weight"]], 0))
                 kv_b.append(torch.cat([sd[ca + "self.key.bias"], sd[ca + "self.value.bias"]], 0))
+                kv_src += [(ca + "self.%s.weight" % n, ca + "self.%s.bias" % n, (2 * l + i) * D_, (2 * l + i + 1) * D_)
+                           for i, n in enumerate(("key", "value"))]
 
                 def ln(prefix):
                     k = prefix + "LayerNorm.weight"
                     return (sd[k].float().contiguous(), sd[prefix + "LayerNorm.bias"].float().contiguous()) if k in sd else None
+
+                def one(prefix):
+                    w = sd[prefix + ".weight"]
+                    return self._lin(w, sd[prefix + ".bias"], [(prefix + ".weight", prefix + ".bias", 0, w.shape[0])])
                 layers.append(dict(
-                    qkv=self._lin(qkv_w, qkv_b), so=self._lin(sd[sa + "output.dense.weight"], sd[sa + "output.dense.bias"]),
-                    so_ln=ln(sa + "output."),
-                    cq=self._lin(sd[ca + "self.query.weight"], sd[ca + "self.query.bias"]),
-                    co=self._lin(sd[ca + "output.dense.weight"], sd[ca + "output.dense.bias"]), co_ln=ln(ca + "output."),
-                    f1=self._lin(sd[lp + "intermediate.dense.weight"], sd[lp + "intermediate.dense.bias"]),
-                    f2=self._lin(sd[lp + "output.dense.weight"], sd[lp + "output.dense.bias"]), f2_ln=ln(lp + "output.")))
+                    qkv=self._lin(qkv_w, qkv_b, qkv_src), so=one(sa + "output.dense"), so_ln=ln(sa + "output."),
+                    so_ln_key=sa + "output.LayerNorm",
+                    cq=one(ca + "self.query"), co=one(ca + "output.dense"), co_ln=ln(ca + "output."),
+                    co_ln_key=ca + "output.LayerNorm",
+                    f1=one(lp + "intermediate.dense"), f2=one(lp + "output.dense"), f2_ln=ln(lp + "output."),
+                    f2_ln_key=lp + "output.LayerNorm"))
             P["layers"] = layers
-            P["kv_all"] = self._lin(torch.cat(kv_w, 0), torch.cat(kv_b, 0))  # [L*2D, D]
-            P["vocab"] = self._lin(sd["tgt_word_prj.weight"], sd.get("tgt_word_prj.bias"))
+            P["kv_all"] = self._lin(torch.cat(kv_w, 0), torch.cat(kv_b, 0), kv_src)  # [L*2D, D]
+            vb = "tgt_word_prj.bias" if "tgt_word_prj.bias" in sd else None
+            P["vocab"] = self._lin(sd["tgt_word_prj.weight"], sd.get("tgt_word_prj.bias"),
+                                   [("tgt_word_prj.weight", vb, 0, sd["tgt_word_prj.weight"].shape[0])])
         self.P = P
         self.D = opt["dim_hidden"]
         self.H = opt["num_attention_heads"]

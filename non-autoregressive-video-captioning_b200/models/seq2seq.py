@@ -91,12 +91,13 @@ class Seq2Seq(nn.Module):
             hidden_states = [hidden_states]
         logprobs = []
         for h in hidden_states:
+            if torch.is_grad_enabled() and self.training:
+                from ..training import vocab_logprobs_train
+                logprobs.append(vocab_logprobs_train(self, h))  # projection + log-softmax, one autograd node
+                continue
             logits = self.tgt_word_prj(h)
-            if logits.requires_grad:
-                logprobs.append(torch.log_softmax(logits, dim=-1))
-            else:
-                shape = logits.shape
-                logprobs.append(self.engine.log_softmax_(logits.view(-1, shape[-1])).view(shape))
+            shape = logits.shape
+            logprobs.append(self.engine.log_softmax_(logits.view(-1, shape[-1])).view(shape))
         results[Constants.mapping["lang"][0]] = logprobs
         results.pop("_navc", None)
         return results

@@ -1,11 +1,604 @@
-"""Training-mode (autograd) entry points.  Forward/backward kernels for training land after the
-inference path; until then training-mode calls fail loudly instead of
-silently running some other implementation."""
+"""Training-mode (autograd) execution of the hot path: forward in train mode and a hand-written
+backward, both through the C ABI of ``include/navc.h``.
+
+The reference trains with ``loss.backward()`` through eager PyTorch modules (misc/run.py:254-261).
+Here the three boundary calls of ``Seq2Seq`` -- ``encode``, ``decoder`` and ``tgt_word_prj`` (+
+``log_softmax``) -- are each ONE ``torch.autograd.Function`` whose forward and backward are
+sequences of navc kernels; autograd only stitches the three together, accumulates parameter
+gradients into ``.grad`` and runs the caller's loss (misc/crit.py) on the returned log-probs.
+
+* Dropout (p=0.5 at every site of the reference, incl. the double dropout of BertOutput,
+  models/bert.py:240-247) uses a counter-based hash: masks are regenerated in the backward pass
+  from per-site seeds drawn from torch's CPU generator (``torch.manual_seed`` reproducible), never
+  stored.  torch's own Philox stream cannot be reproduced bit-exactly, so parity
+  with the reference is tested with dropout disabled and statistically otherwise.
+* BatchNorm uses batch statistics and updates ``running_mean/var/num_batches_tracked`` like
+  ``nn.BatchNorm1d`` in train mode (models/joint_representation.py:43-45).
+* Weight / input gradients are tensor-core GEMMs on transposed operand copies
+  (``navc_transpose_pack``): dX = dY W, dW = dY^T X (split-K, atomic accumulate), db = column sums.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from .config import Constants
+from .engine import Act, Engine, PackedLinear
+
+_GOLD = 0x9E3779B97F4A7C15
+_MASK64 = (1 << 64) - 1
 
 
-def _nyi(*a, **k):
-    raise NotImplementedError("navc training path (backward kernels) is not built yet; call model.eval() "
-                              "or wrap the call in torch.no_grad() for the inference kernels")
+def _up(x, m):
+    return (x + m - 1) // m * m
 
 
-encode_train = decoder_forward_train = vocab_forward_train = _nyi
+class Seeds:
+    """Per-site dropout seeds of one forward call (base from torch's CPU generator)."""
+
+    def __init__(self):
+        self.base = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self.n = 0
+
+    def next(self) -> int:
+        self.n += 1
+        return (self.base + self.n * _GOLD) & _MASK64
+
+
+# --------------------------------------------------------------------------------------------------
+# GEMM helpers
+# --------------------------------------------------------------------------------------------------
+class Operand:
+    """A row-major [rows, K] GEMM operand in the engine's format: fp32 (fp32 mode) or bf16 hi(/lo)."""
+    __slots__ = ("f32", "hi", "lo", "rows", "K", "ld")
+
+    def __init__(self, rows, K, ld, f32=None, hi=None, lo=None):
+        self.rows, self.K, self.ld, self.f32, self.hi, self.lo = rows, K, ld, f32, hi, lo
+
+
+def _alloc_operand(eng: Engine, rows, ld) -> Operand:
+    dev = eng.device
+    if eng.tc:
+        hi = torch.empty((rows, ld), dtype=torch.bfloat16, device=dev)
+        lo = torch.empty((rows, ld), dtype=torch.bfloat16, device=dev) if eng.precision == "bf16x3" else None
+        return Operand(rows, ld, ld, hi=hi, lo=lo)
+    return Operand(rows, ld, ld, f32=torch.empty((rows, ld), dtype=torch.float32, device=dev))
+
+
+def gemm(eng: Engine, x: Operand, w: Operand, M, N, K, out: torch.Tensor, ld_out, bias=None, residual=None,
+         ld_res=0, accumulate=False, split_k=1):
+    """out[M,N] (+)= x[M,K] w[N,K]^T (+bias +residual) in the engine's precision mode."""
+    ep = L.Epilogue(L.ptr(bias), L.ptr(residual), None, 0, ld_res, L.ptr(out), None, None, ld_out, 0,
+                    split_k if eng.tc else 1, 1 if accumulate else 0)
+    if eng.tc:
+        L.call("navc_linear_tc", eng.tc_mode, L.ptr(x.hi), L.ptr(x.lo), x.ld, L.ptr(w.hi), L.ptr(w.lo), w.ld, M, N, K, ep,
+               L.stream())
+    else:
+        L.call("navc_linear_f32", L.ptr(x.f32), x.ld, L.ptr(w.f32), w.ld, M, N, K, ep, L.stream())
+
+
+def transpose_pack(eng: Engine, x: torch.Tensor, M, N, ld, straight=False, transposed=False, colsum=None):
+    """x [M,N] fp32 -> (straight operand [M, N] ld=ld, transposed operand [N, Mp]) in the engine's format."""
+    s = t = None
+    Mp = _up(M, 64)
+    if straight:
+        assert ld % 8 == 0
+        s = Operand(M, N, ld, f32=x) if not eng.tc else _alloc_operand(eng, M, ld)
+        if eng.tc:
+            s.K = N
+    if transposed:
+        t = _alloc_operand(eng, N, Mp)
+    need_kernel = (eng.tc and straight) or transposed or colsum is not None
+    if need_kernel:
+        L.call("navc_transpose_pack", L.ptr(x), M, N, ld,
+               L.ptr(s.hi) if (s is not None and eng.tc) else None, L.ptr(s.lo) if (s is not None and eng.tc) else None, ld,
+               L.ptr(t.f32) if t is not None else None, L.ptr(t.hi) if t is not None else None,
+               L.ptr(t.lo) if t is not None else None, Mp, L.ptr(colsum), L.stream())
+    return s, t
+
+
+def weight_T(eng: Engine, lin: PackedLinear) -> Operand:
+    """W^T [K, Np] (Np = N rounded up to 64, zero padded) for dX = dY W, cached per packed weight."""
+    if lin.T is None:
+        _, lin.T = transpose_pack(eng, lin.w, lin.N, lin.K, lin.K, transposed=True)
+    return lin.T
+
+
+def _split_k(out_rows, out_cols, k):
+    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
+    kb = (k + 63) // 64
+    return max(1, min(kb, (2 * 148) // max(tiles, 1)))
+
+
+class Grads:
+    """Gradient accumulator keyed by state_dict name."""
+
+    def __init__(self):
+        self.g: Dict[str, torch.Tensor] = {}
+
+    def add(self, key, t):
+        if key is None:
+            return
+        self.g[key] = t if key not in self.g else self.g[key] + t
+
+    def add_packed(self, lin: PackedLinear, dW, db):
+        for wk, bk, r0, r1 in lin.src:
+            self.add(wk, dW[r0:r1] if (r0, r1) != (0, dW.shape[0]) else dW)
+            if bk is not None and db is not None:
+                self.add(bk, db[r0:r1] if (r0, r1) != (0, db.shape[0]) else db)
+
+
+def lin_bwd(eng: Engine, x: torch.Tensor, lin: PackedLinear, dY: torch.Tensor, grads: Grads, need_dx=True,
+            dx_residual: Optional[torch.Tensor] = None, ld_dy=None):
+    """Backward of y = x W^T + b.  x [M,K] fp32, dY [M,N] fp32 (leading dimension ld_dy, pad columns
+    zero).  Accumulates dW / db into ``grads``; returns dX [M,K] (+ dx_residual) or None."""
+    M, K = x.shape
+    N = lin.N
+    ld = ld_dy or dY.stride(0)
+    dev = eng.device
+    if ld % 16 != 0 or (need_dx and ld < _up(N, 64)):  # operand alignment: re-lay dY with a zero-padded ld
+        ldp = _up(N, 64)
+        pad = torch.zeros((M, ldp), dtype=torch.float32, device=dev)
+        pad[:, :N].copy_(dY.view(M, -1)[:, :N] if ld == dY.stride(0) else dY.as_strided((M, N), (ld, 1)))
+        dY, ld = pad, ldp
+    db = torch.zeros((N,), dtype=torch.float32, device=dev) if lin.b is not None else None
+    s, t = transpose_pack(eng, dY, M, N, ld, straight=need_dx, transposed=True, colsum=db)
+    _, xt = transpose_pack(eng, x, M, K, x.stride(0), transposed=True)
+    Mp = _up(M, 64)
+    dW = torch.zeros((N, K), dtype=torch.float32, device=dev)
+    gemm(eng, t, xt, N, K, Mp, dW, K, accumulate=True, split_k=_split_k(N, K, Mp))
+    grads.add_packed(lin, dW, db)
+    if not need_dx:
+        return None
+    wt = weight_T(eng, lin)  # [K, Np]
+    dX = torch.empty((M, K), dtype=torch.float32, device=dev)
+    gemm(eng, s, wt, M, K, min(ld, wt.ld), dX, K, residual=dx_residual, ld_res=K if dx_residual is not None else 0)
+    return dX
+
+
+# --------------------------------------------------------------------------------------------------
+# elementwise wrappers
+# --------------------------------------------------------------------------------------------------
+def drop_add(eng, y, res, s1, p1, s2, p2, row_tokens, f32=True, bf=True) -> Act:
+    M, D = y.shape
+    out = eng._new(M, D, f32 or not eng.tc, bf)
+    L.call("navc_drop_add", L.ptr(y), L.ptr(res), s1, p1, s2, p2, L.ptr(row_tokens), M, D, L.ptr(out.f32), L.ptr(out.hi),
+           L.ptr(out.lo), L.stream())
+    return out
+
+
+def drop_add_bwd(dout, s1, p1, s2, p2, row_tokens, want_res=True):
+    M, D = dout.shape
+    d_y = torch.empty_like(dout)
+    d_res = torch.empty_like(dout) if (want_res and p1 > 0) else None
+    L.call("navc_drop_add_bwd", L.ptr(dout), s1, p1, s2, p2, L.ptr(row_tokens), M, D, L.ptr(d_y), L.ptr(d_res), L.stream())
+    if want_res and d_res is None:
+        d_res = d_y  # no first dropout: the two gradients coincide
+    return d_y, d_res
+
+
+def _post(eng, y, res, ln, s1, p1, s2, p2, tok_flat, saved):
+    """dense output -> dropout -> +residual -> [LayerNorm] -> [dropout] -> * non_pad_mask
+    (models/bert.py:193-200 with p2 == 0; bert.py:241-247 with the second dropout)."""
+    if ln is None:
+        return drop_add(eng, y, res, s1, p1, s2, p2, tok_flat)
+    t = drop_add(eng, y, res, s1, p1, 0, 0.0, None, f32=True, bf=False)
+    saved["t"] = t.f32
+    if p2 > 0:
+        z = eng.layernorm(t, ln, None, f32=True, bf=False)
+        return drop_add(eng, z.f32, None, s2, p2, 0, 0.0, tok_flat)
+    return eng.layernorm(t, ln, tok_flat)
+
+
+def _post_bwd(eng, g, ln, ln_key, s1, p1, s2, p2, tok_flat, saved, grads: Grads):
+    """Returns (d_dense_out, d_residual)."""
+    if ln is None:
+        return drop_add_bwd(g, s1, p1, s2, p2, tok_flat)
+    M, D = g.shape
+    if p2 > 0:
+        g, _ = drop_add_bwd(g, s2, p2, 0, 0.0, tok_flat, want_res=False)
+        tok_for_ln = None
+    else:
+        tok_for_ln = tok_flat
+    dx = torch.empty_like(g)
+    dw = torch.zeros((D,), dtype=torch.float32, device=g.device)
+    db = torch.zeros((D,), dtype=torch.float32, device=g.device)
+    L.call("navc_layernorm_bwd", L.ptr(g), L.ptr(saved["t"]), L.ptr(ln[0]), eng.eps, L.ptr(tok_for_ln), M, D, L.ptr(dx),
+           L.ptr(dw), L.ptr(db), L.stream())
+    grads.add(ln_key + ".weight", dw)
+    grads.add(ln_key + ".bias", db)
+    d_y, d_res = drop_add_bwd(dx, s1, p1, 0, 0.0, None)
+    return d_y, d_res
+
+
+def _lin_f32(eng: Engine, w, b, src) -> PackedLinear:
+    """Small head GEMMs (length predictor) always run on the fp32 CUDA-core path."""
+    return PackedLinear(w, b, src)
+
+
+def _gemm_f32(x, w, b, M, N, K, out):
+    ep = L.Epilogue(L.ptr(b), None, None, 0, 0, L.ptr(out), None, None, N, 0, 1, 0)
+    L.call("navc_linear_f32", L.ptr(x), K, L.ptr(w), K, M, N, K, ep, L.stream())
+
+
+class _F32Engine:
+    """View of an engine that forces the fp32 CUDA-core GEMM path (tiny head GEMMs)."""
+
+    def __init__(self, eng):
+        self.device, self.tc, self.precision, self.tc_mode = eng.device, False, "fp32", 0
+
+
+# --------------------------------------------------------------------------------------------------
+# encoder  (models/seq2seq.py:35-63 in train mode)
+# --------------------------------------------------------------------------------------------------
+def _param_list(model, keys):
+    sd = dict(model.named_parameters())
+    return [sd[k] for k in keys]
+
+
+def _encode_param_keys(model):
+    return [k for k, _ in model.named_parameters()
+            if k.startswith(("encoder.", "joint_representation_learner.", "auxiliary_task_predictor."))]
+
+
+class EncodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, keys, n_feats, *tensors):
+        eng: Engine = model.engine
+        eng.sync_weights()
+        opt, P, D = eng.opt, eng.P, eng.D
+        feats = [f.detach() for f in tensors[:n_feats]]
+        dev = eng.device
+        if opt.get("fusion", "temporal_concat") not in ("temporal_concat", "none"):
+            raise NotImplementedError("fusion=%r (broken in the reference, joint_representation.py:41)" % opt["fusion"])
+        B, F_ = feats[0].shape[0], feats[0].shape[1]
+        if any(f.shape[1] != F_ for f in feats):
+            raise NotImplementedError("modalities with different frame counts")
+        E = F_ * len(feats)
+        BF = B * F_
+        seeds = Seeds()
+        p_enc = float(opt.get("encoder_dropout", 0.5))
+        p_hid = float(opt["hidden_dropout_prob"])
+        no_norm = opt.get("fusion", "temporal_concat") == "none" or opt.get("no_encoder_bn", False)
+        enc = Act(B * E, D, f32=torch.empty((B, E, D), dtype=torch.float32, device=dev))
+        enc_hidden = torch.empty((B, D), dtype=torch.float32, device=dev)
+        streams = []
+        jr = model.joint_representation_learner
+        for i, (f, st) in enumerate(zip(feats, P["streams"])):
+            x_in = eng.from_f32(f.reshape(BF, f.shape[2]).to(dev))
+            x = eng.linear(x_in, st["l0"], f32=True, bf=True)
+            yg = eng.linear(x, st["l12"], f32=True, bf=False)
+            o = torch.empty((BF, D), dtype=torch.float32, device=dev)
+            seed = seeds.next()
+            L.call("navc_highway_fwd_train", L.ptr(x.f32), L.ptr(yg.f32), st["gate"], BF, D, seed, p_enc, L.ptr(o), L.stream())
+            norm = None if no_norm else P["norms"][i]
+            mean = var = bw = bb = None
+            if norm is not None:
+                if norm[0] == "ln":
+                    raise NotImplementedError("norm_type='ln' encoder norm")
+                bn = getattr(jr, "bn%d" % i)
+                bw, bb = norm[3], norm[4]
+                mean = torch.empty((D,), dtype=torch.float32, device=dev)
+                var = torch.empty((D,), dtype=torch.float32, device=dev)
+                L.call("navc_bn_stats", L.ptr(o), BF, D, L.ptr(mean), L.ptr(var), float(bn.momentum if bn.momentum is not None else 0.1),
+                       L.ptr(bn.running_mean), L.ptr(bn.running_var), L.stream())
+                bn.num_batches_tracked += 1
+            L.call("navc_bn_apply_concat", L.ptr(o), L.ptr(mean), L.ptr(var), L.ptr(bw), L.ptr(bb), 1e-5, B, F_, D, E, i,
+                   len(feats), int(i > 0), L.ptr(enc_hidden), L.ptr(enc.f32), None, None, L.stream())
+            streams.append(dict(x_in=x_in.f32, x=x.f32, yg=yg.f32, o=o, mean=mean, var=var, bw=bw, seed=seed))
+        outs = [enc.f32, enc_hidden]
+        head = None
+        if P["len_head"] is not None:
+            w1, b1, w2, b2 = P["len_head"]
+            max_len = w2.shape[0]
+            m = torch.empty((B, D), dtype=torch.float32, device=dev)
+            L.call("navc_length_head", L.ptr(enc.f32), B, E, D, None, None, None, None, 0, L.ptr(m), None, L.stream())
+            h_pre = torch.empty((B, D), dtype=torch.float32, device=dev)
+            _gemm_f32(m, w1, b1, B, D, D, h_pre)
+            h = torch.empty_like(h_pre)
+            hseed = seeds.next()
+            L.call("navc_act_drop", L.ptr(h_pre), L.ACT["relu"], hseed, p_hid, h_pre.numel(), L.ptr(h), None, None, L.stream())
+            logits = torch.empty((B, max_len), dtype=torch.float32, device=dev)
+            _gemm_f32(h, w2, b2, B, max_len, D, logits)
+            pred = torch.empty_like(logits)
+            L.call("navc_log_softmax", L.ptr(logits), L.ptr(pred), B, max_len, max_len, L.stream())
+            head = dict(m=m, h_pre=h_pre, h=h, pred=pred, seed=hseed, p=p_hid)
+            outs.append(pred)
+        ctx.model, ctx.keys, ctx.n_feats = model, keys, n_feats
+        ctx.state = dict(streams=streams, head=head, B=B, F=F_, E=E, p_enc=p_enc, pack_id=eng.pack_id)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_enc, d_hidden, *rest):
+        model, st = ctx.model, ctx.state
+        eng: Engine = model.engine
+        P, D = eng.P, eng.D
+        B, F_, E = st["B"], st["F"], st["E"]
+        dev = eng.device
+        BF = B * F_
+        grads = Grads()
+        feng = _F32Engine(eng)
+        d_enc = torch.zeros((B, E, D), dtype=torch.float32, device=dev) if d_enc is None else d_enc.contiguous().clone()
+        d_hidden = None if d_hidden is None else d_hidden.contiguous()
+        head = st["head"]
+        d_pred = rest[0] if rest else None
+        if head is not None and d_pred is not None:
+            w1, b1, w2, b2 = P["len_head"]
+            k1w, k1b, k2w, k2b = P["len_head_keys"]
+            max_len = w2.shape[0]
+            Lp = _up(max_len, 64)
+            dlog = torch.empty((B, Lp), dtype=torch.float32, device=dev)
+            L.call("navc_log_softmax_bwd", L.ptr(d_pred.contiguous()), L.ptr(head["pred"]), B, max_len, max_len, L.ptr(dlog),
+                   Lp, L.stream())
+            lin2 = PackedLinear(w2, b2, [(k2w, k2b, 0, max_len)])
+            dh = lin_bwd(feng, head["h"], lin2, dlog, grads, ld_dy=Lp)
+            dh_pre = torch.empty_like(dh)
+            L.call("navc_act_drop_bwd", L.ptr(dh), L.ptr(head["h_pre"]), L.ACT["relu"], head["seed"], head["p"], dh.numel(),
+                   L.ptr(dh_pre), L.stream())
+            lin1 = PackedLinear(w1, b1, [(k1w, k1b, 0, D)])
+            dm = lin_bwd(feng, head["m"], lin1, dh_pre, grads)
+            L.call("navc_mean_bwd", L.ptr(dm), B, E, D, L.ptr(d_enc), L.stream())
+        n_mod = len(st["streams"])
+        for i, (s, pw) in enumerate(zip(st["streams"], P["streams"])):
+            d_o = torch.empty((BF, D), dtype=torch.float32, device=dev)
+            d_w = d_b = None
+            if s["mean"] is not None:
+                d_w = torch.empty((D,), dtype=torch.float32, device=dev)
+                d_b = torch.empty((D,), dtype=torch.float32, device=dev)
+            L.call("navc_bn_bwd", L.ptr(d_enc), L.ptr(d_hidden), L.ptr(s["o"]), L.ptr(s["mean"]), L.ptr(s["var"]), L.ptr(s["bw"]),
+                   1e-5, B, F_, D, E, i, n_mod, L.ptr(d_w), L.ptr(d_b), L.ptr(d_o), L.stream())
+            if d_w is not None:
+                grads.add(P["norm_keys"][i] + ".weight", d_w)
+                grads.add(P["norm_keys"][i] + ".bias", d_b)
+            gate = pw["gate"]
+            d_x = torch.empty((BF, D), dtype=torch.float32, device=dev)
+            d_yg = torch.empty((BF, (2 if gate else 1) * D), dtype=torch.float32, device=dev)
+            L.call("navc_highway_bwd", L.ptr(d_o), L.ptr(s["x"]), L.ptr(s["yg"]), gate, BF, D, s["seed"], st["p_enc"],
+                   L.ptr(d_x), L.ptr(d_yg), L.stream())
+            d_x = lin_bwd(eng, s["x"], pw["l12"], d_yg, grads, dx_residual=d_x)
+            lin_bwd(eng, s["x_in"], pw["l0"], d_x, grads, need_dx=False)
+        return (None, None, None) + (None,) * ctx.n_feats + tuple(grads.g.get(k) for k in ctx.keys)
+
+
+def encode_train(model, feats):
+    keys = _encode_param_keys(model)
+    feats = list(feats)
+    outs = EncodeFn.apply(model, keys, len(feats), *feats, *_param_list(model, keys))
+    results = {}
+    if len(outs) == 3:
+        results[Constants.mapping["length"][0]] = outs[2]
+    results["enc_output"] = outs[0]
+    results["enc_hidden"] = outs[1]
+    return results
+
+
+# --------------------------------------------------------------------------------------------------
+# decoder  (models/Decoder.py:96-178, models/bert.py:262-303 in train mode)
+# --------------------------------------------------------------------------------------------------
+def _decoder_param_keys(model):
+    return [k for k, _ in model.named_parameters() if k.startswith("decoder.")]
+
+
+class DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, keys, tokens, category, decoding_type, enc_output, *params):
+        eng: Engine = model.engine
+        eng.sync_weights()
+        opt, P, D, H = eng.opt, eng.P, eng.D, eng.H
+        dev = eng.device
+        tokens = tokens.contiguous()
+        N, S = tokens.shape
+        R = N * S
+        Bv, E, _ = enc_output.shape
+        if N != Bv:
+            raise NotImplementedError("training decoder expects one token row per video (N=%d, videos=%d)" % (N, Bv))
+        tok_flat = tokens.reshape(R)
+        cat = category.contiguous() if category is not None else None
+        seeds = Seeds()
+        p = float(opt["hidden_dropout_prob"])
+        enc = eng.from_f32(enc_output.detach().reshape(Bv * E, D))
+        extra = None
+        if decoding_type == "NARFormer":
+            ei = opt.get("enhance_input", 2)
+            if ei == 2:
+                extra = torch.empty((Bv, D), dtype=torch.float32, device=dev)
+                L.call("navc_length_head", L.ptr(enc.f32), Bv, E, D, None, None, None, None, 0, L.ptr(extra), None, L.stream())
+            elif ei != 0:
+                raise NotImplementedError("enhance_input=1 fails in the reference itself (SURVEY 8c)")
+        tc_attn = eng.tc_attention_ok(S, E)
+        kv = eng.linear(enc, P["kv_all"], f32=True, bf=tc_attn)
+        emb = P["emb"]
+        x_ln = torch.empty((R, D), dtype=torch.float32, device=dev)
+        L.call("navc_embed_ln", L.ptr(tokens), L.ptr(cat), L.ptr(emb["word"]), L.ptr(emb["pos"]), L.ptr(emb["cat"]),
+               L.ptr(extra), 1, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), eng.eps, N, S, D, L.ptr(x_ln), None, None, L.stream())
+        seed_e = seeds.next()
+        x = drop_add(eng, x_ln, None, seed_e, p, 0, 0.0, None)
+        mask_kind = L.MASK_KIND[decoding_type]
+        watch = int(opt.get("watch", 0))
+        layers = []
+        for l, lw in enumerate(P["layers"]):
+            sv = dict(x=x.f32)
+            qkv = eng.linear(x, lw["qkv"], f32=True, bf=tc_attn)
+            ctx1 = eng._new(R, D, True, True)
+            if tc_attn:
+                L.call("navc_self_attention_tc", eng.tc_mode, L.ptr(qkv.hi), L.ptr(qkv.lo), 3 * D, L.ptr(tokens), N, S,
+                       D, H, mask_kind, watch, L.ptr(ctx1.f32), L.ptr(ctx1.hi), L.ptr(ctx1.lo), L.stream())
+            else:
+                L.call("navc_self_attention", L.ptr(qkv.f32), 3 * D, L.ptr(tokens), N, S, D, H, mask_kind, watch,
+                       L.ptr(ctx1.f32), L.ptr(ctx1.hi), L.ptr(ctx1.lo), None, L.stream())
+            so = eng.linear(ctx1, lw["so"], f32=True, bf=False)
+            sv["s_so"] = seeds.next()
+            sv["so"] = {}
+            a = _post(eng, so.f32, x.f32, lw["so_ln"], sv["s_so"], p, 0, 0.0, tok_flat, sv["so"])
+            q = eng.linear(a, lw["cq"], f32=True, bf=tc_attn)
+            ctx2 = eng._new(R, D, True, True)
+            if tc_attn:
+                off = l * 2 * D
+                L.call("navc_cross_attention_tc", eng.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D, kv.hi[:, off:].data_ptr(),
+                       kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N, N, S, E, D, H, 1,
+                       L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.stream())
+            else:
+                L.call("navc_cross_attention", L.ptr(q.f32), D, kv.f32[:, l * 2 * D:].data_ptr(), kv.N, N, S, E, D, H, 1,
+                       L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), None, L.stream())
+            co = eng.linear(ctx2, lw["co"], f32=True, bf=False)
+            sv["s_co"] = seeds.next()
+            sv["co"] = {}
+            c = _post(eng, co.f32, a.f32, lw["co_ln"], sv["s_co"], p, 0, 0.0, tok_flat, sv["co"])
+            u = eng.linear(c, lw["f1"], f32=True, bf=False)
+            h = eng._new(R, lw["f1"].N, True, True)
+            L.call("navc_act_drop", L.ptr(u.f32), eng.act, 0, 0.0, u.f32.numel(), L.ptr(h.f32), L.ptr(h.hi), L.ptr(h.lo), L.stream())
+            f2 = eng.linear(h, lw["f2"], f32=True, bf=False)
+            sv["s_f1"], sv["s_f2"] = seeds.next(), seeds.next()
+            sv["f2"] = {}
+            xn = _post(eng, f2.f32, c.f32, lw["f2_ln"], sv["s_f1"], p, sv["s_f2"], p, tok_flat, sv["f2"])
+            sv.update(qkv=qkv.f32, ctx1=ctx1.f32, a=a.f32, q=q.f32, ctx2=ctx2.f32, c=c.f32, u=u.f32, h=h.f32)
+            layers.append(sv)
+            x = xn
+        ctx.model, ctx.keys = model, keys
+        ctx.state = dict(tokens=tokens, tok_flat=tok_flat, cat=cat, enc=enc.f32, extra=extra, kv=kv.f32, layers=layers,
+                         seed_e=seed_e, p=p, N=N, S=S, E=E, Bv=Bv, mask_kind=mask_kind, watch=watch, decoding_type=decoding_type)
+        return x.f32.view(N, S, D)
+
+    @staticmethod
+    def backward(ctx, d_hidden):
+        model, st = ctx.model, ctx.state
+        eng: Engine = model.engine
+        P, D, H = eng.P, eng.D, eng.H
+        dev = eng.device
+        N, S, E, Bv = st["N"], st["S"], st["E"], st["Bv"]
+        R = N * S
+        p = st["p"]
+        tok_flat = st["tok_flat"]
+        grads = Grads()
+        g = d_hidden.contiguous().view(R, D).float()
+        nl = len(P["layers"])
+        d_kv = torch.empty((Bv * E, nl * 2 * D), dtype=torch.float32, device=dev)
+        for l in range(nl - 1, -1, -1):
+            lw, sv = P["layers"][l], st["layers"][l]
+            d_f2, d_c_res = _post_bwd(eng, g, lw["f2_ln"], lw["f2_ln_key"], sv["s_f1"], p, sv["s_f2"], p, tok_flat, sv["f2"], grads)
+            d_h = lin_bwd(eng, sv["h"], lw["f2"], d_f2, grads)
+            d_u = torch.empty_like(d_h)
+            L.call("navc_act_drop_bwd", L.ptr(d_h), L.ptr(sv["u"]), eng.act, 0, 0.0, d_h.numel(), L.ptr(d_u), L.stream())
+            d_c = lin_bwd(eng, sv["c"], lw["f1"], d_u, grads, dx_residual=d_c_res)
+            d_co, d_a_res = _post_bwd(eng, d_c, lw["co_ln"], lw["co_ln_key"], sv["s_co"], p, 0, 0.0, tok_flat, sv["co"], grads)
+            d_ctx2 = lin_bwd(eng, sv["ctx2"], lw["co"], d_co, grads)
+            d_q = torch.empty((R, D), dtype=torch.float32, device=dev)
+            off = l * 2 * D
+            L.call("navc_cross_attention_bwd", L.ptr(sv["q"]), D, st["kv"][:, off:].data_ptr(), st["kv"].shape[1], N, S, E, D, H, 1,
+                   L.ptr(d_ctx2), L.ptr(d_q), D, d_kv[:, off:].data_ptr(), d_kv.shape[1], L.stream())
+            d_a = lin_bwd(eng, sv["a"], lw["cq"], d_q, grads, dx_residual=d_a_res)
+            d_so, d_x_res = _post_bwd(eng, d_a, lw["so_ln"], lw["so_ln_key"], sv["s_so"], p, 0, 0.0, tok_flat, sv["so"], grads)
+            d_ctx1 = lin_bwd(eng, sv["ctx1"], lw["so"], d_so, grads)
+            d_qkv = torch.empty((R, 3 * D), dtype=torch.float32, device=dev)
+            L.call("navc_self_attention_bwd", L.ptr(sv["qkv"]), 3 * D, L.ptr(st["tokens"]), N, S, D, H, st["mask_kind"], st["watch"],
+                   L.ptr(d_ctx1), L.ptr(d_qkv), L.stream())
+            g = lin_bwd(eng, sv["x"], lw["qkv"], d_qkv, grads, dx_residual=d_x_res)
+        # embeddings
+        g_ln, _ = drop_add_bwd(g, st["seed_e"], p, 0, 0.0, None, want_res=False)
+        emb, ep = P["emb"], P["emb_prefix"]
+        d_word = torch.zeros_like(emb["word"])
+        d_pos = torch.zeros_like(emb["pos"])
+        d_cat = torch.zeros_like(emb["cat"]) if emb["cat"] is not None else None
+        d_extra = torch.zeros_like(st["extra"]) if st["extra"] is not None else None
+        d_lw, d_lb = torch.zeros_like(emb["ln_w"]), torch.zeros_like(emb["ln_b"])
+        L.call("navc_embed_ln_bwd", L.ptr(g_ln), L.ptr(st["tokens"]), L.ptr(st["cat"]), L.ptr(emb["word"]), L.ptr(emb["pos"]),
+               L.ptr(emb["cat"]), L.ptr(st["extra"]), 1, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), eng.eps, N, S, D,
+               L.ptr(d_word), L.ptr(d_pos), L.ptr(d_cat), L.ptr(d_extra), L.ptr(d_lw), L.ptr(d_lb), L.stream())
+        grads.add(ep + "word_embeddings.weight", d_word)
+        grads.add(ep + "position_embeddings.weight", d_pos)
+        if d_cat is not None:
+            grads.add(ep + "category_embeddings.weight", d_cat)
+        grads.add(ep + "LayerNorm.weight", d_lw)
+        grads.add(ep + "LayerNorm.bias", d_lb)
+        # encoder memory: through the K|V projection of every layer and the enhance_input mean
+        d_enc = lin_bwd(eng, st["enc"], P["kv_all"], d_kv, grads)
+        if d_extra is not None:
+            L.call("navc_mean_bwd", L.ptr(d_extra), Bv, E, D, L.ptr(d_enc), L.stream())
+        return (None, None, None, None, None, d_enc.view(Bv, E, D)) + tuple(grads.g.get(k) for k in ctx.keys)
+
+
+def decoder_forward_train(decoder, eng, tgt_seq, enc_output, category, decoding_type):
+    model = decoder._engine_ref()
+    keys = _decoder_param_keys(model)
+    hidden = DecoderFn.apply(model, keys, tgt_seq, category, decoding_type, enc_output, *_param_list(model, keys))
+    with torch.no_grad():  # returned, unused downstream (models/bert.py:301)
+        non_pad = tgt_seq.ne(Constants.PAD).float().unsqueeze(-1)
+        embs = hidden.detach().sum(1) / non_pad.sum(1)
+    return ([hidden], embs)
+
+
+# --------------------------------------------------------------------------------------------------
+# vocabulary projection (+ log-softmax)  (models/seq2seq.py:102-103)
+# --------------------------------------------------------------------------------------------------
+class VocabFn(torch.autograd.Function):
+    """hidden [.., D] -> log_softmax(tgt_word_prj(hidden)) [.., V] (log_probs=True) or the logits."""
+
+    @staticmethod
+    def forward(ctx, model, log_probs, hidden, *params):
+        eng: Engine = model.engine
+        eng.sync_weights()
+        lin = eng.P["vocab"]
+        dev = eng.device
+        shape = hidden.shape
+        D, V = lin.K, lin.N
+        h2 = hidden.detach().reshape(-1, D)
+        R = h2.shape[0]
+        h = eng.from_f32(h2)
+        Vp = _up(V, 64)
+        logits = torch.empty((R, Vp), dtype=torch.float32, device=dev)
+        if lin.pad is None:  # weight rows / bias zero-padded to Vp so the GEMM epilogue stays vectorised
+            w_pad = torch.zeros((Vp, D), dtype=torch.float32, device=dev)
+            w_pad[:V].copy_(lin.w)
+            b_pad = None
+            if lin.b is not None:
+                b_pad = torch.zeros((Vp,), dtype=torch.float32, device=dev)
+                b_pad[:V].copy_(lin.b)
+            wop, _ = transpose_pack(eng, w_pad, Vp, D, D, straight=True)
+            lin.pad = (wop, b_pad)
+        wop, b_pad = lin.pad
+        xop = Operand(R, D, D, hi=h.hi, lo=h.lo) if eng.tc else Operand(R, D, D, f32=h.f32)
+        gemm(eng, xop, wop, R, Vp, D, logits, Vp, bias=b_pad)
+        out = torch.empty((R, V), dtype=torch.float32, device=dev)
+        if log_probs:
+            L.call("navc_log_softmax_ld", L.ptr(logits), Vp, L.ptr(out), V, R, V, L.stream())
+        else:
+            out.copy_(logits[:, :V])
+        ctx.model, ctx.log_probs = model, log_probs
+        ctx.state = dict(h=h.f32, out=out if log_probs else None, R=R, V=V, Vp=Vp, shape=shape, n_params=len(params))
+        return out.view(*shape[:-1], V)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        model, st = ctx.model, ctx.state
+        eng: Engine = model.engine
+        lin = eng.P["vocab"]
+        dev = eng.device
+        R, V, Vp = st["R"], st["V"], st["Vp"]
+        grads = Grads()
+        d_out = d_out.contiguous().view(R, V)
+        dlog = torch.empty((R, Vp), dtype=torch.float32, device=dev)
+        if ctx.log_probs:
+            L.call("navc_log_softmax_bwd", L.ptr(d_out), L.ptr(st["out"]), R, V, V, L.ptr(dlog), Vp, L.stream())
+        else:
+            dlog.zero_()
+            dlog[:, :V].copy_(d_out)
+        d_h = lin_bwd(eng, st["h"], lin, dlog, grads, ld_dy=Vp)
+        gw = grads.g.get("tgt_word_prj.weight")
+        gb = grads.g.get("tgt_word_prj.bias")
+        return (None, None, d_h.view(st["shape"])) + ((gw,) if st["n_params"] == 1 else (gw, gb))
+
+
+def _vocab_params(prj):
+    return [prj.weight] + ([prj.bias] if prj.bias is not None else [])
+
+
+def vocab_forward_train(engine, prj, hidden):
+    """model.tgt_word_prj(hidden) under autograd -> logits."""
+    return VocabFn.apply(prj._owner(), False, hidden, *_vocab_params(prj))
+
+
+def vocab_logprobs_train(model, hidden):
+    """log_softmax(tgt_word_prj(hidden)) as one autograd node (projection + log-softmax kernels)."""
+    return VocabFn.apply(model, True, hidden, *_vocab_params(model.tgt_word_prj))

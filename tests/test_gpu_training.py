@@ -1,0 +1,456 @@
+"""Training path parity (forward in train mode + hand-written backward) through the C ABI.
+
+Kernel level: every backward kernel against torch autograd of the same op on the CPU (fp32;
+tolerance 1e-5 of the output scale -- accumulation order only).  Model level: loss and the
+gradient of EVERY parameter against the oracle (``oracle/navc_oracle.py`` under torch autograd, which
+``tests/test_oracle_vs_reference.py`` pins to the reference's own ``loss.backward()``) with dropout
+disabled and BatchNorm in train mode; tolerances: fp32 mode 2e-4, bf16x3
+mode 5e-4 of each gradient's max magnitude.  Dropout itself (not bit-reproducible against torch's
+Philox stream) is checked for keep-rate, scaling and forward/backward mask agreement."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases
+import navc_b200
+from navc_b200 import _lib as L
+from oracle import navc_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    L.ensure_init(DEV)
+    torch.cuda.set_device(0)
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+_KEEP = []
+
+
+def P(t):
+    """Device pointer of a (copied) tensor that stays alive for the rest of the test module: a
+    temporary passed as P(x) would be freed -- and its block re-used by the next
+    temporary -- before the kernel even launches."""
+    t = t.detach().to(DEV).contiguous()
+    _KEEP.append(t)
+    if len(_KEEP) > 64:
+        torch.cuda.synchronize()
+        del _KEEP[:32]
+    return L.ptr(t)
+
+
+def close(a, b, tol, what="", atol=0.0):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    scale = max(b.abs().max().item(), 1e-6)
+    err = (a - b).abs().max().item()
+    assert err < tol * scale + atol, "%s: abs err %.3e, rel %.3e (scale %.3e)" % (what, err, err / scale, scale)
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernels
+# ---------------------------------------------------------------------------------------------------
+def test_drop_add_masks_agree_and_rates():
+    M, D = 512, 256
+    y = torch.ones(M, D, device=DEV)
+    res = torch.full((M, D), 3.0, device=DEV)
+    toks = torch.randint(0, 4, (M,), generator=g(1)).to(DEV)
+    out = torch.empty(M, D, device=DEV)
+    hi = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+    lo = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+    s1, s2 = 12345, 2 ** 63 + 99
+    L.call("navc_drop_add", L.ptr(y), L.ptr(res), s1, 0.5, s2, 0.25, L.ptr(toks), M, D, L.ptr(out), L.ptr(hi), L.ptr(lo), L.stream())
+    d_y = torch.empty(M, D, device=DEV)
+    d_res = torch.empty(M, D, device=DEV)
+    L.call("navc_drop_add_bwd", P(torch.ones(M, D)), s1, 0.5, s2, 0.25, L.ptr(toks), M, D, L.ptr(d_y), L.ptr(d_res), L.stream())
+    torch.cuda.synchronize()
+    live = toks.ne(0).unsqueeze(1).expand(-1, D)
+    assert out[~live].abs().max().item() == 0 and d_y[~live].abs().max().item() == 0
+    # out = m2*(m1*1 + 3) with m1 in {0,2}, m2 in {0,4/3}; d_res = m2, d_y = m1*m2
+    m2 = d_res[live]
+    m1m2 = d_y[live]
+    assert all(v == 0.0 or abs(v - 4 / 3) < 1e-6 for v in torch.unique(m2).tolist())
+    keep2 = (m2 > 0).float().mean().item()
+    keep1 = (m1m2[m2 > 0] > 0).float().mean().item()
+    assert abs(keep2 - 0.75) < 0.01 and abs(keep1 - 0.5) < 0.01
+    m1 = torch.where(m2 > 0, m1m2 / m2.clamp_min(1e-9), torch.zeros_like(m2))
+    assert torch.allclose(out[live], m2 * (m1 + 3.0), atol=1e-6)
+    assert torch.allclose(hi.float() + lo.float(), out, atol=1e-4)
+    # different seeds -> different masks; p = 0 -> identity
+    out2 = torch.empty(M, D, device=DEV)
+    L.call("navc_drop_add", L.ptr(y), L.ptr(res), s1 + 1, 0.5, s2, 0.25, L.ptr(toks), M, D, L.ptr(out2), None, None, L.stream())
+    assert not torch.equal(out, out2)
+    L.call("navc_drop_add", L.ptr(y), L.ptr(res), 0, 0.0, 0, 0.0, None, M, D, L.ptr(out2), None, None, L.stream())
+    assert torch.equal(out2, y + res)
+
+
+@pytest.mark.parametrize("act", ["none", "gelu_new", "gelu", "relu", "swish"])
+def test_act_drop_backward(act):
+    n = 4099
+    u = (2.0 * torch.randn(n, generator=g(2))).requires_grad_(True)
+    dout = torch.randn(n, generator=g(3))
+    ref = O.activation(act)(u) if act != "none" else u * 1.0
+    ref.backward(dout)
+    ud, dd = u.detach().to(DEV), dout.to(DEV)
+    out = torch.empty(n, device=DEV)
+    du = torch.empty(n, device=DEV)
+    L.call("navc_act_drop", L.ptr(ud), L.ACT[act], 0, 0.0, n, L.ptr(out), None, None, L.stream())
+    L.call("navc_act_drop_bwd", L.ptr(dd), L.ptr(ud), L.ACT[act], 0, 0.0, n, L.ptr(du), L.stream())
+    close(out, ref, 2e-6, "act fwd")
+    close(du, u.grad, 1e-5, "act bwd")
+    # with dropout: backward mask == forward mask
+    L.call("navc_act_drop", P(torch.ones(n)), 0, 77, 0.5, n, L.ptr(out), None, None, L.stream())
+    L.call("navc_act_drop_bwd", P(torch.ones(n)), L.ptr(ud), 0, 77, 0.5, n, L.ptr(du), L.stream())
+    assert torch.equal(out, du) and abs((out > 0).float().mean().item() - 0.5) < 0.03
+
+
+@pytest.mark.parametrize("M,N,ld", [(100, 70, 72), (64, 128, 128), (333, 30, 64), (1000, 517, 520)])
+def test_transpose_pack(M, N, ld):
+    x = torch.zeros(M, ld)
+    x[:, :N] = torch.randn(M, N, generator=g(4))
+    xd = x.to(DEV)
+    Mp = (M + 63) // 64 * 64
+    hi = torch.full((M, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+    lo = torch.full((M, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+    t32 = torch.full((N, Mp), 7.0, device=DEV)
+    thi = torch.full((N, Mp), 7.0, dtype=torch.bfloat16, device=DEV)
+    tlo = torch.full((N, Mp), 7.0, dtype=torch.bfloat16, device=DEV)
+    cs = torch.zeros(N, device=DEV)
+    L.call("navc_transpose_pack", L.ptr(xd), M, N, ld, L.ptr(hi), L.ptr(lo), ld, L.ptr(t32), L.ptr(thi), L.ptr(tlo), Mp, L.ptr(cs), L.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(t32[:, :M].cpu(), x[:, :N].t())
+    assert t32[:, M:].abs().max().item() == 0 if Mp > M else True
+    assert torch.allclose((hi.float() + lo.float()).cpu(), x, atol=1e-5) and hi[:, N:].float().abs().max().item() == 0 if ld > N else True
+    assert torch.allclose((thi.float() + tlo.float())[:, :M].cpu(), x[:, :N].t(), atol=1e-5)
+    close(cs, x[:, :N].sum(0), 1e-5, "colsum")
+
+
+@pytest.mark.parametrize("mode", ["f32", "bf16x3"])
+def test_gemm_split_k_accumulate(mode):
+    M, N, K = 300, 520, 4096 + 64
+    x = torch.randn(M, K, generator=g(5)).to(DEV)
+    w = (torch.randn(N, K, generator=g(6)) / math.sqrt(K)).to(DEV)
+    base = torch.randn(M, N, generator=g(7)).to(DEV)
+    out = base.clone()
+    ref = base.double() + x.double() @ w.double().t()
+    ep = L.Epilogue(None, None, None, 0, 0, L.ptr(out), None, None, N, 0, 7, 1)
+    if mode == "f32":
+        L.call("navc_linear_f32", L.ptr(x), K, L.ptr(w), K, M, N, K, ep, L.stream())
+    else:
+        xh, xl = x.to(torch.bfloat16), (x - x.to(torch.bfloat16).float()).to(torch.bfloat16)
+        wh, wl = w.to(torch.bfloat16), (w - w.to(torch.bfloat16).float()).to(torch.bfloat16)
+        L.call("navc_linear_tc", L.TC_BF16X3, L.ptr(xh), L.ptr(xl), K, L.ptr(wh), L.ptr(wl), K, M, N, K, ep, L.stream())
+    close(out, ref, 3e-5, "split-k accumulate")
+
+
+def test_gemm_tc_k_tail():
+    """K not a multiple of 64: the tail of the last k-block is zero-filled by TMA."""
+    M, N, K = 200, 256, 200
+    x = torch.randn(M, K, generator=g(8)).to(DEV)
+    w = torch.randn(N, K, generator=g(9)).to(DEV)
+    out = torch.empty(M, N, device=DEV)
+    xh, xl = x.to(torch.bfloat16), (x - x.to(torch.bfloat16).float()).to(torch.bfloat16)
+    wh, wl = w.to(torch.bfloat16), (w - w.to(torch.bfloat16).float()).to(torch.bfloat16)
+    ep = L.Epilogue(None, None, None, 0, 0, L.ptr(out), None, None, N, 0, 1, 0)
+    L.call("navc_linear_tc", L.TC_BF16X3, L.ptr(xh), L.ptr(xl), K, L.ptr(wh), L.ptr(wl), K, M, N, K, ep, L.stream())
+    close(out, x.double() @ w.double().t(), 3e-5, "k tail")
+
+
+@pytest.mark.parametrize("gate", [1, 0])
+def test_highway_train_and_backward(gate):
+    BF, D = 77, 64
+    x = torch.randn(BF, D, generator=g(10)).requires_grad_(True)
+    yg = torch.randn(BF, (2 if gate else 1) * D, generator=g(11)).requires_grad_(True)
+    y = torch.tanh(yg[:, :D])
+    if gate:
+        gt = torch.sigmoid(yg[:, D:])
+        ref = gt * x + (1 - gt) * y
+    else:
+        ref = x + y
+    d_o = torch.randn(BF, D, generator=g(12))
+    ref.backward(d_o)
+    xd, ygd = x.detach().to(DEV), yg.detach().to(DEV)
+    o = torch.empty(BF, D, device=DEV)
+    L.call("navc_highway_fwd_train", L.ptr(xd), L.ptr(ygd), gate, BF, D, 0, 0.0, L.ptr(o), L.stream())
+    dx = torch.empty(BF, D, device=DEV)
+    dyg = torch.empty_like(ygd)
+    L.call("navc_highway_bwd", P(d_o), L.ptr(xd), L.ptr(ygd), gate, BF, D, 0, 0.0, L.ptr(dx), L.ptr(dyg), L.stream())
+    close(o, ref, 2e-6, "highway fwd")
+    close(dx, x.grad, 1e-5, "highway dx")
+    close(dyg, yg.grad, 1e-5, "highway dyg")
+
+
+@pytest.mark.parametrize("with_bn", [True, False])
+def test_batchnorm_train_forward_backward(with_bn):
+    B, F_, D, E, slot, nm = 5, 6, 96, 12, 1, 2
+    o = (1.5 * torch.randn(B * F_, D, generator=g(13)) + 0.3).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(D, generator=g(14))).requires_grad_(True)
+    b = (0.1 * torch.randn(D, generator=g(15))).requires_grad_(True)
+    rm, rv = 0.1 * torch.randn(D, generator=g(16)), 0.5 + torch.rand(D, generator=g(17))
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y = F.batch_norm(o, rm_ref, rv_ref, w, b, True, 0.1, 1e-5) if with_bn else o
+    hid = o.view(B, F_, D).mean(1) / nm
+    d_enc = torch.randn(B, E, D, generator=g(18))
+    d_hid = torch.randn(B, D, generator=g(19))
+    ((y.view(B, F_, D) * d_enc[:, slot * F_:(slot + 1) * F_]).sum() + (hid * d_hid).sum()).backward()
+    od = o.detach().to(DEV)
+    mean = torch.empty(D, device=DEV)
+    var = torch.empty(D, device=DEV)
+    rmd, rvd = rm.to(DEV), rv.to(DEV)
+    if with_bn:
+        L.call("navc_bn_stats", L.ptr(od), B * F_, D, L.ptr(mean), L.ptr(var), 0.1, L.ptr(rmd), L.ptr(rvd), L.stream())
+        close(rmd, rm_ref, 1e-5, "running_mean")
+        close(rvd, rv_ref, 1e-5, "running_var")
+    enc = torch.zeros(B, E, D, device=DEV)
+    ehid = torch.zeros(B, D, device=DEV)
+    wd, bd = w.detach().to(DEV), b.detach().to(DEV)
+    L.call("navc_bn_apply_concat", L.ptr(od), L.ptr(mean) if with_bn else None, L.ptr(var) if with_bn else None,
+           L.ptr(wd) if with_bn else None, L.ptr(bd) if with_bn else None, 1e-5, B, F_, D, E, slot, nm, 0, L.ptr(ehid),
+           L.ptr(enc), None, None, L.stream())
+    close(enc[:, slot * F_:(slot + 1) * F_], y.view(B, F_, D), 1e-5, "bn fwd")
+    close(ehid, hid, 1e-5, "enc_hidden")
+    d_w, d_b, d_o = torch.empty(D, device=DEV), torch.empty(D, device=DEV), torch.empty(B * F_, D, device=DEV)
+    L.call("navc_bn_bwd", P(d_enc), P(d_hid), L.ptr(od), L.ptr(mean) if with_bn else None,
+           L.ptr(var) if with_bn else None, L.ptr(wd) if with_bn else None, 1e-5, B, F_, D, E, slot, nm,
+           L.ptr(d_w) if with_bn else None, L.ptr(d_b) if with_bn else None, L.ptr(d_o), L.stream())
+    close(d_o, o.grad, 2e-5, "bn d_o")
+    if with_bn:
+        close(d_w, w.grad, 2e-5, "bn d_w")
+        close(d_b, b.grad, 2e-5, "bn d_b")
+
+
+def test_mean_bwd_and_log_softmax_bwd():
+    B, E, D = 4, 7, 64
+    dm = torch.randn(B, D, generator=g(20))
+    base = torch.randn(B, E, D, generator=g(21))
+    acc = base.clone().to(DEV)
+    L.call("navc_mean_bwd", P(dm), B, E, D, L.ptr(acc), L.stream())
+    close(acc, base + dm.unsqueeze(1) / E, 1e-6, "mean bwd")
+    M, V, Vp = 37, 301, 320
+    logits = torch.randn(M, V, generator=g(22)).requires_grad_(True)
+    lp = torch.log_softmax(logits, -1)
+    gg = torch.randn(M, V, generator=g(23)) * (torch.rand(M, V, generator=g(24)) < 0.05).float()
+    lp.backward(gg)
+    out = torch.full((M, Vp), 9.0, device=DEV)
+    L.call("navc_log_softmax_bwd", P(gg), P(lp), M, V, V, L.ptr(out), Vp, L.stream())
+    close(out[:, :V], logits.grad, 1e-5, "log_softmax bwd")
+    assert out[:, V:].abs().max().item() == 0
+
+
+def test_layernorm_backward():
+    M, D = 70, 128
+    x = torch.randn(M, D, generator=g(25)).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(D, generator=g(26))).requires_grad_(True)
+    b = torch.zeros(D, requires_grad=True)
+    toks = torch.randint(0, 3, (M,), generator=g(27))
+    y = F.layer_norm(x, (D,), w, b, 1e-5) * toks.ne(0).float().unsqueeze(1)
+    dy = torch.randn(M, D, generator=g(28))
+    y.backward(dy)
+    dx = torch.empty(M, D, device=DEV)
+    dw, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    L.call("navc_layernorm_bwd", P(dy), P(x), P(w), 1e-5,
+           P(toks), M, D, L.ptr(dx), L.ptr(dw), L.ptr(db), L.stream())
+    close(dx, x.grad, 2e-5, "ln dx")
+    close(dw, w.grad, 2e-5, "ln dw")
+    close(db, b.grad, 2e-5, "ln db")
+
+
+def test_embed_ln_backward():
+    N, S, D, V, C, group = 6, 9, 128, 50, 5, 2
+    word = torch.randn(V, D, generator=g(29)).requires_grad_(True)
+    pos = torch.randn(S + 3, D, generator=g(30)).requires_grad_(True)
+    cat = torch.randn(C, D, generator=g(31)).requires_grad_(True)
+    extra = torch.randn(N // group, D, generator=g(32)).requires_grad_(True)
+    lw = (1 + 0.1 * torch.randn(D, generator=g(33))).requires_grad_(True)
+    lb = (0.1 * torch.randn(D, generator=g(34))).requires_grad_(True)
+    toks = torch.randint(0, V, (N, S), generator=g(35))
+    toks[:, -2:] = 0
+    cats = torch.randint(0, C, (N // group, 1), generator=g(36))
+    idx = torch.arange(N) // group
+    e = F.embedding(toks, word, padding_idx=0) + pos[:S].unsqueeze(0) + cat[cats[idx, 0]].unsqueeze(1) + extra[idx].unsqueeze(1)
+    y = F.layer_norm(e, (D,), lw, lb, 1e-5)
+    dy = torch.randn(N, S, D, generator=g(37))
+    y.backward(dy)
+    outs = [torch.zeros_like(t, device=DEV) for t in (word, pos, cat, extra, lw, lb)]
+    L.call("navc_embed_ln_bwd", P(dy), P(toks), P(cats), P(word), P(pos),
+           P(cat), P(extra), group, P(lw), P(lb), 1e-5, N, S, D, *[L.ptr(o) for o in outs], L.stream())
+    for o, r, name in zip(outs, (word, pos, cat, extra, lw, lb), ("word", "pos", "cat", "extra", "ln_w", "ln_b")):
+        close(o, r.grad, 3e-5, "embed " + name)
+    assert outs[0][0].abs().max().item() == 0  # padding_idx row
+
+
+def _mha_ref(q, k, v, mask, H):
+    n, sq, d = q.shape
+    sk = k.shape[1]
+    dk = d // H
+    qh = q.view(n, sq, H, dk).permute(2, 0, 1, 3)
+    kh = k.view(n, sk, H, dk).permute(2, 0, 1, 3)
+    vh = v.view(n, sk, H, dk).permute(2, 0, 1, 3)
+    sc = torch.matmul(qh, kh.transpose(-1, -2)) / math.sqrt(dk)
+    if mask is not None:
+        sc = sc.masked_fill(mask.unsqueeze(0), O.MASK_FILL)
+    p = torch.softmax(sc, -1)
+    return torch.matmul(p, vh).permute(1, 2, 0, 3).contiguous().view(n, sq, d)
+
+
+@pytest.mark.parametrize("kind", ["NARFormer", "ARFormer", "SelfMask"])
+@pytest.mark.parametrize("D,H,S", [(128, 8, 11), (512, 8, 30), (64, 2, 7)])
+def test_self_attention_backward(kind, D, H, S):
+    N = 5
+    qkv = torch.randn(N, S, 3 * D, generator=g(38)).requires_grad_(True)
+    toks = torch.randint(1, 9, (N, S), generator=g(39))
+    for n in range(N):
+        toks[n, S - n % 4:] = 0 if n % 4 else toks[n, S - 1]
+    mask = O.self_attention_mask(toks, kind, 0)
+    ctx = _mha_ref(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], mask, H)
+    d_ctx = torch.randn(N, S, D, generator=g(40))
+    ctx.backward(d_ctx)
+    d_qkv = torch.empty(N * S, 3 * D, device=DEV)
+    L.call("navc_self_attention_bwd", P(qkv), 3 * D, P(toks), N, S, D, H, L.MASK_KIND[kind], 0,
+           P(d_ctx), L.ptr(d_qkv), L.stream())
+    close(d_qkv.view(N, S, 3 * D), qkv.grad, 2e-5, "self attn bwd")
+
+
+@pytest.mark.parametrize("D,H,S,E,group", [(128, 8, 9, 12, 1), (512, 8, 30, 120, 1), (128, 4, 7, 16, 3)])
+def test_cross_attention_backward(D, H, S, E, group):
+    B = 4
+    N = B * group
+    q = torch.randn(N, S, D, generator=g(41)).requires_grad_(True)
+    kv = torch.randn(B, E, 2 * D, generator=g(42)).requires_grad_(True)
+    kve = kv.unsqueeze(1).expand(-1, group, -1, -1).reshape(N, E, 2 * D)
+    ctx = _mha_ref(q, kve[..., :D], kve[..., D:], None, H)
+    d_ctx = torch.randn(N, S, D, generator=g(43))
+    ctx.backward(d_ctx)
+    d_q = torch.empty(N * S, D, device=DEV)
+    d_kv = torch.empty(B * E, 2 * D, device=DEV)
+    L.call("navc_cross_attention_bwd", P(q), D, P(kv), 2 * D, N, S, E, D, H, group,
+           P(d_ctx), L.ptr(d_q), D, L.ptr(d_kv), 2 * D, L.stream())
+    close(d_q.view(N, S, D), q.grad, 2e-5, "cross attn dq")
+    close(d_kv.view(B, E, 2 * D), kv.grad, 2e-5, "cross attn dkv")
+
+
+# ---------------------------------------------------------------------------------------------------
+# model level: loss + every parameter gradient vs the oracle (dropout off, BatchNorm batch statistics)
+# ---------------------------------------------------------------------------------------------------
+GRAD_TOL = {"fp32": 2e-4, "bf16x3": 5e-4}
+
+
+def _train_case(method, precision, batch=6, **kw):
+    opt = cases.small(method, hidden_dropout_prob=0.0, encoder_dropout=0.0, **kw)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd0 = cases.synth_state_dict(shapes, 11)
+    model.load_state_dict(sd0)
+    model.to(DEV).train()
+    model.set_precision(precision)
+    nar = O.is_nar(opt)
+    feats, category = cases.synth_inputs(opt, batch)
+    toks = cases.synth_tokens(opt, batch, kind="nar" if nar else "ar")
+    dis = opt["decoder"] == "BertDecoderDisentangled"
+    if nar:
+        tgt = [toks["tokens_1"], toks["tokens"]] if dis else toks["tokens"]
+        labels = [toks["labels_1"], toks["labels"]] if dis else toks["labels"]
+        length_target = toks["length_target"]
+    else:
+        tgt = [toks["tokens"], toks["tokens"]] if dis else toks["tokens"]
+        labels = [toks["labels"], toks["labels"]] if dis else toks["labels"]
+        length_target = None
+    # oracle (CPU, autograd)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd0.items()}
+    bn_state = {}
+    ref = O.model_forward(sd, opt, feats, tgt, category, training=True, bn_state=bn_state)
+    ref_loss = O.criterion(opt, ref, labels, length_target)
+    ref_loss.backward()
+    # product path
+    dev = lambda t: [x.to(DEV) for x in t] if isinstance(t, (list, tuple)) else t.to(DEV)
+    res = model(feats=dev(feats), tgt_tokens=dev(tgt), category=category.to(DEV))
+    loss = O.criterion(opt, res, dev(labels), None if length_target is None else length_target.to(DEV))
+    loss.backward()
+    return model, sd, bn_state, ref, ref_loss, res, loss
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("method,kw", [("NACF", {}), ("NAB", {}), ("ARB", {}), ("NACF", {"with_layernorm": True}),
+                                       ("NAB", {"no_encoder_bn": True, "with_category": False})],
+                         ids=["nacf", "nab", "arb", "nacf_ln", "nab_plain"])
+def test_gradients_match_oracle(method, kw, precision):
+    model, sd, bn_state, ref, ref_loss, res, loss = _train_case(method, precision, **kw)
+    tol = GRAD_TOL[precision]
+    assert abs(loss.item() - ref_loss.item()) < tol * max(1.0, abs(ref_loss.item()))
+    for a, b in zip(res["tgt_word_logprobs"], ref["tgt_word_logprobs"]):
+        assert (a.detach().cpu() - b.detach()).abs().max().item() < 5e-4
+    if "pred_length" in ref:
+        assert (res["pred_length"].detach().cpu() - ref["pred_length"].detach()).abs().max().item() < 5e-4
+    checked = 0
+    for name, p in model.named_parameters():
+        rg = sd[name].grad
+        if rg is None or rg.abs().max().item() == 0:
+            assert p.grad is None or p.grad.abs().max().item() < 1e-6, name
+            continue
+        assert p.grad is not None, name
+        # atol: gradients that are analytically zero (softmax is invariant to the key bias) are pure
+        # rounding noise (~1e-8) on both sides
+        close(p.grad, rg, tol, name, atol=2e-7)
+        checked += 1
+    assert checked > 20
+    for k, v in bn_state.items():  # running statistics updated as nn.BatchNorm1d does
+        close(dict(model.named_buffers())[k], v, 1e-5, k)
+
+
+def test_training_with_dropout_runs_and_is_seed_reproducible():
+    opt = cases.small("NACF")  # reference dropout probabilities (0.5)
+    feats, category = cases.synth_inputs(opt, 4)
+    toks = cases.synth_tokens(opt, 4)
+    outs = []
+    for rep in range(3):
+        torch.manual_seed(0)
+        model = navc_b200.get_model(opt).to(DEV).train()
+        torch.manual_seed(5 if rep < 2 else 6)
+        res = model(feats=[f.to(DEV) for f in feats], tgt_tokens=[toks["tokens_1"].to(DEV), toks["tokens"].to(DEV)],
+                    category=category.to(DEV))
+        loss = O.criterion(opt, res, [toks["labels_1"].to(DEV), toks["labels"].to(DEV)], toks["length_target"].to(DEV))
+        loss.backward()
+        gn = torch.stack([p.grad.norm() for p in model.parameters() if p.grad is not None])
+        assert torch.isfinite(loss) and torch.isfinite(gn).all()
+        outs.append((loss.item(), gn.cpu()))
+    # same torch seed -> same dropout masks: identical loss, gradients equal up to the summation
+    # order of the atomic split-K / column-sum accumulations
+    assert outs[0][0] == outs[1][0] and torch.allclose(outs[0][1], outs[1][1], rtol=1e-4)
+    assert outs[0][0] != outs[2][0]
+
+
+def test_train_step_updates_weights_and_eval_sees_them():
+    """forward/backward/clip/Adam as misc/run.py:254-261, then the inference kernels pick up the new weights."""
+    opt = cases.small("NACF", hidden_dropout_prob=0.0, encoder_dropout=0.0)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt).to(DEV)
+    optim = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-4)
+    feats, category = cases.synth_inputs(opt, 6)
+    toks = cases.synth_tokens(opt, 6)
+    fd = [f.to(DEV) for f in feats]
+    losses = []
+    for it in range(4):
+        model.train()
+        optim.zero_grad()
+        res = model(feats=fd, tgt_tokens=[toks["tokens_1"].to(DEV), toks["tokens"].to(DEV)], category=category.to(DEV))
+        loss = O.criterion(opt, res, [toks["labels_1"].to(DEV), toks["labels"].to(DEV)], toks["length_target"].to(DEV))
+        loss.backward()
+        torch.nn.utils.clip_grad_value_(model.parameters(), 5)
+        optim.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    model.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        res = model(feats=fd, tgt_tokens=[toks["tokens_1"].to(DEV), toks["tokens"].to(DEV)], category=category.to(DEV))
+        ref = O.model_forward(sd, opt, feats, [toks["tokens_1"], toks["tokens"]], category)
+    for a, b in zip(res["tgt_word_logprobs"], ref["tgt_word_logprobs"]):
+        assert (a.cpu() - b).abs().max().item() < 5e-4
