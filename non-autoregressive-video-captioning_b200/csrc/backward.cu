@@ -541,9 +541,22 @@ __global__ void embed_ln_bwd_kernel(const float* __restrict__ dout, const int64_
 // ---- attention backward ----------------------------------------------------------------------------------------
 // grid (G, H), 256 threads.  Block (g, h) owns the Sk key/value rows of owner g and its NQ query
 // rows (self: NQ = Sk = S, owner = sequence; cross: NQ = group * S, owner = video), processed in
-// chunks of QB queries.  dK / dV accumulate in shared memory and are written once.
+// chunks of QB = 32 queries.  All four contractions are register tiled 4 x 4 per thread:
+//   A  scores S = Q K^T and dP = dO V^T   (K, V staged transposed: one LDS.128 feeds 4 keys)
+//   B  softmax, dS = P * (dP - rowsum(P dP)) / sqrt(dk), zero at masked positions (warp per row)
+//   C  dV = P^T dO, dK = dS^T Q           D  dQ = dS K
 constexpr float kMaskFillB = -10e6f;  // models/bert.py:161
 constexpr int kAttnBwdQB = 32;
+
+template <int DK>
+struct AttnBwdSmem {
+    static constexpr int LD = DK + 4;  // row stride of the row-major tiles (float4 aligned, 4-bank skew)
+    static __host__ __device__ int kp(int Sk) { return (Sk + 3) / 4 * 4; }          // padded key count
+    static __host__ __device__ int sp(int Sk) { return kp(Sk) + 4; }                // P / dS row stride
+    static __host__ __device__ size_t floats(int Sk) {
+        return (size_t)2 * DK * kp(Sk) + (size_t)kp(Sk) * LD + (size_t)2 * kAttnBwdQB * LD + (size_t)2 * kAttnBwdQB * sp(Sk);
+    }
+};
 
 template <int DK>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(
@@ -551,66 +564,99 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
     const int64_t* __restrict__ tokens, int NQ, int S, int Sk, int mask_kind, int watch,
     const float* __restrict__ d_ctx, int ld_dctx, float* __restrict__ dq, int ld_dq, float* __restrict__ dk,
     float* __restrict__ dv, int ld_dkv) {
-    constexpr int LD = DK + 1;
+    using SM = AttnBwdSmem<DK>;
+    constexpr int LD = SM::LD;
     constexpr int QB = kAttnBwdQB;
-    extern __shared__ float sm[];
-    const int SP = Sk | 1;              // odd row stride for P / dS
-    float* Ks = sm;                     // [Sk][LD]
-    float* Vs = Ks + (size_t)Sk * LD;
-    float* dKs = Vs + (size_t)Sk * LD;
-    float* dVs = dKs + (size_t)Sk * LD;
-    float* Qs = dVs + (size_t)Sk * LD;  // [QB][LD]
-    float* dOs = Qs + QB * LD;
-    float* Ps = dOs + QB * LD;          // [QB][SP]
-    float* dSs = Ps + (size_t)QB * SP;
+    extern __shared__ __align__(16) float sm[];
+    const int KP = SM::kp(Sk), SP = SM::sp(Sk);
+    float* Kt = sm;                         // [DK][KP]   K transposed
+    float* Vt = Kt + (size_t)DK * KP;       // [DK][KP]   V transposed
+    float* Ks = Vt + (size_t)DK * KP;       // [KP][LD]   K row-major (rows >= Sk zero)
+    float* Qs = Ks + (size_t)KP * LD;       // [QB][LD]
+    float* dOs = Qs + QB * LD;              // [QB][LD]
+    float* Ps = dOs + QB * LD;              // [QB][SP]
+    float* dSs = Ps + (size_t)QB * SP;      // [QB][SP]
     const int g = blockIdx.x, h = blockIdx.y;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
 
     const float* kb = k + (size_t)g * Sk * ldkv + h * DK;
     const float* vb = v + (size_t)g * Sk * ldkv + h * DK;
-    for (int idx = tid; idx < Sk * DK; idx += nthr) {
-        const int j = idx / DK, d = idx - j * DK;
-        Ks[j * LD + d] = kb[(size_t)j * ldkv + d];
-        Vs[j * LD + d] = vb[(size_t)j * ldkv + d];
-        dKs[j * LD + d] = 0.f;
-        dVs[j * LD + d] = 0.f;
+    for (int idx = tid; idx < KP * (DK / 4); idx += nthr) {
+        const int j = idx / (DK / 4), d4 = idx - j * (DK / 4);
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+        if (j < Sk) {
+            kk = *reinterpret_cast<const float4*>(kb + (size_t)j * ldkv + d4 * 4);
+            vv = *reinterpret_cast<const float4*>(vb + (size_t)j * ldkv + d4 * 4);
+        }
+        *reinterpret_cast<float4*>(Ks + j * LD + d4 * 4) = kk;
+        Kt[(d4 * 4 + 0) * KP + j] = kk.x; Kt[(d4 * 4 + 1) * KP + j] = kk.y;
+        Kt[(d4 * 4 + 2) * KP + j] = kk.z; Kt[(d4 * 4 + 3) * KP + j] = kk.w;
+        Vt[(d4 * 4 + 0) * KP + j] = vv.x; Vt[(d4 * 4 + 1) * KP + j] = vv.y;
+        Vt[(d4 * 4 + 2) * KP + j] = vv.z; Vt[(d4 * 4 + 3) * KP + j] = vv.w;
     }
     const float inv_sqrt = 1.0f / sqrtf((float)DK);
     const float sqrt_dk = sqrtf((float)DK);
     const bool use_watch = (mask_kind == NAVC_MASK_CAUSAL) && watch != 0 && S >= watch;
     const int64_t* trow = tokens ? tokens + (size_t)g * S : nullptr;
+    const int jt_n = KP / 4;
 
     for (int q0 = 0; q0 < NQ; q0 += QB) {
         const int nq = min(QB, NQ - q0);
         __syncthreads();
         const float* qb = q + ((size_t)g * NQ + q0) * ldq + h * DK;
         const float* ob = d_ctx + ((size_t)g * NQ + q0) * ld_dctx + h * DK;
-        for (int idx = tid; idx < nq * DK; idx += nthr) {
-            const int i = idx / DK, d = idx - i * DK;
-            Qs[i * LD + d] = qb[(size_t)i * ldq + d];
-            dOs[i * LD + d] = ob[(size_t)i * ld_dctx + d];
-        }
-        __syncthreads();
-        // scores and dP
-        for (int idx = tid; idx < nq * Sk; idx += nthr) {
-            const int i = idx / Sk, j = idx - i * Sk;
-            const float* qr = Qs + i * LD;
-            const float* orow = dOs + i * LD;
-            const float* kr = Ks + j * LD;
-            const float* vr = Vs + j * LD;
-            float s = 0.f, dp = 0.f;
-#pragma unroll 8
-            for (int d = 0; d < DK; ++d) {
-                s = fmaf(qr[d], kr[d], s);
-                dp = fmaf(orow[d], vr[d], dp);
+        for (int idx = tid; idx < QB * (DK / 4); idx += nthr) {
+            const int i = idx / (DK / 4), d4 = idx - i * (DK / 4);
+            float4 qq = make_float4(0.f, 0.f, 0.f, 0.f), oo = qq;
+            if (i < nq) {
+                qq = *reinterpret_cast<const float4*>(qb + (size_t)i * ldq + d4 * 4);
+                oo = *reinterpret_cast<const float4*>(ob + (size_t)i * ld_dctx + d4 * 4);
             }
-            Ps[i * SP + j] = s / sqrt_dk;
-            dSs[i * SP + j] = dp;
+            *reinterpret_cast<float4*>(Qs + i * LD + d4 * 4) = qq;
+            *reinterpret_cast<float4*>(dOs + i * LD + d4 * 4) = oo;
         }
         __syncthreads();
-        // softmax + dS, one warp per query row
-        for (int i = warp; i < nq; i += nw) {
+        // ---- A: 4 queries x 4 keys per thread ----
+        for (int t = tid; t < (QB / 4) * jt_n; t += nthr) {
+            const int ti = t / jt_n, tj = t - ti * jt_n;
+            float sacc[4][4], pacc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) { sacc[a][b] = 0.f; pacc[a][b] = 0.f; }
+            const float* qr = Qs + (ti * 4) * LD;
+            const float* orw = dOs + (ti * 4) * LD;
+#pragma unroll 4
+            for (int d = 0; d < DK; ++d) {
+                const float4 kk = *reinterpret_cast<const float4*>(Kt + d * KP + tj * 4);
+                const float4 vv = *reinterpret_cast<const float4*>(Vt + d * KP + tj * 4);
+                const float kf[4] = {kk.x, kk.y, kk.z, kk.w}, vf[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const float qd = qr[a * LD + d], od = orw[a * LD + d];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        sacc[a][b] = fmaf(qd, kf[b], sacc[a][b]);
+                        pacc[a][b] = fmaf(od, vf[b], pacc[a][b]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                *reinterpret_cast<float4*>(Ps + (ti * 4 + a) * SP + tj * 4) =
+                    make_float4(sacc[a][0] / sqrt_dk, sacc[a][1] / sqrt_dk, sacc[a][2] / sqrt_dk, sacc[a][3] / sqrt_dk);
+                *reinterpret_cast<float4*>(dSs + (ti * 4 + a) * SP + tj * 4) =
+                    make_float4(pacc[a][0], pacc[a][1], pacc[a][2], pacc[a][3]);
+            }
+        }
+        __syncthreads();
+        // ---- B: softmax + dS, one warp per query row (rows >= nq and keys >= Sk become zero) ----
+        for (int i = warp; i < QB; i += nw) {
+            if (i >= nq) {
+                for (int j = lane; j < KP; j += 32) { Ps[i * SP + j] = 0.f; dSs[i * SP + j] = 0.f; }
+                continue;
+            }
             const int ipos = (q0 + i) % S;
             float m = -INFINITY;
             for (int j = lane; j < Sk; j += 32) {
@@ -639,7 +685,12 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
                 dot += p * dSs[i * SP + j];
             }
             dot = warp_sum(dot);
-            for (int j = lane; j < Sk; j += 32) {
+            for (int j = lane; j < KP; j += 32) {
+                if (j >= Sk) {
+                    Ps[i * SP + j] = 0.f;
+                    dSs[i * SP + j] = 0.f;
+                    continue;
+                }
                 bool masked = false;
                 if (trow) {
                     masked = trow[j] == NAVC_PAD;
@@ -651,33 +702,75 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
             }
         }
         __syncthreads();
-        // dV += P^T dO ; dK += dS^T Q
-        for (int idx = tid; idx < Sk * DK; idx += nthr) {
-            const int j = idx / DK, d = idx - j * DK;
-            float av = 0.f, ak = 0.f;
-            for (int i = 0; i < nq; ++i) {
-                av = fmaf(Ps[i * SP + j], dOs[i * LD + d], av);
-                ak = fmaf(dSs[i * SP + j], Qs[i * LD + d], ak);
+        // ---- C: dV / dK, 4 keys x 4 columns per thread; accumulated over query chunks in global memory ----
+        float* dkb = dk + (size_t)g * Sk * ld_dkv + h * DK;
+        float* dvb = dv + (size_t)g * Sk * ld_dkv + h * DK;
+        for (int t = tid; t < jt_n * (DK / 4); t += nthr) {
+            const int tj = t / (DK / 4), td = t - tj * (DK / 4);
+            float va[4][4], ka[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) { va[a][b] = 0.f; ka[a][b] = 0.f; }
+#pragma unroll 4
+            for (int i = 0; i < QB; ++i) {
+                const float4 pp = *reinterpret_cast<const float4*>(Ps + i * SP + tj * 4);
+                const float4 ss = *reinterpret_cast<const float4*>(dSs + i * SP + tj * 4);
+                const float4 oo = *reinterpret_cast<const float4*>(dOs + i * LD + td * 4);
+                const float4 qq = *reinterpret_cast<const float4*>(Qs + i * LD + td * 4);
+                const float pf[4] = {pp.x, pp.y, pp.z, pp.w}, sf[4] = {ss.x, ss.y, ss.z, ss.w};
+                const float of[4] = {oo.x, oo.y, oo.z, oo.w}, qf[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        va[a][b] = fmaf(pf[a], of[b], va[a][b]);
+                        ka[a][b] = fmaf(sf[a], qf[b], ka[a][b]);
+                    }
             }
-            dVs[j * LD + d] += av;
-            dKs[j * LD + d] += ak;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int j = tj * 4 + a;
+                if (j < Sk) {
+                    float4* pk = reinterpret_cast<float4*>(dkb + (size_t)j * ld_dkv + td * 4);
+                    float4* pv = reinterpret_cast<float4*>(dvb + (size_t)j * ld_dkv + td * 4);
+                    float4 nk = make_float4(ka[a][0], ka[a][1], ka[a][2], ka[a][3]);
+                    float4 nv = make_float4(va[a][0], va[a][1], va[a][2], va[a][3]);
+                    if (q0 > 0) { nk = add4(nk, *pk); nv = add4(nv, *pv); }
+                    *pk = nk;
+                    *pv = nv;
+                }
+            }
         }
-        // dQ = dS K
+        // ---- D: dQ = dS K, 4 queries x 4 columns per thread ----
         float* dqb = dq + ((size_t)g * NQ + q0) * ld_dq + h * DK;
-        for (int idx = tid; idx < nq * DK; idx += nthr) {
-            const int i = idx / DK, d = idx - i * DK;
-            float a = 0.f;
-            for (int j = 0; j < Sk; ++j) a = fmaf(dSs[i * SP + j], Ks[j * LD + d], a);
-            dqb[(size_t)i * ld_dq + d] = a;
+        for (int t = tid; t < (QB / 4) * (DK / 4); t += nthr) {
+            const int ti = t / (DK / 4), td = t - ti * (DK / 4);
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+            const float* sr = dSs + (ti * 4) * SP;
+#pragma unroll 4
+            for (int j = 0; j < KP; ++j) {
+                const float4 kk = *reinterpret_cast<const float4*>(Ks + j * LD + td * 4);
+                const float kf[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const float sd = sr[a * SP + j];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(sd, kf[b], acc[a][b]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int i = ti * 4 + a;
+                if (i < nq)
+                    *reinterpret_cast<float4*>(dqb + (size_t)i * ld_dq + td * 4) =
+                        make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+            }
         }
-    }
-    __syncthreads();
-    float* dkb = dk + (size_t)g * Sk * ld_dkv + h * DK;
-    float* dvb = dv + (size_t)g * Sk * ld_dkv + h * DK;
-    for (int idx = tid; idx < Sk * DK; idx += nthr) {
-        const int j = idx / DK, d = idx - j * DK;
-        dkb[(size_t)j * ld_dkv + d] = dKs[j * LD + d];
-        dvb[(size_t)j * ld_dkv + d] = dVs[j * LD + d];
     }
 }
 
@@ -685,9 +778,12 @@ template <int DK>
 static int launch_attn_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const int64_t* tokens,
                            int G, int NQ, int S, int Sk, int H, int mask_kind, int watch, const float* d_ctx, int ld_dctx,
                            float* dq, int ld_dq, float* dk, float* dv, int ld_dkv, cudaStream_t st, const char* what) {
-    const int SP = Sk | 1;
-    const size_t smem = ((size_t)4 * Sk * (DK + 1) + (size_t)2 * kAttnBwdQB * (DK + 1) + (size_t)2 * kAttnBwdQB * SP) * sizeof(float);
+    const size_t smem = AttnBwdSmem<DK>::floats(Sk) * sizeof(float);
     NAVC_REQUIRE(smem <= 227 * 1024, "%s: Sk=%d too large for shared memory", what, Sk);
+    NAVC_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0 && ld_dctx % 4 == 0 && ld_dq % 4 == 0 && ld_dkv % 4 == 0 &&
+                     ((((uintptr_t)q) | ((uintptr_t)k) | ((uintptr_t)v) | ((uintptr_t)d_ctx) | ((uintptr_t)dq) |
+                       ((uintptr_t)dk) | ((uintptr_t)dv)) & 15) == 0,
+                 "%s: operands must be 16-byte aligned with leading dimensions multiple of 4", what);
     auto kern = attn_bwd_kernel<DK>;
     if (smem > 48 * 1024) NAVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(G, H), 256, smem, st>>>(q, ldq, k, v, ldkv, tokens, NQ, S, Sk, mask_kind, watch, d_ctx, ld_dctx, dq, ld_dq,

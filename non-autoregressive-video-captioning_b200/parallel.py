@@ -1,0 +1,133 @@
+"""Data parallelism for the hot path: one process per GPU, videos sharded across ranks.
+
+The reference is single-process / single-device.  The path shards on
+independent units (videos), so
+
+* inference: every rank decodes its own slice of the batch -- NO data-path collective
+  (``shard`` / ``shard_batch``; an optional ``gather_hypotheses`` brings the ids to rank 0);
+* training: every rank runs forward/backward on its slice (BatchNorm statistics and dropout
+  streams stay rank-local exactly as in plain DDP) and the gradients are averaged
+  with ONE all-reduce over a flat fp32 buffer per step (``GradientAllReduce``).  The loss of the
+  reference is a token sum divided by the LOCAL batch size (misc/crit.py:40-46), so the mean of
+  the per-rank gradients over equal shards is the global-batch gradient.
+
+``torch.distributed`` (NCCL over NVLink on the GPUs, gloo in the CPU tests) is the transport.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_bounds(n: int, rank_: Optional[int] = None, world_: Optional[int] = None):
+    """Contiguous, balanced split of n units: the first n % world ranks get one extra."""
+    r = rank() if rank_ is None else rank_
+    w = world() if world_ is None else world_
+    base, extra = divmod(n, w)
+    lo = r * base + min(r, extra)
+    return lo, lo + base + (1 if r < extra else 0)
+
+
+def shard(t, rank_: Optional[int] = None, world_: Optional[int] = None):
+    """Slice dim 0 (videos) of a tensor, or of every tensor in a list / tuple / dict."""
+    if isinstance(t, dict):
+        return {k: shard(v, rank_, world_) for k, v in t.items()}
+    if isinstance(t, (list, tuple)):
+        if t and isinstance(t[0], str):  # e.g. video_ids
+            lo, hi = shard_bounds(len(t), rank_, world_)
+            return type(t)(t[lo:hi])
+        return type(t)(shard(v, rank_, world_) for v in t)
+    if torch.is_tensor(t) and t.dim() > 0:
+        lo, hi = shard_bounds(t.shape[0], rank_, world_)
+        return t[lo:hi]
+    return t
+
+
+def broadcast_model(model: torch.nn.Module, src: int = 0):
+    """Make every rank start from rank `src`'s parameters and buffers (done once)."""
+    if world() == 1:
+        return
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src)
+
+
+def gather_hypotheses(hyp: torch.Tensor, pad: int = 0) -> Optional[List[torch.Tensor]]:
+    """Optional: collect the per-rank [B_r, S_r] id tensors on rank 0 (shapes may differ per rank)."""
+    if world() == 1:
+        return [hyp]
+    out = [None] * world() if rank() == 0 else None
+    dist.gather_object(hyp.cpu(), out, dst=0)
+    return out
+
+
+class GradientAllReduce:
+    """Flat fp32 gradient buffer + ONE all-reduce per step.
+
+    ``p.grad`` of every trainable parameter is a view into ``self.flat`` so autograd accumulates
+    straight into the buffer the collective runs on (no pack / unpack copies)::
+
+        dp = GradientAllReduce(model)          # broadcasts weights from rank 0
+        for batch in loader:                    # each rank: its own shard
+            dp.zero_grad()
+            loss = crit(model(**shard(batch)))
+            loss.backward()
+            dp.allreduce()                      # mean over ranks, one collective
+            clip_grad_value_(model.parameters(), 5); optimizer.step()
+    """
+
+    def __init__(self, model: torch.nn.Module, broadcast: bool = True):
+        self.model = model
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("model has no trainable parameters")
+        dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        if broadcast:
+            broadcast_model(model)
+        self.attach()
+
+    def attach(self):
+        """(Re)point p.grad at the flat buffer (optimizers' zero_grad(set_to_none=True) detaches it)."""
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)
+                p.grad = v
+
+    def zero_grad(self):
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def allreduce(self):
+        """Average the gradients over the ranks: one collective on the whole buffer."""
+        self.attach()
+        w = world()
+        if w == 1:
+            return self.flat
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)  # sum and 1/world inside the collective
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(w)
+        return self.flat
+
+    @property
+    def nbytes(self) -> int:
+        return self.numel * 4

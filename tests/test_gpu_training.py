@@ -318,7 +318,7 @@ def test_self_attention_backward(kind, D, H, S):
     close(d_qkv.view(N, S, 3 * D), qkv.grad, 2e-5, "self attn bwd")
 
 
-@pytest.mark.parametrize("D,H,S,E,group", [(128, 8, 9, 12, 1), (512, 8, 30, 120, 1), (128, 4, 7, 16, 3)])
+@pytest.mark.parametrize("D,H,S,E,group", [(128, 8, 9, 12, 1), (512, 8, 30, 120, 1), (128, 4, 7, 16, 3), (128, 8, 9, 13, 6)])
 def test_cross_attention_backward(D, H, S, E, group):
     B = 4
     N = B * group

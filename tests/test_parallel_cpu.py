@@ -1,0 +1,103 @@
+"""Host-side multi-process logic on CPU: world_size-2 gloo.
+Sharding of videos across ranks, weight broadcast, and the single flat-buffer gradient all-reduce:
+the averaged gradient equals the mean of the per-rank gradients, for every parameter, through views
+of ONE buffer.  (The kernels themselves need a GPU; gradients here are synthetic.)"""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import cases
+import navc_b200
+from navc_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        opt = cases.config1()
+        torch.manual_seed(100 + rank)  # different initial weights per rank on purpose
+        model = navc_b200.get_model(opt)
+        dp = parallel.GradientAllReduce(model)  # broadcasts rank 0's weights
+        w0 = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        gathered = [torch.empty_like(w0) for _ in range(world)]
+        dist.all_gather(gathered, w0)
+        same_weights = all(torch.equal(gathered[0], t) for t in gathered)
+        # synthetic per-rank gradients, accumulated the way autograd does (in place into p.grad)
+        dp.zero_grad()
+        g = torch.Generator().manual_seed(7 + rank)
+        local = []
+        for p in dp.params:
+            gr = torch.randn(p.shape, generator=g)
+            p.grad.add_(gr)
+            local.append(gr)
+        is_view = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(dp.params, dp.views))
+        # an optimizer that detaches the grads (set_to_none) must not break the flat buffer
+        model.zero_grad(set_to_none=True)
+        for p, gr in zip(dp.params, local):
+            p.grad = gr.clone()
+        flat = dp.allreduce()
+        expect = []
+        for i in range(len(dp.params)):
+            parts = []
+            for r in range(world):
+                gg = torch.Generator().manual_seed(7 + r)
+                for j, p in enumerate(dp.params):
+                    t = torch.randn(p.shape, generator=gg)
+                    if j == i:
+                        parts.append(t)
+                        break
+            expect.append(sum(parts) / world)
+        ok = all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(dp.params, expect))
+        ok_flat = torch.allclose(flat, torch.cat([e.reshape(-1) for e in expect]), atol=1e-6)
+        # video sharding
+        feats, category = cases.synth_inputs(opt, 7)
+        sh = parallel.shard({"feats": feats, "category": category, "video_ids": ["v%d" % i for i in range(7)]})
+        lo, hi = parallel.shard_bounds(7)
+        q.put((rank, same_weights, is_view, ok, ok_flat, dp.numel, sh["category"].shape[0], sh["feats"][0].shape[0],
+               sh["video_ids"], lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_and_sharding_world2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = 0
+    for rank, same_weights, is_view, ok, ok_flat, numel, nb, nf, ids, lo, hi in res:
+        assert same_weights and is_view and ok and ok_flat
+        assert nb == nf == hi - lo == len(ids)
+        total += nb
+    assert total == 7 and res[0][8] + res[1][8] == ["v%d" % i for i in range(7)]
+    assert res[0][5] == sum(p.numel() for p in navc_b200.get_model(cases.config1()).parameters())
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 128, 1000):
+        for w in (1, 2, 4, 8):
+            spans = [parallel.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,156 @@
+#!/usr/bin/env python
+"""Training-step benchmark (BASELINE.json configs 3 and 5) -- one JSON line on stdout.
+
+    python tools/train_bench.py --method NACF|NAB|ARB [--batch B] [--global-batch G] [--steps K] [--warmup W]
+    torchrun --nproc-per-node N tools/train_bench.py --method NACF --global-batch 1024     (config 5)
+
+A step = forward (train mode, dropout 0.5, BatchNorm batch statistics) + the reference's loss
+(masked NLL sum / batch + KLDiv on the length head: misc/crit.py, caller code in PyTorch) + backward
+(navc kernels) + ONE gradient all-reduce (N > 1) + clip_grad_value_(5) + Adam(lr 5e-4, wd 5e-4)
+(misc/run.py:254-261, misc/optim.py:61-62; caller code).  Metric: samples/s, whole job.
+Inputs are resident in HBM and rotate over distinct batches."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+import cases  # noqa: E402
+
+
+def reference_loss(opt, results, labels, length_target):
+    """misc/crit.py:62-84, 156-181, 223 (the caller's loss, plain PyTorch)."""
+    lps = results["tgt_word_logprobs"]
+    labs = labels if isinstance(labels, (list, tuple)) else [labels] * len(lps)
+    weights = opt.get("nv_weights", [0.8, 1.0]) if opt.get("visual_word_generation", False) else [1.0] * len(lps)
+    bsz = lps[0].shape[0]
+    loss = 0.0
+    for w, lp, lab in zip(weights, lps, labs):
+        nll = F.nll_loss(lp.reshape(-1, lp.shape[-1]), lab.reshape(-1), reduction="none")
+        loss = loss + w * (nll * lab.reshape(-1).ne(0).float()).sum() / bsz
+    if length_target is not None and "pred_length" in results:
+        loss = loss + F.kl_div(results["pred_length"], length_target, reduction="mean")
+    return loss
+
+
+def make_batch(opt, B, seed, dev):
+    nar = opt["decoding_type"] == "NARFormer"
+    feats, category = cases.synth_inputs(opt, B, seed=seed)
+    toks = cases.synth_tokens(opt, B, seed=seed + 1, kind="nar" if nar else "ar")
+    dis = opt["decoder"] == "BertDecoderDisentangled"
+    if nar:
+        tgt = [toks["tokens_1"], toks["tokens"]] if dis else toks["tokens"]
+        labels = [toks["labels_1"], toks["labels"]] if dis else toks["labels"]
+        lt = toks["length_target"]
+    else:
+        tgt, labels, lt = toks["tokens"], toks["labels"], None
+    mv = lambda t: [x.to(dev) for x in t] if isinstance(t, (list, tuple)) else (None if t is None else t.to(dev))
+    return dict(feats=mv(feats), category=category.to(dev), tgt=mv(tgt), labels=mv(labels), lt=mv(lt))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--method", default="NACF")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--global-batch", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--precision", default=os.environ.get("NAVC_PRECISION", "bf16x3"))
+    ap.add_argument("--profile", action="store_true", help="print a per-kernel device-time breakdown of one step")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch.distributed as dist
+    import navc_b200
+    from navc_b200 import _lib as L, parallel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    B = args.global_batch // world if args.global_batch else args.batch
+    kw = dict(dim_hidden=512, num_hidden_layers_decoder=6, intermediate_size=2048, dim_i=2048, dim_m=2048,
+              n_frames=60, max_len=30, vocab_size=10547)
+    opt = cases.make_opt(args.method, **kw)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt).to(dev)
+    model.set_precision(args.precision)
+    model.train()
+    dp = parallel.GradientAllReduce(model)
+    optim = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-4)
+    n_rot = 3
+    batches = [make_batch(opt, B, 1234 + 31 * r + 1000 * rank, dev) for r in range(n_rot)]
+
+    def step(i):
+        b = batches[i % n_rot]
+        dp.zero_grad()
+        res = model(feats=b["feats"], tgt_tokens=b["tgt"], category=b["category"])
+        loss = reference_loss(opt, res, b["labels"], b["lt"])
+        loss.backward()
+        dp.allreduce()
+        torch.nn.utils.clip_grad_value_(model.parameters(), 5)
+        optim.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        loss = step(i)
+    barrier()
+    l0 = L.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    launches = L.launches - l0
+    if rank == 0:
+        nparams = sum(p.numel() for p in model.parameters())
+        line = {"metric": "training samples/sec (%s 6-layer d512, fwd+bwd+allreduce+clip+Adam)" % args.method,
+                "value": world * B * args.steps / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if args.global_batch else "weak", "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": "%s training step, feats 2x60x2048, max_len 30, vocab 10547, dropout 0.5" % args.method,
+                           "batch_per_gpu": B, "global_batch": B * world, "params": nparams,
+                           "allreduce_bytes": dp.nbytes if world > 1 else 0,
+                           "l2": "inputs rotate over %d distinct batches" % n_rot},
+                "gpu_launches": launches, "final_loss": float(loss.item())}
+        print(json.dumps(line), flush=True)
+    if args.profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(0)
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                a = agg.setdefault(ev.name[:80], [0, 0.0]); a[0] += 1; a[1] += ev.device_time
+        tot = sum(v[1] for v in agg.values())
+        print("total device time: %.2f ms over %d kernels" % (tot / 1e3, sum(v[0] for v in agg.values())), file=sys.stderr)
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+            print("%9.1f us %5d x %8.1f us  %5.1f%%  %s" % (v[1], v[0], v[1] / v[0], 100 * v[1] / tot, k), file=sys.stderr)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
