@@ -46,7 +46,7 @@ enum { NAVC_MASK_KEYPAD = 0 /* NARFormer */, NAVC_MASK_CAUSAL = 1 /* ARFormer */
 enum { NAVC_TC_BF16 = 1 /* one product: hi*hi */, NAVC_TC_BF16X3 = 3 /* hi*hi + hi*lo + lo*hi */ };
 
 /* Epilogue applied to a GEMM tile before it is stored:
- *   v = acc + bias[col]; v = act(v); v += residual[row,col]; if (row_tokens[row]==PAD) v = 0;
+ *   v = acc + bias[col]; v = act(v); v += residual[row,col] (fp32, or res_hi + res_lo); if (row_tokens[row]==PAD) v = 0;
  * (bias / activation: nn.Linear + ACT2FN, models/bert.py:227-230; residual: bert.py:196-197, 243;
  *  row mask: `* non_pad_mask`, bert.py:271-272, 293-294, 298-299).  Any output may be NULL. */
 typedef struct {
@@ -63,6 +63,8 @@ typedef struct {
     int32_t split_k;            /* tcgen05 path: > 1 splits the K loop over that many CTAs per output tile;
                                    implies accumulate (out_f32 only, no bias/act/residual/mask) */
     int32_t accumulate;         /* != 0: out_f32 += tile (atomic float adds; caller zero-fills first) */
+    const uint16_t* res_hi;     /* tcgen05 path: residual given as a bf16 hi/lo pair [M, ld_res] (res_lo may be */
+    const uint16_t* res_lo;     /* NULL); needs bf16-only outputs (out_f32 == NULL, residual == NULL), N % 8 == 0 */
 } navc_epilogue_t;
 
 int navc_version(void);
@@ -90,6 +92,9 @@ int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx
 
 /* fp32 -> bf16 hi/lo split of a contiguous buffer (weights are split once when packed). */
 int navc_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int64_t n, void* stream);
+/* The inverse: out = hi + lo (lo may be NULL).  Used at the API boundary when a caller asks for the
+ * fp32 hidden states of a residual stream that the tensor-core path keeps as bf16 hi/lo pairs. */
+int navc_join_bf16(const uint16_t* hi, const uint16_t* lo, float* out, int64_t n, void* stream);
 
 /* ---- vocabulary projection with on-the-fly softmax statistics ------------------------------- */
 /* For logits[M,V] = H[M,K] * Wv[V,K]^T (+bias), never written to memory, emit per row and per

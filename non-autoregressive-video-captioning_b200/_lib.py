@@ -21,7 +21,7 @@ i32, i64, u64, f32, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
 class Epilogue(C.Structure):
     _fields_ = [("bias", vp), ("residual", vp), ("row_tokens", vp), ("act", i32), ("ld_res", i32),
                 ("out_f32", vp), ("out_hi", vp), ("out_lo", vp), ("ld_out", i32), ("reserved", i32),
-                ("split_k", i32), ("accumulate", i32)]
+                ("split_k", i32), ("accumulate", i32), ("res_hi", vp), ("res_lo", vp)]
 
 
 class Step(C.Structure):
@@ -45,6 +45,7 @@ _PROTOS = {
     "navc_linear_f32": [vp, i32, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp],
     "navc_linear_tc": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp],
     "navc_split_bf16": [vp, vp, vp, i64, vp],
+    "navc_join_bf16": [vp, vp, vp, i64, vp],
     "navc_vocab_tile": [i32],
     "navc_vocab_partials_f32": [vp, i32, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "navc_vocab_partials_tc": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],

@@ -169,71 +169,112 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;                 // tile row = TMEM lane
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
-        // keys this query may see
-        int own_lo = 0, own_hi = n_keys, ipos = 0;
+        // Per-thread 32-bit key masks per 32-key chunk: `vis` = keys this query may see at all (its own
+        // sequence / the owner's E keys), `fill` = visible keys whose score is replaced by -1e7
+        // (PAD keys, causal / diagonal masks; models/bert.py:157-161).  Chunks [c_lo, c_hi] (warp
+        // uniform) are the only ones with a visible key for some row of this warp; P is zero elsewhere.
+        int own_lo = 0, own_hi = n_keys, ipos = 0, c_lo = 0, c_hi = 3;
         if (p.is_self) {
             const int si = r / p.S;
             own_lo = si * p.S;
             own_hi = min(own_lo + p.S, n_keys);
             ipos = r - own_lo;
+            const int s_first = (quarter * 32) / p.S, s_last = (quarter * 32 + 31) / p.S;
+            c_lo = min(3, (s_first * p.S) >> 5);
+            c_hi = min(3, ((s_last + 1) * p.S - 1) >> 5);
+        } else {
+            c_hi = min(3, (n_keys - 1) >> 5);
         }
         const bool use_watch = (p.mask_kind == NAVC_MASK_CAUSAL) && p.watch != 0 && p.S >= p.watch;
+        auto range_mask = [](int lo, int hi, int c) -> uint32_t {  // bits of keys [lo, hi) inside chunk c
+            const int a = max(lo - c * 32, 0), b = min(hi - c * 32, 32);
+            if (b <= a) return 0u;
+            const uint32_t upto_b = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
+            return upto_b & ~((1u << a) - 1u);
+        };
+        uint32_t* padw = reinterpret_cast<uint32_t*>(keypad + 128);  // PAD-key bits per 32-key chunk
+        if (p.is_self) {
+            const uint32_t mine = __ballot_sync(0xffffffffu, keypad[r] != 0);
+            if (lane == 0) padw[quarter] = mine;
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four softmax warps only
+        }
+        auto chunk_masks = [&](int c, uint32_t& vm, uint32_t& fm) {
+            vm = range_mask(own_lo, own_hi, c);
+            fm = 0u;
+            if (p.is_self) {
+                uint32_t f = padw[c];
+                if (p.mask_kind == NAVC_MASK_CAUSAL) {
+                    f |= range_mask(own_lo + ipos + 1, own_hi, c);                           // future keys
+                    if (use_watch) f |= range_mask(own_lo, own_lo + ipos - p.watch + 1, c);  // keys older than the window
+                }
+                if (p.mask_kind == NAVC_MASK_SELF) f |= range_mask(own_lo + ipos, own_lo + ipos + 1, c);
+                fm = f & vm;
+            }
+        };
         const float scale = 0.125f;  // 1/sqrt(dk), dk = 64: exact power of two == the reference's division by sqrt(dk)
         constexpr float kLog2e = 1.4426950408889634f;
 
         mbar_wait(bar_s, 0);
         tc_fence_after();
-        // pass 1: row maximum
+        // pass 1: row maximum over the visible keys
         float m = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = c_lo; c <= c_hi; ++c) {
             uint32_t v[32];
             tc_ld32(tS + t_lane + (uint32_t)(c * 32), v);
             tc_wait_ld();
+            uint32_t vis, fill;
+            chunk_masks(c, vis, fill);
+            const uint32_t vm = vis & ~fill;
+            float mc = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int key = c * 32 + j;
-                float s = __uint_as_float(v[j]) * scale;
-                bool visible = key >= own_lo && key < own_hi;
-                if (p.is_self) {
-                    bool masked = keypad[key] != 0;
-                    if (p.mask_kind == NAVC_MASK_CAUSAL) masked = masked || (key - own_lo > ipos) || (use_watch && key - own_lo <= ipos - p.watch);
-                    if (p.mask_kind == NAVC_MASK_SELF) masked = masked || (key - own_lo == ipos);
-                    if (masked) s = kMaskFillTc;
-                }
-                if (visible) m = fmaxf(m, s);
-            }
+            for (int j = 0; j < 32; ++j)
+                if ((vm >> j) & 1u) mc = fmaxf(mc, __uint_as_float(v[j]));
+            m = fmaxf(m, mc * scale);               // scale > 0: max commutes with the scaling
+            if (fill) m = fmaxf(m, kMaskFillTc);
         }
         // pass 2: e = exp(s - m), row sum, P -> shared memory (bf16 hi/lo, K-major 128B swizzle)
         float sum = 0.f;
         const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        const float m2 = m * kLog2e, sc2 = scale * kLog2e;
+        const float e_fill = fast_exp2((kMaskFillTc - m) * kLog2e);  // 0 unless every visible key is filled
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+            uint8_t* panel_hi = gP + (c >> 1) * kAtTile + row_off;
+            if (c < c_lo || c > c_hi) {  // warp-uniform: no visible key in this chunk for any row of the warp
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t ch = (uint32_t)(((c & 1) * 4 + i) ^ (r & 7)) * 16;
+                    *reinterpret_cast<uint4*>(panel_hi + ch) = make_uint4(0u, 0u, 0u, 0u);
+                    if (kX3) *reinterpret_cast<uint4*>(panel_hi + 2 * kAtTile + ch) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                continue;
+            }
             uint32_t v[32];
             tc_ld32(tS + t_lane + (uint32_t)(c * 32), v);
             tc_wait_ld();
+            uint32_t vm, fm;
+            chunk_masks(c, vm, fm);
             uint32_t hi_w[16], lo_w[16];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 float e2[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int key = c * 32 + j + u;
-                    float s = __uint_as_float(v[j + u]) * scale;
-                    bool visible = key >= own_lo && key < own_hi;
-                    if (p.is_self) {
-                        bool masked = keypad[key] != 0;
-                        if (p.mask_kind == NAVC_MASK_CAUSAL) masked = masked || (key - own_lo > ipos) || (use_watch && key - own_lo <= ipos - p.watch);
-                        if (p.mask_kind == NAVC_MASK_SELF) masked = masked || (key - own_lo == ipos);
-                        if (masked) s = kMaskFillTc;
-                    }
-                    e2[u] = visible ? fast_exp2((s - m) * kLog2e) : 0.f;
-                    sum += e2[u];
+                    float e = fast_exp2(fmaf(__uint_as_float(v[j + u]), sc2, -m2));
+                    if ((fm >> (j + u)) & 1u) e = e_fill;
+                    if (!((vm >> (j + u)) & 1u)) e = 0.f;
+                    e2[u] = e;
+                    sum += e;
                 }
-                split_bf16x2(e2[0], e2[1], hi_w[j >> 1], lo_w[j >> 1]);
+                if (kX3) {
+                    split_bf16x2(e2[0], e2[1], hi_w[j >> 1], lo_w[j >> 1]);
+                } else {
+                    const __nv_bfloat162 hb = __floats2bfloat162_rn(e2[0], e2[1]);
+                    hi_w[j >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+                }
             }
             // 32 keys = 64 B = four 16-byte chunks of panel c/2, chunk index (c%2)*4 + i
-            uint8_t* panel_hi = gP + (c >> 1) * kAtTile + row_off;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint32_t ch = (uint32_t)(((c & 1) * 4 + i) ^ (r & 7)) * 16;
@@ -260,16 +301,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
             tc_wait_ld();
             if (store) {
 #pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4) {
-                    const float4 f = make_float4(__uint_as_float(v[g4 * 4]) * inv, __uint_as_float(v[g4 * 4 + 1]) * inv,
-                                                 __uint_as_float(v[g4 * 4 + 2]) * inv, __uint_as_float(v[g4 * 4 + 3]) * inv);
-                    const size_t oo = o + c * 32 + g4 * 4;
-                    if (p.ctx_f32) *reinterpret_cast<float4*>(p.ctx_f32 + oo) = f;
+                for (int g8 = 0; g8 < 4; ++g8) {  // 8 columns per step: 16-byte bf16 stores
+                    const float4 f0 = make_float4(__uint_as_float(v[g8 * 8]) * inv, __uint_as_float(v[g8 * 8 + 1]) * inv,
+                                                  __uint_as_float(v[g8 * 8 + 2]) * inv, __uint_as_float(v[g8 * 8 + 3]) * inv);
+                    const float4 f1 = make_float4(__uint_as_float(v[g8 * 8 + 4]) * inv, __uint_as_float(v[g8 * 8 + 5]) * inv,
+                                                  __uint_as_float(v[g8 * 8 + 6]) * inv, __uint_as_float(v[g8 * 8 + 7]) * inv);
+                    const size_t oo = o + c * 32 + g8 * 8;
+                    if (p.ctx_f32) {
+                        *reinterpret_cast<float4*>(p.ctx_f32 + oo) = f0;
+                        *reinterpret_cast<float4*>(p.ctx_f32 + oo + 4) = f1;
+                    }
                     if (p.ctx_hi) {
-                        uint2 hv, lv;
-                        split_bf16x4(f, hv, lv);
-                        *reinterpret_cast<uint2*>(p.ctx_hi + oo) = hv;
-                        if (p.ctx_lo) *reinterpret_cast<uint2*>(p.ctx_lo + oo) = lv;
+                        uint2 h0, l0, h1, l1;
+                        split_bf16x4(f0, h0, l0);
+                        split_bf16x4(f1, h1, l1);
+                        *reinterpret_cast<uint4*>(p.ctx_hi + oo) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                        if (p.ctx_lo) *reinterpret_cast<uint4*>(p.ctx_lo + oo) = make_uint4(l0.x, l0.y, l1.x, l1.y);
                     }
                 }
             }

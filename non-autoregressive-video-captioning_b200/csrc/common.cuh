@@ -110,6 +110,8 @@ struct EpiParams {
     int dbg;  // profiling aid (navc_epilogue_t.reserved): 1 = skip epilogue, 2 = no phase 2, 3 = no global stores
     int split_k;     // tcgen05 path only
     int accumulate;  // out_f32 += (atomic)
+    const uint16_t* res_hi;  // bf16 hi/lo residual (tcgen05 pair epilogue)
+    const uint16_t* res_lo;
 };
 static inline EpiParams to_params(const navc_epilogue_t* e) {
     EpiParams p;
@@ -119,6 +121,8 @@ static inline EpiParams to_params(const navc_epilogue_t* e) {
     p.dbg = e->reserved;
     p.split_k = e->split_k > 1 ? e->split_k : 1;
     p.accumulate = (e->accumulate != 0 || p.split_k > 1) ? 1 : 0;
+    p.res_hi = e->res_hi;
+    p.res_lo = e->res_lo;
     return p;
 }
 

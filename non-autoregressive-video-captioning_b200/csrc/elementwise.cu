@@ -30,6 +30,12 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, uint16_t* __restr
     }
 }
 
+__global__ void join_bf16_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                                 float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = bf16_to_f32(hi[i]) + (lo ? bf16_to_f32(lo[i]) : 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // one block per video; thread d owns column d (strided), loops over the F frames.
 __global__ void highway_bn_kernel(const float* __restrict__ x, const float* __restrict__ yg, int gate, int F,
@@ -269,6 +275,15 @@ extern "C" int navc_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int64
     if (blocks < 1) blocks = 1;
     split_bf16_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, hi, lo, n);
     return check_launch("navc_split_bf16");
+}
+
+extern "C" int navc_join_bf16(const uint16_t* hi, const uint16_t* lo, float* out, int64_t n, void* stream) {
+    NAVC_REQUIRE(hi && out && n >= 0, "navc_join_bf16: bad arguments");
+    if (n == 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    join_bf16_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(hi, lo, out, n);
+    return check_launch("navc_join_bf16");
 }
 
 extern "C" int navc_highway_bn(const float* x, const float* yg, int gate, int B, int F, int D, int E, int slot,

@@ -45,11 +45,18 @@ struct TcVocab {
     int n_tiles;
 };
 
-template <bool kX3, bool kVocab>
+// kEpi: 0 = generic epilogue (fp32 / bf16 outputs, fp32 residual; smem-transposed coalesced stores),
+//       1 = vocabulary softmax statistics, 2 = "pair" epilogue (lane = row, bf16 hi/lo outputs through
+//       TMA stores, bf16 hi+lo residual): the inference fast path.
+constexpr int kEpiGeneric = 0, kEpiVocab = 1, kEpiPair = 2;
+
+template <bool kX3, int kEpi>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                int M, int N, int K, EpiParams epi, TcVocab vep) {
+    constexpr bool kVocab = kEpi == kEpiVocab;
     using Cfg = TcCfg<kX3>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -163,7 +170,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int row = row0 + lane;
             const int n0 = nb * TBN + half * (TBN / 2);
 
-            if constexpr (!kVocab) {
+            if constexpr (kEpi == kEpiPair) {
+                // ---- pair epilogue: lane = row, 32-column chunks, TMA stores of [32 x 32] bf16 boxes ----
+                const bool row_ok = row < M;
+                const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[row] == NAVC_PAD) : false;
+                uint8_t* stg = reinterpret_cast<uint8_t*>(stage);   // hi box at +0, lo box at +2048
+                const uint32_t stg_s = smem_u32(stg);
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + half * (TBN / 2));
+#pragma unroll 1
+                for (int c = 0; c < TBN / 64; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= N) break;  // warp-uniform
+                    uint32_t r[32];
+                    tc_ld32(t_row + (uint32_t)(c * 32), r);
+                    // operands of this chunk (requested before the TMEM wait)
+                    float4 bv[8];
+                    uint4 rh[4], rl[4];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (epi.bias && col0 + i * 4 < N) bv[i] = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + i * 4));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        rh[i] = make_uint4(0u, 0u, 0u, 0u);
+                        rl[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (epi.res_hi && row_ok && col0 + i * 8 < N) {
+                            const size_t ro = (size_t)row * epi.ld_res + col0 + i * 8;
+                            rh[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
+                            if (epi.res_lo) rl[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
+                        }
+                    }
+                    tc_wait_ld();
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[i * 4 + 0] = __uint_as_float(r[i * 4 + 0]) + bv[i].x;
+                        v[i * 4 + 1] = __uint_as_float(r[i * 4 + 1]) + bv[i].y;
+                        v[i * 4 + 2] = __uint_as_float(r[i * 4 + 2]) + bv[i].z;
+                        v[i * 4 + 3] = __uint_as_float(r[i * 4 + 3]) + bv[i].w;
+                    }
+                    if (epi.act == NAVC_ACT_GELU_NEW) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = act_apply_fast(v[j], NAVC_ACT_GELU_NEW);
+                    } else if (epi.act != NAVC_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = act_apply_fast(v[j], epi.act);
+                    }
+                    if (epi.res_hi) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t hw[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
+                            const uint32_t lw[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                v[i * 8 + u * 2 + 0] += __uint_as_float(hw[u] << 16) + __uint_as_float(lw[u] << 16);
+                                v[i * 8 + u * 2 + 1] += __uint_as_float(hw[u] & 0xffff0000u) + __uint_as_float(lw[u] & 0xffff0000u);
+                            }
+                        }
+                    }
+                    if (rz) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+                    uint32_t hw[16], lw[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
+                    // the previous chunk's TMA stores must have finished reading the staging boxes
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        *reinterpret_cast<uint4*>(stg + lane * 64 + i * 16) = make_uint4(hw[i * 4], hw[i * 4 + 1], hw[i * 4 + 2], hw[i * 4 + 3]);
+                        if (epi.out_lo)
+                            *reinterpret_cast<uint4*>(stg + 2048 + lane * 64 + i * 16) = make_uint4(lw[i * 4], lw[i * 4 + 1], lw[i * 4 + 2], lw[i * 4 + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_o_hi, stg_s, col0, row0);
+                        if (epi.out_lo) tma_store_2d(&map_o_lo, stg_s + 2048u, col0, row0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else if constexpr (!kVocab) {
                 const bool row_ok = row < M;
                 const bool my_rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[row] == NAVC_PAD) : false;
                 const uint32_t rz_mask = __ballot_sync(0xffffffffu, my_rz);
@@ -333,6 +425,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     }
 
+    if constexpr (kEpi == kEpiPair) {
+        if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging stays valid until read
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -356,10 +451,12 @@ int tc_init() {
     NAVC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     NAVC_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "navc_init: cuTensorMapEncodeTiled not available");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, kEpiVocab>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, kEpiPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, kEpiVocab>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, kEpiPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
     g_tc_ready = true;
     return 0;
 }
@@ -377,7 +474,20 @@ int tc_make_map(CUtensorMap* map, const uint16_t* ptr, int rows, int K, int ld, 
     return 0;
 }
 
-template <bool kVocab>
+// 2-D bf16 tensor map for the epilogue's TMA stores: box = [32 rows, 32 columns], no swizzle.
+static int tc_make_store_map(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld) {
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ptr), gdim, gstride, box,
+                          estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NAVC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (store map) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return 0;
+}
+
+template <int kEpi>
 static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi,
                      const uint16_t* w_lo, int ldw, int M, int N, int K, const EpiParams& epi, const TcVocab& vep,
                      cudaStream_t st, const char* what) {
@@ -398,14 +508,19 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
+    CUtensorMap mo_hi = ma_hi, mo_lo = ma_hi;
+    if (kEpi == kEpiPair) {
+        if (tc_make_store_map(&mo_hi, epi.out_hi, M, N, epi.ld_out)) return 1;
+        if (epi.out_lo && tc_make_store_map(&mo_lo, epi.out_lo, M, N, epi.ld_out)) return 1;
+    }
     const int tiles = ((M + TBM - 1) / TBM) * ((N + TBN - 1) / TBN) * epi.split_k;
     int sms = navc_sm_count();
     if (sms <= 0) sms = 148;
     const int grid = tiles < sms ? tiles : sms;
     if (mode == NAVC_TC_BF16X3) {
-        gemm_tc_kernel<true, kVocab><<<grid, kTcThreads, TcCfg<true>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, epi, vep);
+        gemm_tc_kernel<true, kEpi><<<grid, kTcThreads, TcCfg<true>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, vep);
     } else {
-        gemm_tc_kernel<false, kVocab><<<grid, kTcThreads, TcCfg<false>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, epi, vep);
+        gemm_tc_kernel<false, kEpi><<<grid, kTcThreads, TcCfg<false>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, vep);
     }
     return check_launch(what);
 }
@@ -431,7 +546,14 @@ extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_
         p.split_k = (k_blocks + kpb - 1) / kpb;
     }
     TcVocab v = {};
-    return launch_tc<false>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
+    // fast path: bf16 pair outputs only, optional bf16 pair residual, everything 16-byte aligned
+    const bool pair = !p.accumulate && !p.out_f32 && !p.residual && p.out_hi && p.dbg != 9 && p.ld_out % 8 == 0 && N % 8 == 0 &&
+                      ((((uintptr_t)p.out_hi) | ((uintptr_t)p.out_lo)) & 15) == 0 && (((uintptr_t)p.bias) & 15) == 0 &&
+                      (!p.res_hi || (p.ld_res % 8 == 0 && ((((uintptr_t)p.res_hi) | ((uintptr_t)p.res_lo)) & 15) == 0));
+    NAVC_REQUIRE(pair || !p.res_hi, "navc_linear_tc: a bf16 hi/lo residual needs bf16-only outputs (no out_f32 / fp32 residual), "
+                                    "N %% 8 == 0 and 16-byte aligned operands");
+    if (pair) return launch_tc<kEpiPair>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
+    return launch_tc<kEpiGeneric>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
 }
 
 extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,
@@ -443,6 +565,6 @@ extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint
     TcVocab v = {bias, part_max, part_sum, part_idx, target, target_logit, (V + TBN / 2 - 1) / (TBN / 2)};
     EpiParams e = {};
     e.split_k = 1;
-    return launch_tc<true>(mode, h_hi, h_lo, ldh, w_hi, w_lo, ldw, M, V, K, e, v, as_stream(stream),
+    return launch_tc<kEpiVocab>(mode, h_hi, h_lo, ldh, w_hi, w_lo, ldw, M, V, K, e, v, as_stream(stream),
                            "navc_vocab_partials_tc");
 }

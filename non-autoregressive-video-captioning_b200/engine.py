@@ -188,16 +188,25 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # primitive wrappers
     # ------------------------------------------------------------------------------------------
-    def _new(self, M, N, f32, bf):
+    def _new(self, M, N, f32, bf, lo=False):
+        """lo=True forces the bf16 lo copy also in plain bf16 mode (residual stream: hi + lo carries the
+        fp32 value to ~2^-17 relative, so no fp32 copy of the stream has to be written or re-read)."""
         dev = self.device
         a = Act(M, N)
         if f32:
             a.f32 = torch.empty((M, N), dtype=torch.float32, device=dev)
         if bf and self.tc:
             a.hi = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
-            if self.precision == "bf16x3":
+            if self.precision == "bf16x3" or lo:
                 a.lo = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
         return a
+
+    def join_f32(self, a: Act) -> torch.Tensor:
+        """fp32 view of an activation kept as a bf16 hi/lo pair (API boundary only)."""
+        if a.f32 is None:
+            a.f32 = torch.empty((a.M, a.N), dtype=torch.float32, device=self.device)
+            L.call("navc_join_bf16", L.ptr(a.hi), L.ptr(a.lo), L.ptr(a.f32), a.M * a.N, L.stream())
+        return a.f32
 
     def from_f32(self, x2d: torch.Tensor, need_bf=True) -> Act:
         x2d = x2d.contiguous().float()
@@ -208,16 +217,28 @@ class Engine:
             L.call("navc_split_bf16", L.ptr(x2d), L.ptr(a.hi), L.ptr(a.lo), x2d.numel(), L.stream())
         return a
 
-    def linear(self, x: Act, lin: PackedLinear, act=0, residual: Optional[torch.Tensor] = None,
-               row_tokens: Optional[torch.Tensor] = None, f32=True, bf=True, tag=None) -> Act:
-        """nn.Linear + fused epilogue (include/navc.h navc_epilogue_t)."""
+    def linear(self, x: Act, lin: PackedLinear, act=0, residual=None,
+               row_tokens: Optional[torch.Tensor] = None, f32=True, bf=True, tag=None, lo=False) -> Act:
+        """nn.Linear + fused epilogue (include/navc.h navc_epilogue_t).  ``residual`` is an fp32 tensor
+        or an Act; an Act without an fp32 copy is passed as its bf16 hi/lo pair (tcgen05 pair epilogue)."""
         M, N, K = x.M, lin.N, lin.K
         assert x.N == K, (x.N, K)
         use_tc = self.tc and (K % 64 == 0) and x.hi is not None
-        out = self._new(M, N, f32 or not self.tc, bf)
-        ep = L.Epilogue(L.ptr(lin.b), L.ptr(residual), L.ptr(row_tokens), act,
-                        residual.shape[-1] if residual is not None else 0,
-                        L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), N, 0)
+        out = self._new(M, N, f32 or not self.tc, bf, lo)
+        res32 = res_hi = res_lo = None
+        ld_res = 0
+        if isinstance(residual, Act):
+            ld_res = residual.N
+            if residual.f32 is not None and (out.f32 is not None or not use_tc):
+                res32 = residual.f32
+            elif use_tc and out.f32 is None and residual.hi is not None:
+                res_hi, res_lo = residual.hi, residual.lo
+            else:
+                res32 = self.join_f32(residual)
+        elif residual is not None:
+            res32, ld_res = residual, residual.shape[-1]
+        ep = L.Epilogue(L.ptr(lin.b), L.ptr(res32), L.ptr(row_tokens), act, ld_res,
+                        L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), N, 0, 1, 0, L.ptr(res_hi), L.ptr(res_lo))
         timed = tag is not None and tag == self.profile_tag
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -240,10 +261,11 @@ class Engine:
                L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), L.stream())
         return out
 
-    def _proj_res(self, x: Act, lin, ln, residual, row_tokens) -> Act:
-        """dense -> (+residual) -> [LayerNorm] -> * non_pad_mask   (models/bert.py:192-200, 240-247, 271-299)"""
+    def _proj_res(self, x: Act, lin, ln, residual: Act, row_tokens, pair=False) -> Act:
+        """dense -> (+residual) -> [LayerNorm] -> * non_pad_mask   (models/bert.py:192-200, 240-247, 271-299).
+        pair: the residual stream lives as bf16 hi/lo pairs only (tensor-core modes without LayerNorm)."""
         if ln is None:
-            return self.linear(x, lin, residual=residual, row_tokens=row_tokens)
+            return self.linear(x, lin, residual=residual, row_tokens=row_tokens, f32=not pair, bf=True, lo=pair)
         y = self.linear(x, lin, residual=residual, row_tokens=None, f32=True, bf=False)
         return self.layernorm(y, ln, row_tokens)
 
@@ -335,7 +357,7 @@ class Engine:
         return mem["kv"].f32
 
     def decoder_pass(self, tokens: torch.Tensor, mem: dict, group: int, category: Optional[torch.Tensor],
-                     decoding_type: str, want_attn=False):
+                     decoding_type: str, want_attn=False, want_f32=False):
         """One BertDecoder forward (models/Decoder.py:96-178) -> hidden Act [N*S, D] (+ attention probs)."""
         P, D, H = self.P, self.D, self.H
         N, S = tokens.shape
@@ -351,7 +373,11 @@ class Engine:
                 extra = mem["enc_mean"]
             elif ei != 0:
                 raise NotImplementedError("enhance_input=1 fails in the reference itself (SURVEY 8c)")
-        x = self._new(R, D, True, True)
+        # residual stream as bf16 hi/lo pairs only (no fp32 copy written / re-read) when every GEMM of the
+        # layer runs on the tensor cores and no per-sublayer LayerNorm needs the fp32 rows
+        pair = self.tc and D % 64 == 0 and P["layers"][0]["f1"].N % 64 == 0 and \
+            all(lw[k] is None for lw in P["layers"] for k in ("so_ln", "co_ln", "f2_ln"))
+        x = self._new(R, D, not pair, True, lo=pair)
         L.call("navc_embed_ln", L.ptr(tokens), L.ptr(category), L.ptr(emb["word"]), L.ptr(emb["pos"]), L.ptr(emb["cat"]),
                L.ptr(extra), group, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), self.eps, N, S, D,
                L.ptr(x.f32), L.ptr(x.hi), L.ptr(x.lo), L.stream())
@@ -371,7 +397,7 @@ class Engine:
                 p_self = torch.empty((H, N, S, S), dtype=torch.float32, device=self.device) if want_attn else None
                 L.call("navc_self_attention", L.ptr(qkv.f32), 3 * D, L.ptr(tokens), N, S, D, H, mask_kind,
                        watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.ptr(p_self), L.stream())
-            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x.f32, tok_flat)
+            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tok_flat, pair)
             q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn)
             ctx2 = self._new(R, D, not self.tc, True)
             if tc_attn:
@@ -384,11 +410,13 @@ class Engine:
                 kv_l = self._kv_f32(mem)[:, l * 2 * D:]
                 L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, S, E, D, H, group,
                        L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
-            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a.f32, tok_flat)
+            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair)
             h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1")
-            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c.f32, tok_flat)
+            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair)
             if want_attn:
                 attns.append((p_self, p_cross))
+        if want_f32:
+            self.join_f32(x)
         return x, attns
 
     # ------------------------------------------------------------------------------------------

@@ -51,7 +51,7 @@ class BertDecoder(nn.Module):
             tgt_seq = tgt_seq.contiguous()
             mem = eng.memory(enc_output.contiguous().float(), getattr(enc_output, "_navc_cache", None))
             cat = category.contiguous() if category is not None else None
-            hid, attns = eng.decoder_pass(tgt_seq, mem, 1, cat, decoding_type, want_attn=output_attentions)
+            hid, attns = eng.decoder_pass(tgt_seq, mem, 1, cat, decoding_type, want_attn=output_attentions, want_f32=True)
             N, S = tgt_seq.shape
             hidden = hid.f32.view(N, S, -1)
             non_pad = tgt_seq.ne(Constants.PAD).float().unsqueeze(-1)
