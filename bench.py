@@ -132,7 +132,7 @@ def run_reference(args, opt, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="navc")
     ap.add_argument("--precision", default=os.environ.get("NAVC_PRECISION", "bf16x3"))
@@ -182,28 +182,55 @@ def main():
         hyp, _ = tr.translate_batch(enc, category, None, {})
         return hyp
 
-    def step_e2e(i):
+    # e2e: host -> device copies of step i+1 run on a copy stream into a second device buffer while
+    # step i computes (every step's H2D copy and D2H read stay inside the timed region)
+    copy_stream = torch.cuda.Stream()
+    slots = [([torch.empty_like(f) for f in devin[0][0]], torch.empty_like(devin[0][1])) for _ in range(2)]
+    pending = {}
+
+    def issue_copy(i):
         feats_h, cat_h = host[i % n_rot]
-        feats = [f.to(dev, non_blocking=True) for f in feats_h]
-        category = cat_h.to(dev, non_blocking=True)
+        feats_d, cat_d = slots[i % 2]
+        if i in pending:
+            return
+        with torch.cuda.stream(copy_stream):
+            for d, h in zip(feats_d, feats_h):
+                d.copy_(h, non_blocking=True)
+            cat_d.copy_(cat_h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        pending[i] = ev
+
+    def step_e2e(i):
+        if i not in pending:
+            issue_copy(i)
+        torch.cuda.current_stream().wait_event(pending.pop(i))
+        feats, category = slots[i % 2]
         enc = model.encode(feats=feats)
         hyp, _ = tr.translate_batch(enc, category, None, {})
-        return hyp.cpu()
+        issue_copy(i + 1)        # slot (i+1)%2 was last read by step i-1, which has completed (its ids were read back)
+        return hyp.cpu()         # device -> host read of this step's result (synchronises)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_ms = {}
+
     def timed(fn, steps):
+        for i in range(3):  # untimed settle steps of this very loop (PCIe / copy engine / clocks after the idle gap)
+            fn(-3 + i)
+        pending.clear()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        marks[0].record()
         for i in range(steps):
             out = fn(i)
-        e1.record()
+            marks[i + 1].record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = marks[0].elapsed_time(marks[steps])
+        step_ms[fn.__name__] = [round(marks[i].elapsed_time(marks[i + 1]), 2) for i in range(steps)]
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -224,8 +251,12 @@ def main():
         ms, hyp = timed(step_resident, args.steps)
         launches = L.launches - launches0
         stats = dict(navc_b200.generate.last_stats)
+        step_ms["resident"] = step_ms.pop("step_resident")
         # ---- timed region 2: end to end from host buffers ----
+        pending.clear()
+        torch.cuda.synchronize()
         ms_e2e, hyp_host = timed(step_e2e, args.steps)
+        pending.clear()
         # ---- region 3: the same steps launched eagerly (graph replay off) with CUDA events around
         # every FFN up-projection GEMM launch: per-launch duration of the dominant kernel ----
         tr.opt = dict(opt, navc_graphs=False)
@@ -277,7 +308,8 @@ def main():
                            "l2": "inputs rotate over %d distinct batches (%d MB of features > 126 MB L2)" % (n_rot, n_rot * h2d >> 20)},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+                "per_step_ms": {"resident": step_ms.get("resident"), "e2e": step_ms.get("step_e2e")}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -19,17 +19,22 @@
 
 namespace navc {
 
-constexpr int TBM = 128, TBN = 256, TBK = 64;        // CTA tile; TBK bf16 = one 128-byte swizzle row
-constexpr int kEpiWarps = 8;
-constexpr int kTcThreads = 64 + 32 * kEpiWarps;
-constexpr int kStageFloats = 32 * 32;                // per-epilogue-warp transpose buffer (4 KB)
+constexpr int TBM = 128, TBK = 64;   // CTA tile rows; TBK bf16 = one 128-byte swizzle row
+constexpr int kVocabBN = 256;        // the vocabulary epilogue always uses 256-wide tiles
+// Tile width TBN is a template parameter: 256 by default, 128 when the 256-wide tiling would leave
+// a large part of the last wave of the persistent grid empty (e.g. N = 512: 336 tiles on 148 SMs).
+constexpr int kEpiWarps = 8;                         // generic / vocabulary epilogues
+constexpr int kPairEpiWarps = 16;                    // pair epilogue: 4 warps per scheduler to hide its latencies
+constexpr int kStageFloats = 32 * 32;                // per-epilogue-warp transpose buffer (4 KB); 2 KB per warp in pair mode
+__host__ __device__ constexpr int tc_epi_warps(int epi) { return epi == 2 ? kPairEpiWarps : kEpiWarps; }
+__host__ __device__ constexpr int tc_threads(int epi) { return 64 + 32 * tc_epi_warps(epi); }
 constexpr int kTileABytes = TBM * TBK * 2;           // 16 KB
-constexpr int kTileBBytes = TBN * TBK * 2;           // 32 KB
 constexpr int kAccStages = 2;                        // 2 x 256 TMEM columns
 constexpr int kTmemCols = 512;
 
-template <bool kX3> struct TcCfg {
-    static constexpr int kStages = kX3 ? 2 : 4;
+template <bool kX3, int TBN> struct TcCfg {
+    static constexpr int kTileBBytes = TBN * TBK * 2;    // 32 KB (TBN = 256) / 16 KB (TBN = 128)
+    static constexpr int kStages = (kX3 ? 2 : 4) * (TBN == 128 ? 3 : 2) / 2;   // 192 KB ring in every variant
     static constexpr int kStageBytes = (kX3 ? 2 : 1) * (kTileABytes + kTileBBytes);
     static constexpr int kRingBytes = kStages * kStageBytes;
     static constexpr int kSmemBytes = kRingBytes + kEpiWarps * kStageFloats * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -50,14 +55,15 @@ struct TcVocab {
 //       TMA stores, bf16 hi+lo residual): the inference fast path.
 constexpr int kEpiGeneric = 0, kEpiVocab = 1, kEpiPair = 2;
 
-template <bool kX3, int kEpi>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <bool kX3, int kEpi, int TBN>
+__global__ void __launch_bounds__(tc_threads(kEpi), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                int M, int N, int K, EpiParams epi, TcVocab vep) {
     constexpr bool kVocab = kEpi == kEpiVocab;
-    using Cfg = TcCfg<kX3>;
+    using Cfg = TcCfg<kX3, TBN>;
+    constexpr int kTileBBytes = Cfg::kTileBBytes;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -80,7 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), tc_epi_warps(kEpi)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -171,42 +177,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int n0 = nb * TBN + half * (TBN / 2);
 
             if constexpr (kEpi == kEpiPair) {
-                // ---- pair epilogue: lane = row, 32-column chunks, TMA stores of [32 x 32] bf16 boxes ----
-                const bool row_ok = row < M;
-                const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[row] == NAVC_PAD) : false;
-                uint8_t* stg = reinterpret_cast<uint8_t*>(stage);   // hi box at +0, lo box at +2048
+                // ---- pair epilogue: 16 warps; warp = (TMEM lane quarter, column group of TBN/4); lane = row;
+                //      16-column steps; outputs leave through TMA stores of [32 rows x 16 cols] bf16 boxes ----
+                constexpr int GW = TBN / 4;
+                const int grp = ew >> 2;
+                const int rowp = row0 + lane;
+                const bool row_ok = rowp < M;
+                const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[rowp] == NAVC_PAD) : false;
+                uint8_t* stg = reinterpret_cast<uint8_t*>(stage_all) + ew * 2048;   // hi box at +0, lo box at +1024
                 const uint32_t stg_s = smem_u32(stg);
+                const int ng0 = nb * TBN + grp * GW;
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + half * (TBN / 2));
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + grp * GW);
 #pragma unroll 1
-                for (int c = 0; c < TBN / 64; ++c) {
-                    const int col0 = n0 + c * 32;
+                for (int c = 0; c < GW / 16; ++c) {
+                    const int col0 = ng0 + c * 16;
                     if (col0 >= N) break;  // warp-uniform
-                    uint32_t r[32];
-                    tc_ld32(t_row + (uint32_t)(c * 32), r);
-                    // operands of this chunk (requested before the TMEM wait)
-                    float4 bv[8];
-                    uint4 rh[4], rl[4];
+                    uint32_t r[16];
+                    tc_ld16(t_row + (uint32_t)(c * 16), r);
+                    // operands of this step (requested before the TMEM wait)
+                    float4 bv[4];
+                    uint4 rh[2], rl[2];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (epi.bias && col0 + i * 4 < N) bv[i] = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + i * 4));
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 2; ++i) {
                         rh[i] = make_uint4(0u, 0u, 0u, 0u);
                         rl[i] = make_uint4(0u, 0u, 0u, 0u);
                         if (epi.res_hi && row_ok && col0 + i * 8 < N) {
-                            const size_t ro = (size_t)row * epi.ld_res + col0 + i * 8;
+                            const size_t ro = (size_t)rowp * epi.ld_res + col0 + i * 8;
                             rh[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
                             if (epi.res_lo) rl[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
                         }
                     }
                     tc_wait_ld();
-                    float v[32];
+                    float v[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         v[i * 4 + 0] = __uint_as_float(r[i * 4 + 0]) + bv[i].x;
                         v[i * 4 + 1] = __uint_as_float(r[i * 4 + 1]) + bv[i].y;
                         v[i * 4 + 2] = __uint_as_float(r[i * 4 + 2]) + bv[i].z;
@@ -214,44 +225,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                     if (epi.act == NAVC_ACT_GELU_NEW) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = act_apply_fast(v[j], NAVC_ACT_GELU_NEW);
+                        for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], NAVC_ACT_GELU_NEW);
                     } else if (epi.act != NAVC_ACT_NONE) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = act_apply_fast(v[j], epi.act);
+                        for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], epi.act);
                     }
                     if (epi.res_hi) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint32_t hw[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
-                            const uint32_t lw[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
+                        for (int i = 0; i < 2; ++i) {
+                            const uint32_t hw_[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
+                            const uint32_t lw_[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                v[i * 8 + u * 2 + 0] += __uint_as_float(hw[u] << 16) + __uint_as_float(lw[u] << 16);
-                                v[i * 8 + u * 2 + 1] += __uint_as_float(hw[u] & 0xffff0000u) + __uint_as_float(lw[u] & 0xffff0000u);
+                                v[i * 8 + u * 2 + 0] += __uint_as_float(hw_[u] << 16) + __uint_as_float(lw_[u] << 16);
+                                v[i * 8 + u * 2 + 1] += __uint_as_float(hw_[u] & 0xffff0000u) + __uint_as_float(lw_[u] & 0xffff0000u);
                             }
                         }
                     }
                     if (rz) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
                     }
-                    uint32_t hw[16], lw[16];
+                    uint32_t hw[8], lw[8];
+                    if (epi.out_lo) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
-                    // the previous chunk's TMA stores must have finished reading the staging boxes
+                        for (int j = 0; j < 8; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            hw[j] = *reinterpret_cast<const uint32_t*>(&hb);
+                        }
+                    }
+                    // the previous step's TMA stores must have finished reading the staging boxes
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        *reinterpret_cast<uint4*>(stg + lane * 64 + i * 16) = make_uint4(hw[i * 4], hw[i * 4 + 1], hw[i * 4 + 2], hw[i * 4 + 3]);
-                        if (epi.out_lo)
-                            *reinterpret_cast<uint4*>(stg + 2048 + lane * 64 + i * 16) = make_uint4(lw[i * 4], lw[i * 4 + 1], lw[i * 4 + 2], lw[i * 4 + 3]);
+                    *reinterpret_cast<uint4*>(stg + lane * 32) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(stg + lane * 32 + 16) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                    if (epi.out_lo) {
+                        *reinterpret_cast<uint4*>(stg + 1024 + lane * 32) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        *reinterpret_cast<uint4*>(stg + 1024 + lane * 32 + 16) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
                         tma_store_2d(&map_o_hi, stg_s, col0, row0);
-                        if (epi.out_lo) tma_store_2d(&map_o_lo, stg_s + 2048u, col0, row0);
+                        if (epi.out_lo) tma_store_2d(&map_o_lo, stg_s + 1024u, col0, row0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -451,12 +470,14 @@ int tc_init() {
     NAVC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     NAVC_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "navc_init: cuTensorMapEncodeTiled not available");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, kEpiVocab>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, kEpiPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kSmemBytes));
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, kEpiVocab>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, kEpiPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kSmemBytes));
+#define NAVC_TC_ATTR(X3, EPI, BN) \
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<X3, EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<X3, BN>::kSmemBytes))
+    NAVC_TC_ATTR(false, kEpiGeneric, 256); NAVC_TC_ATTR(true, kEpiGeneric, 256);
+    NAVC_TC_ATTR(false, kEpiGeneric, 128); NAVC_TC_ATTR(true, kEpiGeneric, 128);
+    NAVC_TC_ATTR(false, kEpiPair, 256); NAVC_TC_ATTR(true, kEpiPair, 256);
+    NAVC_TC_ATTR(false, kEpiPair, 128); NAVC_TC_ATTR(true, kEpiPair, 128);
+    NAVC_TC_ATTR(false, kEpiVocab, 256); NAVC_TC_ATTR(true, kEpiVocab, 256);
+#undef NAVC_TC_ATTR
     g_tc_ready = true;
     return 0;
 }
@@ -474,11 +495,11 @@ int tc_make_map(CUtensorMap* map, const uint16_t* ptr, int rows, int K, int ld, 
     return 0;
 }
 
-// 2-D bf16 tensor map for the epilogue's TMA stores: box = [32 rows, 32 columns], no swizzle.
+// 2-D bf16 tensor map for the epilogue's TMA stores: box = [32 rows, 16 columns], no swizzle.
 static int tc_make_store_map(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld) {
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t box[2] = {16u, 32u};
     cuuint32_t estride[2] = {1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ptr), gdim, gstride, box,
                           estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -487,17 +508,15 @@ static int tc_make_store_map(CUtensorMap* map, const uint16_t* ptr, int rows, in
     return 0;
 }
 
-template <int kEpi>
-static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi,
-                     const uint16_t* w_lo, int ldw, int M, int N, int K, const EpiParams& epi, const TcVocab& vep,
-                     cudaStream_t st, const char* what) {
-    NAVC_REQUIRE(g_tc_ready, "%s: navc_init() has not been called", what);
-    NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "%s: bad mode %d", what, mode);
-    NAVC_REQUIRE(x_hi && w_hi && (mode == NAVC_TC_BF16 || (x_lo && w_lo)), "%s: null operand", what);
-    NAVC_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0,
-                 "%s: need K%%8==0 and ld%%8==0 (M=%d N=%d K=%d ldx=%d ldw=%d)", what, M, N, K, ldx, ldw);
-    NAVC_REQUIRE((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0,
-                 "%s: operands must be 16-byte aligned", what);
+static int tile_waste_pct(int tiles, int sms) {  // idle share of the last wave of a persistent grid, in percent
+    const int waves = (tiles + sms - 1) / sms;
+    return 100 - (100 * tiles) / (waves * sms);
+}
+
+template <int kEpi, int TBN>
+static int launch_tc_bn(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi,
+                        const uint16_t* w_lo, int ldw, int M, int N, int K, const EpiParams& epi, const TcVocab& vep,
+                        cudaStream_t st, const char* what) {
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     if (tc_make_map(&ma_hi, x_hi, M, K, ldx, TBM)) return 1;
     if (tc_make_map(&mb_hi, w_hi, N, K, ldw, TBN)) return 1;
@@ -518,18 +537,42 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
     if (sms <= 0) sms = 148;
     const int grid = tiles < sms ? tiles : sms;
     if (mode == NAVC_TC_BF16X3) {
-        gemm_tc_kernel<true, kEpi><<<grid, kTcThreads, TcCfg<true>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, vep);
+        gemm_tc_kernel<true, kEpi, TBN><<<grid, tc_threads(kEpi), TcCfg<true, TBN>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, vep);
     } else {
-        gemm_tc_kernel<false, kEpi><<<grid, kTcThreads, TcCfg<false>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, vep);
+        gemm_tc_kernel<false, kEpi, TBN><<<grid, tc_threads(kEpi), TcCfg<false, TBN>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, vep);
     }
     return check_launch(what);
+}
+
+template <int kEpi>
+static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi,
+                     const uint16_t* w_lo, int ldw, int M, int N, int K, const EpiParams& epi, const TcVocab& vep,
+                     cudaStream_t st, const char* what) {
+    NAVC_REQUIRE(g_tc_ready, "%s: navc_init() has not been called", what);
+    NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "%s: bad mode %d", what, mode);
+    NAVC_REQUIRE(x_hi && w_hi && (mode == NAVC_TC_BF16 || (x_lo && w_lo)), "%s: null operand", what);
+    NAVC_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0,
+                 "%s: need K%%8==0 and ld%%8==0 (M=%d N=%d K=%d ldx=%d ldw=%d)", what, M, N, K, ldx, ldw);
+    NAVC_REQUIRE((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0,
+                 "%s: operands must be 16-byte aligned", what);
+    if constexpr (kEpi != kEpiVocab) {
+        // 128-wide tiles when they fill the last wave of the persistent grid markedly better
+        int sms = navc_sm_count();
+        if (sms <= 0) sms = 148;
+        const int mt = (M + TBM - 1) / TBM;
+        const int t256 = mt * ((N + 255) / 256) * epi.split_k, t128 = mt * ((N + 127) / 128) * epi.split_k;
+        const int forced = epi.dbg >= 128 ? epi.dbg : 0;  // profiling aid: reserved = 128 / 256 forces a tile width
+        const bool narrow = forced ? forced == 128 : (N <= 128 || tile_waste_pct(t256, sms) >= tile_waste_pct(t128, sms) + 8);
+        if (narrow) return launch_tc_bn<kEpi, 128>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, vep, st, what);
+    }
+    return launch_tc_bn<kEpi, 256>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, vep, st, what);
 }
 
 }  // namespace navc
 
 using namespace navc;
 
-extern "C" int navc_vocab_tile(int tc) { return tc ? TBN / 2 : 128; }
+extern "C" int navc_vocab_tile(int tc) { return tc ? kVocabBN / 2 : 128; }
 
 extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi,
                               const uint16_t* w_lo, int ldw, int M, int N, int K, const navc_epilogue_t* e,
@@ -562,7 +605,7 @@ extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint
                                       const int64_t* target, float* target_logit, void* stream) {
     NAVC_REQUIRE(part_max && part_sum && part_idx, "navc_vocab_partials_tc: null output");
     NAVC_REQUIRE(!target || target_logit, "navc_vocab_partials_tc: target without target_logit");
-    TcVocab v = {bias, part_max, part_sum, part_idx, target, target_logit, (V + TBN / 2 - 1) / (TBN / 2)};
+    TcVocab v = {bias, part_max, part_sum, part_idx, target, target_logit, (V + kVocabBN / 2 - 1) / (kVocabBN / 2)};
     EpiParams e = {};
     e.split_k = 1;
     return launch_tc<kEpiVocab>(mode, h_hi, h_lo, ldh, w_hi, w_lo, ldw, M, V, K, e, v, as_stream(stream),
