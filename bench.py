@@ -58,9 +58,11 @@ class ClockSampler:
         self.index, self.samples, self.proc = index, [], None
 
     def start(self):
+        if os.environ.get("NAVC_NO_SAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None

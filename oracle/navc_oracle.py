@@ -521,3 +521,73 @@ def translate(sd, opt, feats, category, teacher=None, length_bias=0, return_deta
         enc = encode(sd, opt, feats)
         t_enc = encode(teacher[0], teacher[1], feats) if teacher is not None else None
         return generate(sd, opt, enc, category, teacher, t_enc, length_bias, return_details)
+
+
+# ----------------------------------------------------------------------------------------------
+# autoregressive beam search (models/Translator.py:94-161 + models/Beam.py), per video
+# ----------------------------------------------------------------------------------------------
+def ar_beam_search(sd, opt, encoder_outputs, category):
+    """Restates Translator.translate_batch_ARFormer with Beam (ARFormer branch): returns
+    (hyps[b][n] token lists without BOS, scores[b][n]) for n < topk."""
+    n_bm, max_len = int(opt["beam_size"]), int(opt["max_len"])
+    n_sents = max(n_bm, int(opt.get("topk", 1)))
+    enc = encoder_outputs["enc_output"]
+    B = enc.shape[0]
+    all_h, all_s = [], []
+    for b in range(B):
+        e = enc[b:b + 1].expand(n_bm, -1, -1)
+        c = category[b:b + 1].expand(n_bm, -1)
+        scores = torch.zeros(n_bm)
+        next_ys = [torch.full((n_bm,), PAD, dtype=torch.long)]
+        next_ys[0][0] = BOS
+        prev_ks, finished, done = [], [], False
+        for t in range(1, max_len):
+            if len(next_ys) == 1:
+                seq = next_ys[0].unsqueeze(1)
+            else:
+                hyps = []
+                for k in range(n_bm):
+                    h, kk = [], k
+                    for j in range(len(prev_ks) - 1, -1, -1):
+                        h.append(int(next_ys[j + 1][kk]))
+                        kk = int(prev_ks[j][kk])
+                    hyps.append([BOS] + h[::-1])
+                seq = torch.tensor(hyps, dtype=torch.long)
+            hid, _, _ = decoder_forward(sd, opt, seq, e, c)
+            logp = torch.log_softmax(vocab_logits(sd, hid[:, -1, :]), dim=1)  # Translator.py:108-114
+            V = logp.shape[1]
+            if prev_ks:
+                lk = logp + scores.unsqueeze(1)
+                lk[next_ys[-1].eq(EOS)] = -1e20
+            else:
+                lk = logp[0]
+            best, ids = lk.reshape(-1).topk(n_bm, 0, True, True)
+            scores = best
+            pk = ids // V
+            prev_ks.append(pk)
+            next_ys.append(ids - pk * V)
+            for i in range(n_bm):
+                if int(next_ys[-1][i]) == EOS:
+                    finished.append([float(scores[i]), len(next_ys) - 1, i])
+                    if len(finished) >= n_sents:
+                        done = True
+                        break
+            if not done and len(next_ys) == max_len:
+                done = True
+                if not finished:
+                    for i in range(n_bm):
+                        finished.append([float(scores[i]), len(next_ys) - 1, i])
+            if done:
+                break
+        alpha = opt.get("beam_alpha", 1.0)
+        items = sorted(([sc / (t ** alpha), t, k] for sc, t, k in finished), key=lambda a: -a[0])[:int(opt.get("topk", 1))]
+        hs = []
+        for _, t, k in items:
+            h = []
+            for j in range(t - 1, -1, -1):
+                h.append(int(next_ys[j + 1][k]))
+                k = int(prev_ks[j][k])
+            hs.append(h[::-1])
+        all_h.append(hs)
+        all_s.append([it[0] for it in items])
+    return all_h, all_s

@@ -207,3 +207,29 @@ def test_graph_replay_matches_eager(precision):
         model.tgt_word_prj.weight.mul_(1.0)  # bumps the version -> repack -> graphs dropped
     model.engine.sync_weights()
     assert not model.engine.graphs
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_ar_beam_search_matches_oracle(precision):
+    """Translator.translate_batch for an ARFormer model (beam search; reference Translator.py:94-161)."""
+    opt = cases.small("ARB", beam_size=3, topk=2, beam_alpha=1.0)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = cases.synth_state_dict(shapes, 5)
+    model.load_state_dict(sd)
+    model.to(DEV).eval()
+    model.set_precision(precision)
+    feats, category = cases.synth_inputs(opt, 5)
+    tr = navc_b200.Translator(model, opt, device=DEV)
+    with torch.no_grad():
+        enc = model.encode(feats=to_dev(feats))
+        hyps, scores = tr.translate_batch(enc, category.to(DEV), None, {})
+        o_h, o_s = O.ar_beam_search(sd, opt, O.encode(sd, opt, feats), category)
+    assert len(hyps) == 5 and all(len(h) == len(o) for h, o in zip(hyps, o_h))
+    for b in range(5):
+        for n in range(len(o_h[b])):
+            gap = abs(o_s[b][0] - o_s[b][1]) if len(o_s[b]) > 1 else 1.0
+            assert abs(scores[b][n] - o_s[b][n]) < 2e-3, (b, n, scores[b][n], o_s[b][n])
+            if gap > 1e-2:  # ranking decided by a clear margin -> identical token ids
+                assert hyps[b][n] == o_h[b][n], (b, n)

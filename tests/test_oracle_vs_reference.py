@@ -138,3 +138,25 @@ def test_criterion_matches_reference():
             ref_loss = crit.get_loss(res)
     mine = O.criterion(opt, res, [toks["labels_1"], toks["labels"]], toks["length_target"])
     torch.testing.assert_close(mine, ref_loss, rtol=1e-6, atol=1e-6)
+
+
+def test_ar_beam_search_matches_reference():
+    """Translator.translate_batch_ARFormer + Beam (models/Translator.py:94-161, models/Beam.py) vs the
+    oracle's restatement: same hypotheses, same length-normalised scores."""
+    opt = cases.small("ARB", beam_size=3, topk=2, beam_alpha=1.0)
+    model = refutil.ref_get_model(opt)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    feats, category = cases.synth_inputs(opt, 4)
+    with refutil.reference_on_path():
+        from models.Translator import Translator
+        tr = Translator(model, dict(opt), device=torch.device("cpu"))
+        with torch.no_grad():
+            enc = model.encode(feats=[f.clone() for f in feats])
+            ref_h, ref_s = tr.translate_batch(enc, category, None, {})
+    with torch.no_grad():
+        mine_h, mine_s = O.ar_beam_search(sd, opt, O.encode(sd, opt, feats), category)
+    assert mine_h == ref_h
+    for a, b in zip(mine_s, ref_s):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert abs(x - float(y)) < 1e-4
