@@ -319,6 +319,24 @@ int navc_embed_ln_bwd(const float* dout, const int64_t* tokens, const int64_t* c
                       int N, int S, int D, float* d_word, float* d_pos, float* d_cat, float* d_extra,
                       float* d_ln_w, float* d_ln_b, void* stream);
 
+/* Fused cross-entropy (projection + log-softmax + masked NLL, seq2seq.py:102-103 + misc/crit.py:62-84)
+ * without a [rows, V] log-prob tensor.  Forward: navc_vocab_partials_* with target = labels, then
+ * navc_ce_stats: lse[r], nll[r] = lse - logit[label] (0 where label == PAD), argmax[r].  Backward, per
+ * row chunk: logits chunk (GEMM) -> navc_ce_grad in place: (softmax - onehot) * scale[0] * (label != PAD),
+ * pad columns zeroed -> the usual gradient GEMMs.  `scale` is a device scalar (upstream gradient). */
+int navc_ce_stats(const float* part_max, const float* part_sum, const int32_t* part_idx, int n_tiles,
+                  const float* target_logit, const int64_t* labels, int R, float* lse, float* nll,
+                  int32_t* argmax, void* stream);
+int navc_ce_grad(float* logits, const float* lse, const int64_t* labels, const float* scale, int rows,
+                 int V, int ld, void* stream);
+
+/* Fused clip_grad_value_ + Adam with L2 weight decay over flat fp32 buffers (misc/run.py:260-261,
+ * misc/optim.py:61-62; torch.optim.Adam semantics, bias correction by `step` >= 1):
+ *   g = clamp(g, -clip, clip) (clip <= 0: off); g += wd*p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).   One launch per optimizer step. */
+int navc_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float clip, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* Attention backward (softmax recomputed from Q, K; masks as the forward).  Self: d_qkv [N*S, ld]
  * receives dQ | dK | dV at column offsets 0, D, 2D.  Cross: d_q [N*S, ld_dq]; d_kv [(N/group)*E,
  * ld_dkv] receives dK | dV at 0, D summed over the `group` rows of each video. */

@@ -80,6 +80,9 @@ _PROTOS = {
     "navc_log_softmax_bwd": [vp, vp, i32, i32, i32, vp, i32, vp],
     "navc_layernorm_bwd": [vp, vp, vp, f32, vp, i32, i32, vp, vp, vp, vp],
     "navc_embed_ln_bwd": [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+    "navc_ce_stats": [vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp],
+    "navc_ce_grad": [vp, vp, vp, vp, i32, i32, i32, vp],
+    "navc_clip_adam": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i32, vp],
     "navc_self_attention_bwd": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
     "navc_cross_attention_bwd": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, vp],
 }

@@ -538,6 +538,79 @@ __global__ void embed_ln_bwd_kernel(const float* __restrict__ dout, const int64_
     }
 }
 
+// ---- fused cross-entropy (seq2seq.py:102-103 + misc/crit.py:62-84 without the [rows, V] log-prob tensor) ----
+// one thread per row: combine the vocabulary partials of navc_vocab_partials_* into lse / nll / argmax
+__global__ void ce_stats_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const int32_t* __restrict__ pi,
+                                int nt, const float* __restrict__ tl, const int64_t* __restrict__ labels, int R,
+                                float* __restrict__ lse, float* __restrict__ nll, int32_t* __restrict__ arg) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float m = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int t = 0; t < nt; ++t) {
+        const float v = pm[(size_t)r * nt + t];
+        const int i = pi[(size_t)r * nt + t];
+        if (v > m || (v == m && i < idx)) { m = v; idx = i; }
+    }
+    float s = 0.f;
+    for (int t = 0; t < nt; ++t) {
+        const float q = ps[(size_t)r * nt + t];
+        if (q != 0.f) s += q * expf(pm[(size_t)r * nt + t] - m);
+    }
+    const float l = m + logf(s);
+    lse[r] = l;
+    nll[r] = (labels[r] == NAVC_PAD) ? 0.f : l - tl[r];
+    arg[r] = idx;
+}
+// block per row, in place: logits -> (softmax - onehot(label)) * scale[0] * (label != PAD); columns V..ld-1 zero
+__global__ void ce_grad_kernel(float* __restrict__ logits, const float* __restrict__ lse,
+                               const int64_t* __restrict__ labels, const float* __restrict__ scale, int V, int ld) {
+    float* row = logits + (size_t)blockIdx.x * ld;
+    const int64_t lab = labels[blockIdx.x];
+    const float g = (lab == NAVC_PAD) ? 0.f : scale[0];
+    const float l = lse[blockIdx.x];
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+        float v = 0.f;
+        if (i < V && g != 0.f) v = (expf(row[i] - l) - ((int64_t)i == lab ? 1.f : 0.f)) * g;
+        row[i] = v;
+    }
+}
+
+// ---- fused clip + Adam (misc/run.py:260-261, misc/optim.py:61-62: torch.optim.Adam with L2 weight decay) ----
+__global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, int64_t n, float clip, float lr_over_bc1, float b1, float b2,
+                                 float eps, float wd, float inv_sqrt_bc2) {
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (int64_t)gridDim.x * blockDim.x * 4) {
+        if (i + 4 <= n) {
+            float4 pp = *reinterpret_cast<const float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
+            float4 mm = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i);
+            float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float gr = ga[k];
+                if (clip > 0.f) gr = fminf(fmaxf(gr, -clip), clip);       // clip_grad_value_
+                gr = fmaf(wd, pa[k], gr);                                  // L2 weight decay
+                ma[k] = fmaf(1.0f - b1, gr - ma[k], ma[k]);                // exp_avg.lerp_(grad, 1 - beta1)
+                va[k] = fmaf(1.0f - b2, gr * gr, b2 * va[k]);
+                const float denom = sqrtf(va[k]) * inv_sqrt_bc2 + eps;
+                pa[k] -= lr_over_bc1 * (ma[k] / denom);
+            }
+            *reinterpret_cast<float4*>(p + i) = pp;
+            *reinterpret_cast<float4*>(m + i) = mm;
+            *reinterpret_cast<float4*>(v + i) = vv;
+        } else {
+            for (int64_t j = i; j < n; ++j) {
+                float gr = g[j];
+                if (clip > 0.f) gr = fminf(fmaxf(gr, -clip), clip);
+                gr = fmaf(wd, p[j], gr);
+                m[j] = fmaf(1.0f - b1, gr - m[j], m[j]);
+                v[j] = fmaf(1.0f - b2, gr * gr, b2 * v[j]);
+                p[j] -= lr_over_bc1 * (m[j] / (sqrtf(v[j]) * inv_sqrt_bc2 + eps));
+            }
+        }
+    }
+}
+
 // ---- attention backward ----------------------------------------------------------------------------------------
 // grid (G, H), 256 threads.  Block (g, h) owns the Sk key/value rows of owner g and its NQ query
 // rows (self: NQ = Sk = S, owner = sequence; cross: NQ = group * S, owner = video), processed in
@@ -966,6 +1039,33 @@ extern "C" int navc_embed_ln_bwd(const float* dout, const int64_t* tokens, const
         dout, tokens, category, word_emb, pos_emb, cat_emb, extra, group, ln_w, eps, R, S, D, d_word, d_pos,
         cat_emb ? d_cat : nullptr, extra ? d_extra : nullptr, d_ln_w, d_ln_b);
     return check_launch("navc_embed_ln_bwd");
+}
+
+extern "C" int navc_ce_stats(const float* part_max, const float* part_sum, const int32_t* part_idx, int n_tiles,
+                             const float* target_logit, const int64_t* labels, int R, float* lse, float* nll,
+                             int32_t* argmax, void* stream) {
+    NAVC_REQUIRE(part_max && part_sum && part_idx && target_logit && labels && lse && nll && argmax && R > 0 && n_tiles > 0,
+                 "navc_ce_stats: bad arguments");
+    ce_stats_kernel<<<(R + 127) / 128, 128, 0, as_stream(stream)>>>(part_max, part_sum, part_idx, n_tiles, target_logit, labels,
+                                                                    R, lse, nll, argmax);
+    return check_launch("navc_ce_stats");
+}
+
+extern "C" int navc_ce_grad(float* logits, const float* lse, const int64_t* labels, const float* scale, int rows, int V,
+                            int ld, void* stream) {
+    NAVC_REQUIRE(logits && lse && labels && scale && rows > 0 && V > 0 && ld >= V, "navc_ce_grad: bad arguments");
+    ce_grad_kernel<<<rows, 256, 0, as_stream(stream)>>>(logits, lse, labels, scale, V, ld);
+    return check_launch("navc_ce_grad");
+}
+
+extern "C" int navc_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float clip, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int step, void* stream) {
+    NAVC_REQUIRE(p && g && m && v && n > 0 && step >= 1, "navc_clip_adam: bad arguments");
+    NAVC_REQUIRE(((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0, "navc_clip_adam: buffers must be 16-byte aligned");
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    clip_adam_kernel<<<ew_blocks((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(
+        p, g, m, v, n, clip, (float)((double)lr / bc1), beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)));
+    return check_launch("navc_clip_adam");
 }
 
 extern "C" int navc_self_attention_bwd(const float* qkv, int ld, const int64_t* tokens, int N, int S, int D, int H,

@@ -26,18 +26,23 @@ constexpr int kVocabBN = 256;        // the vocabulary epilogue always uses 256-
 constexpr int kEpiWarps = 8;                         // generic / vocabulary epilogues
 constexpr int kPairEpiWarps = 16;                    // pair epilogue: 4 warps per scheduler to hide its latencies
 constexpr int kStageFloats = 32 * 32;                // per-epilogue-warp transpose buffer (4 KB); 2 KB per warp in pair mode
-__host__ __device__ constexpr int tc_epi_warps(int epi) { return epi == 2 ? kPairEpiWarps : kEpiWarps; }
+__host__ __device__ constexpr int tc_epi_warps(int epi) { return epi >= 2 ? kPairEpiWarps : kEpiWarps; }
+constexpr int kResBufBytes = 2048;                   // per warp and buffer: residual hi box (1 KB) + lo box (1 KB)
 __host__ __device__ constexpr int tc_threads(int epi) { return 64 + 32 * tc_epi_warps(epi); }
 constexpr int kTileABytes = TBM * TBK * 2;           // 16 KB
 constexpr int kAccStages = 2;                        // 2 x 256 TMEM columns
 constexpr int kTmemCols = 512;
 
-template <bool kX3, int TBN> struct TcCfg {
+template <bool kX3, int TBN, int kEpi = 0> struct TcCfg {
     static constexpr int kTileBBytes = TBN * TBK * 2;    // 32 KB (TBN = 256) / 16 KB (TBN = 128)
-    static constexpr int kStages = (kX3 ? 2 : 4) * (TBN == 128 ? 3 : 2) / 2;   // 192 KB ring in every variant
     static constexpr int kStageBytes = (kX3 ? 2 : 1) * (kTileABytes + kTileBBytes);
+    // 192 KB operand ring; the residual-prefetching epilogue (kEpi == 3) trades 64 KB of it for its
+    // per-warp double-buffered residual boxes
+    static constexpr int kResBytes = kEpi == 3 ? kPairEpiWarps * 2 * kResBufBytes : 0;
+    static constexpr int kStages = (196608 - kResBytes) / kStageBytes;
     static constexpr int kRingBytes = kStages * kStageBytes;
-    static constexpr int kSmemBytes = kRingBytes + kEpiWarps * kStageFloats * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kRingBytes + kEpiWarps * kStageFloats * 4 + kResBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+    static_assert(kStages >= 2, "operand ring needs at least two stages");
 };
 
 struct TcVocab {
@@ -53,23 +58,27 @@ struct TcVocab {
 // kEpi: 0 = generic epilogue (fp32 / bf16 outputs, fp32 residual; smem-transposed coalesced stores),
 //       1 = vocabulary softmax statistics, 2 = "pair" epilogue (lane = row, bf16 hi/lo outputs through
 //       TMA stores, bf16 hi+lo residual): the inference fast path.
-constexpr int kEpiGeneric = 0, kEpiVocab = 1, kEpiPair = 2;
+constexpr int kEpiGeneric = 0, kEpiVocab = 1, kEpiPair = 2, kEpiPairRes = 3;  // 3 = pair + TMA-prefetched residual
 
 template <bool kX3, int kEpi, int TBN>
 __global__ void __launch_bounds__(tc_threads(kEpi), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+               const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
                int M, int N, int K, EpiParams epi, TcVocab vep) {
     constexpr bool kVocab = kEpi == kEpiVocab;
-    using Cfg = TcCfg<kX3, TBN>;
+    constexpr bool kPairAny = kEpi == kEpiPair || kEpi == kEpiPairRes;
+    constexpr bool kResTma = kEpi == kEpiPairRes;
+    using Cfg = TcCfg<kX3, TBN, kEpi>;
     constexpr int kTileBBytes = Cfg::kTileBBytes;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     // barriers live after the tile ring
     float* stage_all = reinterpret_cast<float*>(smem_gen + Cfg::kRingBytes);
-    const uint32_t bar_off = Cfg::kRingBytes + kEpiWarps * kStageFloats * 4;
+    const uint32_t res_off = Cfg::kRingBytes + kEpiWarps * kStageFloats * 4;   // residual boxes (kEpi == 3)
+    const uint32_t bar_off = res_off + Cfg::kResBytes;
     const uint32_t bar_base = smem_base + bar_off;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
@@ -87,6 +96,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), tc_epi_warps(kEpi)); }
+        if constexpr (kResTma) {
+            for (int s = 0; s < 2 * kPairEpiWarps; ++s) mbar_init(bar_base + 256u + 8u * s, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -169,6 +181,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         float* stage = stage_all + ew * kStageFloats;
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t rstep = 0;  // residual boxes consumed so far by this warp (kEpi == 3)
+        (void)rstep;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int mn = tile / split;
             const int mb = mn / n_blocks, nb = mn % n_blocks;
@@ -176,7 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int row = row0 + lane;
             const int n0 = nb * TBN + half * (TBN / 2);
 
-            if constexpr (kEpi == kEpiPair) {
+            if constexpr (kPairAny) {
                 // ---- pair epilogue: 16 warps; warp = (TMEM lane quarter, column group of TBN/4); lane = row;
                 //      16-column steps; outputs leave through TMA stores of [32 rows x 16 cols] bf16 boxes ----
                 constexpr int GW = TBN / 4;
@@ -187,6 +201,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 uint8_t* stg = reinterpret_cast<uint8_t*>(stage_all) + ew * 2048;   // hi box at +0, lo box at +1024
                 const uint32_t stg_s = smem_u32(stg);
                 const int ng0 = nb * TBN + grp * GW;
+                // residual boxes of step `rstep` (per warp, double buffered) arrive through TMA: no LSU traffic
+                const uint32_t rbuf_s = smem_base + res_off + (uint32_t)(ew * 2 * kResBufBytes);
+                const uint8_t* rbuf_g = smem_gen + res_off + ew * 2 * kResBufBytes;
+                auto res_issue = [&](uint32_t step, int col) {
+                    if (lane == 0) {
+                        const uint32_t b = step & 1u, bar = bar_base + 256u + 8u * (uint32_t)(ew * 2 + (int)b);
+                        mbar_expect_tx(bar, epi.res_lo ? 2048u : 1024u);
+                        tma_load_2d(rbuf_s + b * kResBufBytes, &map_r_hi, bar, col, row0);
+                        if (epi.res_lo) tma_load_2d(rbuf_s + b * kResBufBytes + 1024u, &map_r_lo, bar, col, row0);
+                    }
+                };
+                if constexpr (kResTma) {
+                    if (ng0 < N) res_issue(rstep, ng0);
+                }
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + grp * GW);
@@ -196,6 +224,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     if (col0 >= N) break;  // warp-uniform
                     uint32_t r[16];
                     tc_ld16(t_row + (uint32_t)(c * 16), r);
+                    if constexpr (kResTma) {
+                        if (c + 1 < GW / 16 && col0 + 16 < N) res_issue(rstep + 1u, col0 + 16);  // prefetch the next step
+                    }
                     // operands of this step (requested before the TMEM wait)
                     float4 bv[4];
                     uint4 rh[2], rl[2];
@@ -208,11 +239,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     for (int i = 0; i < 2; ++i) {
                         rh[i] = make_uint4(0u, 0u, 0u, 0u);
                         rl[i] = make_uint4(0u, 0u, 0u, 0u);
-                        if (epi.res_hi && row_ok && col0 + i * 8 < N) {
-                            const size_t ro = (size_t)rowp * epi.ld_res + col0 + i * 8;
-                            rh[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
-                            if (epi.res_lo) rl[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
+                        if constexpr (!kResTma) {
+                            if (epi.res_hi && row_ok && col0 + i * 8 < N) {
+                                const size_t ro = (size_t)rowp * epi.ld_res + col0 + i * 8;
+                                rh[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
+                                if (epi.res_lo) rl[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
+                            }
                         }
+                    }
+                    if constexpr (kResTma) {
+                        const uint32_t b = rstep & 1u;
+                        mbar_wait(bar_base + 256u + 8u * (uint32_t)(ew * 2 + (int)b), (rstep >> 1) & 1u);
+                        const uint8_t* rb = rbuf_g + b * kResBufBytes + lane * 32;   // rows/cols beyond M/N arrive as zeros
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            rh[i] = *reinterpret_cast<const uint4*>(rb + i * 16);
+                            if (epi.res_lo) rl[i] = *reinterpret_cast<const uint4*>(rb + 1024 + i * 16);
+                        }
+                        ++rstep;
                     }
                     tc_wait_ld();
                     float v[16];
@@ -230,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], epi.act);
                     }
-                    if (epi.res_hi) {
+                    if (kResTma || epi.res_hi) {
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
                             const uint32_t hw_[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
@@ -444,7 +488,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     }
 
-    if constexpr (kEpi == kEpiPair) {
+    if constexpr (kPairAny) {
         if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging stays valid until read
     }
     tc_fence_before();
@@ -471,11 +515,12 @@ int tc_init() {
     NAVC_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "navc_init: cuTensorMapEncodeTiled not available");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
 #define NAVC_TC_ATTR(X3, EPI, BN) \
-    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<X3, EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<X3, BN>::kSmemBytes))
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<X3, EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<X3, BN, EPI>::kSmemBytes))
     NAVC_TC_ATTR(false, kEpiGeneric, 256); NAVC_TC_ATTR(true, kEpiGeneric, 256);
     NAVC_TC_ATTR(false, kEpiGeneric, 128); NAVC_TC_ATTR(true, kEpiGeneric, 128);
     NAVC_TC_ATTR(false, kEpiPair, 256); NAVC_TC_ATTR(true, kEpiPair, 256);
     NAVC_TC_ATTR(false, kEpiPair, 128); NAVC_TC_ATTR(true, kEpiPair, 128);
+    NAVC_TC_ATTR(false, kEpiPairRes, 128); NAVC_TC_ATTR(true, kEpiPairRes, 128);
     NAVC_TC_ATTR(false, kEpiVocab, 256); NAVC_TC_ATTR(true, kEpiVocab, 256);
 #undef NAVC_TC_ATTR
     g_tc_ready = true;
@@ -527,19 +572,23 @@ static int launch_tc_bn(int mode, const uint16_t* x_hi, const uint16_t* x_lo, in
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
-    CUtensorMap mo_hi = ma_hi, mo_lo = ma_hi;
-    if (kEpi == kEpiPair) {
+    CUtensorMap mo_hi = ma_hi, mo_lo = ma_hi, mr_hi = ma_hi, mr_lo = ma_hi;
+    if (kEpi == kEpiPair || kEpi == kEpiPairRes) {
         if (tc_make_store_map(&mo_hi, epi.out_hi, M, N, epi.ld_out)) return 1;
         if (epi.out_lo && tc_make_store_map(&mo_lo, epi.out_lo, M, N, epi.ld_out)) return 1;
+    }
+    if (kEpi == kEpiPairRes) {
+        if (tc_make_store_map(&mr_hi, epi.res_hi, M, N, epi.ld_res)) return 1;
+        if (epi.res_lo && tc_make_store_map(&mr_lo, epi.res_lo, M, N, epi.ld_res)) return 1;
     }
     const int tiles = ((M + TBM - 1) / TBM) * ((N + TBN - 1) / TBN) * epi.split_k;
     int sms = navc_sm_count();
     if (sms <= 0) sms = 148;
     const int grid = tiles < sms ? tiles : sms;
     if (mode == NAVC_TC_BF16X3) {
-        gemm_tc_kernel<true, kEpi, TBN><<<grid, tc_threads(kEpi), TcCfg<true, TBN>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, vep);
+        gemm_tc_kernel<true, kEpi, TBN><<<grid, tc_threads(kEpi), TcCfg<true, TBN, kEpi>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, mr_hi, mr_lo, M, N, K, epi, vep);
     } else {
-        gemm_tc_kernel<false, kEpi, TBN><<<grid, tc_threads(kEpi), TcCfg<false, TBN>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, vep);
+        gemm_tc_kernel<false, kEpi, TBN><<<grid, tc_threads(kEpi), TcCfg<false, TBN, kEpi>::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, mr_hi, mr_lo, M, N, K, epi, vep);
     }
     return check_launch(what);
 }
@@ -563,6 +612,11 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
         const int t256 = mt * ((N + 255) / 256) * epi.split_k, t128 = mt * ((N + 127) / 128) * epi.split_k;
         const int forced = epi.dbg >= 128 ? epi.dbg : 0;  // profiling aid: reserved = 128 / 256 forces a tile width
         const bool narrow = forced ? forced == 128 : (N <= 128 || tile_waste_pct(t256, sms) >= tile_waste_pct(t128, sms) + 8);
+        if constexpr (kEpi == kEpiPair) {
+            // a bf16 hi/lo residual is prefetched by TMA (128-wide tiles only: the boxes need 64 KB of the ring)
+            if (epi.res_hi && (narrow || N <= 1024) && forced != 256)
+                return launch_tc_bn<kEpiPairRes, 128>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, vep, st, what);
+        }
         if (narrow) return launch_tc_bn<kEpi, 128>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, vep, st, what);
     }
     return launch_tc_bn<kEpi, 256>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, vep, st, what);

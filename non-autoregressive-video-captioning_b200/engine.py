@@ -30,6 +30,12 @@ def default_precision(opt=None) -> str:
     return p
 
 
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous and 16-byte aligned view / copy of a parameter (kernels use 128-bit loads)."""
+    t = t.detach().contiguous().float()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 class Act:
     """An activation matrix [M, N]: fp32 copy and/or bf16 hi(/lo) copies."""
     __slots__ = ("f32", "hi", "lo", "M", "N")
@@ -45,8 +51,8 @@ class PackedLinear:
     __slots__ = ("w", "b", "w_hi", "w_lo", "N", "K", "src", "T", "pad")
 
     def __init__(self, w, b, src=()):
-        self.w = w.detach().contiguous().float()
-        self.b = None if b is None else b.detach().contiguous().float()
+        self.w = _f32(w)
+        self.b = None if b is None else _f32(b)
         self.N, self.K = self.w.shape
         self.w_hi = self.w_lo = None
         self.src = tuple(src)
@@ -93,6 +99,10 @@ class Engine:
         self.pack_id += 1
         self.graphs.clear()  # captured graphs hold pointers into the previous packed weights
 
+    def invalidate(self):
+        """Force a repack at the next use (for writers that bypass torch's version counters)."""
+        self._sig = None
+
     def _lin(self, w, b=None, src=()) -> PackedLinear:
         pl = PackedLinear(w, b, src)
         if self.tc:
@@ -124,10 +134,10 @@ class Engine:
             jr = "joint_representation_learner."
             for i in range(len(opt["modality"])):
                 if (jr + "bn%d.weight" % i) in sd:
-                    P["norms"].append(("bn", sd[jr + "bn%d.running_mean" % i].float(), sd[jr + "bn%d.running_var" % i].float(),
-                                       sd[jr + "bn%d.weight" % i].float(), sd[jr + "bn%d.bias" % i].float()))
+                    P["norms"].append(("bn", _f32(sd[jr + "bn%d.running_mean" % i]), _f32(sd[jr + "bn%d.running_var" % i]),
+                                       _f32(sd[jr + "bn%d.weight" % i]), _f32(sd[jr + "bn%d.bias" % i])))
                 elif (jr + "ln%d.weight" % i) in sd:
-                    P["norms"].append(("ln", sd[jr + "ln%d.weight" % i].float(), sd[jr + "ln%d.bias" % i].float()))
+                    P["norms"].append(("ln", _f32(sd[jr + "ln%d.weight" % i]), _f32(sd[jr + "ln%d.bias" % i])))
                 else:
                     P["norms"].append(None)
             # length head
@@ -135,16 +145,16 @@ class Engine:
             P["len_head"] = None
             P["norm_keys"] = [jr + ("bn%d" if (jr + "bn%d.weight" % i) in sd else "ln%d") % i for i in range(len(opt["modality"]))]
             if (ap + "0.weight") in sd:
-                P["len_head"] = tuple(sd[ap + k].float().contiguous() for k in ("0.weight", "0.bias", "3.weight", "3.bias"))
+                P["len_head"] = tuple(_f32(sd[ap + k]) for k in ("0.weight", "0.bias", "3.weight", "3.bias"))
                 P["len_head_keys"] = tuple(ap + k for k in ("0.weight", "0.bias", "3.weight", "3.bias"))
             # decoder
             dp = "decoder.bert." if ("decoder.bert.embedding.LayerNorm.weight" in sd) else "decoder."
             e = dp + "embedding."
             P["emb_prefix"] = e
-            P["emb"] = dict(word=sd[e + "word_embeddings.weight"].float().contiguous(),
-                            pos=sd[e + "position_embeddings.weight"].float().contiguous(),
-                            cat=sd[e + "category_embeddings.weight"].float().contiguous() if (e + "category_embeddings.weight") in sd else None,
-                            ln_w=sd[e + "LayerNorm.weight"].float().contiguous(), ln_b=sd[e + "LayerNorm.bias"].float().contiguous())
+            P["emb"] = dict(word=_f32(sd[e + "word_embeddings.weight"]),
+                            pos=_f32(sd[e + "position_embeddings.weight"]),
+                            cat=_f32(sd[e + "category_embeddings.weight"]) if (e + "category_embeddings.weight") in sd else None,
+                            ln_w=_f32(sd[e + "LayerNorm.weight"]), ln_b=_f32(sd[e + "LayerNorm.bias"]))
             layers, kv_w, kv_b, kv_src = [], [], [], []
             D_ = opt["dim_hidden"]
             for l in range(opt["num_hidden_layers_decoder"]):
@@ -161,7 +171,7 @@ class Engine:
 
                 def ln(prefix):
                     k = prefix + "LayerNorm.weight"
-                    return (sd[k].float().contiguous(), sd[prefix + "LayerNorm.bias"].float().contiguous()) if k in sd else None
+                    return (_f32(sd[k]), _f32(sd[prefix + "LayerNorm.bias"])) if k in sd else None
 
                 def one(prefix):
                     w = sd[prefix + ".weight"]

@@ -92,8 +92,12 @@ class Seq2Seq(nn.Module):
         logprobs = []
         for h in hidden_states:
             if torch.is_grad_enabled() and self.training:
-                from ..training import vocab_logprobs_train
-                logprobs.append(vocab_logprobs_train(self, h))  # projection + log-softmax, one autograd node
+                from ..training import LazyLogProbs, vocab_logprobs_train
+                if self.opt.get("navc_fused_ce", False):
+                    # consumed by navc_b200.misc.crit: projection + log-softmax + masked NLL fused, no [B,S,V] tensor
+                    logprobs.append(LazyLogProbs(self, h))
+                else:
+                    logprobs.append(vocab_logprobs_train(self, h))  # projection + log-softmax, one autograd node
                 continue
             logits = self.tgt_word_prj(h)
             shape = logits.shape

@@ -21,6 +21,9 @@ import torch
 import torch.distributed as dist
 
 
+ALIGN = 64  # floats
+
+
 def world() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
@@ -91,13 +94,15 @@ class GradientAllReduce:
         if not self.params:
             raise ValueError("model has no trainable parameters")
         dev = self.params[0].device
-        self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
-        self.views = []
-        off = 0
+        # every tensor starts on a 256-byte boundary of the flat buffer (the vectorised / TMA kernels
+        # need 16-byte aligned operands); the padding stays zero and rides along in the collective
+        self.offsets, off = [], 0
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
         if broadcast:
             broadcast_model(model)
         self.attach()

@@ -602,3 +602,90 @@ def vocab_forward_train(engine, prj, hidden):
 def vocab_logprobs_train(model, hidden):
     """log_softmax(tgt_word_prj(hidden)) as one autograd node (projection + log-softmax kernels)."""
     return VocabFn.apply(model, True, hidden, *_vocab_params(model.tgt_word_prj))
+
+
+# --------------------------------------------------------------------------------------------------
+# fused cross-entropy: projection + log-softmax + masked NLL without the [rows, V] log-prob tensor
+# (SURVEY.md section 8(f) row 1; reference seq2seq.py:102-103 + misc/crit.py:62-84)
+# --------------------------------------------------------------------------------------------------
+class LazyLogProbs:
+    """Stands in for one ``tgt_word_logprobs`` entry when ``opt['navc_fused_ce']`` is set: the hidden
+    states plus the model, consumed by ``navc_b200.misc.crit.LanguageGeneration`` (fused loss) --
+    ``materialize()`` gives the reference's [B, S, V] log-prob tensor for any other consumer."""
+
+    def __init__(self, model, hidden):
+        self.model, self.hidden = model, hidden
+        self.stats = None  # (nll [R], argmax [R]) of the last fused loss evaluation
+
+    def size(self, dim=None):
+        shape = tuple(self.hidden.shape[:-1]) + (self.model.engine.P["vocab"].N if self.model.engine.P else self.model.opt["vocab_size"],)
+        return shape if dim is None else shape[dim]
+
+    def materialize(self):
+        return vocab_logprobs_train(self.model, self.hidden)
+
+    def nll_sum(self, labels):
+        """sum over non-PAD positions of -log p(label) as ONE autograd node."""
+        out = FusedCEFn.apply(self, labels, self.hidden, *_vocab_params(self.model.tgt_word_prj))
+        return out
+
+
+class FusedCEFn(torch.autograd.Function):
+    CHUNK = 2048  # rows per backward chunk: a [2048, V] fp32 logits slab (86 MB at V = 10547) stays L2 resident
+
+    @staticmethod
+    def forward(ctx, lazy, labels, hidden, *params):
+        model = lazy.model
+        eng: Engine = model.engine
+        eng.sync_weights()
+        lin = eng.P["vocab"]
+        dev = eng.device
+        D = lin.K
+        h = eng.from_f32(hidden.detach().reshape(-1, D))
+        R = h.M
+        lab = labels.contiguous().view(-1)
+        pm, ps, pi, nt, tl = eng.vocab_partials(h, target=lab)
+        lse = torch.empty((R,), dtype=torch.float32, device=dev)
+        nll = torch.empty((R,), dtype=torch.float32, device=dev)
+        arg = torch.empty((R,), dtype=torch.int32, device=dev)
+        L.call("navc_ce_stats", L.ptr(pm), L.ptr(ps), L.ptr(pi), nt, L.ptr(tl), L.ptr(lab), R, L.ptr(lse), L.ptr(nll), L.ptr(arg), L.stream())
+        lazy.stats = (nll.view(labels.shape), arg.view(labels.shape))
+        ctx.lazy, ctx.n_params = lazy, len(params)
+        ctx.state = dict(h=h, lse=lse, lab=lab, shape=hidden.shape)
+        return nll.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        model = ctx.lazy.model
+        eng: Engine = model.engine
+        st = ctx.state
+        lin = eng.P["vocab"]
+        dev = eng.device
+        h, lse, lab = st["h"], st["lse"], st["lab"]
+        R, D, V = h.M, lin.K, lin.N
+        Vp = _up(V, 64)
+        if lin.pad is None:
+            w_pad = torch.zeros((Vp, D), dtype=torch.float32, device=dev)
+            w_pad[:V].copy_(lin.w)
+            b_pad = None
+            if lin.b is not None:
+                b_pad = torch.zeros((Vp,), dtype=torch.float32, device=dev)
+                b_pad[:V].copy_(lin.b)
+            wop, _ = transpose_pack(eng, w_pad, Vp, D, D, straight=True)
+            lin.pad = (wop, b_pad)
+        wop, b_pad = lin.pad
+        scale = g.detach().reshape(1).float().contiguous()
+        grads = Grads()
+        d_h = torch.empty((R, D), dtype=torch.float32, device=dev)
+        C = FusedCEFn.CHUNK
+        slab = torch.empty((min(C, R), Vp), dtype=torch.float32, device=dev)
+        for r0 in range(0, R, C):
+            n = min(C, R - r0)
+            xop = Operand(n, D, D, hi=h.hi[r0:r0 + n], lo=None if h.lo is None else h.lo[r0:r0 + n]) if eng.tc \
+                else Operand(n, D, D, f32=h.f32[r0:r0 + n])
+            gemm(eng, xop, wop, n, Vp, D, slab, Vp, bias=b_pad)                      # logits of this row chunk
+            L.call("navc_ce_grad", L.ptr(slab), lse[r0:].data_ptr(), lab[r0:].data_ptr(), L.ptr(scale), n, V, Vp, L.stream())
+            d_h[r0:r0 + n] = lin_bwd(eng, h.f32[r0:r0 + n], lin, slab[:n], grads, ld_dy=Vp)
+        gw = grads.g.get("tgt_word_prj.weight")
+        gb = grads.g.get("tgt_word_prj.bias")
+        return (None, None, d_h.view(st["shape"])) + ((gw,) if ctx.n_params == 1 else (gw, gb))

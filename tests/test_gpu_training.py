@@ -454,3 +454,123 @@ def test_train_step_updates_weights_and_eval_sees_them():
         ref = O.model_forward(sd, opt, feats, [toks["tokens_1"], toks["tokens"]], category)
     for a, b in zip(res["tgt_word_logprobs"], ref["tgt_word_logprobs"]):
         assert (a.cpu() - b).abs().max().item() < 5e-4
+
+
+def test_fused_clip_adam_matches_torch():
+    """navc_clip_adam (one launch over flat buffers) vs clip_grad_value_ + torch.optim.Adam(weight_decay)
+    (misc/run.py:260-261, misc/optim.py:61-62) with the reference's per-step / per-epoch LR schedule."""
+    from navc_b200 import optim as nopt
+    opt = cases.small("NACF")
+    opt.update(optim="adam", learning_rate=5e-3, minimum_learning_rate=5e-4, decay=0.9, weight_decay=5e-4, grad_clip=0.05)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt).to(DEV)
+    ref = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+    tref = torch.optim.Adam(ref, lr=opt["learning_rate"], weight_decay=opt["weight_decay"])
+    sched = nopt.get_optimizer(opt, model)
+    lr = opt["learning_rate"]
+    for it in range(5):
+        sched.zero_grad()
+        tref.zero_grad()
+        gen = torch.Generator().manual_seed(50 + it)
+        for p, r in zip(model.parameters(), ref):
+            gr = (0.1 * torch.randn(p.shape, generator=gen)).to(DEV)
+            p.grad.add_(gr)           # autograd-style in-place accumulation into the flat buffer views
+            r.grad = gr.clone()
+        sched.step()
+        torch.nn.utils.clip_grad_value_(ref, opt["grad_clip"])
+        for gp in tref.param_groups:
+            gp["lr"] = lr
+        tref.step()
+        if it == 2:
+            sched.epoch_update_learning_rate()
+            lr = max(opt["minimum_learning_rate"], opt["decay"] * lr)
+    for p, r in zip(model.parameters(), ref):
+        close(p, r, 2e-5, "fused adam param")
+    assert abs(sched.get_lr() - lr) < 1e-12
+    assert model.engine._sig is None  # the engine repacks the updated weights at its next use
+
+
+def test_train_steps_with_fused_optimizer_and_flat_gradients():
+    from navc_b200 import optim as nopt, parallel
+    opt = cases.small("NACF", hidden_dropout_prob=0.0, encoder_dropout=0.0)
+    opt.update(optim="adam", learning_rate=5e-4, minimum_learning_rate=5e-5, decay=0.9, weight_decay=5e-4, grad_clip=5)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt).to(DEV)
+    dp = parallel.GradientAllReduce(model)
+    sched = nopt.get_optimizer(opt, model, grads=dp)
+    feats, category = cases.synth_inputs(opt, 6)
+    toks = cases.synth_tokens(opt, 6)
+    fd = [f.to(DEV) for f in feats]
+    losses = []
+    for it in range(4):
+        model.train()
+        sched.zero_grad()
+        res = model(feats=fd, tgt_tokens=[toks["tokens_1"].to(DEV), toks["tokens"].to(DEV)], category=category.to(DEV))
+        loss = O.criterion(opt, res, [toks["labels_1"].to(DEV), toks["labels"].to(DEV)], toks["length_target"].to(DEV))
+        loss.backward()
+        dp.allreduce()
+        sched.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    model.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        res = model(feats=fd, tgt_tokens=[toks["tokens_1"].to(DEV), toks["tokens"].to(DEV)], category=category.to(DEV))
+        ref = O.model_forward(sd, opt, feats, [toks["tokens_1"], toks["tokens"]], category)
+    for a, b in zip(res["tgt_word_logprobs"], ref["tgt_word_logprobs"]):
+        assert (a.cpu() - b).abs().max().item() < 5e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_fused_cross_entropy_matches_oracle(precision):
+    """opt['navc_fused_ce']: projection + log-softmax + masked NLL as one autograd node (no [B,S,V]
+    log-prob tensor) behind navc_b200.misc.crit -- loss, every gradient and the meters vs the oracle."""
+    from navc_b200.misc import crit as ncrit
+    from navc_b200.training import FusedCEFn, LazyLogProbs
+    opt = cases.small("NACF", hidden_dropout_prob=0.0, encoder_dropout=0.0, navc_fused_ce=True)
+    opt.update(crit_key=[("tgt_word_logprobs", "tgt_word_labels"), ("pred_length", "tgt_length")],
+               crit_name=["Cap Loss", "Length Loss"], crit_scale=[1.0, 1.0])
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd0 = cases.synth_state_dict(shapes, 11)
+    model.load_state_dict(sd0)
+    model.to(DEV).train()
+    model.set_precision(precision)
+    B = 7
+    feats, category = cases.synth_inputs(opt, B)
+    toks = cases.synth_tokens(opt, B)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd0.items()}
+    ref = O.model_forward(sd, opt, feats, [toks["tokens_1"], toks["tokens"]], category, training=True)
+    ref_loss = O.criterion(opt, ref, [toks["labels_1"], toks["labels"]], toks["length_target"])
+    ref_loss.backward()
+    old_chunk, FusedCEFn.CHUNK = FusedCEFn.CHUNK, 40  # several backward chunks even at this small size
+    try:
+        res = model(feats=[f.to(DEV) for f in feats], tgt_tokens=[toks["tokens_1"].to(DEV), toks["tokens"].to(DEV)],
+                    category=category.to(DEV))
+        assert all(isinstance(x, LazyLogProbs) for x in res["tgt_word_logprobs"])
+        res["tgt_word_labels"] = [toks["labels_1"].to(DEV), toks["labels"].to(DEV)]
+        res["tgt_length"] = toks["length_target"].to(DEV)
+        crit = ncrit.get_criterion(opt)
+        crit.reset_loss_recorder()
+        loss = crit.get_loss(res)
+        loss.backward()
+    finally:
+        FusedCEFn.CHUNK = old_chunk
+    tol = GRAD_TOL[precision]
+    assert abs(loss.item() - ref_loss.item()) < tol * max(1.0, abs(ref_loss.item()))
+    for name, p in model.named_parameters():
+        rg = sd[name].grad
+        if rg is None or rg.abs().max().item() == 0:
+            continue
+        close(p.grad, rg, tol, name, atol=2e-7)
+    # meters: top-1 accuracy and perplexity from the fused statistics vs the oracle's log-probs
+    names, info = crit.get_loss_info()
+    lp = ref["tgt_word_logprobs"][1].detach()
+    lab = toks["labels"]
+    mask = lab.ne(0)
+    ppl = math.exp(float(-(lp.gather(2, lab.unsqueeze(2)).squeeze(2) * mask).sum() / mask.sum()))
+    acc1 = float((lp.argmax(-1)[mask] == lab[mask]).float().mean())
+    got = dict(zip(names, info))
+    assert abs(got["Perplexity"] - ppl) < 1e-3 * ppl and abs(got["Word Acc1"] - acc1) < 1e-6
+    assert torch.allclose(res["tgt_word_logprobs"][1].materialize().detach().cpu(), lp, atol=5e-4)

@@ -160,3 +160,39 @@ def test_ar_beam_search_matches_reference():
         assert len(a) == len(b)
         for x, y in zip(a, b):
             assert abs(x - float(y)) < 1e-4
+
+
+def test_product_criterion_mirrors_reference_criterion():
+    """navc_b200.misc.crit (the criterion API the fused cross-entropy plugs into) against the
+    reference's misc/crit.py on the same log-prob tensors: loss, loss records, accuracy / perplexity meters."""
+    import warnings
+    import navc_b200
+    from navc_b200.misc import crit as ncrit
+    opt = cases.small("NACF", hidden_dropout_prob=0.0, encoder_dropout=0.0)
+    opt.update(crit_key=[("tgt_word_logprobs", "tgt_word_labels"), ("pred_length", "tgt_length")],
+               crit_name=["Cap Loss", "Length Loss"], crit_scale=[1.0, 1.0])
+    model = refutil.ref_get_model(opt)
+    feats, category = cases.synth_inputs(opt, 5)
+    toks = cases.synth_tokens(opt, 5)
+    with torch.no_grad():
+        res = model(feats=feats, tgt_tokens=[toks["tokens_1"], toks["tokens"]], category=category)
+    res["tgt_word_labels"] = [toks["labels_1"], toks["labels"]]
+    res["tgt_length"] = toks["length_target"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with refutil.reference_on_path():
+            from misc.crit import get_criterion
+            import copy
+            rc = get_criterion(copy.deepcopy(opt))  # (the reference appends the meter names to opt['crit_name'] in place)
+            rc.reset_loss_recorder()
+            ref_loss = rc.get_loss(res)
+            ref_fields = rc.get_fieldsnames()
+            ref_names, ref_info = rc.get_loss_info()
+        mc = ncrit.get_criterion(copy.deepcopy(opt))
+        mc.reset_loss_recorder()
+        loss = mc.get_loss(res)
+        names, info = mc.get_loss_info()
+    torch.testing.assert_close(loss, ref_loss, rtol=1e-6, atol=1e-6)
+    assert list(names) == list(ref_names) and mc.get_fieldsnames() == ref_fields
+    for a, b in zip(info, ref_info):
+        assert abs(a - b) < 1e-4 * max(1.0, abs(b))

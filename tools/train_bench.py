@@ -64,6 +64,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default=os.environ.get("NAVC_PRECISION", "bf16x3"))
+    ap.add_argument("--torch-optim", action="store_true", help="caller-side clip_grad_value_ + torch.optim.Adam instead of the fused navc_clip_adam step")
     ap.add_argument("--profile", action="store_true", help="print a per-kernel device-time breakdown of one step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -87,7 +88,12 @@ def main():
     model.set_precision(args.precision)
     model.train()
     dp = parallel.GradientAllReduce(model)
-    optim = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-4)
+    if args.torch_optim:
+        optim = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-4)
+    else:
+        from navc_b200 import optim as nopt
+        opt.update(optim="adam", learning_rate=5e-4, minimum_learning_rate=5e-5, decay=0.9, weight_decay=5e-4, grad_clip=5)
+        optim = nopt.get_optimizer(opt, model, grads=dp)
     n_rot = 3
     batches = [make_batch(opt, B, 1234 + 31 * r + 1000 * rank, dev) for r in range(n_rot)]
 
@@ -98,7 +104,8 @@ def main():
         loss = reference_loss(opt, res, b["labels"], b["lt"])
         loss.backward()
         dp.allreduce()
-        torch.nn.utils.clip_grad_value_(model.parameters(), 5)
+        if args.torch_optim:
+            torch.nn.utils.clip_grad_value_(model.parameters(), 5)
         optim.step()
         return loss
 
@@ -131,6 +138,7 @@ def main():
                 "scaling": "strong" if args.global_batch else "weak", "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": "%s training step, feats 2x60x2048, max_len 30, vocab 10547, dropout 0.5" % args.method,
                            "batch_per_gpu": B, "global_batch": B * world, "params": nparams,
+                           "optimizer": "torch clip_grad_value_ + Adam" if args.torch_optim else "fused navc_clip_adam (one launch)",
                            "allreduce_bytes": dp.nbytes if world > 1 else 0,
                            "l2": "inputs rotate over %d distinct batches" % n_rot},
                 "gpu_launches": launches, "final_loss": float(loss.item())}
