@@ -280,7 +280,8 @@ def main():
     if events:
         durs = [a.elapsed_time(b) for a, b in events]
         mean_ms = sum(durs) / len(durs)
-        R = stats["N"] * stats["S"]
+        # rows the launch really computes: sum of the candidate lengths when the rows are packed
+        R = stats["rows_real"] if stats.get("packed") else stats["N"] * stats["S"]
         flops = 2.0 * R * opt["dim_hidden"] * opt["intermediate_size"]
         achieved = flops / (mean_ms / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"]
@@ -307,6 +308,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "precision": args.precision, "passes": stats.get("passes"),
                            "S": stats.get("S"), "rows": stats.get("N"), "cuda_graph": bool(stats.get("graph")),
+                           "packed_rows": bool(stats.get("packed")), "positions_real": stats.get("rows_real"),
+                           "positions_padded": (stats.get("N") or 0) * (stats.get("S") or 0),
                            "l2": "inputs rotate over %d distinct batches (%d MB of features > 126 MB L2)" % (n_rot, n_rot * h2d >> 20)},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},

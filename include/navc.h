@@ -65,6 +65,8 @@ typedef struct {
     int32_t accumulate;         /* != 0: out_f32 += tile (atomic float adds; caller zero-fills first) */
     const uint16_t* res_hi;     /* tcgen05 path: residual given as a bf16 hi/lo pair [M, ld_res] (res_lo may be */
     const uint16_t* res_lo;     /* NULL); needs bf16-only outputs (out_f32 == NULL, residual == NULL), N % 8 == 0 */
+    const int32_t* m_dev;       /* tcgen05 path: optional DEVICE scalar; only the first min(M, *m_dev) rows are computed
+                                   (packed-row decoding: the row count is known on the device only) */
 } navc_epilogue_t;
 
 int navc_version(void);
@@ -178,6 +180,37 @@ int navc_cross_attention_tc(int mode, const uint16_t* q_hi, const uint16_t* q_lo
                             int D, int H, int group, float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo,
                             void* stream);
 
+/* ---- packed rows ---------------------------------------------------------------------------
+ * The reference runs every decoder op over all N*S positions although positions >= len are PAD and
+ * every one of their outputs is multiplied by non_pad_mask = 0 (models/bert.py:271-299).  In the
+ * packed layout only the sum(len) real positions exist: row seq_off[n] + s holds position (n, s).
+ * Row counts are device-side (m_dev / count pointers), launch shapes stay at the N*S maximum, so
+ * the refinement loop remains one CUDA graph. */
+/* seq_off[0..N] = exclusive prefix sum of lens (seq_off[N] = row count); rowmap[i] = n*S + s. */
+int navc_pack_rows(const int32_t* lens, int N, int S, int32_t* seq_off, int32_t* rowmap, void* stream);
+/* navc_embed_ln over packed rows: row i < seq_off[N] is position rowmap[i]; also emits the row's
+ * token id (tok_out[i], int64) for the GEMM epilogues' `* non_pad_mask`. */
+int navc_embed_ln_packed(const int64_t* tokens, const int64_t* category, const float* word_emb,
+                         const float* pos_emb, const float* cat_emb, const float* extra, int group,
+                         const float* ln_w, const float* ln_b, float eps, int N, int S, int D,
+                         const int32_t* seq_off, const int32_t* rowmap, int64_t* tok_out,
+                         float* out_f32, uint16_t* out_hi, uint16_t* out_lo, void* stream);
+/* tcgen05 attention cores over packed rows (same arithmetic and masks as the padded entry points;
+ * tokens stays the padded [N,S] canvas, qkv / q / ctx are packed). */
+int navc_self_attention_tc_packed(int mode, const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld,
+                                  const int64_t* tokens, const int32_t* seq_off, int N, int S, int D, int H,
+                                  int mask_kind, int watch, float* ctx_f32, uint16_t* ctx_hi,
+                                  uint16_t* ctx_lo, void* stream);
+int navc_cross_attention_tc_packed(int mode, const uint16_t* q_hi, const uint16_t* q_lo, int ldq,
+                                   const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv,
+                                   const int32_t* seq_off, int N, int S, int E, int D, int H, int group,
+                                   float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream);
+/* navc_vocab_partials_tc over the first min(M, *m_dev) rows. */
+int navc_vocab_partials_tc_dyn(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,
+                               const uint16_t* w_hi, const uint16_t* w_lo, int ldw, const float* bias,
+                               int M, int V, int K, const int32_t* m_dev, float* part_max, float* part_sum,
+                               int32_t* part_idx, void* stream);
+
 /* ---- iterative refinement (decoding/na_generate.py, decoding/algorithms.py) ----------------- */
 /* Length beam + canvas (na_generate.py:33-50, 116-135): beam[b,:] = clamp(top-lbs indices of
  * pred_length[b,:] + length_bias, 4, max_len-1) (descending value, lowest index on ties);
@@ -225,6 +258,8 @@ typedef struct {
                                   after the merge, [1] positions selected for re-masking */
     uint8_t* visual;           /* [N,S] out or NULL: token != MASK && != PAD after the merge */
     uint8_t* masked0;          /* [N,S] out or NULL: token == MASK && s < len after the merge */
+    const int32_t* seq_off;    /* NULL, or [N+1] packed-row offsets: the partials of position (n, s < len) live in
+                                  row seq_off[n] + s instead of n*S + s (navc_pack_rows) */
 } navc_step_t;
 /* One launch per refinement iteration: combine the vocabulary partials into (argmax, max prob),
  * apply the pad rules, merge into the state, choose the next positions to re-mask, write the next

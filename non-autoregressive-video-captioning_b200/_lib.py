@@ -21,7 +21,7 @@ i32, i64, u64, f32, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
 class Epilogue(C.Structure):
     _fields_ = [("bias", vp), ("residual", vp), ("row_tokens", vp), ("act", i32), ("ld_res", i32),
                 ("out_f32", vp), ("out_hi", vp), ("out_lo", vp), ("ld_out", i32), ("reserved", i32),
-                ("split_k", i32), ("accumulate", i32), ("res_hi", vp), ("res_lo", vp)]
+                ("split_k", i32), ("accumulate", i32), ("res_hi", vp), ("res_lo", vp), ("m_dev", vp)]
 
 
 class Step(C.Structure):
@@ -30,7 +30,7 @@ class Step(C.Structure):
                 ("win_lo", i32), ("win_hi", i32),
                 ("lens", vp), ("teacher", vp), ("given", vp), ("tokens", vp), ("probs", vp),
                 ("upd_mask", vp), ("canvas", vp), ("lprobs", vp), ("counters", vp), ("visual", vp),
-                ("masked0", vp)]
+                ("masked0", vp), ("seq_off", vp)]
 
 
 ACT = {"none": 0, None: 0, "gelu_new": 1, "gelu": 2, "relu": 3, "swish": 4}
@@ -59,6 +59,11 @@ _PROTOS = {
     "navc_cross_attention": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "navc_self_attention_tc": [i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
     "navc_cross_attention_tc": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_pack_rows": [vp, i32, i32, vp, vp, vp],
+    "navc_embed_ln_packed": [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+    "navc_self_attention_tc_packed": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_cross_attention_tc_packed": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_vocab_partials_tc_dyn": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp],
     "navc_length_beam": [vp, i32, i32, i32, i32, vp, vp, vp],
     "navc_init_canvas": [vp, i32, i32, i64, vp, vp, vp, vp],
     "navc_refine_step": [C.POINTER(Step), i32, i32, vp],

@@ -42,6 +42,8 @@ struct AtParams {
     int S;                        // tokens per sequence
     int is_self, mask_kind, watch;
     const int64_t* tokens;        // self: [N,S]
+    const int32_t* seq_off;       // packed rows: [n_seq + 1] row offsets (NULL = padded layout)
+    int n_seq, group;             // packed rows: sequences in total, sequences per video (cross)
     int D;
     float* ctx_f32; uint16_t* ctx_hi; uint16_t* ctx_lo;
 };
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(kAtThreads, kX3 ? 2 : 4)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
                AtParams p) {
+    // Packed self-attention (p.seq_off && p.is_self): a tile holds 4 sequences in 32-row slots; the maps
+    // then have 32-row boxes and every operand tile is four TMA loads at the sequences' row offsets.
     using Cfg = AtCfg<kX3>;
     constexpr int P = Cfg::kParts;
     extern __shared__ uint8_t smem_raw[];
@@ -73,16 +77,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     const int h = blockIdx.y;
 
     // tile geometry
+    const bool packed = p.seq_off != nullptr;
     int q_row0, k_row0, nq_valid, n_keys;
-    if (p.is_self) {
+    int seq0 = 0;              // packed self: first sequence of this tile
+    int slot_len = 0;          // packed self: length of the sequence whose 32-row slot this thread's row is in
+    int slot_row0 = 0;         // packed self: first packed row of that sequence
+    if (p.is_self && packed) {
+        seq0 = blockIdx.x * 4;
+        q_row0 = k_row0 = 0;   // unused
+        nq_valid = 128;
+        n_keys = 128;
+    } else if (p.is_self) {
         q_row0 = blockIdx.x * p.rows_per_tile;
         k_row0 = q_row0;
         nq_valid = min(p.rows_per_tile, p.total_q_rows - q_row0);
         n_keys = nq_valid;
     } else {
         const int g = blockIdx.x / p.tiles_per_owner, z = blockIdx.x % p.tiles_per_owner;
-        q_row0 = g * p.nq_per_owner + z * 128;
-        nq_valid = min(128, p.nq_per_owner - z * 128);
+        if (packed) {
+            const int r0 = __ldg(p.seq_off + g * p.group), r1 = __ldg(p.seq_off + min((g + 1) * p.group, p.n_seq));
+            q_row0 = r0 + z * 128;
+            nq_valid = min(128, r1 - q_row0);
+            if (nq_valid <= 0) return;  // this video has fewer query rows than the launch maximum (whole CTA exits)
+        } else {
+            q_row0 = g * p.nq_per_owner + z * 128;
+            nq_valid = min(128, p.nq_per_owner - z * 128);
+        }
         k_row0 = g * p.keys_per_owner;
         n_keys = p.keys_per_owner;
     }
@@ -98,7 +118,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     if (warp >= 2) {
         const int r = (warp - 2) * 32 + lane;
         uint8_t kp = 0;
-        if (p.is_self && p.tokens && r < nq_valid) kp = p.tokens[(size_t)q_row0 + r] == NAVC_PAD ? 1 : 0;
+        if (p.is_self && packed) {
+            const int seq = seq0 + (r >> 5), j = r & 31;
+            int len = 0;
+            if (seq < p.n_seq) len = __ldg(p.seq_off + seq + 1) - __ldg(p.seq_off + seq);
+            if (p.tokens && j < len) kp = p.tokens[(size_t)seq * p.S + j] == NAVC_PAD ? 1 : 0;
+            // the slot this thread serves in the softmax / epilogue phases is its TMEM lane quarter (warp & 3)
+            const int myseq = seq0 + (warp & 3);
+            if (myseq < p.n_seq) {
+                slot_row0 = __ldg(p.seq_off + myseq);
+                slot_len = __ldg(p.seq_off + myseq + 1) - slot_row0;
+            }
+        } else if (p.is_self && p.tokens && r < nq_valid) {
+            kp = p.tokens[(size_t)q_row0 + r] == NAVC_PAD ? 1 : 0;
+        }
         keypad[r] = kp;
     }
     tc_fence_before();
@@ -110,15 +143,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(bar_qk, 2 * P * kAtTile);
-            tma_load_2d(sQ_hi, &map_q_hi, bar_qk, p.q_col + h * 64, q_row0);
-            tma_load_2d(sK_hi, &map_kv_hi, bar_qk, p.k_col + h * 64, k_row0);
-            if (kX3) {
-                tma_load_2d(sQ_lo, &map_q_lo, bar_qk, p.q_col + h * 64, q_row0);
-                tma_load_2d(sK_lo, &map_kv_lo, bar_qk, p.k_col + h * 64, k_row0);
+            if (p.is_self && packed) {
+                // four 32-row boxes per operand tile: slot i <- rows of sequence seq0 + i (4 KB apart: 8-row swizzle atoms)
+                for (int i = 0; i < 4; ++i) {
+                    const int row = __ldg(p.seq_off + min(seq0 + i, p.n_seq - 1));
+                    const uint32_t so = (uint32_t)(i * 4096);
+                    tma_load_2d(sQ_hi + so, &map_q_hi, bar_qk, p.q_col + h * 64, row);
+                    tma_load_2d(sK_hi + so, &map_kv_hi, bar_qk, p.k_col + h * 64, row);
+                    if (kX3) {
+                        tma_load_2d(sQ_lo + so, &map_q_lo, bar_qk, p.q_col + h * 64, row);
+                        tma_load_2d(sK_lo + so, &map_kv_lo, bar_qk, p.k_col + h * 64, row);
+                    }
+                }
+                mbar_expect_tx(bar_v, P * kAtTile);
+                for (int i = 0; i < 4; ++i) {
+                    const int row = __ldg(p.seq_off + min(seq0 + i, p.n_seq - 1));
+                    const uint32_t so = (uint32_t)(i * 4096);
+                    tma_load_2d(sV_hi + so, &map_kv_hi, bar_v, p.v_col + h * 64, row);
+                    if (kX3) tma_load_2d(sV_lo + so, &map_kv_lo, bar_v, p.v_col + h * 64, row);
+                }
+            } else {
+                tma_load_2d(sQ_hi, &map_q_hi, bar_qk, p.q_col + h * 64, q_row0);
+                tma_load_2d(sK_hi, &map_kv_hi, bar_qk, p.k_col + h * 64, k_row0);
+                if (kX3) {
+                    tma_load_2d(sQ_lo, &map_q_lo, bar_qk, p.q_col + h * 64, q_row0);
+                    tma_load_2d(sK_lo, &map_kv_lo, bar_qk, p.k_col + h * 64, k_row0);
+                }
+                mbar_expect_tx(bar_v, P * kAtTile);
+                tma_load_2d(sV_hi, &map_kv_hi, bar_v, p.v_col + h * 64, k_row0);
+                if (kX3) tma_load_2d(sV_lo, &map_kv_lo, bar_v, p.v_col + h * 64, k_row0);
             }
-            mbar_expect_tx(bar_v, P * kAtTile);
-            tma_load_2d(sV_hi, &map_kv_hi, bar_v, p.v_col + h * 64, k_row0);
-            if (kX3) tma_load_2d(sV_lo, &map_kv_lo, bar_v, p.v_col + h * 64, k_row0);
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -174,7 +228,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         // (PAD keys, causal / diagonal masks; models/bert.py:157-161).  Chunks [c_lo, c_hi] (warp
         // uniform) are the only ones with a visible key for some row of this warp; P is zero elsewhere.
         int own_lo = 0, own_hi = n_keys, ipos = 0, c_lo = 0, c_hi = 3;
-        if (p.is_self) {
+        if (p.is_self && packed) {
+            own_lo = quarter * 32;             // one sequence per warp / per 32-key chunk
+            own_hi = own_lo + slot_len;
+            ipos = lane;
+            c_lo = c_hi = quarter;
+        } else if (p.is_self) {
             const int si = r / p.S;
             own_lo = si * p.S;
             own_hi = min(own_lo + p.S, n_keys);
@@ -283,6 +342,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     *reinterpret_cast<uint4*>(panel_hi + 2 * kAtTile + ch) = make_uint4(lo_w[i * 4], lo_w[i * 4 + 1], lo_w[i * 4 + 2], lo_w[i * 4 + 3]);
             }
         }
+        if (p.is_self && packed) {
+            // slot rows beyond the sequence hold whatever follows it in memory: P is 0 there, but 0 * NaN
+            // would poison O, so those V rows are cleared (each key row = one 128-byte swizzled row)
+            mbar_wait(bar_v, 0);
+            if (lane >= slot_len) {
+                uint8_t* vrow = smem_gen + Cfg::kQKBytes + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    *reinterpret_cast<uint4*>(vrow + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    if (kX3) *reinterpret_cast<uint4*>(vrow + kAtTile + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
@@ -292,8 +364,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         mbar_wait(bar_o, 0);
         tc_fence_after();
         const float inv = 1.0f / sum;
-        const bool store = r < nq_valid;
-        const size_t o = ((size_t)q_row0 + r) * p.D + h * 64;
+        const bool store = (p.is_self && packed) ? (lane < slot_len) : (r < nq_valid);
+        const size_t o = ((p.is_self && packed) ? (size_t)(slot_row0 + lane) : ((size_t)q_row0 + r)) * p.D + h * 64;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
@@ -342,7 +414,7 @@ static int at_init() {
 
 static int launch_attn_tc(int mode, const uint16_t* q_hi, const uint16_t* q_lo, int ldq, int q_cols, int q_rows,
                           const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv, int kv_cols, int kv_rows,
-                          const AtParams& p, int n_tiles, int H, cudaStream_t st, const char* what) {
+                          const AtParams& p, int n_tiles, int H, cudaStream_t st, const char* what, int box_rows = 128) {
     NAVC_REQUIRE(tc_ready(), "%s: navc_init() has not been called", what);
     NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "%s: bad mode %d", what, mode);
     NAVC_REQUIRE(q_hi && kv_hi && (mode == NAVC_TC_BF16 || (q_lo && kv_lo)), "%s: null operand", what);
@@ -351,11 +423,12 @@ static int launch_attn_tc(int mode, const uint16_t* q_hi, const uint16_t* q_lo, 
                  "%s: operands must be 16-byte aligned", what);
     if (at_init()) return 2;
     CUtensorMap mq_hi, mq_lo, mk_hi, mk_lo;
-    if (tc_make_map(&mq_hi, q_hi, q_rows, q_cols, ldq, 128)) return 1;
-    if (tc_make_map(&mk_hi, kv_hi, kv_rows, kv_cols, ldkv, 128)) return 1;
+    const int kv_box = p.is_self ? box_rows : 128;
+    if (tc_make_map(&mq_hi, q_hi, q_rows, q_cols, ldq, box_rows)) return 1;
+    if (tc_make_map(&mk_hi, kv_hi, kv_rows, kv_cols, ldkv, kv_box)) return 1;
     if (mode == NAVC_TC_BF16X3) {
-        if (tc_make_map(&mq_lo, q_lo, q_rows, q_cols, ldq, 128)) return 1;
-        if (tc_make_map(&mk_lo, kv_lo, kv_rows, kv_cols, ldkv, 128)) return 1;
+        if (tc_make_map(&mq_lo, q_lo, q_rows, q_cols, ldq, box_rows)) return 1;
+        if (tc_make_map(&mk_lo, kv_lo, kv_rows, kv_cols, ldkv, kv_box)) return 1;
     } else {
         mq_lo = mq_hi;
         mk_lo = mk_hi;
@@ -404,4 +477,41 @@ extern "C" int navc_cross_attention_tc(int mode, const uint16_t* q_hi, const uin
     p.ctx_f32 = ctx_f32; p.ctx_hi = ctx_hi; p.ctx_lo = ctx_lo;
     return launch_attn_tc(mode, q_hi, q_lo, ldq, D, N * S, kv_hi, kv_lo, ldkv, 2 * D, G * E, p, G * tpo, H,
                           as_stream(stream), "navc_cross_attention_tc");
+}
+
+extern "C" int navc_self_attention_tc_packed(int mode, const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld,
+                                             const int64_t* tokens, const int32_t* seq_off, int N, int S, int D, int H,
+                                             int mask_kind, int watch, float* ctx_f32, uint16_t* ctx_hi,
+                                             uint16_t* ctx_lo, void* stream) {
+    NAVC_REQUIRE(tokens && seq_off && (ctx_f32 || ctx_hi), "navc_self_attention_tc_packed: null pointer");
+    NAVC_REQUIRE(N > 0 && S > 0 && S <= 32 && H > 0 && D == H * 64 && ld >= 3 * D,
+                 "navc_self_attention_tc_packed: needs dk == 64 and S <= 32 (N=%d S=%d D=%d H=%d)", N, S, D, H);
+    NAVC_REQUIRE(mask_kind >= 0 && mask_kind <= 2, "navc_self_attention_tc_packed: bad mask kind");
+    const int R = N * S;  // row maximum of the packed buffers
+    AtParams p = {};
+    p.q_col = 0; p.k_col = D; p.v_col = 2 * D;
+    p.rows_per_tile = 128; p.total_q_rows = R; p.S = S; p.is_self = 1; p.mask_kind = mask_kind; p.watch = watch;
+    p.tokens = tokens; p.seq_off = seq_off; p.n_seq = N; p.group = 1; p.D = D;
+    p.ctx_f32 = ctx_f32; p.ctx_hi = ctx_hi; p.ctx_lo = ctx_lo;
+    return launch_attn_tc(mode, qkv_hi, qkv_lo, ld, 3 * D, R, qkv_hi, qkv_lo, ld, 3 * D, R, p, (N + 3) / 4, H,
+                          as_stream(stream), "navc_self_attention_tc_packed", 32);
+}
+
+extern "C" int navc_cross_attention_tc_packed(int mode, const uint16_t* q_hi, const uint16_t* q_lo, int ldq,
+                                              const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv,
+                                              const int32_t* seq_off, int N, int S, int E, int D, int H, int group,
+                                              float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream) {
+    NAVC_REQUIRE(seq_off && (ctx_f32 || ctx_hi), "navc_cross_attention_tc_packed: null pointer");
+    NAVC_REQUIRE(N > 0 && S > 0 && E > 0 && E <= 128 && H > 0 && D == H * 64 && group >= 1 && N % group == 0 &&
+                     ldq >= D && ldkv >= 2 * D,
+                 "navc_cross_attention_tc_packed: needs dk == 64 and E <= 128 (N=%d S=%d E=%d D=%d H=%d)", N, S, E, D, H);
+    const int G = N / group, nq = group * S, tpo = (nq + 127) / 128;
+    AtParams p = {};
+    p.q_col = 0; p.k_col = 0; p.v_col = D;
+    p.rows_per_tile = 128; p.nq_per_owner = nq; p.tiles_per_owner = tpo; p.keys_per_owner = E;
+    p.total_q_rows = N * S; p.S = S; p.is_self = 0; p.D = D;
+    p.seq_off = seq_off; p.n_seq = N; p.group = group;
+    p.ctx_f32 = ctx_f32; p.ctx_hi = ctx_hi; p.ctx_lo = ctx_lo;
+    return launch_attn_tc(mode, q_hi, q_lo, ldq, D, N * S, kv_hi, kv_lo, ldkv, 2 * D, G * E, p, G * tpo, H,
+                          as_stream(stream), "navc_cross_attention_tc_packed");
 }

@@ -112,6 +112,7 @@ struct EpiParams {
     int accumulate;  // out_f32 += (atomic)
     const uint16_t* res_hi;  // bf16 hi/lo residual (tcgen05 pair epilogue)
     const uint16_t* res_lo;
+    const int* m_dev;        // device-side row count (tcgen05 path)
 };
 static inline EpiParams to_params(const navc_epilogue_t* e) {
     EpiParams p;
@@ -123,6 +124,7 @@ static inline EpiParams to_params(const navc_epilogue_t* e) {
     p.accumulate = (e->accumulate != 0 || p.split_k > 1) ? 1 : 0;
     p.res_hi = e->res_hi;
     p.res_lo = e->res_lo;
+    p.m_dev = e->m_dev;
     return p;
 }
 

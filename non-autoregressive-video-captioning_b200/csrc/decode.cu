@@ -76,8 +76,9 @@ __global__ void refine_step_kernel(StepArgs a, int S) {
     if (p.merge != NAVC_MERGE_NONE) {
         int64_t ntok = NAVC_PAD;
         float nprob = 1.f;
-        if (active) {
-            const size_t pr = o * p.n_tiles;
+        if (active && !(pad && p.seq_off)) {
+            // packed rows: the partials of (n, i < len) live in row seq_off[n] + i; PAD positions have none
+            const size_t pr = (p.seq_off ? (size_t)(p.seq_off[n] + i) : o) * p.n_tiles;
             SoftPart acc;
             acc.m = -INFINITY; acc.s = 0.f; acc.i = 0x7fffffff;
             for (int t = 0; t < p.n_tiles; ++t) {

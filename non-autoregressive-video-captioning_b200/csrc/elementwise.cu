@@ -183,16 +183,58 @@ __device__ __forceinline__ void warp_ln_store(float4 (&v)[kMaxChunks], int nchun
     }
 }
 
+// single block: exclusive prefix sum of lens -> seq_off[0..N]; rowmap[seq_off[n] + s] = n*S + s
+__global__ void pack_rows_kernel(const int32_t* __restrict__ lens, int N, int S, int32_t* __restrict__ seq_off,
+                                 int32_t* __restrict__ rowmap) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < N; base += blockDim.x) {
+        const int n = base + threadIdx.x;
+        const int len = n < N ? min(max(lens[n], 0), S) : 0;
+        int inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+        const int start = carry + woff + inc - len;
+        if (n < N) {
+            seq_off[n] = start;
+            for (int j = 0; j < len; ++j) rowmap[start + j] = n * S + j;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = start + len;
+        __syncthreads();
+        (void)nw;
+    }
+    if (threadIdx.x == 0) seq_off[N] = carry;
+}
+
 __global__ void embed_ln_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ category,
                                 const float* __restrict__ word, const float* __restrict__ pos,
                                 const float* __restrict__ cat, const float* __restrict__ extra, int group,
                                 const float* __restrict__ lw, const float* __restrict__ lb, float eps, int R,
-                                int S, int D, float* out_f32, uint16_t* out_hi, uint16_t* out_lo) {
+                                int S, int D, float* out_f32, uint16_t* out_hi, uint16_t* out_lo,
+                                const int32_t* __restrict__ rowmap, const int32_t* __restrict__ count,
+                                int64_t* __restrict__ tok_out) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= R) return;
-    const int n = row / S, s = row % S;
-    const int64_t tok = tokens[row];
+    int src = row;
+    if (rowmap) {  // packed rows: row -> padded position
+        if (row >= __ldg(count)) return;
+        src = rowmap[row];
+    }
+    const int n = src / S, s = src % S;
+    const int64_t tok = tokens[src];
+    if (tok_out && lane == 0) tok_out[row] = tok;
     const float* wr = word + (size_t)tok * D;
     const float* pr = pos + (size_t)s * D;
     const float* cr = cat ? cat + (size_t)category[n / group] * D : nullptr;
@@ -324,8 +366,29 @@ extern "C" int navc_embed_ln(const int64_t* tokens, const int64_t* category, con
     int wpb = 8;
     embed_ln_kernel<<<(R + wpb - 1) / wpb, wpb * 32, 0, as_stream(stream)>>>(
         tokens, category, word_emb, pos_emb, cat_emb, extra, group, ln_w, ln_b, eps, R, S, D, out_f32, out_hi,
-        out_lo);
+        out_lo, nullptr, nullptr, nullptr);
     return check_launch("navc_embed_ln");
+}
+
+extern "C" int navc_pack_rows(const int32_t* lens, int N, int S, int32_t* seq_off, int32_t* rowmap, void* stream) {
+    NAVC_REQUIRE(lens && seq_off && rowmap && N > 0 && S > 0, "navc_pack_rows: bad arguments");
+    pack_rows_kernel<<<1, 1024, 0, as_stream(stream)>>>(lens, N, S, seq_off, rowmap);
+    return check_launch("navc_pack_rows");
+}
+
+extern "C" int navc_embed_ln_packed(const int64_t* tokens, const int64_t* category, const float* word_emb,
+                                    const float* pos_emb, const float* cat_emb, const float* extra, int group,
+                                    const float* ln_w, const float* ln_b, float eps, int N, int S, int D,
+                                    const int32_t* seq_off, const int32_t* rowmap, int64_t* tok_out, float* out_f32,
+                                    uint16_t* out_hi, uint16_t* out_lo, void* stream) {
+    NAVC_REQUIRE(tokens && word_emb && pos_emb && ln_w && ln_b && seq_off && rowmap, "navc_embed_ln_packed: null pointer");
+    NAVC_REQUIRE(!cat_emb || category, "navc_embed_ln_packed: category embeddings without category ids");
+    NAVC_REQUIRE(D % 4 == 0 && D <= 4 * 32 * kMaxChunks && group >= 1, "navc_embed_ln_packed: bad shape");
+    const int R = N * S, wpb = 8;
+    embed_ln_kernel<<<(R + wpb - 1) / wpb, wpb * 32, 0, as_stream(stream)>>>(
+        tokens, category, word_emb, pos_emb, cat_emb, extra, group, ln_w, ln_b, eps, R, S, D, out_f32, out_hi,
+        out_lo, rowmap, seq_off + N, tok_out);
+    return check_launch("navc_embed_ln_packed");
 }
 
 extern "C" int navc_layernorm(const float* x, const float* w, const float* b, float eps, const int64_t* row_tokens,

@@ -66,7 +66,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
-               int M, int N, int K, EpiParams epi, TcVocab vep) {
+               int M_max, int N, int K, EpiParams epi, TcVocab vep) {
+    // device-side row count (packed-row decoding): only the first *m_dev rows are computed
+    const int M = epi.m_dev ? min(M_max, __ldg(epi.m_dev)) : M_max;
     constexpr bool kVocab = kEpi == kEpiVocab;
     constexpr bool kPairAny = kEpi == kEpiPair || kEpi == kEpiPairRes;
     constexpr bool kResTma = kEpi == kEpiPairRes;
@@ -664,4 +666,17 @@ extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint
     e.split_k = 1;
     return launch_tc<kEpiVocab>(mode, h_hi, h_lo, ldh, w_hi, w_lo, ldw, M, V, K, e, v, as_stream(stream),
                            "navc_vocab_partials_tc");
+}
+
+extern "C" int navc_vocab_partials_tc_dyn(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,
+                                          const uint16_t* w_hi, const uint16_t* w_lo, int ldw, const float* bias, int M,
+                                          int V, int K, const int32_t* m_dev, float* part_max, float* part_sum,
+                                          int32_t* part_idx, void* stream) {
+    NAVC_REQUIRE(part_max && part_sum && part_idx, "navc_vocab_partials_tc_dyn: null output");
+    TcVocab v = {bias, part_max, part_sum, part_idx, nullptr, nullptr, (V + kVocabBN / 2 - 1) / (kVocabBN / 2)};
+    EpiParams e = {};
+    e.split_k = 1;
+    e.m_dev = m_dev;
+    return launch_tc<kEpiVocab>(mode, h_hi, h_lo, ldh, w_hi, w_lo, ldw, M, V, K, e, v, as_stream(stream),
+                                "navc_vocab_partials_tc_dyn");
 }

@@ -10,6 +10,8 @@ pass for their data-dependent stopping rule (as the reference does).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import _lib as L
@@ -35,6 +37,12 @@ class Refiner:
         self.visual = torch.zeros((N, S), dtype=torch.uint8, device=dev)
         self.masked0 = torch.zeros((N, S), dtype=torch.uint8, device=dev)
         self.counters = torch.zeros((256, 2), dtype=torch.int32, device=dev)
+        # packed rows (only the sum(len) real positions are decoder rows) when the whole layer runs on the
+        # tensor cores; opt['navc_packed'] / $NAVC_PACKED = 0 keeps the reference's padded [N, S] layout
+        want = opt.get("navc_packed", os.environ.get("NAVC_PACKED", "1"))
+        self.packed = None
+        if str(want).lower() not in ("0", "false", "no", "off") and self.eng.can_pack(S, mem["E"]):
+            self.packed = self.eng.pack_rows(self.lens, S)
         self.n_steps = 0
         self.passes = 0
         self.pending = None  # (partials, merge kind, is_ct) of the pass not yet merged
@@ -51,8 +59,9 @@ class Refiner:
 
     def run_pass(self, merge, is_ct=False):
         """decoder + vocabulary statistics on the current canvas (algorithms.py:143-167)."""
-        hid, _ = self.eng.decoder_pass(self.canvas, self.mem, self.group, self.category, "NARFormer")
-        self.pending = (self.eng.vocab_partials(hid), merge, is_ct)
+        hid, _ = self.eng.decoder_pass(self.canvas, self.mem, self.group, self.category, "NARFormer", packed=self.packed)
+        m_dev = self.packed["count"] if self.packed is not None else None
+        self.pending = (self.eng.vocab_partials(hid, m_dev=m_dev), merge, is_ct)
         self.passes += 1
 
     def step(self, select, ratio=0.0, given=None, q=1, win=(0, 0), use_teacher=False, emit_flags=False):
@@ -78,6 +87,7 @@ class Refiner:
         st.counters = self.counters[slot].data_ptr()
         st.visual = L.ptr(self.visual) if emit_flags else None
         st.masked0 = L.ptr(self.masked0) if emit_flags else None
+        st.seq_off = L.ptr(self.packed["seq_off"]) if (self.packed is not None and self.pending is not None) else None
         L.call("navc_refine_step", st, self.N, self.S, L.stream())
         self.pending = None
         self.n_steps += 1

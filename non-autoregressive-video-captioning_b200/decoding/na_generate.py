@@ -94,7 +94,7 @@ def _run(opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping):
     hyp = torch.empty((B, S), dtype=torch.int64, device=beam.device)
     L.call("navc_select_best", L.ptr(tokens), L.ptr(lprobs), L.ptr(ref.lens), B, lbs, S,
            float(opt.get("beam_alpha", 1.0)), L.ptr(hyp), None, L.stream())
-    return hyp, {"passes": ref.passes, "S": S, "N": ref.N, "steps": ref.n_steps}
+    return hyp, {"passes": ref.passes, "S": S, "N": ref.N, "steps": ref.n_steps, "packed": ref.packed is not None}
 
 
 def generate(opt, model, teacher_model, encoder_outputs, teacher_encoder_outputs, category, tgt_tokens,
@@ -117,7 +117,7 @@ def generate(opt, model, teacher_model, encoder_outputs, teacher_encoder_outputs
     beam = torch.empty((B, lbs), dtype=torch.int32, device=dev)
     smax = torch.zeros((1,), dtype=torch.int32, device=dev)
     L.call("navc_length_beam", L.ptr(pred_length), B, max_len, lbs, int(length_bias), L.ptr(beam), L.ptr(smax), L.stream())
-    S = int(smax.item())
+    S, rows_real = torch.cat([smax, beam.sum().to(torch.int32).view(1)]).tolist()  # ONE host read: Smax and sum(len)
 
     mem = eng.enc_inputs(encoder_outputs["enc_output"], encoder_outputs.get("_navc"))
     tmem = None
@@ -146,12 +146,12 @@ def generate(opt, model, teacher_model, encoder_outputs, teacher_encoder_outputs
             if entry == "warm":  # second call with this shape: capture
                 entry = eng.graphs[key] = _DecodeGraph(_run, opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping)
             hyp = entry.replay(mem, tmem, cat, beam)
-            generate.last_stats = dict(entry.stats, graph=True)
+            generate.last_stats = dict(entry.stats, graph=True, rows_real=rows_real)
             return hyp, None
         eng.graphs[key] = "warm"  # first call: run eagerly (also warms up lazily initialised kernels)
 
     hyp, stats = _run(opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping)
-    generate.last_stats = dict(stats, graph=False)
+    generate.last_stats = dict(stats, graph=False, rows_real=rows_real)
     return hyp, None
 
 

@@ -228,7 +228,7 @@ class Engine:
         return a
 
     def linear(self, x: Act, lin: PackedLinear, act=0, residual=None,
-               row_tokens: Optional[torch.Tensor] = None, f32=True, bf=True, tag=None, lo=False) -> Act:
+               row_tokens: Optional[torch.Tensor] = None, f32=True, bf=True, tag=None, lo=False, m_dev=None) -> Act:
         """nn.Linear + fused epilogue (include/navc.h navc_epilogue_t).  ``residual`` is an fp32 tensor
         or an Act; an Act without an fp32 copy is passed as its bf16 hi/lo pair (tcgen05 pair epilogue)."""
         M, N, K = x.M, lin.N, lin.K
@@ -248,7 +248,8 @@ class Engine:
         elif residual is not None:
             res32, ld_res = residual, residual.shape[-1]
         ep = L.Epilogue(L.ptr(lin.b), L.ptr(res32), L.ptr(row_tokens), act, ld_res,
-                        L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), N, 0, 1, 0, L.ptr(res_hi), L.ptr(res_lo))
+                        L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), N, 0, 1, 0, L.ptr(res_hi), L.ptr(res_lo),
+                        m_dev.data_ptr() if m_dev is not None else None)
         timed = tag is not None and tag == self.profile_tag
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,11 +272,11 @@ class Engine:
                L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), L.stream())
         return out
 
-    def _proj_res(self, x: Act, lin, ln, residual: Act, row_tokens, pair=False) -> Act:
+    def _proj_res(self, x: Act, lin, ln, residual: Act, row_tokens, pair=False, m_dev=None) -> Act:
         """dense -> (+residual) -> [LayerNorm] -> * non_pad_mask   (models/bert.py:192-200, 240-247, 271-299).
         pair: the residual stream lives as bf16 hi/lo pairs only (tensor-core modes without LayerNorm)."""
         if ln is None:
-            return self.linear(x, lin, residual=residual, row_tokens=row_tokens, f32=not pair, bf=True, lo=pair)
+            return self.linear(x, lin, residual=residual, row_tokens=row_tokens, f32=not pair, bf=True, lo=pair, m_dev=m_dev)
         y = self.linear(x, lin, residual=residual, row_tokens=None, f32=True, bf=False)
         return self.layernorm(y, ln, row_tokens)
 
@@ -366,8 +367,23 @@ class Engine:
             mem["kv"].f32 = self.linear(mem["enc"], self.P["kv_all"], f32=True, bf=False).f32
         return mem["kv"].f32
 
+    def pack_rows(self, lens: torch.Tensor, S: int):
+        """Packed-row bookkeeping for a fixed set of candidate lengths (include/navc.h "packed rows"):
+        seq_off [N+1] (seq_off[N] = row count, device side), rowmap [N*S]."""
+        N = lens.numel()
+        seq_off = torch.empty((N + 1,), dtype=torch.int32, device=self.device)
+        rowmap = torch.zeros((N * S,), dtype=torch.int32, device=self.device)
+        L.call("navc_pack_rows", L.ptr(lens), N, S, L.ptr(seq_off), L.ptr(rowmap), L.stream())
+        return dict(seq_off=seq_off, rowmap=rowmap, count=seq_off[N:], N=N, S=S)
+
+    def can_pack(self, S, E):
+        """Packed rows need the all-tensor-core layer (pair epilogues + tcgen05 attention cores)."""
+        P = self.P
+        return self.tc_attention_ok(S, E) and self.D % 64 == 0 and P["layers"][0]["f1"].N % 64 == 0 and \
+            all(lw[k] is None for lw in P["layers"] for k in ("so_ln", "co_ln", "f2_ln"))
+
     def decoder_pass(self, tokens: torch.Tensor, mem: dict, group: int, category: Optional[torch.Tensor],
-                     decoding_type: str, want_attn=False, want_f32=False):
+                     decoding_type: str, want_attn=False, want_f32=False, packed: Optional[dict] = None):
         """One BertDecoder forward (models/Decoder.py:96-178) -> hidden Act [N*S, D] (+ attention probs)."""
         P, D, H = self.P, self.D, self.H
         N, S = tokens.shape
@@ -388,29 +404,50 @@ class Engine:
         pair = self.tc and D % 64 == 0 and P["layers"][0]["f1"].N % 64 == 0 and \
             all(lw[k] is None for lw in P["layers"] for k in ("so_ln", "co_ln", "f2_ln"))
         x = self._new(R, D, not pair, True, lo=pair)
-        L.call("navc_embed_ln", L.ptr(tokens), L.ptr(category), L.ptr(emb["word"]), L.ptr(emb["pos"]), L.ptr(emb["cat"]),
-               L.ptr(extra), group, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), self.eps, N, S, D,
-               L.ptr(x.f32), L.ptr(x.hi), L.ptr(x.lo), L.stream())
+        m_dev = None
+        if packed is not None:
+            # only the sum(len) real positions are rows (R stays the launch maximum, the count is device side)
+            assert pair and not want_attn and packed["N"] == N and packed["S"] == S
+            m_dev = packed["count"]
+            tok_flat = torch.empty((R,), dtype=torch.int64, device=self.device)  # token id of every packed row
+            L.call("navc_embed_ln_packed", L.ptr(tokens), L.ptr(category), L.ptr(emb["word"]), L.ptr(emb["pos"]),
+                   L.ptr(emb["cat"]), L.ptr(extra), group, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), self.eps, N, S, D,
+                   L.ptr(packed["seq_off"]), L.ptr(packed["rowmap"]), L.ptr(tok_flat), L.ptr(x.f32), L.ptr(x.hi),
+                   L.ptr(x.lo), L.stream())
+        else:
+            L.call("navc_embed_ln", L.ptr(tokens), L.ptr(category), L.ptr(emb["word"]), L.ptr(emb["pos"]), L.ptr(emb["cat"]),
+                   L.ptr(extra), group, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), self.eps, N, S, D,
+                   L.ptr(x.f32), L.ptr(x.hi), L.ptr(x.lo), L.stream())
         kv = mem["kv"]
         attns = []
         mask_kind = L.MASK_KIND[decoding_type]
         tc_attn = self.tc_attention_ok(S, E) and not want_attn and kv.hi is not None
         watch = int(self.opt.get("watch", 0))
         for l, lw in enumerate(P["layers"]):
-            qkv = self.linear(x, lw["qkv"], f32=not tc_attn, bf=tc_attn)
+            qkv = self.linear(x, lw["qkv"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev)
             ctx = self._new(R, D, not self.tc, True)
             p_self = p_cross = None
-            if tc_attn:
+            if packed is not None:
+                L.call("navc_self_attention_tc_packed", self.tc_mode, L.ptr(qkv.hi), L.ptr(qkv.lo), 3 * D, L.ptr(tokens),
+                       L.ptr(packed["seq_off"]), N, S, D, H, mask_kind, watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo),
+                       L.stream())
+            elif tc_attn:
                 L.call("navc_self_attention_tc", self.tc_mode, L.ptr(qkv.hi), L.ptr(qkv.lo), 3 * D, L.ptr(tokens), N, S,
                        D, H, mask_kind, watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.stream())
             else:
                 p_self = torch.empty((H, N, S, S), dtype=torch.float32, device=self.device) if want_attn else None
                 L.call("navc_self_attention", L.ptr(qkv.f32), 3 * D, L.ptr(tokens), N, S, D, H, mask_kind,
                        watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.ptr(p_self), L.stream())
-            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tok_flat, pair)
-            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn)
+            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tok_flat, pair, m_dev)
+            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev)
             ctx2 = self._new(R, D, not self.tc, True)
-            if tc_attn:
+            if packed is not None:
+                off = l * 2 * D
+                L.call("navc_cross_attention_tc_packed", self.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D,
+                       kv.hi[:, off:].data_ptr(), kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N,
+                       L.ptr(packed["seq_off"]), N, S, E, D, H, group, L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo),
+                       L.stream())
+            elif tc_attn:
                 off = l * 2 * D
                 L.call("navc_cross_attention_tc", self.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D,
                        kv.hi[:, off:].data_ptr(), kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N,
@@ -420,9 +457,9 @@ class Engine:
                 kv_l = self._kv_f32(mem)[:, l * 2 * D:]
                 L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, S, E, D, H, group,
                        L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
-            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair)
-            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1")
-            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair)
+            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair, m_dev)
+            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1", m_dev=m_dev)
+            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair, m_dev)
             if want_attn:
                 attns.append((p_self, p_cross))
         if want_f32:
@@ -432,7 +469,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # vocabulary projection
     # ------------------------------------------------------------------------------------------
-    def vocab_partials(self, hidden: Act, target: Optional[torch.Tensor] = None):
+    def vocab_partials(self, hidden: Act, target: Optional[torch.Tensor] = None, m_dev: Optional[torch.Tensor] = None):
         """tgt_word_prj + softmax statistics without materialising logits (algorithms.py:7-15)."""
         lin = self.P["vocab"]
         R, V, K = hidden.M, lin.N, lin.K
@@ -444,7 +481,11 @@ class Engine:
         ps = torch.empty((R, nt), dtype=torch.float32, device=dev)
         pi = torch.empty((R, nt), dtype=torch.int32, device=dev)
         tl = torch.empty((R,), dtype=torch.float32, device=dev) if target is not None else None
-        if use_tc:
+        if m_dev is not None:
+            assert use_tc and target is None
+            L.call("navc_vocab_partials_tc_dyn", self.tc_mode, L.ptr(hidden.hi), L.ptr(hidden.lo), K, L.ptr(lin.w_hi),
+                   L.ptr(lin.w_lo), K, L.ptr(lin.b), R, V, K, m_dev.data_ptr(), L.ptr(pm), L.ptr(ps), L.ptr(pi), L.stream())
+        elif use_tc:
             L.call("navc_vocab_partials_tc", self.tc_mode, L.ptr(hidden.hi), L.ptr(hidden.lo), K, L.ptr(lin.w_hi),
                    L.ptr(lin.w_lo), K, L.ptr(lin.b), R, V, K, L.ptr(pm), L.ptr(ps), L.ptr(pi), L.ptr(target), L.ptr(tl),
                    L.stream())
