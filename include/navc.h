@@ -205,6 +205,9 @@ int navc_cross_attention_tc_packed(int mode, const uint16_t* q_hi, const uint16_
                                    const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv,
                                    const int32_t* seq_off, int N, int S, int E, int D, int H, int group,
                                    float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream);
+/* out[k, :] = in[rows[k], :] for k < *count (bf16 hi / lo pairs, D % 8 == 0; lo may be NULL). */
+int navc_gather_rows(const uint16_t* in_hi, const uint16_t* in_lo, int D, const int32_t* rows,
+                     const int32_t* count, int max_rows, uint16_t* out_hi, uint16_t* out_lo, void* stream);
 /* navc_vocab_partials_tc over the first min(M, *m_dev) rows. */
 int navc_vocab_partials_tc_dyn(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,
                                const uint16_t* w_hi, const uint16_t* w_lo, int ldw, const float* bias,
@@ -260,6 +263,12 @@ typedef struct {
     uint8_t* masked0;          /* [N,S] out or NULL: token == MASK && s < len after the merge */
     const int32_t* seq_off;    /* NULL, or [N+1] packed-row offsets: the partials of position (n, s < len) live in
                                   row seq_off[n] + s instead of n*S + s (navc_pack_rows) */
+    /* second-level packing of the vocabulary projection (needs seq_off): the next pass only needs
+     * logits at the positions this step re-masks (the MERGE_MASKED merge ignores all others) */
+    const int32_t* part_slot;  /* in, or NULL: partials of packed row r live in row part_slot[r] (a previous step's sel_slot) */
+    int32_t* sel_rows;         /* out, or NULL: packed rows of the positions selected for re-masking, in any order */
+    int32_t* sel_count;        /* out: their number (device scalar, atomicAdd; caller zeroes) */
+    int32_t* sel_slot;         /* out: [N*S] packed row -> index in sel_rows */
 } navc_step_t;
 /* One launch per refinement iteration: combine the vocabulary partials into (argmax, max prob),
  * apply the pad rules, merge into the state, choose the next positions to re-mask, write the next

@@ -30,7 +30,7 @@ class Step(C.Structure):
                 ("win_lo", i32), ("win_hi", i32),
                 ("lens", vp), ("teacher", vp), ("given", vp), ("tokens", vp), ("probs", vp),
                 ("upd_mask", vp), ("canvas", vp), ("lprobs", vp), ("counters", vp), ("visual", vp),
-                ("masked0", vp), ("seq_off", vp)]
+                ("masked0", vp), ("seq_off", vp), ("part_slot", vp), ("sel_rows", vp), ("sel_count", vp), ("sel_slot", vp)]
 
 
 ACT = {"none": 0, None: 0, "gelu_new": 1, "gelu": 2, "relu": 3, "swish": 4}
@@ -63,6 +63,7 @@ _PROTOS = {
     "navc_embed_ln_packed": [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
     "navc_self_attention_tc_packed": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
     "navc_cross_attention_tc_packed": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_gather_rows": [vp, vp, i32, vp, vp, i32, vp, vp, vp],
     "navc_vocab_partials_tc_dyn": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp],
     "navc_length_beam": [vp, i32, i32, i32, i32, vp, vp, vp],
     "navc_init_canvas": [vp, i32, i32, i64, vp, vp, vp, vp],

@@ -74,21 +74,52 @@ __global__ void refine_step_kernel(StepArgs a, int S) {
     float prob = active ? p.probs[o] : 1.f;
 
     if (p.merge != NAVC_MERGE_NONE) {
-        int64_t ntok = NAVC_PAD;
-        float nprob = 1.f;
-        if (active && !(pad && p.seq_off)) {
-            // packed rows: the partials of (n, i < len) live in row seq_off[n] + i; PAD positions have none
-            const size_t pr = (p.seq_off ? (size_t)(p.seq_off[n] + i) : o) * p.n_tiles;
+        // phase A: the warps of the block combine the vocabulary partials of the row's positions (lane t takes
+        // tiles t, t+32, ...; coalesced loads, shuffle reduction) into shared memory
+        int* s_tok = flag + S;
+        float* s_prob = reinterpret_cast<float*>(s_tok + S);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int pos = warp; pos < S; pos += nwarps) {
+            const bool pad_p = pos >= len;
+            const size_t op = (size_t)n * S + pos;
+            // packed rows: the partials of (n, pos < len) live in row seq_off[n] + pos; PAD positions have none
+            size_t prow = p.seq_off ? (size_t)(p.seq_off[n] + pos) : op;
+            bool have = !(pad_p && p.seq_off);
+            // second-level packing: only the previously re-masked positions have partials (the merge below
+            // ignores the others)
+            if (have && p.part_slot) {
+                have = p.upd_mask[op] != 0;
+                if (have) prow = (size_t)p.part_slot[prow];
+            }
             SoftPart acc;
             acc.m = -INFINITY; acc.s = 0.f; acc.i = 0x7fffffff;
-            for (int t = 0; t < p.n_tiles; ++t) {
-                SoftPart q;
-                q.m = p.part_max[pr + t]; q.s = p.part_sum[pr + t]; q.i = p.part_idx[pr + t];
-                acc = soft_combine(acc, q);
+            if (have) {
+                const size_t pr = prow * p.n_tiles;
+                for (int t = lane; t < p.n_tiles; t += 32) {
+                    SoftPart q;
+                    q.m = p.part_max[pr + t]; q.s = p.part_sum[pr + t]; q.i = p.part_idx[pr + t];
+                    acc = soft_combine(acc, q);
+                }
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) {
+                    SoftPart q;
+                    q.m = __shfl_xor_sync(0xffffffffu, acc.m, sh);
+                    q.s = __shfl_xor_sync(0xffffffffu, acc.s, sh);
+                    q.i = __shfl_xor_sync(0xffffffffu, acc.i, sh);
+                    acc = soft_combine(acc, q);
+                }
             }
-            ntok = acc.i;
-            nprob = 1.0f / acc.s;
-            if (pad) { ntok = NAVC_PAD; nprob = 1.0f; }
+            if (lane == 0) {
+                s_tok[pos] = (have && !pad_p) ? acc.i : NAVC_PAD;
+                s_prob[pos] = (have && !pad_p) ? 1.0f / acc.s : 1.0f;
+            }
+        }
+        __syncthreads();
+        int64_t ntok = NAVC_PAD;
+        float nprob = 1.f;
+        if (active) {
+            ntok = s_tok[i];
+            nprob = s_prob[i];
             if (p.is_ct && ntok == NAVC_MASK) nprob = 0.0f;
         }
         if (p.merge == NAVC_MERGE_ALL) {
@@ -155,6 +186,12 @@ __global__ void refine_step_kernel(StepArgs a, int S) {
         p.probs[o] = prob;
         if (p.upd_mask) p.upd_mask[o] = sel ? 1 : 0;
         if (p.canvas) p.canvas[o] = sel ? (int64_t)NAVC_MASK : tok;
+        if (sel && p.sel_rows && !pad) {
+            const int prow = p.seq_off[n] + i;
+            const int k = atomicAdd(p.sel_count, 1);
+            p.sel_rows[k] = prow;
+            p.sel_slot[prow] = k;
+        }
         if (p.select == NAVC_SELECT_NONE && p.lprobs) p.lprobs[o] = logf(prob * tprob);
     }
     if (i == 0 && p.counters) {
@@ -244,12 +281,15 @@ extern "C" int navc_refine_step(const navc_step_t* p, int N, int S, void* stream
     NAVC_REQUIRE(p->merge == NAVC_MERGE_NONE || (p->part_max && p->part_sum && p->part_idx && p->n_tiles > 0),
                  "navc_refine_step: merge requested without partials");
     NAVC_REQUIRE(p->merge != NAVC_MERGE_MASKED || p->upd_mask, "navc_refine_step: MERGE_MASKED needs upd_mask");
+    NAVC_REQUIRE(!p->part_slot || (p->seq_off && p->merge == NAVC_MERGE_MASKED), "navc_refine_step: part_slot needs seq_off and MERGE_MASKED");
+    NAVC_REQUIRE(!p->sel_rows || (p->seq_off && p->sel_count && p->sel_slot), "navc_refine_step: sel_rows needs seq_off, sel_count, sel_slot");
     NAVC_REQUIRE((p->select != NAVC_SELECT_GIVEN && p->select != NAVC_SELECT_WINDOW) || p->given,
                  "navc_refine_step: selection needs `given`");
     StepArgs a;
     a.p = *p;
     int threads = ((S + 31) / 32) * 32;
-    size_t smem = (size_t)S * (sizeof(float) + sizeof(int));
+    if (threads < 256) threads = 256;  // extra warps only help phase A (combining the vocabulary partials)
+    size_t smem = (size_t)S * 2 * (sizeof(float) + sizeof(int));
     refine_step_kernel<<<N, threads, smem, as_stream(stream)>>>(a, S);
     return check_launch("navc_refine_step");
 }

@@ -349,7 +349,7 @@ extern "C" int navc_length_head(const float* enc_out, int B, int E, int D, const
     NAVC_REQUIRE(enc_out && B > 0 && E > 0 && D > 0, "navc_length_head: bad arguments");
     NAVC_REQUIRE(!w1 || (b1 && w2 && b2 && pred_length && max_len > 0), "navc_length_head: missing head weights");
     size_t smem = (size_t)(2 * D + (max_len > 0 ? max_len : 0)) * sizeof(float);
-    length_head_kernel<<<B, 256, smem, as_stream(stream)>>>(enc_out, E, D, w1, b1, w2, b2, max_len, enc_mean,
+    length_head_kernel<<<B, w1 ? 1024 : 256, smem, as_stream(stream)>>>(enc_out, E, D, w1, b1, w2, b2, max_len, enc_mean,
                                                            pred_length);
     return check_launch("navc_length_head");
 }
@@ -368,6 +368,28 @@ extern "C" int navc_embed_ln(const int64_t* tokens, const int64_t* category, con
         tokens, category, word_emb, pos_emb, cat_emb, extra, group, ln_w, ln_b, eps, R, S, D, out_f32, out_hi,
         out_lo, nullptr, nullptr, nullptr);
     return check_launch("navc_embed_ln");
+}
+
+// one warp per output row: 16-byte copies of the bf16 hi / lo rows
+__global__ void gather_rows_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo, int D,
+                                   const int32_t* __restrict__ rows, const int32_t* __restrict__ count, int max_rows,
+                                   uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= max_rows || k >= __ldg(count)) return;
+    const size_t src = (size_t)rows[k] * D, dst = (size_t)k * D;
+    for (int c = lane * 8; c < D; c += 256) {
+        *reinterpret_cast<uint4*>(out_hi + dst + c) = *reinterpret_cast<const uint4*>(in_hi + src + c);
+        if (in_lo) *reinterpret_cast<uint4*>(out_lo + dst + c) = *reinterpret_cast<const uint4*>(in_lo + src + c);
+    }
+}
+
+extern "C" int navc_gather_rows(const uint16_t* in_hi, const uint16_t* in_lo, int D, const int32_t* rows,
+                                const int32_t* count, int max_rows, uint16_t* out_hi, uint16_t* out_lo, void* stream) {
+    NAVC_REQUIRE(in_hi && rows && count && out_hi && (!in_lo || out_lo) && D % 8 == 0 && max_rows > 0,
+                 "navc_gather_rows: bad arguments");
+    gather_rows_kernel<<<(max_rows + 7) / 8, 256, 0, as_stream(stream)>>>(in_hi, in_lo, D, rows, count, max_rows, out_hi, out_lo);
+    return check_launch("navc_gather_rows");
 }
 
 extern "C" int navc_pack_rows(const int32_t* lens, int N, int S, int32_t* seq_off, int32_t* rowmap, void* stream) {

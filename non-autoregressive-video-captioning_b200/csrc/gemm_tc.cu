@@ -616,7 +616,8 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
         const bool narrow = forced ? forced == 128 : (N <= 128 || tile_waste_pct(t256, sms) >= tile_waste_pct(t128, sms) + 8);
         if constexpr (kEpi == kEpiPair) {
             // a bf16 hi/lo residual is prefetched by TMA (128-wide tiles only: the boxes need 64 KB of the ring)
-            if (epi.res_hi && (narrow || N <= 1024) && forced != 256)
+            // (plain bf16 only: the split mode cannot spare two of its three 64 KB stages' worth of ring)
+            if (mode == NAVC_TC_BF16 && epi.res_hi && (narrow || N <= 1024) && forced != 256)
                 return launch_tc_bn<kEpiPairRes, 128>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, vep, st, what);
         }
         if (narrow) return launch_tc_bn<kEpi, 128>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, vep, st, what);

@@ -43,6 +43,14 @@ class Refiner:
         self.packed = None
         if str(want).lower() not in ("0", "false", "no", "off") and self.eng.can_pack(S, mem["E"]):
             self.packed = self.eng.pack_rows(self.lens, S)
+        # second-level packing of the vocabulary projection: logits only at the positions the previous step
+        # re-masked (double-buffered row lists / slot maps; counts are device scalars)
+        self.vsel = None       # (rows, count, slot) written by the last selecting step
+        self.vbuf = None
+        if self.packed is not None:
+            R = N * S
+            self.vbuf = [(torch.empty((R,), dtype=torch.int32, device=dev), torch.zeros((1,), dtype=torch.int32, device=dev),
+                          torch.zeros((R,), dtype=torch.int32, device=dev)) for _ in range(2)]
         self.n_steps = 0
         self.passes = 0
         self.pending = None  # (partials, merge kind, is_ct) of the pass not yet merged
@@ -61,7 +69,17 @@ class Refiner:
         """decoder + vocabulary statistics on the current canvas (algorithms.py:143-167)."""
         hid, _ = self.eng.decoder_pass(self.canvas, self.mem, self.group, self.category, "NARFormer", packed=self.packed)
         m_dev = self.packed["count"] if self.packed is not None else None
-        self.pending = (self.eng.vocab_partials(hid, m_dev=m_dev), merge, is_ct)
+        slot = None
+        if merge == L.MERGE_MASKED and self.vsel is not None:
+            # only the re-masked positions are merged: project just their rows onto the vocabulary
+            rows, count, slot = self.vsel
+            from ..engine import Act
+            sub = Act(hid.M, hid.N, hi=torch.empty_like(hid.hi), lo=None if hid.lo is None else torch.empty_like(hid.lo))
+            L.call("navc_gather_rows", L.ptr(hid.hi), L.ptr(hid.lo), hid.N, L.ptr(rows), L.ptr(count), hid.M,
+                   L.ptr(sub.hi), L.ptr(sub.lo), L.stream())
+            hid, m_dev = sub, count
+        self.vsel = None
+        self.pending = (self.eng.vocab_partials(hid, m_dev=m_dev), merge, is_ct, slot)
         self.passes += 1
 
     def step(self, select, ratio=0.0, given=None, q=1, win=(0, 0), use_teacher=False, emit_flags=False):
@@ -69,7 +87,8 @@ class Refiner:
         next canvas.  Returns the index of the counter row written by this launch."""
         st = L.Step()
         if self.pending is not None:
-            (pm, ps, pi, nt, _), merge, is_ct = self.pending
+            (pm, ps, pi, nt, _), merge, is_ct, part_slot = self.pending
+            st.part_slot = L.ptr(part_slot)
             st.part_max, st.part_sum, st.part_idx, st.n_tiles = L.ptr(pm), L.ptr(ps), L.ptr(pi), nt
             st.merge, st.is_ct = merge, int(is_ct)
         else:
@@ -87,7 +106,12 @@ class Refiner:
         st.counters = self.counters[slot].data_ptr()
         st.visual = L.ptr(self.visual) if emit_flags else None
         st.masked0 = L.ptr(self.masked0) if emit_flags else None
-        st.seq_off = L.ptr(self.packed["seq_off"]) if (self.packed is not None and self.pending is not None) else None
+        st.seq_off = L.ptr(self.packed["seq_off"]) if self.packed is not None else None
+        if self.packed is not None and select in (L.SELECT_WORST, L.SELECT_MASKTOK, L.SELECT_GIVEN):
+            rows, count, slot_map = self.vbuf[self.n_steps % 2]
+            count.zero_()
+            st.sel_rows, st.sel_count, st.sel_slot = L.ptr(rows), L.ptr(count), L.ptr(slot_map)
+            self.vsel = (rows, count, slot_map)
         L.call("navc_refine_step", st, self.N, self.S, L.stream())
         self.pending = None
         self.n_steps += 1

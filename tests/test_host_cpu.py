@@ -38,7 +38,7 @@ def test_ctypes_struct_layout_matches_header():
     navc = _navc()
     # navc_epilogue_t: 3 pointers, 2 int32, 3 pointers, 2 int32 ; navc_step_t per include/navc.h
     assert ctypes.sizeof(navc._lib.Epilogue) == 3 * 8 + 8 + 3 * 8 + 8 + 8 + 16 + 8
-    assert ctypes.sizeof(navc._lib.Step) == 3 * 8 + 8 * 4 + 12 * 8
+    assert ctypes.sizeof(navc._lib.Step) == 3 * 8 + 8 * 4 + 16 * 8
 
 
 def test_product_path_fails_loudly_without_gpu():
