@@ -107,6 +107,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         n_keys = p.keys_per_owner;
     }
 
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 4); mbar_init(bar_o, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -115,6 +116,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();  // tokens / Q / K / V below may still be in flight in the preceding kernel
     if (warp >= 2) {
         const int r = (warp - 2) * 32 + lane;
         uint8_t kp = 0;
@@ -435,9 +437,9 @@ static int launch_attn_tc(int mode, const uint16_t* q_hi, const uint16_t* q_lo, 
     }
     dim3 grid(n_tiles, H);
     if (mode == NAVC_TC_BF16X3)
-        attn_tc_kernel<true><<<grid, kAtThreads, AtCfg<true>::kSmemBytes, st>>>(mq_hi, mq_lo, mk_hi, mk_lo, p);
+        NAVC_CUDA(launch_pdl(attn_tc_kernel<true>, grid, dim3(kAtThreads), AtCfg<true>::kSmemBytes, st, mq_hi, mq_lo, mk_hi, mk_lo, p));
     else
-        attn_tc_kernel<false><<<grid, kAtThreads, AtCfg<false>::kSmemBytes, st>>>(mq_hi, mq_lo, mk_hi, mk_lo, p);
+        NAVC_CUDA(launch_pdl(attn_tc_kernel<false>, grid, dim3(kAtThreads), AtCfg<false>::kSmemBytes, st, mq_hi, mq_lo, mk_hi, mk_lo, p));
     return check_launch(what);
 }
 

@@ -110,6 +110,30 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
 // instruction descriptor with B operand MN-major (bit 16)
 __host__ __device__ constexpr uint32_t make_idesc_bmn(int m, int n) { return make_idesc(m, n) | (1u << 16); }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------
+// Every tcgen05 kernel lets its successor launch early (its CTAs become resident as ours exit, during
+// the partially filled last wave) and runs its own prologue -- barrier init, TMEM allocation -- before
+// waiting for the predecessor's memory to be complete.  No-ops when launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // gemm_tc.cu ($NAVC_PDL=1; default off: no measurable gain under graph replay)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements),
 // box = [box_rows, 64 columns], 128B swizzle.  Defined in gemm_tc.cu (needs navc_init()).
 int tc_make_map(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld, int box_rows);
