@@ -286,8 +286,12 @@ def main():
         achieved = flops / (mean_ms / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         mma_mult = {"bf16x3": 3.0, "bf16": 1.0}.get(args.precision, 0.0)
+        # DRAM bytes of this launch from the committed `ncu --set full` capture (profiles/r1i_ncu_table_layer_*_packed.txt,
+        # same B=128 workload; dram__bytes_read.sum + dram__bytes_write.sum): below the algorithmic operand + result
+        # bytes because the bf16 results stay in the 126 MB L2 until the down-projection consumes them
+        traffic = {"bf16x3": 62.9e6, "bf16": 13.7e6}.get(args.precision) if (stats.get("packed") and B == 128) else None
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_tc_kernel (FFN up-projection, M=%d N=%d K=%d)" % (R, opt["intermediate_size"], opt["dim_hidden"]),
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)", "kernel": "gemm_tc_kernel (FFN up-projection, M=%d N=%d K=%d)" % (R, opt["intermediate_size"], opt["dim_hidden"]),
                 "launches_timed": len(durs), "timed_in": "eager re-run of the same steps (graph replay off), CUDA events on the launching stream", "mean_us": mean_ms * 1e3, "peak_source": pk_src + " (sustained cuBLAS bf16)",
                 "algorithmic_flops_per_launch": flops,
                 "issued_mma_frac": achieved * mma_mult / peak if mma_mult else None,
