@@ -452,3 +452,145 @@ def test_split_and_log_softmax():
     xd = x.to(DEV).contiguous()
     L.call("navc_log_softmax", L.ptr(xd), L.ptr(xd), 1000, 333, 333, L.stream())
     assert (xd.cpu() - torch.log_softmax(x, -1)).abs().max().item() < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# packed rows (include/navc.h "packed rows")
+# ---------------------------------------------------------------------------------------------------
+def _packing(N, S, seed):
+    gen = g(seed)
+    lens = torch.randint(1, S + 1, (N,), generator=gen).int()
+    lens[0] = S
+    if N > 3:
+        lens[3] = 1
+    off = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int32), lens]), 0).int()
+    return lens, off
+
+
+@pytest.mark.parametrize("N,S", [(1, 5), (45, 27), (768, 28), (3000, 30)])
+def test_pack_rows(N, S):
+    lens, off = _packing(N, S, 41)
+    seq_off = torch.empty(N + 1, dtype=torch.int32, device=DEV)
+    rowmap = torch.full((N * S,), -1, dtype=torch.int32, device=DEV)
+    lens_d = lens.to(DEV)
+    L.call("navc_pack_rows", L.ptr(lens_d), N, S, L.ptr(seq_off), L.ptr(rowmap), L.stream())
+    assert torch.equal(seq_off.cpu(), off)
+    want = torch.cat([n * S + torch.arange(int(lens[n])) for n in range(N)]).int()
+    assert torch.equal(rowmap.cpu()[:want.numel()], want)
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_linear_device_row_count_and_gather(mode):
+    """navc_epilogue_t.m_dev: only the first *m_dev rows are computed (rows beyond keep their old contents);
+    navc_gather_rows; navc_vocab_partials_tc_dyn."""
+    M, N, K, cnt = 1000, 512, 256, 389
+    x = torch.randn(M, K, generator=g(42))
+    w = torch.randn(N, K, generator=g(43)) / math.sqrt(K)
+    xh, xl = [t.to(DEV) for t in split(x)]
+    wh, wl = [t.to(DEV) for t in split(w)]
+    ohi = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    olo = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    m_dev = torch.tensor([cnt], dtype=torch.int32, device=DEV)
+    ep = L.Epilogue(None, None, None, 0, 0, None, L.ptr(ohi), L.ptr(olo), N, 0, 1, 0, None, None, L.ptr(m_dev))
+    L.call("navc_linear_tc", L.TC_BF16X3 if mode == "bf16x3" else L.TC_BF16, L.ptr(xh), L.ptr(xl), K, L.ptr(wh), L.ptr(wl), K,
+           M, N, K, ep, L.stream())
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double().t()
+    got = (ohi.float() + olo.float()).cpu()
+    tol = 3e-5 if mode == "bf16x3" else 2e-2
+    assert (got[:cnt] - ref[:cnt]).abs().max().item() < tol * ref.abs().max().item()
+    tile_end = (cnt + 127) // 128 * 128
+    assert (ohi[tile_end:].float() == 7.0).all() and (olo[tile_end:].float() == 7.0).all()
+    # gather
+    rows = torch.randperm(M, generator=g(44))[:300].int().to(DEV)
+    count = torch.tensor([257], dtype=torch.int32, device=DEV)
+    ghi = torch.zeros((M, K), dtype=torch.bfloat16, device=DEV)
+    glo = torch.zeros((M, K), dtype=torch.bfloat16, device=DEV)
+    L.call("navc_gather_rows", L.ptr(xh), L.ptr(xl), K, L.ptr(rows), L.ptr(count), M, L.ptr(ghi), L.ptr(glo), L.stream())
+    assert torch.equal(ghi[:257], xh[rows[:257].long()]) and torch.equal(glo[:257], xl[rows[:257].long()])
+    assert ghi[257:].float().abs().max().item() == 0
+    # vocabulary partials over a device-side row count
+    V = 777
+    wv = torch.randn(V, K, generator=g(45)) / math.sqrt(K)
+    vh, vl = [t.to(DEV) for t in split(wv)]
+    tile = L._lib.navc_vocab_tile(1)
+    nt = (V + tile - 1) // tile
+    pm = torch.full((M, nt), 5.0, device=DEV)
+    ps = torch.full((M, nt), 5.0, device=DEV)
+    pi = torch.full((M, nt), -5, dtype=torch.int32, device=DEV)
+    L.call("navc_vocab_partials_tc_dyn", L.TC_BF16X3 if mode == "bf16x3" else L.TC_BF16, L.ptr(xh), L.ptr(xl), K, L.ptr(vh),
+           L.ptr(vl), K, None, M, V, K, L.ptr(m_dev), L.ptr(pm), L.ptr(ps), L.ptr(pi), L.stream())
+    logits = (x.double() @ wv.double().t())[:cnt]
+    m = pm[:cnt].max(1).values.cpu().double()
+    assert (m - logits.max(1).values).abs().max().item() < (1e-4 if mode == "bf16x3" else 5e-2)
+    if mode == "bf16x3":
+        arg = pi[:cnt].gather(1, pm[:cnt].argmax(1, keepdim=True)).squeeze(1).cpu()
+        assert (arg == logits.argmax(1)).float().mean().item() > 0.995
+    assert (pm[tile_end:] == 5.0).all()
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("kind", ["NARFormer", "ARFormer", "SelfMask"])
+@pytest.mark.parametrize("N,S", [(7, 11), (45, 27), (130, 32)])
+def test_self_attention_tc_packed(mode, tol, kind, N, S):
+    D, H = 512, 8
+    lens, off = _packing(N, S, 46)
+    R = int(off[-1])
+    gen = g(47)
+    qkv = torch.randn(N * S, 3 * D, generator=gen)          # packed rows first, garbage (finite) beyond
+    toks = torch.zeros(N, S, dtype=torch.int64)
+    for n in range(N):
+        toks[n, :lens[n]] = torch.randint(1, 50, (int(lens[n]),), generator=gen)
+    if lens[1] > 2:
+        toks[1, 1] = 0                                       # an interior (predicted) <pad>
+    hi, lo = split(qkv)
+    chi = torch.zeros(N * S, D, dtype=torch.bfloat16, device=DEV)
+    clo = torch.zeros(N * S, D, dtype=torch.bfloat16, device=DEV)
+    ctx = torch.zeros(N * S, D, device=DEV)
+    hi_d, lo_d, toks_d, off_d = hi.to(DEV), lo.to(DEV), toks.to(DEV), off.to(DEV)   # (kept alive until the kernel has run)
+    L.call("navc_self_attention_tc_packed", L.TC_BF16X3 if mode == "bf16x3" else L.TC_BF16, L.ptr(hi_d), L.ptr(lo_d),
+           3 * D, L.ptr(toks_d), L.ptr(off_d), N, S, D, H, L.MASK_KIND[kind], 0, L.ptr(ctx), L.ptr(chi), L.ptr(clo),
+           L.stream())
+    torch.cuda.synchronize()
+    dk = D // H
+    worst = 0.0
+    for n in range(N):
+        ln, r0 = int(lens[n]), int(off[n])
+        blk = qkv[r0:r0 + ln]
+        q, k, v = [t.view(ln, H, dk).permute(1, 0, 2) for t in blk.split(D, dim=1)]
+        mask = O.self_attention_mask(toks[n:n + 1, :ln], kind, 0)[0]
+        sc = ((q @ k.transpose(-1, -2)) / math.sqrt(dk)).masked_fill(mask.unsqueeze(0), O.MASK_FILL)
+        ref = (torch.softmax(sc, -1) @ v).permute(1, 0, 2).reshape(ln, D)
+        worst = max(worst, (ctx[r0:r0 + ln].cpu() - ref).abs().max().item() / max(1.0, ref.abs().max().item()))
+    assert worst < tol, worst
+    assert ctx[R:].abs().max().item() == 0                   # rows beyond the packed count are never written
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("B,group,S,E", [(3, 1, 9, 16), (5, 6, 28, 120), (2, 10, 30, 128)])
+def test_cross_attention_tc_packed(mode, tol, B, group, S, E):
+    D, H = 512, 8
+    N = B * group
+    lens, off = _packing(N, S, 48)
+    R = int(off[-1])
+    gen = g(49)
+    q = torch.randn(N * S, D, generator=gen)
+    kv = torch.randn(B * E, 2 * D, generator=gen)
+    qh, ql = split(q)
+    kh, kl_ = split(kv)
+    ctx = torch.zeros(N * S, D, device=DEV)
+    qh_d, ql_d, kh_d, kl_d, off_d = qh.to(DEV), ql.to(DEV), kh.to(DEV), kl_.to(DEV), off.to(DEV)
+    L.call("navc_cross_attention_tc_packed", L.TC_BF16X3 if mode == "bf16x3" else L.TC_BF16, L.ptr(qh_d), L.ptr(ql_d), D,
+           L.ptr(kh_d), L.ptr(kl_d), 2 * D, L.ptr(off_d), N, S, E, D, H, group, L.ptr(ctx), None, None, L.stream())
+    torch.cuda.synchronize()
+    dk = D // H
+    worst = 0.0
+    for n in range(N):
+        ln, r0, b = int(lens[n]), int(off[n]), n // group
+        qq = q[r0:r0 + ln].view(ln, H, dk).permute(1, 0, 2)
+        kk = kv[b * E:(b + 1) * E, :D].view(E, H, dk).permute(1, 0, 2)
+        vv = kv[b * E:(b + 1) * E, D:].view(E, H, dk).permute(1, 0, 2)
+        ref = (torch.softmax(qq @ kk.transpose(-1, -2) / math.sqrt(dk), -1) @ vv).permute(1, 0, 2).reshape(ln, D)
+        worst = max(worst, (ctx[r0:r0 + ln].cpu() - ref).abs().max().item() / max(1.0, ref.abs().max().item()))
+    assert worst < tol, worst
+    assert ctx[R:].abs().max().item() == 0
