@@ -162,6 +162,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version / debug lines off stdout (one JSON line)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     torch.manual_seed(0)

@@ -78,6 +78,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version / debug lines off stdout (one JSON line)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     B = args.global_batch // world if args.global_batch else args.batch
     kw = dict(dim_hidden=512, num_hidden_layers_decoder=6, intermediate_size=2048, dim_i=2048, dim_m=2048,
