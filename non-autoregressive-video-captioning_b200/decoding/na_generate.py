@@ -144,6 +144,9 @@ def generate(opt, model, teacher_model, encoder_outputs, teacher_encoder_outputs
         entry = eng.graphs.get(key)
         if entry is not None and (not isinstance(entry, _DecodeGraph) or entry.pack_ids == pack_ids):
             if entry == "warm":  # second call with this shape: capture
+                live = [k for k, v in eng.graphs.items() if isinstance(v, _DecodeGraph)]
+                for k in live[:max(0, len(live) - (_MAX_GRAPHS - 1))]:  # each graph owns its activations: keep a few shapes
+                    del eng.graphs[k]
                 entry = eng.graphs[key] = _DecodeGraph(_run, opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping)
             hyp = entry.replay(mem, tmem, cat, beam)
             generate.last_stats = dict(entry.stats, graph=True, rows_real=rows_real)
@@ -155,6 +158,7 @@ def generate(opt, model, teacher_model, encoder_outputs, teacher_encoder_outputs
     return hyp, None
 
 
-_GRAPH_OPT_KEYS = ("iterations", "use_ct", "beam_alpha", "masking_decision", "no_candidate_decision", "q",
+_MAX_GRAPHS = 8
+_GRAPH_OPT_KEYS = ("iterations", "use_ct", "beam_alpha", "masking_decision", "no_candidate_decision", "q", "navc_packed",
                    "q_iterations", "enhance_input", "watch", "paradigm")
 generate.last_stats = {}
