@@ -56,7 +56,30 @@ def make_batch(opt, B, seed, dev):
     return dict(feats=mv(feats), category=category.to(dev), tgt=mv(tgt), labels=mv(labels), lt=mv(lt))
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: point fd 1 at stderr for everything else (NCCL prints its
+    version banner with printf) and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--method", default="NACF")
     ap.add_argument("--batch", type=int, default=256)
@@ -157,7 +180,7 @@ def main():
                            "allreduce_bytes": dp.nbytes if world > 1 else 0,
                            "l2": "inputs rotate over %d distinct batches" % n_rot},
                 "gpu_launches": launches, "final_loss": float(loss.item())}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if args.profile and rank == 0:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
