@@ -291,7 +291,6 @@ class Engine:
             raise NotImplementedError("fusion=%r (broken in the reference, joint_representation.py:41)" % opt["fusion"])
         B = feats[0].shape[0]
         frames = [f.shape[1] for f in feats]
-        assert len(set(frames)) == 1 or True
         E = sum(frames)
         dev = self.device
         enc = Act(B * E, D, f32=torch.empty((B, E, D), dtype=torch.float32, device=dev))
