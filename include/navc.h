@@ -92,6 +92,14 @@ int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx
                    const uint16_t* w_hi, const uint16_t* w_lo, int ldw, int M, int N, int K,
                    const navc_epilogue_t* epi, void* stream);
 
+/* Weight gradient on the tensor cores, straight from row-major operands (no transposed copies):
+ *   out_f32[n, k] += sum_r dY[r, n] * X[r, k]      dY [rows, n_out] (ld_dy), X [rows, k_in] (ld_x), bf16 hi(/lo).
+ * Both operands are consumed MN-major (TMA boxes of 64 rows x 64 columns).  The epilogue only honours
+ * out_f32 / ld_out / split_k (atomic accumulate: the caller zero-fills out_f32 first). */
+int navc_wgrad_tc(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld_dy, const uint16_t* x_hi,
+                  const uint16_t* x_lo, int ld_x, int rows, int n_out, int k_in, const navc_epilogue_t* epi,
+                  void* stream);
+
 /* fp32 -> bf16 hi/lo split of a contiguous buffer (weights are split once when packed). */
 int navc_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int64_t n, void* stream);
 /* The inverse: out = hi + lo (lo may be NULL).  Used at the API boundary when a caller asks for the

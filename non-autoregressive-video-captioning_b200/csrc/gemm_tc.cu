@@ -28,7 +28,7 @@ constexpr int kVocabBN = 256;        // the vocabulary epilogue always uses 256-
 constexpr int kEpiWarps = 8;                         // generic / vocabulary epilogues
 constexpr int kPairEpiWarps = 16;                    // pair epilogue: 4 warps per scheduler to hide its latencies
 constexpr int kStageFloats = 32 * 32;                // per-epilogue-warp transpose buffer (4 KB); 2 KB per warp in pair mode
-__host__ __device__ constexpr int tc_epi_warps(int epi) { return epi >= 2 ? kPairEpiWarps : kEpiWarps; }
+__host__ __device__ constexpr int tc_epi_warps(int epi) { return (epi == 2 || epi == 3) ? kPairEpiWarps : kEpiWarps; }
 constexpr int kResBufBytes = 2048;                   // per warp and buffer: residual hi box (1 KB) + lo box (1 KB)
 __host__ __device__ constexpr int tc_threads(int epi) { return 64 + 32 * tc_epi_warps(epi); }
 constexpr int kTileABytes = TBM * TBK * 2;           // 16 KB
@@ -61,6 +61,11 @@ struct TcVocab {
 //       1 = vocabulary softmax statistics, 2 = "pair" epilogue (lane = row, bf16 hi/lo outputs through
 //       TMA stores, bf16 hi+lo residual): the inference fast path.
 constexpr int kEpiGeneric = 0, kEpiVocab = 1, kEpiPair = 2, kEpiPairRes = 3;  // 3 = pair + TMA-prefetched residual
+// 4 = generic epilogue over MN-major operands: Y[n, k] = sum_m A[m, n] * B[m, k] with A [rows, N_out] and
+// B [rows, K_in] both row-major (the weight gradient dW = dY^T X straight from dY and X: no transposed copies).
+// A k-block is 64 reduction rows; each operand tile is loaded as 64-column TMA boxes of 64 rows (8 KB, 128B
+// swizzle), i.e. the canonical MN-major layout with 8 KB between 64-wide MN blocks and 1 KB between 8-row groups.
+constexpr int kEpiWgrad = 4;
 
 template <bool kX3, int kEpi, int TBN>
 __global__ void __launch_bounds__(tc_threads(kEpi), 1)
@@ -73,6 +78,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int M = epi.m_dev ? min(M_max, __ldg(epi.m_dev)) : M_max;
     constexpr bool kVocab = kEpi == kEpiVocab;
     constexpr bool kPairAny = kEpi == kEpiPair || kEpi == kEpiPairRes;
+    constexpr bool kMN = kEpi == kEpiWgrad;
     constexpr bool kResTma = kEpi == kEpiPairRes;
     using Cfg = TcCfg<kX3, TBN, kEpi>;
     constexpr int kTileBBytes = Cfg::kTileBBytes;
@@ -129,6 +135,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    if constexpr (kMN) {
+                        const int row = kb * TBK;  // reduction rows [row, row + 64); rows beyond the tensor arrive as zeros
+#pragma unroll
+                        for (int j = 0; j < TBM / 64; ++j) {
+                            tma_load_2d(sa + j * 8192, &map_a_hi, full_bar(stage), mb * TBM + j * 64, row);
+                            if (kX3) tma_load_2d(sa + kTileABytes + kTileBBytes + j * 8192, &map_a_lo, full_bar(stage), mb * TBM + j * 64, row);
+                        }
+#pragma unroll
+                        for (int j = 0; j < TBN / 64; ++j) {
+                            tma_load_2d(sa + kTileABytes + j * 8192, &map_b_hi, full_bar(stage), nb * TBN + j * 64, row);
+                            if (kX3) tma_load_2d(sa + 2 * kTileABytes + kTileBBytes + j * 8192, &map_b_lo, full_bar(stage), nb * TBN + j * 64, row);
+                        }
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * TBK, mb * TBM);
                     tma_load_2d(sa + kTileABytes, &map_b_hi, full_bar(stage), kb * TBK, nb * TBN);
                     if (kX3) {
@@ -142,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TBM, TBN);
+            constexpr uint32_t idesc = make_idesc(TBM, TBN) | (kMN ? ((1u << 15) | (1u << 16)) : 0u);  // A / B MN-major bits
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -156,13 +177,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                    const uint64_t da_hi = make_smem_desc(sa);
-                    const uint64_t db_hi = make_smem_desc(sa + kTileABytes);
-                    const uint64_t da_lo = make_smem_desc(sa + kTileABytes + kTileBBytes);
-                    const uint64_t db_lo = make_smem_desc(sa + 2 * kTileABytes + kTileBBytes);
+                    const uint64_t da_hi = kMN ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+                    const uint64_t db_hi = kMN ? make_smem_desc_mn(sa + kTileABytes) : make_smem_desc(sa + kTileABytes);
+                    const uint64_t da_lo = kMN ? make_smem_desc_mn(sa + kTileABytes + kTileBBytes) : make_smem_desc(sa + kTileABytes + kTileBBytes);
+                    const uint64_t db_lo = kMN ? make_smem_desc_mn(sa + 2 * kTileABytes + kTileBBytes) : make_smem_desc(sa + 2 * kTileABytes + kTileBBytes);
 #pragma unroll
                     for (int k = 0; k < TBK / UMMA_K; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // 32 bytes per k-step
+                        // K-major: 32 bytes per k-step inside the 128-byte rows; MN-major: 16 rows of 128 bytes
+                        const uint64_t koff = kMN ? (uint64_t)((k * UMMA_K * 128) >> 4) : (uint64_t)((k * UMMA_K * 2) >> 4);
                         if (kX3) {
                             // small cross terms first, the dominant hi*hi product last
                             tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, ((kb - kb0) | k) ? 1u : 0u);
@@ -537,6 +559,8 @@ int tc_init() {
     NAVC_TC_ATTR(false, kEpiPair, 128); NAVC_TC_ATTR(true, kEpiPair, 128);
     NAVC_TC_ATTR(false, kEpiPairRes, 128); NAVC_TC_ATTR(true, kEpiPairRes, 128);
     NAVC_TC_ATTR(false, kEpiVocab, 256); NAVC_TC_ATTR(true, kEpiVocab, 256);
+    NAVC_TC_ATTR(false, kEpiWgrad, 256); NAVC_TC_ATTR(true, kEpiWgrad, 256);
+    NAVC_TC_ATTR(false, kEpiWgrad, 128); NAVC_TC_ATTR(true, kEpiWgrad, 128);
 #undef NAVC_TC_ATTR
     g_tc_ready = true;
     return 0;
@@ -578,9 +602,20 @@ static int launch_tc_bn(int mode, const uint16_t* x_hi, const uint16_t* x_lo, in
                         const uint16_t* w_lo, int ldw, int M, int N, int K, const EpiParams& epi, const TcVocab& vep,
                         cudaStream_t st, const char* what) {
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    if (tc_make_map(&ma_hi, x_hi, M, K, ldx, TBM)) return 1;
-    if (tc_make_map(&mb_hi, w_hi, N, K, ldw, TBN)) return 1;
-    if (mode == NAVC_TC_BF16X3) {
+    if (kEpi == kEpiWgrad) {
+        // operands are [K reduction rows, M] and [K reduction rows, N] row-major: 64 x 64 boxes
+        if (tc_make_map(&ma_hi, x_hi, K, M, ldx, 64)) return 1;
+        if (tc_make_map(&mb_hi, w_hi, K, N, ldw, 64)) return 1;
+        if (mode == NAVC_TC_BF16X3) {
+            if (tc_make_map(&ma_lo, x_lo, K, M, ldx, 64)) return 1;
+            if (tc_make_map(&mb_lo, w_lo, K, N, ldw, 64)) return 1;
+        } else {
+            ma_lo = ma_hi;
+            mb_lo = mb_hi;
+        }
+    } else if (tc_make_map(&ma_hi, x_hi, M, K, ldx, TBM) || tc_make_map(&mb_hi, w_hi, N, K, ldw, TBN)) {
+        return 1;
+    } else if (mode == NAVC_TC_BF16X3) {
         if (tc_make_map(&ma_lo, x_lo, M, K, ldx, TBM)) return 1;
         if (tc_make_map(&mb_lo, w_lo, N, K, ldw, TBN)) return 1;
     } else {
@@ -617,7 +652,7 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
     NAVC_REQUIRE(g_tc_ready, "%s: navc_init() has not been called", what);
     NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "%s: bad mode %d", what, mode);
     NAVC_REQUIRE(x_hi && w_hi && (mode == NAVC_TC_BF16 || (x_lo && w_lo)), "%s: null operand", what);
-    NAVC_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0,
+    NAVC_REQUIRE(M > 0 && N > 0 && K > 0 && (kEpi == kEpiWgrad || K % 8 == 0) && ldx % 8 == 0 && ldw % 8 == 0,
                  "%s: need K%%8==0 and ld%%8==0 (M=%d N=%d K=%d ldx=%d ldw=%d)", what, M, N, K, ldx, ldw);
     NAVC_REQUIRE((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0,
                  "%s: operands must be 16-byte aligned", what);
@@ -669,6 +704,24 @@ extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_
                                     "N %% 8 == 0 and 16-byte aligned operands");
     if (pair) return launch_tc<kEpiPair>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
     return launch_tc<kEpiGeneric>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
+}
+
+extern "C" int navc_wgrad_tc(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld_dy, const uint16_t* x_hi,
+                             const uint16_t* x_lo, int ld_x, int rows, int n_out, int k_in, const navc_epilogue_t* e,
+                             void* stream) {
+    NAVC_REQUIRE(e && e->out_f32, "navc_wgrad_tc: needs out_f32");
+    EpiParams p = to_params(e);
+    NAVC_REQUIRE(!p.bias && !p.residual && !p.row_tokens && p.act == NAVC_ACT_NONE && !p.res_hi && !p.m_dev,
+                 "navc_wgrad_tc: the weight-gradient GEMM takes no bias / activation / residual / row mask");
+    NAVC_REQUIRE(rows > 0 && n_out % 8 == 0 && k_in % 8 == 0, "navc_wgrad_tc: n_out and k_in must be multiples of 8");
+    p.accumulate = 1;
+    const int k_blocks = (rows + TBK - 1) / TBK;
+    if (p.split_k > k_blocks) p.split_k = k_blocks;
+    const int kpb = (k_blocks + p.split_k - 1) / p.split_k;
+    p.split_k = (k_blocks + kpb - 1) / kpb;
+    TcVocab v = {};
+    return launch_tc<kEpiWgrad>(mode, dy_hi, dy_lo, ld_dy, x_hi, x_lo, ld_x, n_out, k_in, rows, p, v, as_stream(stream),
+                                "navc_wgrad_tc");
 }
 
 extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,

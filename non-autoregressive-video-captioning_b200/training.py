@@ -130,26 +130,47 @@ class Grads:
                 self.add(bk, db[r0:r1] if (r0, r1) != (0, db.shape[0]) else db)
 
 
-def lin_bwd(eng: Engine, x: torch.Tensor, lin: PackedLinear, dY: torch.Tensor, grads: Grads, need_dx=True,
+def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, need_dx=True,
             dx_residual: Optional[torch.Tensor] = None, ld_dy=None):
-    """Backward of y = x W^T + b.  x [M,K] fp32, dY [M,N] fp32 (leading dimension ld_dy, pad columns
-    zero).  Accumulates dW / db into ``grads``; returns dX [M,K] (+ dx_residual) or None."""
-    M, K = x.shape
+    """Backward of y = x W^T + b.  x: the forward input, an fp32 tensor [M,K] or the Act the forward GEMM
+    consumed (its bf16 hi/lo copies are reused); dY [M,N] fp32 (leading dimension ld_dy, pad columns zero).
+    Accumulates dW / db into ``grads``; returns dX [M,K] (+ dx_residual) or None.
+
+    Tensor-core modes: dY is split once (hi/lo, + column sums = db); dW = dY^T X runs straight on the
+    row-major operands (``navc_wgrad_tc``, MN-major tcgen05 operands, split-K) and dX = dY W on the
+    pre-transposed weights -- no transposed activation copies."""
+    x_act = x if isinstance(x, Act) else None
+    x32 = x.f32 if x_act is not None else x
+    M, K = (x_act.M, x_act.N) if x_act is not None else x.shape
     N = lin.N
     ld = ld_dy or dY.stride(0)
     dev = eng.device
-    if ld % 16 != 0 or (need_dx and ld < _up(N, 64)):  # operand alignment: re-lay dY with a zero-padded ld
+    if ld % 16 != 0 or (need_dx and ld < _up(N, 64)) or (eng.tc and N % 8 != 0 and ld < _up(N, 64)):
+        # operand alignment: re-lay dY with a zero-padded leading dimension
         ldp = _up(N, 64)
         pad = torch.zeros((M, ldp), dtype=torch.float32, device=dev)
         pad[:, :N].copy_(dY.view(M, -1)[:, :N] if ld == dY.stride(0) else dY.as_strided((M, N), (ld, 1)))
         dY, ld = pad, ldp
     db = torch.zeros((N,), dtype=torch.float32, device=dev) if lin.b is not None else None
-    s, t = transpose_pack(eng, dY, M, N, ld, straight=need_dx, transposed=True, colsum=db)
-    _, xt = transpose_pack(eng, x, M, K, x.stride(0), transposed=True)
-    Mp = _up(M, 64)
-    dW = torch.zeros((N, K), dtype=torch.float32, device=dev)
-    gemm(eng, t, xt, N, K, Mp, dW, K, accumulate=True, split_k=_split_k(N, K, Mp))
-    grads.add_packed(lin, dW, db)
+    if eng.tc and K % 8 == 0:
+        s, _ = transpose_pack(eng, dY, M, N, ld, straight=True, colsum=db)
+        if x_act is not None and x_act.hi is not None and (x_act.lo is not None or eng.precision != "bf16x3"):
+            x_hi, x_lo = x_act.hi, x_act.lo
+        else:
+            xs, _ = transpose_pack(eng, x32, M, K, x32.stride(0), straight=True)
+            x_hi, x_lo = xs.hi, xs.lo
+        n_eff = N if N % 8 == 0 else ld       # pad columns of dY are zero -> zero rows of dW, sliced off below
+        dW = torch.zeros((n_eff, K), dtype=torch.float32, device=dev)
+        ep = L.Epilogue(None, None, None, 0, 0, L.ptr(dW), None, None, K, 0, _split_k(n_eff, K, M), 1)
+        L.call("navc_wgrad_tc", eng.tc_mode, L.ptr(s.hi), L.ptr(s.lo), ld, L.ptr(x_hi), L.ptr(x_lo), K, M, n_eff, K, ep, L.stream())
+        grads.add_packed(lin, dW[:N] if n_eff != N else dW, db)
+    else:
+        s, t = transpose_pack(eng, dY, M, N, ld, straight=need_dx, transposed=True, colsum=db)
+        _, xt = transpose_pack(eng, x32, M, K, x32.stride(0), transposed=True)
+        Mp = _up(M, 64)
+        dW = torch.zeros((N, K), dtype=torch.float32, device=dev)
+        gemm(eng, t, xt, N, K, Mp, dW, K, accumulate=True, split_k=_split_k(N, K, Mp))
+        grads.add_packed(lin, dW, db)
     if not need_dx:
         return None
     wt = weight_T(eng, lin)  # [K, Np]
@@ -287,7 +308,7 @@ class EncodeFn(torch.autograd.Function):
                 bn.num_batches_tracked += 1
             L.call("navc_bn_apply_concat", L.ptr(o), L.ptr(mean), L.ptr(var), L.ptr(bw), L.ptr(bb), 1e-5, B, F_, D, E, i,
                    len(feats), int(i > 0), L.ptr(enc_hidden), L.ptr(enc.f32), None, None, L.stream())
-            streams.append(dict(x_in=x_in.f32, x=x.f32, yg=yg.f32, o=o, mean=mean, var=var, bw=bw, seed=seed))
+            streams.append(dict(x_in=x_in, x=x, yg=yg.f32, o=o, mean=mean, var=var, bw=bw, seed=seed))
         outs = [enc.f32, enc_hidden]
         head = None
         if P["len_head"] is not None:
@@ -355,7 +376,7 @@ class EncodeFn(torch.autograd.Function):
             gate = pw["gate"]
             d_x = torch.empty((BF, D), dtype=torch.float32, device=dev)
             d_yg = torch.empty((BF, (2 if gate else 1) * D), dtype=torch.float32, device=dev)
-            L.call("navc_highway_bwd", L.ptr(d_o), L.ptr(s["x"]), L.ptr(s["yg"]), gate, BF, D, s["seed"], st["p_enc"],
+            L.call("navc_highway_bwd", L.ptr(d_o), L.ptr(s["x"].f32), L.ptr(s["yg"]), gate, BF, D, s["seed"], st["p_enc"],
                    L.ptr(d_x), L.ptr(d_yg), L.stream())
             d_x = lin_bwd(eng, s["x"], pw["l12"], d_yg, grads, dx_residual=d_x)
             lin_bwd(eng, s["x_in"], pw["l0"], d_x, grads, need_dx=False)
@@ -419,7 +440,7 @@ class DecoderFn(torch.autograd.Function):
         watch = int(opt.get("watch", 0))
         layers = []
         for l, lw in enumerate(P["layers"]):
-            sv = dict(x=x.f32)
+            sv = dict(x=x)
             qkv = eng.linear(x, lw["qkv"], f32=True, bf=tc_attn)
             ctx1 = eng._new(R, D, True, True)
             if tc_attn:
@@ -453,11 +474,11 @@ class DecoderFn(torch.autograd.Function):
             sv["s_f1"], sv["s_f2"] = seeds.next(), seeds.next()
             sv["f2"] = {}
             xn = _post(eng, f2.f32, c.f32, lw["f2_ln"], sv["s_f1"], p, sv["s_f2"], p, tok_flat, sv["f2"])
-            sv.update(qkv=qkv.f32, ctx1=ctx1.f32, a=a.f32, q=q.f32, ctx2=ctx2.f32, c=c.f32, u=u.f32, h=h.f32)
+            sv.update(qkv=qkv.f32, ctx1=ctx1, a=a, q=q.f32, ctx2=ctx2, c=c, u=u.f32, h=h)
             layers.append(sv)
             x = xn
         ctx.model, ctx.keys = model, keys
-        ctx.state = dict(tokens=tokens, tok_flat=tok_flat, cat=cat, enc=enc.f32, extra=extra, kv=kv.f32, layers=layers,
+        ctx.state = dict(tokens=tokens, tok_flat=tok_flat, cat=cat, enc=enc, extra=extra, kv=kv.f32, layers=layers,
                          seed_e=seed_e, p=p, N=N, S=S, E=E, Bv=Bv, mask_kind=mask_kind, watch=watch, decoding_type=decoding_type)
         return x.f32.view(N, S, D)
 
@@ -566,7 +587,7 @@ class VocabFn(torch.autograd.Function):
         else:
             out.copy_(logits[:, :V])
         ctx.model, ctx.log_probs = model, log_probs
-        ctx.state = dict(h=h.f32, out=out if log_probs else None, R=R, V=V, Vp=Vp, shape=shape, n_params=len(params))
+        ctx.state = dict(h=h, out=out if log_probs else None, R=R, V=V, Vp=Vp, shape=shape, n_params=len(params))
         return out.view(*shape[:-1], V)
 
     @staticmethod
@@ -685,7 +706,8 @@ class FusedCEFn(torch.autograd.Function):
                 else Operand(n, D, D, f32=h.f32[r0:r0 + n])
             gemm(eng, xop, wop, n, Vp, D, slab, Vp, bias=b_pad)                      # logits of this row chunk
             L.call("navc_ce_grad", L.ptr(slab), lse[r0:].data_ptr(), lab[r0:].data_ptr(), L.ptr(scale), n, V, Vp, L.stream())
-            d_h[r0:r0 + n] = lin_bwd(eng, h.f32[r0:r0 + n], lin, slab[:n], grads, ld_dy=Vp)
+            xa = Act(n, D, f32=h.f32[r0:r0 + n], hi=None if h.hi is None else h.hi[r0:r0 + n], lo=None if h.lo is None else h.lo[r0:r0 + n])
+            d_h[r0:r0 + n] = lin_bwd(eng, xa, lin, slab[:n], grads, ld_dy=Vp)
         gw = grads.g.get("tgt_word_prj.weight")
         gb = grads.g.get("tgt_word_prj.bias")
         return (None, None, d_h.view(st["shape"])) + ((gw,) if ctx.n_params == 1 else (gw, gb))

@@ -574,3 +574,21 @@ def test_fused_cross_entropy_matches_oracle(precision):
     got = dict(zip(names, info))
     assert abs(got["Perplexity"] - ppl) < 1e-3 * ppl and abs(got["Word Acc1"] - acc1) < 1e-6
     assert torch.allclose(res["tgt_word_logprobs"][1].materialize().detach().cpu(), lp, atol=5e-4)
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("rows,n_out,k_in,split", [(300, 512, 256, 1), (7680, 2048, 512, 4), (1000, 136, 520, 3), (70, 64, 64, 1)])
+def test_wgrad_tc_mn_major(mode, tol, rows, n_out, k_in, split):
+    """navc_wgrad_tc: dW += dY^T X straight from the row-major operands (MN-major tcgen05 operands)."""
+    dy = torch.randn(rows, n_out, generator=g(60)) / math.sqrt(rows)
+    x = torch.randn(rows, k_in, generator=g(61))
+    base = torch.randn(n_out, k_in, generator=g(62))
+    out = base.clone().to(DEV)
+    sp = lambda t: (t.to(torch.bfloat16).to(DEV), (t - t.to(torch.bfloat16).float()).to(torch.bfloat16).to(DEV))
+    dh, dl = sp(dy)
+    xh, xl = sp(x)
+    ep = L.Epilogue(None, None, None, 0, 0, L.ptr(out), None, None, k_in, 0, split, 1)
+    L.call("navc_wgrad_tc", L.TC_BF16X3 if mode == "bf16x3" else L.TC_BF16, L.ptr(dh), L.ptr(dl), n_out, L.ptr(xh), L.ptr(xl), k_in,
+           rows, n_out, k_in, ep, L.stream())
+    ref = base.double() + dy.double().t() @ x.double()
+    close(out, ref, tol, "wgrad")
