@@ -213,6 +213,16 @@ int navc_cross_attention_tc_packed(int mode, const uint16_t* q_hi, const uint16_
                                    const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv,
                                    const int32_t* seq_off, int N, int S, int E, int D, int H, int group,
                                    float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream);
+/* The same with the row count of the packed buffers given explicitly (`rows` >= seq_off[N]; the _packed entry
+ * points assume buffers of N*S rows): the training path sizes its buffers to the real positions. */
+int navc_self_attention_tc_rows(int mode, const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld,
+                                const int64_t* tokens, const int32_t* seq_off, int rows, int N, int S, int D, int H,
+                                int mask_kind, int watch, float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo,
+                                void* stream);
+int navc_cross_attention_tc_rows(int mode, const uint16_t* q_hi, const uint16_t* q_lo, int ldq,
+                                 const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv, const int32_t* seq_off,
+                                 int rows, int N, int S, int E, int D, int H, int group, float* ctx_f32,
+                                 uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream);
 /* out[k, :] = in[rows[k], :] for k < *count (bf16 hi / lo pairs, D % 8 == 0; lo may be NULL). */
 int navc_gather_rows(const uint16_t* in_hi, const uint16_t* in_lo, int D, const int32_t* rows,
                      const int32_t* count, int max_rows, uint16_t* out_hi, uint16_t* out_lo, void* stream);
@@ -370,6 +380,32 @@ int navc_embed_ln_bwd(const float* dout, const int64_t* tokens, const int64_t* c
                       const float* extra, int group, const float* ln_w, const float* ln_b, float eps,
                       int N, int S, int D, float* d_word, float* d_pos, float* d_cat, float* d_extra,
                       float* d_ln_w, float* d_ln_b, void* stream);
+
+/* Packed-row variants for the training path (row counts are host-side there): the query rows of sequence n are
+ * rows [seq_off[n], seq_off[n+1]) of qkv / q / d_ctx / d_q(kv); tokens stays the padded [N,S] tensor. */
+int navc_self_attention_bwd_packed(const float* qkv, int ld, const int64_t* tokens, const int32_t* seq_off, int N,
+                                   int S, int D, int H, int mask_kind, int watch, const float* d_ctx, float* d_qkv,
+                                   void* stream);
+int navc_cross_attention_bwd_packed(const float* q, int ldq, const float* kv, int ldkv, const int32_t* seq_off, int N,
+                                    int S, int E, int D, int H, const float* d_ctx, float* d_q, int ld_dq, float* d_kv,
+                                    int ld_dkv, void* stream);
+int navc_embed_ln_bwd_packed(const float* dout, const int64_t* tokens, const int64_t* category, const float* word_emb,
+                             const float* pos_emb, const float* cat_emb, const float* extra, int group,
+                             const float* ln_w, float eps, int S, int D, const int32_t* rowmap, int rows,
+                             float* d_word, float* d_pos, float* d_cat, float* d_extra, float* d_ln_w, float* d_ln_b,
+                             void* stream);
+/* log_softmax of packed logits rows written to padded rows (out row = rowmap[i]) and its backward reading the
+ * padded g / logp rows; fp32 row gather (scatter = 0: out[i] = in[rowmap[i]]) / scatter (out[rowmap[i]] = in[i]). */
+int navc_log_softmax_rows(const float* logits, int ld_in, float* out, int ld_out, const int32_t* rowmap, int rows,
+                          int V, void* stream);
+int navc_log_softmax_bwd_rows(const float* g, const float* logp, const int32_t* rowmap, int rows, int V, int ld_in,
+                              float* dlogits, int ld_out, void* stream);
+/* Bias gradient of the rows a packed vocabulary projection skipped (PAD positions: hidden == 0, log-probs ==
+ * const_logp = log_softmax(bias)): db[v] += sum over pad rows r of g[r,v] - exp(const_logp[v]) * sum_v g[r,:].
+ * All-zero rows of g (a loss that ignores PAD) cost one read. */
+int navc_log_softmax_bwd_padrows(const float* g, int ld, const int32_t* pad_rows, int n_pad, const float* const_logp,
+                                 int V, float* db, void* stream);
+int navc_rows_f32(const float* in, float* out, int D, const int32_t* rowmap, int rows, int scatter, void* stream);
 
 /* Fused cross-entropy (projection + log-softmax + masked NLL, seq2seq.py:102-103 + misc/crit.py:62-84)
  * without a [rows, V] log-prob tensor.  Forward: navc_vocab_partials_* with target = labels, then

@@ -87,6 +87,15 @@ _PROTOS = {
     "navc_log_softmax_bwd": [vp, vp, i32, i32, i32, vp, i32, vp],
     "navc_layernorm_bwd": [vp, vp, vp, f32, vp, i32, i32, vp, vp, vp, vp],
     "navc_embed_ln_bwd": [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+    "navc_self_attention_tc_rows": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_cross_attention_tc_rows": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_self_attention_bwd_packed": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
+    "navc_cross_attention_bwd_packed": [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, vp],
+    "navc_embed_ln_bwd_packed": [vp, vp, vp, vp, vp, vp, vp, i32, vp, f32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp],
+    "navc_log_softmax_rows": [vp, i32, vp, i32, vp, i32, i32, vp],
+    "navc_log_softmax_bwd_rows": [vp, vp, vp, i32, i32, i32, vp, i32, vp],
+    "navc_log_softmax_bwd_padrows": [vp, i32, vp, i32, vp, i32, vp, vp],
+    "navc_rows_f32": [vp, vp, i32, vp, i32, i32, vp],
     "navc_ce_stats": [vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp],
     "navc_ce_grad": [vp, vp, vp, vp, i32, i32, i32, vp],
     "navc_clip_adam": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i32, vp],
@@ -153,4 +162,17 @@ def ptr(t):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current stream on the current device (the fast C entry point:
+    torch.cuda.current_stream() costs ~15 us of Python per call, and every launch asks)."""
+    return _raw_stream(_current_device())
+
+
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+    _current_device = torch._C._cuda_getDevice
+except AttributeError:  # pragma: no cover - older / CPU-only torch builds
+    def _raw_stream(_idx):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _current_device():
+        return 0

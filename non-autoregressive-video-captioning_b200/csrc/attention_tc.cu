@@ -485,11 +485,19 @@ extern "C" int navc_self_attention_tc_packed(int mode, const uint16_t* qkv_hi, c
                                              const int64_t* tokens, const int32_t* seq_off, int N, int S, int D, int H,
                                              int mask_kind, int watch, float* ctx_f32, uint16_t* ctx_hi,
                                              uint16_t* ctx_lo, void* stream) {
-    NAVC_REQUIRE(tokens && seq_off && (ctx_f32 || ctx_hi), "navc_self_attention_tc_packed: null pointer");
+    return navc_self_attention_tc_rows(mode, qkv_hi, qkv_lo, ld, tokens, seq_off, N * S, N, S, D, H, mask_kind, watch,
+                                       ctx_f32, ctx_hi, ctx_lo, stream);
+}
+
+extern "C" int navc_self_attention_tc_rows(int mode, const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld,
+                                           const int64_t* tokens, const int32_t* seq_off, int rows, int N, int S, int D,
+                                           int H, int mask_kind, int watch, float* ctx_f32, uint16_t* ctx_hi,
+                                           uint16_t* ctx_lo, void* stream) {
+    NAVC_REQUIRE(tokens && seq_off && (ctx_f32 || ctx_hi) && rows > 0, "navc_self_attention_tc_packed: null pointer");
     NAVC_REQUIRE(N > 0 && S > 0 && S <= 32 && H > 0 && D == H * 64 && ld >= 3 * D,
                  "navc_self_attention_tc_packed: needs dk == 64 and S <= 32 (N=%d S=%d D=%d H=%d)", N, S, D, H);
     NAVC_REQUIRE(mask_kind >= 0 && mask_kind <= 2, "navc_self_attention_tc_packed: bad mask kind");
-    const int R = N * S;  // row maximum of the packed buffers
+    const int R = rows;  // rows the packed buffers hold (TMA zero-fills beyond)
     AtParams p = {};
     p.q_col = 0; p.k_col = D; p.v_col = 2 * D;
     p.rows_per_tile = 128; p.total_q_rows = R; p.S = S; p.is_self = 1; p.mask_kind = mask_kind; p.watch = watch;
@@ -503,7 +511,15 @@ extern "C" int navc_cross_attention_tc_packed(int mode, const uint16_t* q_hi, co
                                               const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv,
                                               const int32_t* seq_off, int N, int S, int E, int D, int H, int group,
                                               float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream) {
-    NAVC_REQUIRE(seq_off && (ctx_f32 || ctx_hi), "navc_cross_attention_tc_packed: null pointer");
+    return navc_cross_attention_tc_rows(mode, q_hi, q_lo, ldq, kv_hi, kv_lo, ldkv, seq_off, N * S, N, S, E, D, H, group,
+                                        ctx_f32, ctx_hi, ctx_lo, stream);
+}
+
+extern "C" int navc_cross_attention_tc_rows(int mode, const uint16_t* q_hi, const uint16_t* q_lo, int ldq,
+                                            const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv,
+                                            const int32_t* seq_off, int rows, int N, int S, int E, int D, int H, int group,
+                                            float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream) {
+    NAVC_REQUIRE(seq_off && (ctx_f32 || ctx_hi) && rows > 0, "navc_cross_attention_tc_packed: null pointer");
     NAVC_REQUIRE(N > 0 && S > 0 && E > 0 && E <= 128 && H > 0 && D == H * 64 && group >= 1 && N % group == 0 &&
                      ldq >= D && ldkv >= 2 * D,
                  "navc_cross_attention_tc_packed: needs dk == 64 and E <= 128 (N=%d S=%d E=%d D=%d H=%d)", N, S, E, D, H);
@@ -514,6 +530,6 @@ extern "C" int navc_cross_attention_tc_packed(int mode, const uint16_t* q_hi, co
     p.total_q_rows = N * S; p.S = S; p.is_self = 0; p.D = D;
     p.seq_off = seq_off; p.n_seq = N; p.group = group;
     p.ctx_f32 = ctx_f32; p.ctx_hi = ctx_hi; p.ctx_lo = ctx_lo;
-    return launch_attn_tc(mode, q_hi, q_lo, ldq, D, N * S, kv_hi, kv_lo, ldkv, 2 * D, G * E, p, G * tpo, H,
+    return launch_attn_tc(mode, q_hi, q_lo, ldq, D, rows, kv_hi, kv_lo, ldkv, 2 * D, G * E, p, G * tpo, H,
                           as_stream(stream), "navc_cross_attention_tc_packed");
 }

@@ -377,10 +377,11 @@ __global__ void mean_bwd_kernel(const float* __restrict__ d_mean, int E, int D, 
 
 // ---- log-softmax backward -------------------------------------------------------------------------------
 __global__ void log_softmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ logp, int V, int ld_in,
-                                       float* __restrict__ out, int ld_out) {
+                                       float* __restrict__ out, int ld_out, const int32_t* __restrict__ rowmap) {
     __shared__ float red[32];
-    const float* gr = g + (size_t)blockIdx.x * ld_in;
-    const float* lr = logp + (size_t)blockIdx.x * ld_in;
+    const size_t src = rowmap ? (size_t)rowmap[blockIdx.x] : (size_t)blockIdx.x;   // packed rows: g / logp live in the padded layout
+    const float* gr = g + src * ld_in;
+    const float* lr = logp + src * ld_in;
     float* orow = out + (size_t)blockIdx.x * ld_out;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     float s = 0.f;
@@ -491,7 +492,7 @@ __global__ void embed_ln_bwd_kernel(const float* __restrict__ dout, const int64_
                                     const float* __restrict__ pos, const float* __restrict__ cat,
                                     const float* __restrict__ extra, int group, const float* __restrict__ lw, float eps,
                                     int R, int S, int D, float* d_word, float* d_pos, float* d_cat, float* d_extra,
-                                    float* d_lw, float* d_lb) {
+                                    float* d_lw, float* d_lb, const int32_t* __restrict__ rowmap) {
     extern __shared__ float sm[];
     float* sm_dw = sm;
     float* sm_db = sm + D;
@@ -500,8 +501,9 @@ __global__ void embed_ln_bwd_kernel(const float* __restrict__ dout, const int64_
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int nchunk = (D / 4 + 31) / 32;
     for (int row = blockIdx.x * wpb + wib; row < R; row += gridDim.x * wpb) {
-        const int n = row / S, s = row % S;
-        const int64_t tok = tokens[row];
+        const int src = rowmap ? rowmap[row] : row;   // packed rows: row -> padded position
+        const int n = src / S, s = src % S;
+        const int64_t tok = tokens[src];
         const float* wr = word + (size_t)tok * D;
         const float* pr = pos + (size_t)s * D;
         const int64_t ci = cat ? category[n / group] : 0;
@@ -636,7 +638,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
     const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v, int ldkv,
     const int64_t* __restrict__ tokens, int NQ, int S, int Sk, int mask_kind, int watch,
     const float* __restrict__ d_ctx, int ld_dctx, float* __restrict__ dq, int ld_dq, float* __restrict__ dk,
-    float* __restrict__ dv, int ld_dkv) {
+    float* __restrict__ dv, int ld_dkv, const int32_t* __restrict__ seq_off, int packed_self) {
     using SM = AttnBwdSmem<DK>;
     constexpr int LD = SM::LD;
     constexpr int QB = kAttnBwdQB;
@@ -653,12 +655,24 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
 
-    const float* kb = k + (size_t)g * Sk * ldkv + h * DK;
-    const float* vb = v + (size_t)g * Sk * ldkv + h * DK;
-    for (int idx = tid; idx < KP * (DK / 4); idx += nthr) {
+    // packed rows (seq_off != NULL): the query rows of owner g are rows [seq_off[g], seq_off[g+1]) of q / d_ctx / dq;
+    // for self-attention the keys are those same rows (sk = len), for cross-attention the owner's Sk rows of kv.
+    // Shared-memory layout always uses the maximum Sk; `sk` is the number of keys that exist.
+    size_t q_row = (size_t)g * NQ, kv_row = (size_t)g * Sk;
+    int sk = Sk;
+    if (seq_off) {
+        const int r0 = seq_off[g];
+        NQ = seq_off[g + 1] - r0;
+        q_row = (size_t)r0;
+        if (packed_self) { kv_row = (size_t)r0; sk = NQ; }
+    }
+    const float* kb = k + kv_row * ldkv + h * DK;
+    const float* vb = v + kv_row * ldkv + h * DK;
+    const int KE = SM::kp(sk);  // keys that are looped over (sk rounded up to the 4-key register tile)
+    for (int idx = tid; idx < KE * (DK / 4); idx += nthr) {
         const int j = idx / (DK / 4), d4 = idx - j * (DK / 4);
         float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
-        if (j < Sk) {
+        if (j < sk) {
             kk = *reinterpret_cast<const float4*>(kb + (size_t)j * ldkv + d4 * 4);
             vv = *reinterpret_cast<const float4*>(vb + (size_t)j * ldkv + d4 * 4);
         }
@@ -672,13 +686,13 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
     const float sqrt_dk = sqrtf((float)DK);
     const bool use_watch = (mask_kind == NAVC_MASK_CAUSAL) && watch != 0 && S >= watch;
     const int64_t* trow = tokens ? tokens + (size_t)g * S : nullptr;
-    const int jt_n = KP / 4;
+    const int jt_n = KE / 4;
 
     for (int q0 = 0; q0 < NQ; q0 += QB) {
         const int nq = min(QB, NQ - q0);
         __syncthreads();
-        const float* qb = q + ((size_t)g * NQ + q0) * ldq + h * DK;
-        const float* ob = d_ctx + ((size_t)g * NQ + q0) * ld_dctx + h * DK;
+        const float* qb = q + (q_row + q0) * ldq + h * DK;
+        const float* ob = d_ctx + (q_row + q0) * ld_dctx + h * DK;
         for (int idx = tid; idx < QB * (DK / 4); idx += nthr) {
             const int i = idx / (DK / 4), d4 = idx - i * (DK / 4);
             float4 qq = make_float4(0.f, 0.f, 0.f, 0.f), oo = qq;
@@ -727,12 +741,12 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
         // ---- B: softmax + dS, one warp per query row (rows >= nq and keys >= Sk become zero) ----
         for (int i = warp; i < QB; i += nw) {
             if (i >= nq) {
-                for (int j = lane; j < KP; j += 32) { Ps[i * SP + j] = 0.f; dSs[i * SP + j] = 0.f; }
+                for (int j = lane; j < KE; j += 32) { Ps[i * SP + j] = 0.f; dSs[i * SP + j] = 0.f; }
                 continue;
             }
             const int ipos = (q0 + i) % S;
             float m = -INFINITY;
-            for (int j = lane; j < Sk; j += 32) {
+            for (int j = lane; j < sk; j += 32) {
                 float sv = Ps[i * SP + j];
                 if (trow) {
                     bool masked = trow[j] == NAVC_PAD;
@@ -745,21 +759,21 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
             }
             m = warp_max(m);
             float sum = 0.f;
-            for (int j = lane; j < Sk; j += 32) {
+            for (int j = lane; j < sk; j += 32) {
                 const float e = expf(Ps[i * SP + j] - m);
                 Ps[i * SP + j] = e;
                 sum += e;
             }
             sum = warp_sum(sum);
             float dot = 0.f;
-            for (int j = lane; j < Sk; j += 32) {
+            for (int j = lane; j < sk; j += 32) {
                 const float p = Ps[i * SP + j] / sum;
                 Ps[i * SP + j] = p;
                 dot += p * dSs[i * SP + j];
             }
             dot = warp_sum(dot);
-            for (int j = lane; j < KP; j += 32) {
-                if (j >= Sk) {
+            for (int j = lane; j < KE; j += 32) {
+                if (j >= sk) {
                     Ps[i * SP + j] = 0.f;
                     dSs[i * SP + j] = 0.f;
                     continue;
@@ -776,8 +790,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
         }
         __syncthreads();
         // ---- C: dV / dK, 4 keys x 4 columns per thread; accumulated over query chunks in global memory ----
-        float* dkb = dk + (size_t)g * Sk * ld_dkv + h * DK;
-        float* dvb = dv + (size_t)g * Sk * ld_dkv + h * DK;
+        float* dkb = dk + kv_row * ld_dkv + h * DK;
+        float* dvb = dv + kv_row * ld_dkv + h * DK;
         for (int t = tid; t < jt_n * (DK / 4); t += nthr) {
             const int tj = t / (DK / 4), td = t - tj * (DK / 4);
             float va[4][4], ka[4][4];
@@ -804,7 +818,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int j = tj * 4 + a;
-                if (j < Sk) {
+                if (j < sk) {
                     float4* pk = reinterpret_cast<float4*>(dkb + (size_t)j * ld_dkv + td * 4);
                     float4* pv = reinterpret_cast<float4*>(dvb + (size_t)j * ld_dkv + td * 4);
                     float4 nk = make_float4(ka[a][0], ka[a][1], ka[a][2], ka[a][3]);
@@ -816,7 +830,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
             }
         }
         // ---- D: dQ = dS K, 4 queries x 4 columns per thread ----
-        float* dqb = dq + ((size_t)g * NQ + q0) * ld_dq + h * DK;
+        float* dqb = dq + (q_row + q0) * ld_dq + h * DK;
         for (int t = tid; t < (QB / 4) * (DK / 4); t += nthr) {
             const int ti = t / (DK / 4), td = t - ti * (DK / 4);
             float acc[4][4];
@@ -826,7 +840,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
             const float* sr = dSs + (ti * 4) * SP;
 #pragma unroll 4
-            for (int j = 0; j < KP; ++j) {
+            for (int j = 0; j < KE; ++j) {
                 const float4 kk = *reinterpret_cast<const float4*>(Ks + j * LD + td * 4);
                 const float kf[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
@@ -850,7 +864,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
 template <int DK>
 static int launch_attn_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const int64_t* tokens,
                            int G, int NQ, int S, int Sk, int H, int mask_kind, int watch, const float* d_ctx, int ld_dctx,
-                           float* dq, int ld_dq, float* dk, float* dv, int ld_dkv, cudaStream_t st, const char* what) {
+                           float* dq, int ld_dq, float* dk, float* dv, int ld_dkv, cudaStream_t st, const char* what,
+                           const int32_t* seq_off = nullptr, int packed_self = 0) {
     const size_t smem = AttnBwdSmem<DK>::floats(Sk) * sizeof(float);
     NAVC_REQUIRE(smem <= 227 * 1024, "%s: Sk=%d too large for shared memory", what, Sk);
     NAVC_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0 && ld_dctx % 4 == 0 && ld_dq % 4 == 0 && ld_dkv % 4 == 0 &&
@@ -860,16 +875,16 @@ static int launch_attn_bwd(const float* q, int ldq, const float* k, const float*
     auto kern = attn_bwd_kernel<DK>;
     if (smem > 48 * 1024) NAVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(G, H), 256, smem, st>>>(q, ldq, k, v, ldkv, tokens, NQ, S, Sk, mask_kind, watch, d_ctx, ld_dctx, dq, ld_dq,
-                                        dk, dv, ld_dkv);
+                                        dk, dv, ld_dkv, seq_off, packed_self);
     return check_launch(what);
 }
 
 static int dispatch_attn_bwd(int dkk, const float* q, int ldq, const float* k, const float* v, int ldkv,
                              const int64_t* tokens, int G, int NQ, int S, int Sk, int H, int mask_kind, int watch,
                              const float* d_ctx, int ld_dctx, float* dq, int ld_dq, float* dk, float* dv, int ld_dkv,
-                             cudaStream_t st, const char* what) {
+                             cudaStream_t st, const char* what, const int32_t* seq_off = nullptr, int packed_self = 0) {
 #define NAVC_ATTN_BWD(DKV) \
-    if (dkk == DKV) return launch_attn_bwd<DKV>(q, ldq, k, v, ldkv, tokens, G, NQ, S, Sk, H, mask_kind, watch, d_ctx, ld_dctx, dq, ld_dq, dk, dv, ld_dkv, st, what)
+    if (dkk == DKV) return launch_attn_bwd<DKV>(q, ldq, k, v, ldkv, tokens, G, NQ, S, Sk, H, mask_kind, watch, d_ctx, ld_dctx, dq, ld_dq, dk, dv, ld_dkv, st, what, seq_off, packed_self)
     NAVC_ATTN_BWD(64);
     NAVC_ATTN_BWD(32);
     NAVC_ATTN_BWD(16);
@@ -1007,8 +1022,33 @@ extern "C" int navc_mean_bwd(const float* d_mean, int B, int E, int D, float* d_
 extern "C" int navc_log_softmax_bwd(const float* g, const float* logp, int M, int V, int ld_in, float* dlogits,
                                     int ld_out, void* stream) {
     NAVC_REQUIRE(g && logp && dlogits && M > 0 && V > 0 && ld_in >= V && ld_out >= V, "navc_log_softmax_bwd: bad arguments");
-    log_softmax_bwd_kernel<<<M, 256, 0, as_stream(stream)>>>(g, logp, V, ld_in, dlogits, ld_out);
+    log_softmax_bwd_kernel<<<M, 256, 0, as_stream(stream)>>>(g, logp, V, ld_in, dlogits, ld_out, nullptr);
     return check_launch("navc_log_softmax_bwd");
+}
+
+extern "C" int navc_log_softmax_bwd_rows(const float* g, const float* logp, const int32_t* rowmap, int rows, int V, int ld_in,
+                                         float* dlogits, int ld_out, void* stream) {
+    NAVC_REQUIRE(g && logp && rowmap && dlogits && rows > 0 && V > 0 && ld_in >= V && ld_out >= V,
+                 "navc_log_softmax_bwd_rows: bad arguments");
+    log_softmax_bwd_kernel<<<rows, 256, 0, as_stream(stream)>>>(g, logp, V, ld_in, dlogits, ld_out, rowmap);
+    return check_launch("navc_log_softmax_bwd_rows");
+}
+
+// out[rowmap[i], :] = in[i, :] (scatter) or out[i, :] = in[rowmap[i], :] (gather), fp32 rows of D % 4 == 0 floats
+__global__ void rows_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int D, const int32_t* __restrict__ rowmap,
+                                int rows, int scatter) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= rows) return;
+    const size_t m = (size_t)rowmap[i];
+    const float* src = in + (scatter ? (size_t)i : m) * D;
+    float* dst = out + (scatter ? m : (size_t)i) * D;
+    for (int c = (threadIdx.x & 31) * 4; c < D; c += 128) *reinterpret_cast<float4*>(dst + c) = *reinterpret_cast<const float4*>(src + c);
+}
+
+extern "C" int navc_rows_f32(const float* in, float* out, int D, const int32_t* rowmap, int rows, int scatter, void* stream) {
+    NAVC_REQUIRE(in && out && rowmap && rows > 0 && D % 4 == 0, "navc_rows_f32: bad arguments");
+    rows_f32_kernel<<<(rows + 7) / 8, 256, 0, as_stream(stream)>>>(in, out, D, rowmap, rows, scatter);
+    return check_launch("navc_rows_f32");
 }
 
 extern "C" int navc_layernorm_bwd(const float* dy, const float* x, const float* w, float eps, const int64_t* row_tokens,
@@ -1037,8 +1077,26 @@ extern "C" int navc_embed_ln_bwd(const float* dout, const int64_t* tokens, const
     if (blocks > 148 * 4) blocks = 148 * 4;
     embed_ln_bwd_kernel<<<blocks, 256, 2 * D * sizeof(float), as_stream(stream)>>>(
         dout, tokens, category, word_emb, pos_emb, cat_emb, extra, group, ln_w, eps, R, S, D, d_word, d_pos,
-        cat_emb ? d_cat : nullptr, extra ? d_extra : nullptr, d_ln_w, d_ln_b);
+        cat_emb ? d_cat : nullptr, extra ? d_extra : nullptr, d_ln_w, d_ln_b, nullptr);
     return check_launch("navc_embed_ln_bwd");
+}
+
+extern "C" int navc_embed_ln_bwd_packed(const float* dout, const int64_t* tokens, const int64_t* category,
+                                        const float* word_emb, const float* pos_emb, const float* cat_emb,
+                                        const float* extra, int group, const float* ln_w, float eps, int S, int D,
+                                        const int32_t* rowmap, int rows, float* d_word, float* d_pos, float* d_cat,
+                                        float* d_extra, float* d_ln_w, float* d_ln_b, void* stream) {
+    NAVC_REQUIRE(dout && tokens && word_emb && pos_emb && ln_w && d_word && d_pos && d_ln_w && d_ln_b && rowmap && rows > 0,
+                 "navc_embed_ln_bwd_packed: bad arguments");
+    NAVC_REQUIRE(!cat_emb || (category && d_cat), "navc_embed_ln_bwd_packed: category embeddings without ids / gradient");
+    NAVC_REQUIRE(!extra || d_extra, "navc_embed_ln_bwd_packed: extra without gradient buffer");
+    NAVC_REQUIRE(D % 4 == 0 && D <= 4 * 32 * kLnChunks && group >= 1, "navc_embed_ln_bwd_packed: bad shape");
+    int blocks = (rows + 7) / 8;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    embed_ln_bwd_kernel<<<blocks, 256, 2 * D * sizeof(float), as_stream(stream)>>>(
+        dout, tokens, category, word_emb, pos_emb, cat_emb, extra, group, ln_w, eps, rows, S, D, d_word, d_pos,
+        cat_emb ? d_cat : nullptr, extra ? d_extra : nullptr, d_ln_w, d_ln_b, rowmap);
+    return check_launch("navc_embed_ln_bwd_packed");
 }
 
 extern "C" int navc_ce_stats(const float* part_max, const float* part_sum, const int32_t* part_idx, int n_tiles,
@@ -1084,4 +1142,58 @@ extern "C" int navc_cross_attention_bwd(const float* q, int ldq, const float* kv
                  "navc_cross_attention_bwd: bad shape");
     return dispatch_attn_bwd(D / H, q, ldq, kv, kv + D, ldkv, nullptr, N / group, group * S, S, E, H, 0, 0, d_ctx, D, d_q,
                              ld_dq, d_kv, d_kv + D, ld_dkv, as_stream(stream), "navc_cross_attention_bwd");
+}
+
+extern "C" int navc_self_attention_bwd_packed(const float* qkv, int ld, const int64_t* tokens, const int32_t* seq_off, int N,
+                                              int S, int D, int H, int mask_kind, int watch, const float* d_ctx,
+                                              float* d_qkv, void* stream) {
+    NAVC_REQUIRE(qkv && tokens && seq_off && d_ctx && d_qkv, "navc_self_attention_bwd_packed: null pointer");
+    NAVC_REQUIRE(N > 0 && S > 0 && H > 0 && D % H == 0 && ld >= 3 * D, "navc_self_attention_bwd_packed: bad shape");
+    return dispatch_attn_bwd(D / H, qkv, ld, qkv + D, qkv + 2 * D, ld, tokens, N, S, S, S, H, mask_kind, watch, d_ctx, D,
+                             d_qkv, ld, d_qkv + D, d_qkv + 2 * D, ld, as_stream(stream), "navc_self_attention_bwd_packed",
+                             seq_off, 1);
+}
+
+extern "C" int navc_cross_attention_bwd_packed(const float* q, int ldq, const float* kv, int ldkv, const int32_t* seq_off,
+                                               int N, int S, int E, int D, int H, const float* d_ctx, float* d_q, int ld_dq,
+                                               float* d_kv, int ld_dkv, void* stream) {
+    NAVC_REQUIRE(q && kv && seq_off && d_ctx && d_q && d_kv, "navc_cross_attention_bwd_packed: null pointer");
+    NAVC_REQUIRE(N > 0 && S > 0 && E > 0 && H > 0 && D % H == 0, "navc_cross_attention_bwd_packed: bad shape");
+    // one owner (video) per sequence: the training path has one token row per video
+    return dispatch_attn_bwd(D / H, q, ldq, kv, kv + D, ldkv, nullptr, N, S, S, E, H, 0, 0, d_ctx, D, d_q, ld_dq, d_kv,
+                             d_kv + D, ld_dkv, as_stream(stream), "navc_cross_attention_bwd_packed", seq_off, 0);
+}
+
+// Packed vocabulary projection: rows that were not computed (PAD positions, hidden == 0) all have the same
+// log-probabilities const_logp = log_softmax(bias).  Their dlogits only reach the bias gradient.  A loss that
+// ignores PAD positions (misc/crit.py:62-84) leaves these rows of g all zero -> one read pass, no atomics.
+__global__ void log_softmax_bwd_padrows_kernel(const float* __restrict__ g, int ld, const int32_t* __restrict__ pad_rows,
+                                               const float* __restrict__ const_logp, int V, float* __restrict__ db) {
+    __shared__ float red[32];
+    __shared__ int any;
+    const float* gr = g + (size_t)pad_rows[blockIdx.x] * ld;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    float sum = 0.f;
+    bool nz = false;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const float x = gr[v];
+        sum += x;
+        nz = nz || (x != 0.f);
+    }
+    if (nz) any = 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (!any) return;
+    sum = warp_sum(lane < nw ? red[lane] : 0.f);
+    for (int v = threadIdx.x; v < V; v += blockDim.x) atomicAdd(db + v, gr[v] - expf(const_logp[v]) * sum);
+}
+
+extern "C" int navc_log_softmax_bwd_padrows(const float* g, int ld, const int32_t* pad_rows, int n_pad,
+                                            const float* const_logp, int V, float* db, void* stream) {
+    NAVC_REQUIRE(g && pad_rows && const_logp && db && n_pad > 0 && V > 0 && ld >= V, "navc_log_softmax_bwd_padrows: bad arguments");
+    log_softmax_bwd_padrows_kernel<<<n_pad, 256, 0, as_stream(stream)>>>(g, ld, pad_rows, const_logp, V, db);
+    return check_launch("navc_log_softmax_bwd_padrows");
 }

@@ -281,10 +281,11 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 
 // ------------------------------------------------------------------------------------------------
 // one block per row: log_softmax over V columns
-__global__ void log_softmax_kernel(const float* __restrict__ x, float* __restrict__ out, int V, int ld, int ld_out) {
+__global__ void log_softmax_kernel(const float* __restrict__ x, float* __restrict__ out, int V, int ld, int ld_out,
+                                   const int32_t* __restrict__ rowmap) {
     __shared__ float red[32];
     const float* r = x + (size_t)blockIdx.x * ld;
-    float* o = out + (size_t)blockIdx.x * ld_out;
+    float* o = out + (rowmap ? (size_t)rowmap[blockIdx.x] : (size_t)blockIdx.x) * ld_out;   // packed rows -> padded output
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     float m = -INFINITY;
     for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, r[i]);
@@ -425,12 +426,19 @@ extern "C" int navc_layernorm(const float* x, const float* w, const float* b, fl
 
 extern "C" int navc_log_softmax(const float* logits, float* out, int M, int V, int ld, void* stream) {
     NAVC_REQUIRE(logits && out && M > 0 && V > 0 && ld >= V, "navc_log_softmax: bad arguments");
-    log_softmax_kernel<<<M, 256, 0, as_stream(stream)>>>(logits, out, V, ld, ld);
+    log_softmax_kernel<<<M, 256, 0, as_stream(stream)>>>(logits, out, V, ld, ld, nullptr);
     return check_launch("navc_log_softmax");
 }
 
 extern "C" int navc_log_softmax_ld(const float* logits, int ld_in, float* out, int ld_out, int M, int V, void* stream) {
     NAVC_REQUIRE(logits && out && M > 0 && V > 0 && ld_in >= V && ld_out >= V, "navc_log_softmax_ld: bad arguments");
-    log_softmax_kernel<<<M, 256, 0, as_stream(stream)>>>(logits, out, V, ld_in, ld_out);
+    log_softmax_kernel<<<M, 256, 0, as_stream(stream)>>>(logits, out, V, ld_in, ld_out, nullptr);
     return check_launch("navc_log_softmax_ld");
+}
+
+extern "C" int navc_log_softmax_rows(const float* logits, int ld_in, float* out, int ld_out, const int32_t* rowmap, int rows,
+                                     int V, void* stream) {
+    NAVC_REQUIRE(logits && out && rowmap && rows > 0 && V > 0 && ld_in >= V && ld_out >= V, "navc_log_softmax_rows: bad arguments");
+    log_softmax_kernel<<<rows, 256, 0, as_stream(stream)>>>(logits, out, V, ld_in, ld_out, rowmap);
+    return check_launch("navc_log_softmax_rows");
 }

@@ -68,6 +68,8 @@ class Engine:
         self.tc = self.precision != "fp32"
         self.tc_mode = {"bf16": L.TC_BF16, "bf16x3": L.TC_BF16X3}.get(self.precision, 0)
         self._sig = None
+        self._members = None
+        self._named = None
         self.device = None
         self.P: Dict[str, object] = {}
         # optional live timing of one class of launches (bench.py roofline): CUDA events recorded on
@@ -80,15 +82,30 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # weight packing
     # ------------------------------------------------------------------------------------------
+    def members(self):
+        """(named parameters, tracked buffers) of the model, walked once: nn.Module.named_parameters() visits
+        every sub-module and was ~30 % of the host time of a training step.  Parameter OBJECTS are stable under
+        load_state_dict / .to() / optimizer steps; after replacing one (``m.weight = nn.Parameter(..)``) call
+        ``invalidate()``."""
+        if self._members is None:
+            self._members = (list(self.model.named_parameters()),
+                             [(n, b) for n, b in self.model.named_buffers() if not n.endswith("num_batches_tracked")])
+        return self._members
+
+    def named_params(self) -> Dict[str, torch.Tensor]:
+        if self._named is None:
+            self._named = dict(self.members()[0])
+        return self._named
+
     def _signature(self):
         # num_batches_tracked is bookkeeping only (BatchNorm momentum is fixed); the running statistics
         # are referenced in place, so train-mode updates need no repack
-        return tuple((p.data_ptr(), p._version) for p in self.model.parameters()) + \
-            tuple((b.data_ptr(), b._version) for n, b in self.model.named_buffers() if not n.endswith("num_batches_tracked"))
+        params, bufs = self.members()
+        return tuple((p.data_ptr(), p._version) for _, p in params) + tuple((b.data_ptr(), b._version) for _, b in bufs)
 
     def sync_weights(self):
         """(Re)pack weights if any parameter changed (optimizer step, load_state_dict, .to())."""
-        dev = next(self.model.parameters()).device
+        dev = self.members()[0][0][1].device
         L.ensure_init(dev)
         sig = self._signature()
         if sig == self._sig and dev == self.device:
@@ -100,8 +117,11 @@ class Engine:
         self.graphs.clear()  # captured graphs hold pointers into the previous packed weights
 
     def invalidate(self):
-        """Force a repack at the next use (for writers that bypass torch's version counters)."""
+        """Force a repack at the next use (for writers that bypass torch's version counters, or after a
+        parameter / sub-module object was replaced)."""
         self._sig = None
+        self._members = None
+        self._named = None
 
     def _lin(self, w, b=None, src=()) -> PackedLinear:
         pl = PackedLinear(w, b, src)
@@ -113,7 +133,9 @@ class Engine:
 
     def _pack(self):
         m, opt = self.model, self.opt
-        sd = {k: v for k, v in m.state_dict().items()}
+        params, bufs = self.members()  # what state_dict() holds (minus num_batches_tracked), without the module walk
+        sd = {k: v.detach() for k, v in params}
+        sd.update(bufs)
         P = {}
         with torch.no_grad():
             # encoder streams (models/Encoder.py)

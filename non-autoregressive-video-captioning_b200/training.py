@@ -19,6 +19,9 @@ gradients into ``.grad`` and runs the caller's loss (misc/crit.py) on the return
 """
 from __future__ import annotations
 
+import math
+import os
+
 from typing import Dict, List, Optional
 
 import torch
@@ -255,12 +258,12 @@ class _F32Engine:
 # encoder  (models/seq2seq.py:35-63 in train mode)
 # --------------------------------------------------------------------------------------------------
 def _param_list(model, keys):
-    sd = dict(model.named_parameters())
+    sd = model.engine.named_params()
     return [sd[k] for k in keys]
 
 
 def _encode_param_keys(model):
-    return [k for k, _ in model.named_parameters()
+    return [k for k in model.engine.named_params()
             if k.startswith(("encoder.", "joint_representation_learner.", "auxiliary_task_predictor."))]
 
 
@@ -398,8 +401,39 @@ def encode_train(model, feats):
 # --------------------------------------------------------------------------------------------------
 # decoder  (models/Decoder.py:96-178, models/bert.py:262-303 in train mode)
 # --------------------------------------------------------------------------------------------------
+def train_packed_enabled(opt) -> bool:
+    """Packed rows on the training path: opt['navc_train_packed'] or $NAVC_TRAIN_PACKED (default on)."""
+    v = opt.get("navc_train_packed", None)
+    if v is None:
+        v = os.environ.get("NAVC_TRAIN_PACKED", "1")
+    return str(v).lower() not in ("0", "false", "no", "off")
+
+
+def plan_packing(eng: Engine, tokens: torch.Tensor, E: int):
+    """Packed rows for one training batch, or None.  PAD positions carry no signal on this path: their keys
+    are masked out of every softmax and their rows are zeroed by ``* non_pad_mask`` after every sub-layer
+    (models/bert.py:271-299), so only the sum(len) real positions are rows of the decoder / vocabulary GEMMs.
+    Needs the tcgen05 attention cores and PAD only as a suffix (what the reference's loaders produce);
+    costs ONE small host read (sum(len), the suffix check, min(len))."""
+    N, S = tokens.shape
+    if not (eng.tc_attention_ok(S, E) and train_packed_enabled(eng.opt)):
+        return None
+    nonpad = tokens.ne(Constants.PAD)
+    lens = nonpad.sum(1, dtype=torch.int32)
+    suffix = (nonpad == (torch.arange(S, device=tokens.device).unsqueeze(0) < lens.unsqueeze(1))).all()
+    total, ok, shortest = torch.stack([lens.sum().to(torch.int32), suffix.to(torch.int32), lens.min()]).tolist()
+    if not ok or shortest < 1 or total > 0.92 * N * S:
+        return None
+    pk = eng.pack_rows(lens, S)
+    pk["rows"] = int(total)
+    pk["rowmap"] = pk["rowmap"][:total]
+    # padded row ids that are not packed (size known on the host: no second read)
+    pk["pad_rows"] = torch.nonzero_static(~nonpad.reshape(-1), size=N * S - int(total)).to(torch.int32).reshape(-1)
+    return pk
+
+
 def _decoder_param_keys(model):
-    return [k for k, _ in model.named_parameters() if k.startswith("decoder.")]
+    return [k for k in model.engine.named_params() if k.startswith("decoder.")]
 
 
 class DecoderFn(torch.autograd.Function):
@@ -429,11 +463,20 @@ class DecoderFn(torch.autograd.Function):
             elif ei != 0:
                 raise NotImplementedError("enhance_input=1 fails in the reference itself (SURVEY 8c)")
         tc_attn = eng.tc_attention_ok(S, E)
+        pk = plan_packing(eng, tokens, E)
         kv = eng.linear(enc, P["kv_all"], f32=True, bf=tc_attn)
         emb = P["emb"]
-        x_ln = torch.empty((R, D), dtype=torch.float32, device=dev)
-        L.call("navc_embed_ln", L.ptr(tokens), L.ptr(cat), L.ptr(emb["word"]), L.ptr(emb["pos"]), L.ptr(emb["cat"]),
-               L.ptr(extra), 1, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), eng.eps, N, S, D, L.ptr(x_ln), None, None, L.stream())
+        if pk is not None:  # rows = real positions only; every row is non-PAD, so `* non_pad_mask` is the identity
+            R = pk["rows"]
+            tok_flat = None
+            x_ln = torch.empty((R, D), dtype=torch.float32, device=dev)
+            L.call("navc_embed_ln_packed", L.ptr(tokens), L.ptr(cat), L.ptr(emb["word"]), L.ptr(emb["pos"]), L.ptr(emb["cat"]),
+                   L.ptr(extra), 1, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), eng.eps, N, S, D, L.ptr(pk["seq_off"]),
+                   L.ptr(pk["rowmap"]), None, L.ptr(x_ln), None, None, L.stream())
+        else:
+            x_ln = torch.empty((R, D), dtype=torch.float32, device=dev)
+            L.call("navc_embed_ln", L.ptr(tokens), L.ptr(cat), L.ptr(emb["word"]), L.ptr(emb["pos"]), L.ptr(emb["cat"]),
+                   L.ptr(extra), 1, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), eng.eps, N, S, D, L.ptr(x_ln), None, None, L.stream())
         seed_e = seeds.next()
         x = drop_add(eng, x_ln, None, seed_e, p, 0, 0.0, None)
         mask_kind = L.MASK_KIND[decoding_type]
@@ -443,7 +486,11 @@ class DecoderFn(torch.autograd.Function):
             sv = dict(x=x)
             qkv = eng.linear(x, lw["qkv"], f32=True, bf=tc_attn)
             ctx1 = eng._new(R, D, True, True)
-            if tc_attn:
+            if pk is not None:
+                L.call("navc_self_attention_tc_rows", eng.tc_mode, L.ptr(qkv.hi), L.ptr(qkv.lo), 3 * D, L.ptr(tokens),
+                       L.ptr(pk["seq_off"]), R, N, S, D, H, mask_kind, watch, L.ptr(ctx1.f32), L.ptr(ctx1.hi), L.ptr(ctx1.lo),
+                       L.stream())
+            elif tc_attn:
                 L.call("navc_self_attention_tc", eng.tc_mode, L.ptr(qkv.hi), L.ptr(qkv.lo), 3 * D, L.ptr(tokens), N, S,
                        D, H, mask_kind, watch, L.ptr(ctx1.f32), L.ptr(ctx1.hi), L.ptr(ctx1.lo), L.stream())
             else:
@@ -455,7 +502,12 @@ class DecoderFn(torch.autograd.Function):
             a = _post(eng, so.f32, x.f32, lw["so_ln"], sv["s_so"], p, 0, 0.0, tok_flat, sv["so"])
             q = eng.linear(a, lw["cq"], f32=True, bf=tc_attn)
             ctx2 = eng._new(R, D, True, True)
-            if tc_attn:
+            if pk is not None:
+                off = l * 2 * D
+                L.call("navc_cross_attention_tc_rows", eng.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D, kv.hi[:, off:].data_ptr(),
+                       kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N, L.ptr(pk["seq_off"]), R, N, S, E, D, H, 1,
+                       L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.stream())
+            elif tc_attn:
                 off = l * 2 * D
                 L.call("navc_cross_attention_tc", eng.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D, kv.hi[:, off:].data_ptr(),
                        kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N, N, S, E, D, H, 1,
@@ -479,8 +531,15 @@ class DecoderFn(torch.autograd.Function):
             x = xn
         ctx.model, ctx.keys = model, keys
         ctx.state = dict(tokens=tokens, tok_flat=tok_flat, cat=cat, enc=enc, extra=extra, kv=kv.f32, layers=layers,
-                         seed_e=seed_e, p=p, N=N, S=S, E=E, Bv=Bv, mask_kind=mask_kind, watch=watch, decoding_type=decoding_type)
-        return x.f32.view(N, S, D)
+                         seed_e=seed_e, p=p, N=N, S=S, E=E, Bv=Bv, mask_kind=mask_kind, watch=watch, decoding_type=decoding_type,
+                         pk=pk)
+        ctx.pk = pk
+        eng.last_train_rows = (R, N * S)  # rows that went through the decoder GEMMs / padded rows (stats only)
+        if pk is None:
+            return x.f32.view(N, S, D)
+        hidden = torch.zeros((N, S, D), dtype=torch.float32, device=dev)  # PAD rows are exactly zero, as in the reference
+        L.call("navc_rows_f32", L.ptr(x.f32), L.ptr(hidden), D, L.ptr(pk["rowmap"]), R, 1, L.stream())
+        return hidden
 
     @staticmethod
     def backward(ctx, d_hidden):
@@ -492,8 +551,14 @@ class DecoderFn(torch.autograd.Function):
         R = N * S
         p = st["p"]
         tok_flat = st["tok_flat"]
+        pk = st["pk"]
         grads = Grads()
         g = d_hidden.contiguous().view(R, D).float()
+        if pk is not None:  # gradient rows of the real positions (PAD rows get none: `* non_pad_mask`)
+            R = pk["rows"]
+            gp = torch.empty((R, D), dtype=torch.float32, device=dev)
+            L.call("navc_rows_f32", L.ptr(g), L.ptr(gp), D, L.ptr(pk["rowmap"]), R, 0, L.stream())
+            g = gp
         nl = len(P["layers"])
         d_kv = torch.empty((Bv * E, nl * 2 * D), dtype=torch.float32, device=dev)
         for l in range(nl - 1, -1, -1):
@@ -507,14 +572,23 @@ class DecoderFn(torch.autograd.Function):
             d_ctx2 = lin_bwd(eng, sv["ctx2"], lw["co"], d_co, grads)
             d_q = torch.empty((R, D), dtype=torch.float32, device=dev)
             off = l * 2 * D
-            L.call("navc_cross_attention_bwd", L.ptr(sv["q"]), D, st["kv"][:, off:].data_ptr(), st["kv"].shape[1], N, S, E, D, H, 1,
-                   L.ptr(d_ctx2), L.ptr(d_q), D, d_kv[:, off:].data_ptr(), d_kv.shape[1], L.stream())
+            if pk is not None:
+                L.call("navc_cross_attention_bwd_packed", L.ptr(sv["q"]), D, st["kv"][:, off:].data_ptr(), st["kv"].shape[1],
+                       L.ptr(pk["seq_off"]), N, S, E, D, H, L.ptr(d_ctx2), L.ptr(d_q), D, d_kv[:, off:].data_ptr(),
+                       d_kv.shape[1], L.stream())
+            else:
+                L.call("navc_cross_attention_bwd", L.ptr(sv["q"]), D, st["kv"][:, off:].data_ptr(), st["kv"].shape[1], N, S, E, D, H, 1,
+                       L.ptr(d_ctx2), L.ptr(d_q), D, d_kv[:, off:].data_ptr(), d_kv.shape[1], L.stream())
             d_a = lin_bwd(eng, sv["a"], lw["cq"], d_q, grads, dx_residual=d_a_res)
             d_so, d_x_res = _post_bwd(eng, d_a, lw["so_ln"], lw["so_ln_key"], sv["s_so"], p, 0, 0.0, tok_flat, sv["so"], grads)
             d_ctx1 = lin_bwd(eng, sv["ctx1"], lw["so"], d_so, grads)
             d_qkv = torch.empty((R, 3 * D), dtype=torch.float32, device=dev)
-            L.call("navc_self_attention_bwd", L.ptr(sv["qkv"]), 3 * D, L.ptr(st["tokens"]), N, S, D, H, st["mask_kind"], st["watch"],
-                   L.ptr(d_ctx1), L.ptr(d_qkv), L.stream())
+            if pk is not None:
+                L.call("navc_self_attention_bwd_packed", L.ptr(sv["qkv"]), 3 * D, L.ptr(st["tokens"]), L.ptr(pk["seq_off"]), N, S,
+                       D, H, st["mask_kind"], st["watch"], L.ptr(d_ctx1), L.ptr(d_qkv), L.stream())
+            else:
+                L.call("navc_self_attention_bwd", L.ptr(sv["qkv"]), 3 * D, L.ptr(st["tokens"]), N, S, D, H, st["mask_kind"],
+                       st["watch"], L.ptr(d_ctx1), L.ptr(d_qkv), L.stream())
             g = lin_bwd(eng, sv["x"], lw["qkv"], d_qkv, grads, dx_residual=d_x_res)
         # embeddings
         g_ln, _ = drop_add_bwd(g, st["seed_e"], p, 0, 0.0, None, want_res=False)
@@ -524,9 +598,15 @@ class DecoderFn(torch.autograd.Function):
         d_cat = torch.zeros_like(emb["cat"]) if emb["cat"] is not None else None
         d_extra = torch.zeros_like(st["extra"]) if st["extra"] is not None else None
         d_lw, d_lb = torch.zeros_like(emb["ln_w"]), torch.zeros_like(emb["ln_b"])
-        L.call("navc_embed_ln_bwd", L.ptr(g_ln), L.ptr(st["tokens"]), L.ptr(st["cat"]), L.ptr(emb["word"]), L.ptr(emb["pos"]),
-               L.ptr(emb["cat"]), L.ptr(st["extra"]), 1, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), eng.eps, N, S, D,
-               L.ptr(d_word), L.ptr(d_pos), L.ptr(d_cat), L.ptr(d_extra), L.ptr(d_lw), L.ptr(d_lb), L.stream())
+        if pk is not None:
+            L.call("navc_embed_ln_bwd_packed", L.ptr(g_ln), L.ptr(st["tokens"]), L.ptr(st["cat"]), L.ptr(emb["word"]),
+                   L.ptr(emb["pos"]), L.ptr(emb["cat"]), L.ptr(st["extra"]), 1, L.ptr(emb["ln_w"]), eng.eps, S, D,
+                   L.ptr(pk["rowmap"]), R, L.ptr(d_word), L.ptr(d_pos), L.ptr(d_cat), L.ptr(d_extra), L.ptr(d_lw), L.ptr(d_lb),
+                   L.stream())
+        else:
+            L.call("navc_embed_ln_bwd", L.ptr(g_ln), L.ptr(st["tokens"]), L.ptr(st["cat"]), L.ptr(emb["word"]), L.ptr(emb["pos"]),
+                   L.ptr(emb["cat"]), L.ptr(st["extra"]), 1, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), eng.eps, N, S, D,
+                   L.ptr(d_word), L.ptr(d_pos), L.ptr(d_cat), L.ptr(d_extra), L.ptr(d_lw), L.ptr(d_lb), L.stream())
         grads.add(ep + "word_embeddings.weight", d_word)
         grads.add(ep + "position_embeddings.weight", d_pos)
         if d_cat is not None:
@@ -544,6 +624,9 @@ def decoder_forward_train(decoder, eng, tgt_seq, enc_output, category, decoding_
     model = decoder._engine_ref()
     keys = _decoder_param_keys(model)
     hidden = DecoderFn.apply(model, keys, tgt_seq, category, decoding_type, enc_output, *_param_list(model, keys))
+    pk = getattr(hidden.grad_fn, "pk", None)
+    if pk is not None:  # the vocabulary projection of exactly this tensor may skip the PAD rows too (vocab_logprobs_train)
+        hidden._navc_pack = pk
     with torch.no_grad():  # returned, unused downstream (models/bert.py:301)
         non_pad = tgt_seq.ne(Constants.PAD).float().unsqueeze(-1)
         embs = hidden.detach().sum(1) / non_pad.sum(1)
@@ -557,7 +640,7 @@ class VocabFn(torch.autograd.Function):
     """hidden [.., D] -> log_softmax(tgt_word_prj(hidden)) [.., V] (log_probs=True) or the logits."""
 
     @staticmethod
-    def forward(ctx, model, log_probs, hidden, *params):
+    def forward(ctx, model, log_probs, pk, hidden, *params):
         eng: Engine = model.engine
         eng.sync_weights()
         lin = eng.P["vocab"]
@@ -565,7 +648,14 @@ class VocabFn(torch.autograd.Function):
         shape = hidden.shape
         D, V = lin.K, lin.N
         h2 = hidden.detach().reshape(-1, D)
-        R = h2.shape[0]
+        R = R_all = h2.shape[0]
+        # packed rows (pk): `hidden` is the untouched tensor DecoderFn produced (PAD rows exactly zero) -> only the real
+        # positions go through the projection; the PAD rows of the output are log_softmax(bias), a constant row
+        if pk is not None:
+            R = pk["rows"]
+            hp = torch.empty((R, D), dtype=torch.float32, device=dev)
+            L.call("navc_rows_f32", L.ptr(h2), L.ptr(hp), D, L.ptr(pk["rowmap"]), R, 0, L.stream())
+            h2 = hp
         h = eng.from_f32(h2)
         Vp = _up(V, 64)
         logits = torch.empty((R, Vp), dtype=torch.float32, device=dev)
@@ -581,13 +671,24 @@ class VocabFn(torch.autograd.Function):
         wop, b_pad = lin.pad
         xop = Operand(R, D, D, hi=h.hi, lo=h.lo) if eng.tc else Operand(R, D, D, f32=h.f32)
         gemm(eng, xop, wop, R, Vp, D, logits, Vp, bias=b_pad)
-        out = torch.empty((R, V), dtype=torch.float32, device=dev)
-        if log_probs:
-            L.call("navc_log_softmax_ld", L.ptr(logits), Vp, L.ptr(out), V, R, V, L.stream())
+        const_lp = None
+        if pk is not None:
+            if lin.b is not None:
+                const_lp = torch.empty((1, V), dtype=torch.float32, device=dev)
+                L.call("navc_log_softmax_ld", L.ptr(b_pad), Vp, L.ptr(const_lp), V, 1, V, L.stream())
+            else:
+                const_lp = torch.full((1, V), -math.log(V), dtype=torch.float32, device=dev)
+            out = const_lp.expand(R_all, V).contiguous()
+            L.call("navc_log_softmax_rows", L.ptr(logits), Vp, L.ptr(out), V, L.ptr(pk["rowmap"]), R, V, L.stream())
         else:
-            out.copy_(logits[:, :V])
+            out = torch.empty((R, V), dtype=torch.float32, device=dev)
+            if log_probs:
+                L.call("navc_log_softmax_ld", L.ptr(logits), Vp, L.ptr(out), V, R, V, L.stream())
+            else:
+                out.copy_(logits[:, :V])
         ctx.model, ctx.log_probs = model, log_probs
-        ctx.state = dict(h=h, out=out if log_probs else None, R=R, V=V, Vp=Vp, shape=shape, n_params=len(params))
+        ctx.state = dict(h=h, out=out if log_probs else None, R=R, V=V, Vp=Vp, shape=shape, n_params=len(params), pk=pk,
+                         R_all=R_all, const_lp=const_lp)
         return out.view(*shape[:-1], V)
 
     @staticmethod
@@ -596,11 +697,14 @@ class VocabFn(torch.autograd.Function):
         eng: Engine = model.engine
         lin = eng.P["vocab"]
         dev = eng.device
-        R, V, Vp = st["R"], st["V"], st["Vp"]
+        R, V, Vp, pk = st["R"], st["V"], st["Vp"], st["pk"]
         grads = Grads()
-        d_out = d_out.contiguous().view(R, V)
+        d_out = d_out.contiguous().view(st["R_all"], V)
         dlog = torch.empty((R, Vp), dtype=torch.float32, device=dev)
-        if ctx.log_probs:
+        if pk is not None:
+            L.call("navc_log_softmax_bwd_rows", L.ptr(d_out), L.ptr(st["out"]), L.ptr(pk["rowmap"]), R, V, V, L.ptr(dlog), Vp,
+                   L.stream())
+        elif ctx.log_probs:
             L.call("navc_log_softmax_bwd", L.ptr(d_out), L.ptr(st["out"]), R, V, V, L.ptr(dlog), Vp, L.stream())
         else:
             dlog.zero_()
@@ -608,7 +712,14 @@ class VocabFn(torch.autograd.Function):
         d_h = lin_bwd(eng, st["h"], lin, dlog, grads, ld_dy=Vp)
         gw = grads.g.get("tgt_word_prj.weight")
         gb = grads.g.get("tgt_word_prj.bias")
-        return (None, None, d_h.view(st["shape"])) + ((gw,) if st["n_params"] == 1 else (gw, gb))
+        if pk is not None:
+            if gb is not None and st["R_all"] > R:  # the skipped PAD rows only reach the bias (zero for PAD-ignoring losses)
+                L.call("navc_log_softmax_bwd_padrows", L.ptr(d_out), V, L.ptr(pk["pad_rows"]), st["R_all"] - R,
+                       L.ptr(st["const_lp"]), V, L.ptr(gb), L.stream())
+            dp = torch.zeros((st["R_all"], d_h.shape[1]), dtype=torch.float32, device=dev)
+            L.call("navc_rows_f32", L.ptr(d_h), L.ptr(dp), d_h.shape[1], L.ptr(pk["rowmap"]), R, 1, L.stream())
+            d_h = dp
+        return (None, None, None, d_h.view(st["shape"])) + ((gw,) if st["n_params"] == 1 else (gw, gb))
 
 
 def _vocab_params(prj):
@@ -617,12 +728,16 @@ def _vocab_params(prj):
 
 def vocab_forward_train(engine, prj, hidden):
     """model.tgt_word_prj(hidden) under autograd -> logits."""
-    return VocabFn.apply(prj._owner(), False, hidden, *_vocab_params(prj))
+    return VocabFn.apply(prj._owner(), False, None, hidden, *_vocab_params(prj))
 
 
 def vocab_logprobs_train(model, hidden):
     """log_softmax(tgt_word_prj(hidden)) as one autograd node (projection + log-softmax kernels)."""
-    return VocabFn.apply(model, True, hidden, *_vocab_params(model.tgt_word_prj))
+    pk = getattr(hidden, "_navc_pack", None)
+    if pk is not None and not (hidden._version == 0 and hidden.is_contiguous() and hidden.dim() == 3
+                               and hidden.shape[0] * hidden.shape[1] == pk["N"] * pk["S"]):
+        pk = None  # modified since the decoder produced it: PAD rows may no longer be zero
+    return VocabFn.apply(model, True, pk, hidden, *_vocab_params(model.tgt_word_prj))
 
 
 # --------------------------------------------------------------------------------------------------

@@ -337,6 +337,161 @@ def test_cross_attention_backward(D, H, S, E, group):
 
 
 # ---------------------------------------------------------------------------------------------------
+# packed rows (training): only the real positions are rows; same numbers as the padded kernels
+# ---------------------------------------------------------------------------------------------------
+def _pack(lens, S):
+    off = [0]
+    for l in lens:
+        off.append(off[-1] + l)
+    rowmap = [n * S + s for n, l in enumerate(lens) for s in range(l)]
+    return torch.tensor(off, dtype=torch.int32), torch.tensor(rowmap, dtype=torch.int64)
+
+
+@pytest.mark.parametrize("kind", ["NARFormer", "ARFormer", "SelfMask"])
+@pytest.mark.parametrize("D,H,S", [(128, 2, 11), (512, 8, 30), (64, 2, 7)])
+def test_self_attention_backward_packed(kind, D, H, S):
+    lens = [S, 1, S - 3, 5, 2, S - 1]
+    N = len(lens)
+    seq_off, rowmap = _pack(lens, S)
+    Rp = int(seq_off[-1])
+    toks = torch.randint(1, 9, (N, S), generator=g(60))
+    for n, l in enumerate(lens):
+        toks[n, l:] = 0
+    qkv = torch.randn(Rp, 3 * D, generator=g(61)).requires_grad_(True)
+    d_ctx = torch.randn(Rp, D, generator=g(62))
+    for n, l in enumerate(lens):  # reference: every sequence on its own, only its real positions
+        r0 = int(seq_off[n])
+        x = qkv[r0:r0 + l].unsqueeze(0)
+        mask = O.self_attention_mask(toks[n:n + 1, :l], kind, 0)
+        ctx = _mha_ref(x[..., :D], x[..., D:2 * D], x[..., 2 * D:], mask, H)
+        ctx.backward(d_ctx[r0:r0 + l].unsqueeze(0))
+    d_qkv = torch.full((Rp, 3 * D), float("nan"), device=DEV)
+    L.call("navc_self_attention_bwd_packed", P(qkv), 3 * D, P(toks), P(seq_off), N, S, D, H, L.MASK_KIND[kind], 0,
+           P(d_ctx), L.ptr(d_qkv), L.stream())
+    close(d_qkv, qkv.grad, 2e-5, "packed self attn bwd")
+
+
+@pytest.mark.parametrize("D,H,S,E", [(128, 2, 9, 12), (512, 8, 30, 120), (128, 4, 7, 16)])
+def test_cross_attention_backward_packed(D, H, S, E):
+    lens = [S, 1, S - 3, 5, 2]
+    N = len(lens)
+    seq_off, _ = _pack(lens, S)
+    Rp = int(seq_off[-1])
+    q = torch.randn(Rp, D, generator=g(63)).requires_grad_(True)
+    kv = torch.randn(N, E, 2 * D, generator=g(64)).requires_grad_(True)
+    d_ctx = torch.randn(Rp, D, generator=g(65))
+    for n, l in enumerate(lens):
+        r0 = int(seq_off[n])
+        ctx = _mha_ref(q[r0:r0 + l].unsqueeze(0), kv[n:n + 1, :, :D], kv[n:n + 1, :, D:], None, H)
+        ctx.backward(d_ctx[r0:r0 + l].unsqueeze(0))
+    d_q = torch.full((Rp, D), float("nan"), device=DEV)
+    d_kv = torch.full((N * E, 2 * D), float("nan"), device=DEV)
+    L.call("navc_cross_attention_bwd_packed", P(q), D, P(kv), 2 * D, P(seq_off), N, S, E, D, H, P(d_ctx), L.ptr(d_q), D,
+           L.ptr(d_kv), 2 * D, L.stream())
+    close(d_q, q.grad, 2e-5, "packed cross attn dq")
+    close(d_kv.view(N, E, 2 * D), kv.grad, 2e-5, "packed cross attn dkv")
+
+
+def test_packed_row_helpers():
+    S, D, V = 7, 64, 301
+    lens = [7, 2, 5, 1]
+    N = len(lens)
+    seq_off, rowmap64 = _pack(lens, S)
+    rowmap = rowmap64.to(torch.int32).to(DEV)
+    Rp, R = int(seq_off[-1]), N * S
+    pad_rows = torch.tensor(sorted(set(range(R)) - set(rowmap64.tolist())), dtype=torch.int32, device=DEV)
+    # gather / scatter of fp32 rows
+    x = torch.randn(R, D, generator=g(66)).to(DEV)
+    xp = torch.empty(Rp, D, device=DEV)
+    L.call("navc_rows_f32", L.ptr(x), L.ptr(xp), D, L.ptr(rowmap), Rp, 0, L.stream())
+    assert torch.equal(xp.cpu(), x.cpu()[rowmap64])
+    back = torch.zeros(R, D, device=DEV)
+    L.call("navc_rows_f32", L.ptr(xp), L.ptr(back), D, L.ptr(rowmap), Rp, 1, L.stream())
+    want = torch.zeros(R, D)
+    want[rowmap64] = x.cpu()[rowmap64]
+    assert torch.equal(back.cpu(), want)
+    # log-softmax of packed logits into padded rows; backward from padded g / logp into packed dlogits
+    Vp = 320
+    bias = torch.randn(V, generator=g(67))
+    logits = torch.randn(Rp, Vp, generator=g(68)).to(DEV)
+    const_lp = torch.log_softmax(bias, 0).view(1, V).to(DEV)
+    out = const_lp.expand(R, V).contiguous()
+    L.call("navc_log_softmax_rows", L.ptr(logits), Vp, L.ptr(out), V, L.ptr(rowmap), Rp, V, L.stream())
+    want = const_lp.cpu().expand(R, V).clone()
+    want[rowmap64] = torch.log_softmax(logits.cpu()[:, :V], -1)
+    close(out, want, 1e-6, "log_softmax_rows")
+    gr = torch.randn(R, V, generator=g(69))
+    gr[pad_rows.cpu().long()[0]] = 0.0  # one all-zero PAD row (the PAD-ignoring loss case), the others not
+    grd = gr.to(DEV)
+    dlog = torch.empty(Rp, Vp, device=DEV)
+    L.call("navc_log_softmax_bwd_rows", L.ptr(grd), L.ptr(out), L.ptr(rowmap), Rp, V, V, L.ptr(dlog), Vp, L.stream())
+    full = gr - torch.exp(want) * gr.sum(-1, keepdim=True)  # d log_softmax, every padded row
+    close(dlog[:, :V], full[rowmap64], 1e-5, "log_softmax_bwd_rows")
+    assert dlog[:, V:].abs().max().item() == 0.0
+    db = torch.zeros(V, device=DEV)
+    L.call("navc_log_softmax_bwd_padrows", L.ptr(grd), V, L.ptr(pad_rows), pad_rows.numel(), L.ptr(const_lp), V, L.ptr(db),
+           L.stream())
+    close(db, full[pad_rows.cpu().long()].sum(0), 1e-5, "pad rows bias gradient")
+
+
+GRAD_TOL_PACKED = 5e-4
+
+
+@pytest.mark.parametrize("method,kw", [("NACF", {}), ("NAB", {}), ("ARB", {}), ("NACF", {"with_layernorm": True})],
+                         ids=["nacf", "nab", "arb", "nacf_ln"])
+def test_packed_training_matches_oracle_and_padded_path(method, kw):
+    """dk == 64 (tcgen05 attention cores) -> the training path packs the real positions; loss and every gradient
+    against the oracle, and against the padded path of the same build (navc_train_packed=0)."""
+    kw = dict(kw, num_attention_heads=2)
+    model, sd, bn_state, ref, ref_loss, res, loss = _train_case(method, "bf16x3", **kw)
+    rows, padded = model.engine.last_train_rows
+    assert rows < padded, "packing did not engage"
+    model2, _, _, _, _, res2, loss2 = _train_case(method, "bf16x3", navc_train_packed=0, **kw)
+    assert model2.engine.last_train_rows[0] == padded
+    tol = GRAD_TOL_PACKED
+    assert abs(loss.item() - ref_loss.item()) < tol * max(1.0, abs(ref_loss.item()))
+    assert abs(loss.item() - loss2.item()) < 1e-5 * max(1.0, abs(loss2.item()))
+    for a, b, c in zip(res["tgt_word_logprobs"], ref["tgt_word_logprobs"], res2["tgt_word_logprobs"]):
+        assert (a.detach().cpu() - b.detach()).abs().max().item() < 5e-4
+        # PAD rows included (log_softmax(bias)); real rows differ by bf16x3 rounding only (the softmax tiles differ)
+        assert (a.detach() - c.detach()).abs().max().item() < 1e-4
+    grads2 = dict(model2.named_parameters())
+    checked = 0
+    for name, p in model.named_parameters():
+        rg = sd[name].grad
+        if rg is None or rg.abs().max().item() == 0:
+            assert p.grad is None or p.grad.abs().max().item() < 1e-6, name
+            continue
+        close(p.grad, rg, tol, name, atol=2e-7)
+        close(p.grad, grads2[name].grad, 1e-4, name + " (packed vs padded)", atol=2e-7)
+        checked += 1
+    assert checked > 20
+
+
+def test_packed_vocab_bias_gradient_with_unmasked_loss():
+    """A loss that does NOT ignore PAD positions: the skipped rows still reach the bias gradient."""
+    out = {}
+    for packed in (1, 0):
+        opt = cases.small("NAB", hidden_dropout_prob=0.0, encoder_dropout=0.0, num_attention_heads=2, navc_train_packed=packed)
+        torch.manual_seed(0)
+        model = navc_b200.get_model(opt)
+        model.load_state_dict(cases.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 11))
+        model.to(DEV).train()
+        model.set_precision("bf16x3")
+        feats, category = cases.synth_inputs(opt, 5)
+        toks = cases.synth_tokens(opt, 5, kind="nar")
+        res = model(feats=[f.to(DEV) for f in feats], tgt_tokens=toks["tokens"].to(DEV), category=category.to(DEV))
+        lp = res["tgt_word_logprobs"][0]
+        w = torch.randn(lp.shape, generator=g(70)).to(DEV)
+        (lp * w).sum().backward()
+        out[packed] = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        out[packed, "rows"] = model.engine.last_train_rows
+    assert out[1, "rows"][0] < out[0, "rows"][0]
+    for k, v in out[0].items():
+        close(out[1][k], v, 1e-4, k, atol=2e-6)  # atol: the key-bias gradients are analytically zero (rounding noise)
+
+
+# ---------------------------------------------------------------------------------------------------
 # model level: loss + every parameter gradient vs the oracle (dropout off, BatchNorm batch statistics)
 # ---------------------------------------------------------------------------------------------------
 GRAD_TOL = {"fp32": 2e-4, "bf16x3": 5e-4}

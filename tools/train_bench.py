@@ -155,13 +155,14 @@ def main():
         loss = step(i)
     barrier()
     l0 = L.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    marks[0].record()
     for i in range(args.steps):
         loss = step(i)
-    e1.record()
+        marks[i + 1].record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = marks[0].elapsed_time(marks[-1])
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -179,7 +180,11 @@ def main():
                            "loss": "torch log-probs + NLL" if not args.fused_ce else "fused cross-entropy (navc_b200.misc.crit, incl. its accuracy / perplexity meters)",
                            "allreduce_bytes": dp.nbytes if world > 1 else 0,
                            "l2": "inputs rotate over %d distinct batches" % n_rot},
-                "gpu_launches": launches, "final_loss": float(loss.item())}
+                "gpu_launches": launches, "final_loss": float(loss.item()),
+                "per_step_ms": {"min": round(per_step[0], 3), "median": round(per_step[len(per_step) // 2], 3),
+                                "max": round(per_step[-1], 3)},
+                "rows": "%d of %d decoder rows (packed)" % model.engine.last_train_rows
+                        if getattr(model.engine, "last_train_rows", None) else None}
         emit(line)
     if args.profile and rank == 0:
         from torch.profiler import profile, ProfilerActivity
