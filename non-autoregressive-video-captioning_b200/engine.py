@@ -86,7 +86,7 @@ class Engine:
         """(named parameters, tracked buffers) of the model, walked once: nn.Module.named_parameters() visits
         every sub-module and was ~30 % of the host time of a training step.  Parameter OBJECTS are stable under
         load_state_dict / .to() / optimizer steps; after replacing one (``m.weight = nn.Parameter(..)``) call
-        ``invalidate()``."""
+        ``invalidate(structure=True)``."""
         if self._members is None:
             self._members = (list(self.model.named_parameters()),
                              [(n, b) for n, b in self.model.named_buffers() if not n.endswith("num_batches_tracked")])
@@ -116,12 +116,13 @@ class Engine:
         self.pack_id += 1
         self.graphs.clear()  # captured graphs hold pointers into the previous packed weights
 
-    def invalidate(self):
-        """Force a repack at the next use (for writers that bypass torch's version counters, or after a
-        parameter / sub-module object was replaced)."""
+    def invalidate(self, structure: bool = False):
+        """Force a repack at the next use (for writers that bypass torch's version counters);
+        structure=True also drops the cached parameter list (a parameter / sub-module OBJECT was replaced)."""
         self._sig = None
-        self._members = None
-        self._named = None
+        if structure:
+            self._members = None
+            self._named = None
 
     def _lin(self, w, b=None, src=()) -> PackedLinear:
         pl = PackedLinear(w, b, src)

@@ -328,7 +328,9 @@ class EncodeFn(torch.autograd.Function):
             _gemm_f32(h, w2, b2, B, max_len, D, logits)
             pred = torch.empty_like(logits)
             L.call("navc_log_softmax", L.ptr(logits), L.ptr(pred), B, max_len, max_len, L.stream())
-            head = dict(m=m, h_pre=h_pre, h=h, pred=pred, seed=hseed, p=p_hid)
+            # pred is an OUTPUT: keeping that very object on ctx would close a reference cycle
+            # (pred -> grad_fn -> ctx.state -> pred) and park every saved activation until the cyclic GC runs
+            head = dict(m=m, h_pre=h_pre, h=h, pred=pred.detach(), seed=hseed, p=p_hid)
             outs.append(pred)
         ctx.model, ctx.keys, ctx.n_feats = model, keys, n_feats
         ctx.state = dict(streams=streams, head=head, B=B, F=F_, E=E, p_enc=p_enc, pack_id=eng.pack_id)

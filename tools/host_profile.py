@@ -51,6 +51,19 @@ def main():
     for i in range(3):
         step(i)
     torch.cuda.synchronize()
+    print("allocator:", torch.cuda.get_allocator_backend(), os.environ.get("PYTORCH_CUDA_ALLOC_CONF"))
+    for i in range(12):  # per-step host time and allocator activity (cudaMalloc calls, reserved bytes)
+        ms0 = torch.cuda.memory_stats()
+        t0 = time.perf_counter()
+        step(i)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        ms1 = torch.cuda.memory_stats()
+        print("step %2d: host %.2f ms, drained %.2f ms, cudaMalloc +%d, cudaFree +%d, reserved %.2f GB, rows %s" % (
+            i, (t1 - t0) * 1e3, (t2 - t0) * 1e3, ms1["num_device_alloc"] - ms0["num_device_alloc"],
+            ms1["num_device_free"] - ms0["num_device_free"], ms1["reserved_bytes.all.current"] / 2**30,
+            model.engine.last_train_rows))
     # pure host time: launch without waiting (the GPU queue is deep enough for a few steps)
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -65,8 +78,9 @@ def main():
         step(i)
     pr.disable()
     torch.cuda.synchronize()
-    st = pstats.Stats(pr)
-    st.sort_stats("tottime").print_stats(28)
+    st = pstats.Stats(pr).strip_dirs()
+    st.sort_stats("tottime").print_stats(22)
+    st.sort_stats("cumulative").print_stats(40)
 
 
 if __name__ == "__main__":
