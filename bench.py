@@ -21,6 +21,7 @@ Multi-GPU: videos are independent -> each rank decodes its own B=128 batch (weak
 data-path collective; time = max over ranks.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -248,6 +249,8 @@ def main():
         for i in range(3):  # untimed settle steps of this very loop (PCIe / copy engine / clocks after the idle gap)
             fn(-3 + i)
         pending.clear()
+        gc.collect()
+        gc.freeze()  # long-lived objects (modules, captured graphs) out of the young generations: no multi-ms collections mid-run
         barrier()
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         marks[0].record()

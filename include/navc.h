@@ -99,6 +99,12 @@ int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx
 int navc_wgrad_tc(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld_dy, const uint16_t* x_hi,
                   const uint16_t* x_lo, int ld_x, int rows, int n_out, int k_in, const navc_epilogue_t* epi,
                   void* stream);
+/* Data gradient dX[rows, k_in] = dY[rows, n_out] W[n_out, k_in] (+ e->residual) on the tensor cores, straight from
+ * the forward's row-major bf16 weight copies (B operand consumed MN-major: no transposed weights).  fp32 output
+ * (e->out_f32, e->ld_out), optional fp32 residual; dY pad columns [n_out, ld_dy) must be finite. */
+int navc_dgrad_tc(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld_dy, const uint16_t* w_hi,
+                  const uint16_t* w_lo, int ld_w, int rows, int n_out, int k_in, const navc_epilogue_t* e,
+                  void* stream);
 
 /* fp32 -> bf16 hi/lo split of a contiguous buffer (weights are split once when packed). */
 int navc_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int64_t n, void* stream);

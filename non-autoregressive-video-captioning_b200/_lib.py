@@ -45,6 +45,7 @@ _PROTOS = {
     "navc_linear_f32": [vp, i32, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp],
     "navc_linear_tc": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp],
     "navc_wgrad_tc": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp],
+    "navc_dgrad_tc": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp],
     "navc_split_bf16": [vp, vp, vp, i64, vp],
     "navc_join_bf16": [vp, vp, vp, i64, vp],
     "navc_vocab_tile": [i32],

@@ -66,6 +66,9 @@ constexpr int kEpiGeneric = 0, kEpiVocab = 1, kEpiPair = 2, kEpiPairRes = 3;  //
 // A k-block is 64 reduction rows; each operand tile is loaded as 64-column TMA boxes of 64 rows (8 KB, 128B
 // swizzle), i.e. the canonical MN-major layout with 8 KB between 64-wide MN blocks and 1 KB between 8-row groups.
 constexpr int kEpiWgrad = 4;
+// 5 = generic epilogue, A K-major as usual but B MN-major: Y[m, k] = sum_n A[m, n] * B[n, k] with B [N, K_out]
+// row-major (the data gradient dX = dY W straight from the forward's weight copies: no transposed weights).
+constexpr int kEpiDgrad = 5;
 
 template <bool kX3, int kEpi, int TBN>
 __global__ void __launch_bounds__(tc_threads(kEpi), 1)
@@ -78,7 +81,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int M = epi.m_dev ? min(M_max, __ldg(epi.m_dev)) : M_max;
     constexpr bool kVocab = kEpi == kEpiVocab;
     constexpr bool kPairAny = kEpi == kEpiPair || kEpi == kEpiPairRes;
-    constexpr bool kMN = kEpi == kEpiWgrad;
+    constexpr bool kMNA = kEpi == kEpiWgrad;                        // A tile MN-major (reduction rows x 64-wide M boxes)
+    constexpr bool kMNB = kEpi == kEpiWgrad || kEpi == kEpiDgrad;   // B tile MN-major
     constexpr bool kResTma = kEpi == kEpiPairRes;
     using Cfg = TcCfg<kX3, TBN, kEpi>;
     constexpr int kTileBBytes = Cfg::kTileBBytes;
@@ -135,26 +139,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                    if constexpr (kMN) {
-                        const int row = kb * TBK;  // reduction rows [row, row + 64); rows beyond the tensor arrive as zeros
+                    const int row = kb * TBK;  // MN-major tiles: reduction rows [row, row + 64); rows beyond the tensor arrive as zeros
+                    if constexpr (kMNA) {
 #pragma unroll
                         for (int j = 0; j < TBM / 64; ++j) {
                             tma_load_2d(sa + j * 8192, &map_a_hi, full_bar(stage), mb * TBM + j * 64, row);
                             if (kX3) tma_load_2d(sa + kTileABytes + kTileBBytes + j * 8192, &map_a_lo, full_bar(stage), mb * TBM + j * 64, row);
                         }
+                    } else {
+                        tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * TBK, mb * TBM);
+                        if (kX3) tma_load_2d(sa + kTileABytes + kTileBBytes, &map_a_lo, full_bar(stage), kb * TBK, mb * TBM);
+                    }
+                    if constexpr (kMNB) {
 #pragma unroll
                         for (int j = 0; j < TBN / 64; ++j) {
                             tma_load_2d(sa + kTileABytes + j * 8192, &map_b_hi, full_bar(stage), nb * TBN + j * 64, row);
                             if (kX3) tma_load_2d(sa + 2 * kTileABytes + kTileBBytes + j * 8192, &map_b_lo, full_bar(stage), nb * TBN + j * 64, row);
                         }
-                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-                        continue;
-                    }
-                    tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * TBK, mb * TBM);
-                    tma_load_2d(sa + kTileABytes, &map_b_hi, full_bar(stage), kb * TBK, nb * TBN);
-                    if (kX3) {
-                        tma_load_2d(sa + kTileABytes + kTileBBytes, &map_a_lo, full_bar(stage), kb * TBK, mb * TBM);
-                        tma_load_2d(sa + 2 * kTileABytes + kTileBBytes, &map_b_lo, full_bar(stage), kb * TBK, nb * TBN);
+                    } else {
+                        tma_load_2d(sa + kTileABytes, &map_b_hi, full_bar(stage), kb * TBK, nb * TBN);
+                        if (kX3) tma_load_2d(sa + 2 * kTileABytes + kTileBBytes, &map_b_lo, full_bar(stage), kb * TBK, nb * TBN);
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -163,7 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TBM, TBN) | (kMN ? ((1u << 15) | (1u << 16)) : 0u);  // A / B MN-major bits
+            constexpr uint32_t idesc = make_idesc(TBM, TBN) | (kMNA ? (1u << 15) : 0u) | (kMNB ? (1u << 16) : 0u);  // A / B MN-major bits
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -177,21 +181,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                    const uint64_t da_hi = kMN ? make_smem_desc_mn(sa) : make_smem_desc(sa);
-                    const uint64_t db_hi = kMN ? make_smem_desc_mn(sa + kTileABytes) : make_smem_desc(sa + kTileABytes);
-                    const uint64_t da_lo = kMN ? make_smem_desc_mn(sa + kTileABytes + kTileBBytes) : make_smem_desc(sa + kTileABytes + kTileBBytes);
-                    const uint64_t db_lo = kMN ? make_smem_desc_mn(sa + 2 * kTileABytes + kTileBBytes) : make_smem_desc(sa + 2 * kTileABytes + kTileBBytes);
+                    const uint64_t da_hi = kMNA ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+                    const uint64_t db_hi = kMNB ? make_smem_desc_mn(sa + kTileABytes) : make_smem_desc(sa + kTileABytes);
+                    const uint64_t da_lo = kMNA ? make_smem_desc_mn(sa + kTileABytes + kTileBBytes) : make_smem_desc(sa + kTileABytes + kTileBBytes);
+                    const uint64_t db_lo = kMNB ? make_smem_desc_mn(sa + 2 * kTileABytes + kTileBBytes) : make_smem_desc(sa + 2 * kTileABytes + kTileBBytes);
 #pragma unroll
                     for (int k = 0; k < TBK / UMMA_K; ++k) {
                         // K-major: 32 bytes per k-step inside the 128-byte rows; MN-major: 16 rows of 128 bytes
-                        const uint64_t koff = kMN ? (uint64_t)((k * UMMA_K * 128) >> 4) : (uint64_t)((k * UMMA_K * 2) >> 4);
+                        const uint64_t koff_a = kMNA ? (uint64_t)((k * UMMA_K * 128) >> 4) : (uint64_t)((k * UMMA_K * 2) >> 4);
+                        const uint64_t koff_b = kMNB ? (uint64_t)((k * UMMA_K * 128) >> 4) : (uint64_t)((k * UMMA_K * 2) >> 4);
                         if (kX3) {
                             // small cross terms first, the dominant hi*hi product last
-                            tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, ((kb - kb0) | k) ? 1u : 0u);
-                            tc_mma_bf16(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
-                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
+                            tc_mma_bf16(d_tmem, da_lo + koff_a, db_hi + koff_b, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, da_hi + koff_a, db_lo + koff_b, idesc, 1u);
+                            tc_mma_bf16(d_tmem, da_hi + koff_a, db_hi + koff_b, idesc, 1u);
                         } else {
-                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, da_hi + koff_a, db_hi + koff_b, idesc, ((kb - kb0) | k) ? 1u : 0u);
                         }
                     }
                     tc_commit(empty_bar(stage));                       // frees the smem slot when the MMAs retire
@@ -561,6 +566,8 @@ int tc_init() {
     NAVC_TC_ATTR(false, kEpiVocab, 256); NAVC_TC_ATTR(true, kEpiVocab, 256);
     NAVC_TC_ATTR(false, kEpiWgrad, 256); NAVC_TC_ATTR(true, kEpiWgrad, 256);
     NAVC_TC_ATTR(false, kEpiWgrad, 128); NAVC_TC_ATTR(true, kEpiWgrad, 128);
+    NAVC_TC_ATTR(false, kEpiDgrad, 256); NAVC_TC_ATTR(true, kEpiDgrad, 256);
+    NAVC_TC_ATTR(false, kEpiDgrad, 128); NAVC_TC_ATTR(true, kEpiDgrad, 128);
 #undef NAVC_TC_ATTR
     g_tc_ready = true;
     return 0;
@@ -592,6 +599,8 @@ static int tc_make_store_map(CUtensorMap* map, const uint16_t* ptr, int rows, in
     return 0;
 }
 
+static thread_local int g_dgrad_w_rows = 0;  // true row count of the dgrad B operand (launch_tc_dgrad)
+
 static int tile_waste_pct(int tiles, int sms) {  // idle share of the last wave of a persistent grid, in percent
     const int waves = (tiles + sms - 1) / sms;
     return 100 - (100 * tiles) / (waves * sms);
@@ -609,6 +618,18 @@ static int launch_tc_bn(int mode, const uint16_t* x_hi, const uint16_t* x_lo, in
         if (mode == NAVC_TC_BF16X3) {
             if (tc_make_map(&ma_lo, x_lo, K, M, ldx, 64)) return 1;
             if (tc_make_map(&mb_lo, w_lo, K, N, ldw, 64)) return 1;
+        } else {
+            ma_lo = ma_hi;
+            mb_lo = mb_hi;
+        }
+    } else if (kEpi == kEpiDgrad) {
+        // A [M, K reduction] K-major as usual; B [K reduction rows, N] row-major: 64 x 64 boxes
+        if (tc_make_map(&ma_hi, x_hi, M, K, ldx, TBM)) return 1;
+        const int w_rows = g_dgrad_w_rows > 0 ? g_dgrad_w_rows : K;
+        if (tc_make_map(&mb_hi, w_hi, w_rows, N, ldw, 64)) return 1;
+        if (mode == NAVC_TC_BF16X3) {
+            if (tc_make_map(&ma_lo, x_lo, M, K, ldx, TBM)) return 1;
+            if (tc_make_map(&mb_lo, w_lo, w_rows, N, ldw, 64)) return 1;
         } else {
             ma_lo = ma_hi;
             mb_lo = mb_hi;
@@ -675,6 +696,17 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
     return launch_tc_bn<kEpi, 256>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, vep, st, what);
 }
 
+// dX[rows, k_in] = dY[rows, kred] W[n_out, k_in]: the B map is declared with its true n_out rows so that the
+// reduction tail (kred > n_out, and the k-block tail) reads zeros.
+static int launch_tc_dgrad(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld_dy, const uint16_t* w_hi,
+                           const uint16_t* w_lo, int ld_w, int rows, int n_out, int k_in, int kred, const EpiParams& epi,
+                           const TcVocab& vep, cudaStream_t st) {
+    g_dgrad_w_rows = n_out;
+    const int rc = launch_tc<kEpiDgrad>(mode, dy_hi, dy_lo, ld_dy, w_hi, w_lo, ld_w, rows, k_in, kred, epi, vep, st, "navc_dgrad_tc");
+    g_dgrad_w_rows = 0;
+    return rc;
+}
+
 }  // namespace navc
 
 using namespace navc;
@@ -722,6 +754,23 @@ extern "C" int navc_wgrad_tc(int mode, const uint16_t* dy_hi, const uint16_t* dy
     TcVocab v = {};
     return launch_tc<kEpiWgrad>(mode, dy_hi, dy_lo, ld_dy, x_hi, x_lo, ld_x, n_out, k_in, rows, p, v, as_stream(stream),
                                 "navc_wgrad_tc");
+}
+
+extern "C" int navc_dgrad_tc(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld_dy, const uint16_t* w_hi,
+                             const uint16_t* w_lo, int ld_w, int rows, int n_out, int k_in, const navc_epilogue_t* e,
+                             void* stream) {
+    NAVC_REQUIRE(e && e->out_f32, "navc_dgrad_tc: needs out_f32");
+    EpiParams p = to_params(e);
+    NAVC_REQUIRE(!p.res_hi && !p.m_dev && !p.accumulate && p.split_k <= 1, "navc_dgrad_tc: no bf16 residual / device row count / split-K");
+    NAVC_REQUIRE(rows > 0 && n_out > 0 && k_in % 8 == 0 && ld_dy >= n_out, "navc_dgrad_tc: k_in must be a multiple of 8");
+    p.split_k = 1;
+    // reduction over the n_out weight rows; the A map is declared 8-aligned wide (dY's pad columns, if any, meet
+    // weight rows beyond n_out, which TMA delivers as zeros)
+    int kred = (n_out + 7) / 8 * 8;
+    if (kred > ld_dy) kred = ld_dy;
+    NAVC_REQUIRE(kred % 8 == 0, "navc_dgrad_tc: ld_dy must be a multiple of 8");
+    TcVocab v = {};
+    return launch_tc_dgrad(mode, dy_hi, dy_lo, ld_dy, w_hi, w_lo, ld_w, rows, n_out, k_in, kred, p, v, as_stream(stream));
 }
 
 extern "C" int navc_vocab_partials_tc(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,

@@ -84,6 +84,14 @@ class Seq2Seq(nn.Module):
             raise ValueError("unsupported decoding_type %r" % self.opt["decoding_type"])
         return fn(kwargs)
 
+    def _plan_train(self, feats, tgt_tokens):
+        """Training only: decide the packed-row layout of this batch before anything is launched (training.py)."""
+        if torch.is_grad_enabled() and self.training and tgt_tokens is not None:
+            from ..training import plan_packing_ahead
+            feats = list(feats)
+            plan_packing_ahead(self, tgt_tokens if isinstance(tgt_tokens, (list, tuple)) else [tgt_tokens],
+                               sum(int(f.shape[1]) for f in feats))
+
     def _decode_and_project(self, results, tgt_tokens, category, **dec_kwargs):
         inputs = self.prepare_inputs_for_decoder(results, category)
         hidden_states, embs, *_ = self.decoder(tgt_seq=tgt_tokens, **inputs, **dec_kwargs)
@@ -109,6 +117,7 @@ class Seq2Seq(nn.Module):
     # -- reference seq2seq.py:86-108 -------------------------------------------------------------
     def forward_NARFormer(self, kwargs):
         feats, tgt_tokens, category = (kwargs.get(k, None) for k in ("feats", "tgt_tokens", "category"))
+        self._plan_train(feats, tgt_tokens)
         results = self.encode(feats)
         return self._decode_and_project(results, tgt_tokens, category)
 
@@ -118,6 +127,7 @@ class Seq2Seq(nn.Module):
         decoding_type = kwargs.get("decoding_type", self.opt["decoding_type"])
         cut = (lambda t: t[:, 1:]) if decoding_type == "SelfMask" else (lambda t: t[:, :-1])
         tgt_tokens = [cut(t) for t in tgt_tokens] if isinstance(tgt_tokens, list) else cut(tgt_tokens)
+        self._plan_train(feats, tgt_tokens)
         results = self.encode(feats)
         return self._decode_and_project(results, tgt_tokens, category, decoding_type=decoding_type,
                                         output_attentions=kwargs.get("output_attentions", False))

@@ -109,6 +109,10 @@ def weight_T(eng: Engine, lin: PackedLinear) -> Operand:
     return lin.T
 
 
+# dX = dY W on the row-major weights (navc_dgrad_tc); NAVC_DGRAD_T=1 restores the transposed-weight GEMM
+DGRAD_MN = os.environ.get("NAVC_DGRAD_T", "0") in ("0", "", "false")
+
+
 def _split_k(out_rows, out_cols, k):
     tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
     kb = (k + 63) // 64
@@ -176,8 +180,14 @@ def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, n
         grads.add_packed(lin, dW, db)
     if not need_dx:
         return None
-    wt = weight_T(eng, lin)  # [K, Np]
     dX = torch.empty((M, K), dtype=torch.float32, device=dev)
+    if eng.tc and K % 8 == 0 and lin.w_hi is not None and (lin.w_lo is not None or eng.precision != "bf16x3") and DGRAD_MN:
+        # dX = dY W straight from the forward's row-major bf16 weight copies (B operand consumed MN-major)
+        ep = L.Epilogue(None, L.ptr(dx_residual), None, 0, K if dx_residual is not None else 0, L.ptr(dX), None, None, K, 0, 1, 0)
+        L.call("navc_dgrad_tc", eng.tc_mode, L.ptr(s.hi), L.ptr(s.lo), ld, L.ptr(lin.w_hi), L.ptr(lin.w_lo), lin.K, M, N, K, ep,
+               L.stream())
+        return dX
+    wt = weight_T(eng, lin)  # [K, Np]
     gemm(eng, s, wt, M, K, min(ld, wt.ld), dX, K, residual=dx_residual, ld_res=K if dx_residual is not None else 0)
     return dX
 
@@ -411,27 +421,56 @@ def train_packed_enabled(opt) -> bool:
     return str(v).lower() not in ("0", "false", "no", "off")
 
 
-def plan_packing(eng: Engine, tokens: torch.Tensor, E: int):
-    """Packed rows for one training batch, or None.  PAD positions carry no signal on this path: their keys
-    are masked out of every softmax and their rows are zeroed by ``* non_pad_mask`` after every sub-layer
-    (models/bert.py:271-299), so only the sum(len) real positions are rows of the decoder / vocabulary GEMMs.
-    Needs the tcgen05 attention cores and PAD only as a suffix (what the reference's loaders produce);
-    costs ONE small host read (sum(len), the suffix check, min(len))."""
-    N, S = tokens.shape
-    if not (eng.tc_attention_ok(S, E) and train_packed_enabled(eng.opt)):
-        return None
-    nonpad = tokens.ne(Constants.PAD)
-    lens = nonpad.sum(1, dtype=torch.int32)
-    suffix = (nonpad == (torch.arange(S, device=tokens.device).unsqueeze(0) < lens.unsqueeze(1))).all()
-    total, ok, shortest = torch.stack([lens.sum().to(torch.int32), suffix.to(torch.int32), lens.min()]).tolist()
-    if not ok or shortest < 1 or total > 0.92 * N * S:
-        return None
-    pk = eng.pack_rows(lens, S)
-    pk["rows"] = int(total)
-    pk["rowmap"] = pk["rowmap"][:total]
-    # padded row ids that are not packed (size known on the host: no second read)
-    pk["pad_rows"] = torch.nonzero_static(~nonpad.reshape(-1), size=N * S - int(total)).to(torch.int32).reshape(-1)
-    return pk
+def _plan_key(t: torch.Tensor):
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version)
+
+
+def plan_packing(eng: Engine, token_sets, E: int):
+    """Packed rows for the token tensors of one training batch: {key: plan or None}, ONE small host read for
+    all of them.  PAD positions carry no signal on this path: their keys are masked out of every softmax and
+    their rows are zeroed by ``* non_pad_mask`` after every sub-layer (models/bert.py:271-299), so only the
+    sum(len) real positions are rows of the decoder / vocabulary GEMMs.  Needs the tcgen05 attention cores
+    and PAD only as a suffix (what the reference's loaders produce)."""
+    plans, todo = {}, []
+    for t in token_sets:
+        N, S = t.shape
+        if eng.tc_attention_ok(S, E) and train_packed_enabled(eng.opt):
+            nonpad = t.ne(Constants.PAD)
+            lens = nonpad.sum(1, dtype=torch.int32)
+            suffix = (nonpad == (torch.arange(S, device=t.device).unsqueeze(0) < lens.unsqueeze(1))).all()
+            todo.append((t, nonpad, lens, torch.stack([lens.sum().to(torch.int32), suffix.to(torch.int32), lens.min()])))
+        else:
+            plans[_plan_key(t)] = None
+    if not todo:
+        return plans
+    stats = torch.stack([x[3] for x in todo]).tolist()  # the host read
+    for (t, nonpad, lens, _), (total, ok, shortest) in zip(todo, stats):
+        N, S = t.shape
+        pk = None
+        if ok and shortest >= 1 and total <= 0.92 * N * S:
+            pk = eng.pack_rows(lens, S)
+            pk["rows"] = int(total)
+            pk["rowmap"] = pk["rowmap"][:total]
+            # padded row ids that are not packed (size known on the host: no second read)
+            pk["pad_rows"] = torch.nonzero_static(~nonpad.reshape(-1), size=N * S - int(total)).to(torch.int32).reshape(-1)
+        plans[_plan_key(t)] = pk
+    return plans
+
+
+def plan_packing_ahead(model, token_sets, E: int):
+    """Called at the top of the training forward, BEFORE the encoder is launched: the host read then waits
+    only for the previous step's tail instead of stalling the launch stream between encoder and decoder."""
+    eng: Engine = model.engine
+    eng.sync_weights()
+    eng.train_plans = plan_packing(eng, [t for t in token_sets if torch.is_tensor(t) and t.dim() == 2], E)
+
+
+def _take_plan(eng: Engine, tokens: torch.Tensor, E: int):
+    plans = getattr(eng, "train_plans", None) or {}
+    key = _plan_key(tokens)
+    if key in plans:
+        return plans.pop(key)
+    return plan_packing(eng, [tokens], E)[key]  # decoder called on its own: plan now (one host read here)
 
 
 def _decoder_param_keys(model):
@@ -445,6 +484,7 @@ class DecoderFn(torch.autograd.Function):
         eng.sync_weights()
         opt, P, D, H = eng.opt, eng.P, eng.D, eng.H
         dev = eng.device
+        raw_tokens = tokens
         tokens = tokens.contiguous()
         N, S = tokens.shape
         R = N * S
@@ -465,7 +505,7 @@ class DecoderFn(torch.autograd.Function):
             elif ei != 0:
                 raise NotImplementedError("enhance_input=1 fails in the reference itself (SURVEY 8c)")
         tc_attn = eng.tc_attention_ok(S, E)
-        pk = plan_packing(eng, tokens, E)
+        pk = _take_plan(eng, raw_tokens, E)
         kv = eng.linear(enc, P["kv_all"], f32=True, bf=tc_attn)
         emb = P["emb"]
         if pk is not None:  # rows = real positions only; every row is non-PAD, so `* non_pad_mask` is the identity

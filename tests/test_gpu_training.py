@@ -339,6 +339,31 @@ def test_cross_attention_backward(D, H, S, E, group):
 # ---------------------------------------------------------------------------------------------------
 # packed rows (training): only the real positions are rows; same numbers as the padded kernels
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(200, 512, 512), (4195, 2048, 512), (333, 10547, 512), (77, 1536, 512), (130, 30, 512),
+                                   (64, 512, 2048), (300, 136, 72)])
+def test_dgrad_tc_matches_fp32(mode, M, N, K):
+    """dX = dY W (+ residual) from row-major bf16 weights; N need not be a multiple of 8 (padded dY columns)."""
+    ld = (N + 63) // 64 * 64
+    dy = torch.zeros(M, ld)
+    dy[:, :N] = torch.randn(M, N, generator=g(80))
+    w = torch.randn(N, K, generator=g(81)) * 0.1
+    res = torch.randn(M, K, generator=g(82))
+    want = dy[:, :N].double() @ w.double() + res.double()
+    dyd, wd = dy.to(DEV), w.to(DEV)
+    hi = lambda t: t.to(torch.bfloat16)
+    lo = lambda t: (t - hi(t).float()).to(torch.bfloat16)
+    dy_hi, dy_lo, w_hi, w_lo = hi(dyd), lo(dyd), hi(wd), lo(wd)
+    x3 = mode == "bf16x3"
+    out = torch.full((M, K), float("nan"), device=DEV)
+    resd = res.to(DEV)
+    ep = L.Epilogue(None, L.ptr(resd), None, 0, K, L.ptr(out), None, None, K, 0, 1, 0)
+    L.call("navc_dgrad_tc", L.TC_BF16X3 if x3 else L.TC_BF16, L.ptr(dy_hi), L.ptr(dy_lo) if x3 else None, ld, L.ptr(w_hi),
+           L.ptr(w_lo) if x3 else None, K, M, N, K, ep, L.stream())
+    # bf16x3 carries ~16 mantissa bits per operand: ~2e-5 relative per product, accumulated over N terms
+    close(out, want, (2e-5 if N < 4096 else 1e-4) if x3 else 1.5e-2, "dgrad %s" % mode)
+
+
 def _pack(lens, S):
     off = [0]
     for l in lens:
