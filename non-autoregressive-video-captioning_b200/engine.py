@@ -70,6 +70,7 @@ class Engine:
         self._sig = None
         self._members = None
         self._named = None
+        self.grad_sink = None   # set by parallel.GradientAllReduce: parameter -> its p.grad view, for in-place accumulation
         self.device = None
         self.P: Dict[str, object] = {}
         # optional live timing of one class of launches (bench.py roofline): CUDA events recorded on
@@ -382,7 +383,7 @@ class Engine:
 
     def tc_attention_ok(self, S, E):
         """tcgen05 attention cores need dk == 64, S <= 32 and E <= 128 (navc.h)."""
-        return self.tc and self.D == self.H * 64 and S <= 32 and E <= 128
+        return self.tc and self.opt["dim_hidden"] == self.opt["num_attention_heads"] * 64 and S <= 32 and E <= 128
 
     def _kv_f32(self, mem):
         if mem["kv"].f32 is None:  # fp32 cores requested (attention probabilities) after a tensor-core cache

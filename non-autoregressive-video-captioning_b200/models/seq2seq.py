@@ -51,7 +51,9 @@ class Seq2Seq(nn.Module):
         self.tgt_word_prj.bias = nn.Parameter(torch.zeros(vocab_size).float(), requires_grad=True)
 
     def set_precision(self, precision):
+        sink = getattr(self.__dict__.get("engine"), "grad_sink", None)
         self.__dict__["engine"] = Engine(self, precision)
+        self.engine.grad_sink = sink  # a GradientAllReduce attached earlier keeps accumulating in place
         return self
 
     # -- reference seq2seq.py:35-63 -------------------------------------------------------------

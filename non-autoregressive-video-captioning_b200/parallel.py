@@ -106,6 +106,16 @@ class GradientAllReduce:
         if broadcast:
             broadcast_model(model)
         self.attach()
+        self._view_of = {id(p): v for p, v in zip(self.params, self.views)}
+        eng = getattr(model, "engine", None)
+        if eng is not None:
+            eng.grad_sink = self.sink
+
+    def sink(self, p):
+        """The flat-buffer view a backward kernel may accumulate into directly: only while p.grad IS that view
+        (zero_grad() / attach() keep it so; an optimizer's zero_grad(set_to_none=True) detaches it)."""
+        v = self._view_of.get(id(p))
+        return v if (v is not None and p.grad is v) else None
 
     def attach(self):
         """(Re)point p.grad at the flat buffer (optimizers' zero_grad(set_to_none=True) detaches it)."""

@@ -122,8 +122,19 @@ def _split_k(out_rows, out_cols, k):
 class Grads:
     """Gradient accumulator keyed by state_dict name."""
 
-    def __init__(self):
+    def __init__(self, eng=None):
         self.g: Dict[str, torch.Tensor] = {}
+        # direct accumulation (parallel.GradientAllReduce owns p.grad as views of one flat buffer): kernels that
+        # accumulate anyway (split-K weight gradients, bias column sums) add straight into p.grad and autograd gets
+        # None for that parameter -- no zero-filled temporary, no AccumulateGrad add
+        self.sink = getattr(eng, "grad_sink", None) if eng is not None else None
+        self.named = eng.named_params() if self.sink is not None else None
+
+    def target(self, key):
+        if self.sink is None or key is None:
+            return None
+        p = self.named.get(key)
+        return None if p is None else self.sink(p)
 
     def add(self, key, t):
         if key is None:
@@ -158,7 +169,11 @@ def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, n
         pad = torch.zeros((M, ldp), dtype=torch.float32, device=dev)
         pad[:, :N].copy_(dY.view(M, -1)[:, :N] if ld == dY.stride(0) else dY.as_strided((M, N), (ld, 1)))
         dY, ld = pad, ldp
-    db = torch.zeros((N,), dtype=torch.float32, device=dev) if lin.b is not None else None
+    tw = tb = None
+    if eng.tc and K % 8 == 0 and N % 8 == 0 and len(lin.src) == 1:  # one parameter behind this GEMM: accumulate in place
+        tw = grads.target(lin.src[0][0])
+        tb = grads.target(lin.src[0][1]) if lin.b is not None else None
+    db = tb if tb is not None else (torch.zeros((N,), dtype=torch.float32, device=dev) if lin.b is not None else None)
     if eng.tc and K % 8 == 0:
         s, _ = transpose_pack(eng, dY, M, N, ld, straight=True, colsum=db)
         if x_act is not None and x_act.hi is not None and (x_act.lo is not None or eng.precision != "bf16x3"):
@@ -167,10 +182,17 @@ def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, n
             xs, _ = transpose_pack(eng, x32, M, K, x32.stride(0), straight=True)
             x_hi, x_lo = xs.hi, xs.lo
         n_eff = N if N % 8 == 0 else ld       # pad columns of dY are zero -> zero rows of dW, sliced off below
-        dW = torch.zeros((n_eff, K), dtype=torch.float32, device=dev)
+        dW = tw if tw is not None else torch.zeros((n_eff, K), dtype=torch.float32, device=dev)
         ep = L.Epilogue(None, None, None, 0, 0, L.ptr(dW), None, None, K, 0, _split_k(n_eff, K, M), 1)
         L.call("navc_wgrad_tc", eng.tc_mode, L.ptr(s.hi), L.ptr(s.lo), ld, L.ptr(x_hi), L.ptr(x_lo), K, M, n_eff, K, ep, L.stream())
-        grads.add_packed(lin, dW[:N] if n_eff != N else dW, db)
+        if tw is None and tb is None:
+            grads.add_packed(lin, dW[:N] if n_eff != N else dW, db)
+        else:  # single source: hand over only what did not go straight into p.grad
+            wk, bk = lin.src[0][0], lin.src[0][1]
+            if tw is None:
+                grads.add(wk, dW)
+            if tb is None and db is not None:
+                grads.add(bk, db)
     else:
         s, t = transpose_pack(eng, dY, M, N, ld, straight=need_dx, transposed=True, colsum=db)
         _, xt = transpose_pack(eng, x32, M, K, x32.stride(0), transposed=True)
@@ -354,7 +376,7 @@ class EncodeFn(torch.autograd.Function):
         B, F_, E = st["B"], st["F"], st["E"]
         dev = eng.device
         BF = B * F_
-        grads = Grads()
+        grads = Grads(eng)
         feng = _F32Engine(eng)
         d_enc = torch.zeros((B, E, D), dtype=torch.float32, device=dev) if d_enc is None else d_enc.contiguous().clone()
         d_hidden = None if d_hidden is None else d_hidden.contiguous()
@@ -425,12 +447,13 @@ def _plan_key(t: torch.Tensor):
     return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version)
 
 
-def plan_packing(eng: Engine, token_sets, E: int):
+def plan_packing(eng: Engine, token_sets, E: int, between=None):
     """Packed rows for the token tensors of one training batch: {key: plan or None}, ONE small host read for
     all of them.  PAD positions carry no signal on this path: their keys are masked out of every softmax and
     their rows are zeroed by ``* non_pad_mask`` after every sub-layer (models/bert.py:271-299), so only the
     sum(len) real positions are rows of the decoder / vocabulary GEMMs.  Needs the tcgen05 attention cores
-    and PAD only as a suffix (what the reference's loaders produce)."""
+    and PAD only as a suffix (what the reference's loaders produce).  ``between`` runs after the length
+    kernels are queued and before the host read (host work that does not depend on the answer)."""
     plans, todo = {}, []
     for t in token_sets:
         N, S = t.shape
@@ -441,10 +464,13 @@ def plan_packing(eng: Engine, token_sets, E: int):
             todo.append((t, nonpad, lens, torch.stack([lens.sum().to(torch.int32), suffix.to(torch.int32), lens.min()])))
         else:
             plans[_plan_key(t)] = None
+    stats = torch.stack([x[3] for x in todo]).to("cpu", non_blocking=True) if todo else None
+    if between is not None:
+        between()
     if not todo:
         return plans
-    stats = torch.stack([x[3] for x in todo]).tolist()  # the host read
-    for (t, nonpad, lens, _), (total, ok, shortest) in zip(todo, stats):
+    torch.cuda.current_stream().synchronize()
+    for (t, nonpad, lens, _), (total, ok, shortest) in zip(todo, stats.tolist()):  # the host read
         N, S = t.shape
         pk = None
         if ok and shortest >= 1 and total <= 0.92 * N * S:
@@ -459,10 +485,11 @@ def plan_packing(eng: Engine, token_sets, E: int):
 
 def plan_packing_ahead(model, token_sets, E: int):
     """Called at the top of the training forward, BEFORE the encoder is launched: the host read then waits
-    only for the previous step's tail instead of stalling the launch stream between encoder and decoder."""
+    only for the previous step's tail instead of stalling the launch stream between encoder and decoder, and
+    the per-step weight repack is queued while that tail drains."""
     eng: Engine = model.engine
-    eng.sync_weights()
-    eng.train_plans = plan_packing(eng, [t for t in token_sets if torch.is_tensor(t) and t.dim() == 2], E)
+    eng.train_plans = plan_packing(eng, [t for t in token_sets if torch.is_tensor(t) and t.dim() == 2], E,
+                                   between=eng.sync_weights)
 
 
 def _take_plan(eng: Engine, tokens: torch.Tensor, E: int):
@@ -594,7 +621,7 @@ class DecoderFn(torch.autograd.Function):
         p = st["p"]
         tok_flat = st["tok_flat"]
         pk = st["pk"]
-        grads = Grads()
+        grads = Grads(eng)
         g = d_hidden.contiguous().view(R, D).float()
         if pk is not None:  # gradient rows of the real positions (PAD rows get none: `* non_pad_mask`)
             R = pk["rows"]
@@ -740,7 +767,7 @@ class VocabFn(torch.autograd.Function):
         lin = eng.P["vocab"]
         dev = eng.device
         R, V, Vp, pk = st["R"], st["V"], st["Vp"], st["pk"]
-        grads = Grads()
+        grads = Grads(eng)
         d_out = d_out.contiguous().view(st["R_all"], V)
         dlog = torch.empty((R, Vp), dtype=torch.float32, device=dev)
         if pk is not None:
@@ -853,7 +880,7 @@ class FusedCEFn(torch.autograd.Function):
             lin.pad = (wop, b_pad)
         wop, b_pad = lin.pad
         scale = g.detach().reshape(1).float().contiguous()
-        grads = Grads()
+        grads = Grads(eng)
         d_h = torch.empty((R, D), dtype=torch.float32, device=dev)
         C = FusedCEFn.CHUNK
         slab = torch.empty((min(C, R), Vp), dtype=torch.float32, device=dev)

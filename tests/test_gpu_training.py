@@ -627,6 +627,35 @@ def test_training_step_releases_activations_without_gc(method):
     assert m2 <= m1, "activations of finished steps are still referenced: %d -> %d bytes" % (m1, m2)
 
 
+def test_direct_gradient_accumulation_matches_autograd():
+    """With parallel.GradientAllReduce owning p.grad (views of one flat buffer) the weight / bias gradient kernels
+    accumulate straight into it; same gradients as the plain autograd route, also over two micro-batches."""
+    from navc_b200 import parallel
+    grads = {}
+    for direct in (False, True):
+        opt = cases.small("NACF", hidden_dropout_prob=0.0, encoder_dropout=0.0, num_attention_heads=2)
+        torch.manual_seed(0)
+        model = navc_b200.get_model(opt)
+        model.load_state_dict(cases.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 11))
+        model.to(DEV).train()
+        model.set_precision("bf16x3")
+        dp = parallel.GradientAllReduce(model, broadcast=False) if direct else None
+        assert (model.engine.grad_sink is not None) == direct
+        if dp is not None:
+            dp.zero_grad()
+        for mb in range(2):
+            feats, category = cases.synth_inputs(opt, 5, seed=100 + mb)
+            toks = cases.synth_tokens(opt, 5, seed=200 + mb, kind="nar")
+            res = model(feats=[f.to(DEV) for f in feats], tgt_tokens=[toks["tokens_1"].to(DEV), toks["tokens"].to(DEV)],
+                        category=category.to(DEV))
+            loss = O.criterion(opt, res, [toks["labels_1"].to(DEV), toks["labels"].to(DEV)], toks["length_target"].to(DEV))
+            loss.backward()
+        grads[direct] = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    assert set(grads[True]) == set(grads[False])
+    for k, v in grads[False].items():
+        close(grads[True][k], v, 2e-5, k, atol=2e-7)
+
+
 def test_training_with_dropout_runs_and_is_seed_reproducible():
     opt = cases.small("NACF")  # reference dropout probabilities (0.5)
     feats, category = cases.synth_inputs(opt, 4)
