@@ -628,8 +628,10 @@ struct AttnBwdSmem {
     static constexpr int LD = DK + 4;  // row stride of the row-major tiles (float4 aligned, 4-bank skew)
     static __host__ __device__ int kp(int Sk) { return (Sk + 3) / 4 * 4; }          // padded key count
     static __host__ __device__ int sp(int Sk) { return kp(Sk) + 4; }                // P / dS row stride
+    static __host__ __device__ int kpt(int Sk) { return kp(Sk) + 4; }               // K^T / V^T row stride (bank skew for phase D)
     static __host__ __device__ size_t floats(int Sk) {
-        return (size_t)2 * DK * kp(Sk) + (size_t)kp(Sk) * LD + (size_t)2 * kAttnBwdQB * LD + (size_t)2 * kAttnBwdQB * sp(Sk);
+        // E = 120 keys: 112.6 KB -> two blocks per SM (a third, row-major copy of K used to cost the second block)
+        return (size_t)2 * DK * kpt(Sk) + (size_t)2 * kAttnBwdQB * LD + (size_t)2 * kAttnBwdQB * sp(Sk);
     }
 };
 
@@ -643,11 +645,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
     constexpr int LD = SM::LD;
     constexpr int QB = kAttnBwdQB;
     extern __shared__ __align__(16) float sm[];
-    const int KP = SM::kp(Sk), SP = SM::sp(Sk);
-    float* Kt = sm;                         // [DK][KP]   K transposed
-    float* Vt = Kt + (size_t)DK * KP;       // [DK][KP]   V transposed
-    float* Ks = Vt + (size_t)DK * KP;       // [KP][LD]   K row-major (rows >= Sk zero)
-    float* Qs = Ks + (size_t)KP * LD;       // [QB][LD]
+    const int SP = SM::sp(Sk), KPT = SM::kpt(Sk);
+    float* Kt = sm;                         // [DK][KPT]  K transposed (columns >= sk zero)
+    float* Vt = Kt + (size_t)DK * KPT;      // [DK][KPT]  V transposed
+    float* Qs = Vt + (size_t)DK * KPT;      // [QB][LD]
     float* dOs = Qs + QB * LD;              // [QB][LD]
     float* Ps = dOs + QB * LD;              // [QB][SP]
     float* dSs = Ps + (size_t)QB * SP;      // [QB][SP]
@@ -676,11 +677,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
             kk = *reinterpret_cast<const float4*>(kb + (size_t)j * ldkv + d4 * 4);
             vv = *reinterpret_cast<const float4*>(vb + (size_t)j * ldkv + d4 * 4);
         }
-        *reinterpret_cast<float4*>(Ks + j * LD + d4 * 4) = kk;
-        Kt[(d4 * 4 + 0) * KP + j] = kk.x; Kt[(d4 * 4 + 1) * KP + j] = kk.y;
-        Kt[(d4 * 4 + 2) * KP + j] = kk.z; Kt[(d4 * 4 + 3) * KP + j] = kk.w;
-        Vt[(d4 * 4 + 0) * KP + j] = vv.x; Vt[(d4 * 4 + 1) * KP + j] = vv.y;
-        Vt[(d4 * 4 + 2) * KP + j] = vv.z; Vt[(d4 * 4 + 3) * KP + j] = vv.w;
+        Kt[(d4 * 4 + 0) * KPT + j] = kk.x; Kt[(d4 * 4 + 1) * KPT + j] = kk.y;
+        Kt[(d4 * 4 + 2) * KPT + j] = kk.z; Kt[(d4 * 4 + 3) * KPT + j] = kk.w;
+        Vt[(d4 * 4 + 0) * KPT + j] = vv.x; Vt[(d4 * 4 + 1) * KPT + j] = vv.y;
+        Vt[(d4 * 4 + 2) * KPT + j] = vv.z; Vt[(d4 * 4 + 3) * KPT + j] = vv.w;
     }
     const float inv_sqrt = 1.0f / sqrtf((float)DK);
     const float sqrt_dk = sqrtf((float)DK);
@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
 
     for (int q0 = 0; q0 < NQ; q0 += QB) {
         const int nq = min(QB, NQ - q0);
+        const int nq4 = (nq + 3) & ~3;  // query rows that are looped over (packed rows: len is ~half of QB on average)
         __syncthreads();
         const float* qb = q + (q_row + q0) * ldq + h * DK;
         const float* ob = d_ctx + (q_row + q0) * ld_dctx + h * DK;
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
         }
         __syncthreads();
         // ---- A: 4 queries x 4 keys per thread ----
-        for (int t = tid; t < (QB / 4) * jt_n; t += nthr) {
+        for (int t = tid; t < (nq4 / 4) * jt_n; t += nthr) {
             const int ti = t / jt_n, tj = t - ti * jt_n;
             float sacc[4][4], pacc[4][4];
 #pragma unroll
@@ -716,8 +717,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
             const float* orw = dOs + (ti * 4) * LD;
 #pragma unroll 4
             for (int d = 0; d < DK; ++d) {
-                const float4 kk = *reinterpret_cast<const float4*>(Kt + d * KP + tj * 4);
-                const float4 vv = *reinterpret_cast<const float4*>(Vt + d * KP + tj * 4);
+                const float4 kk = *reinterpret_cast<const float4*>(Kt + d * KPT + tj * 4);
+                const float4 vv = *reinterpret_cast<const float4*>(Vt + d * KPT + tj * 4);
                 const float kf[4] = {kk.x, kk.y, kk.z, kk.w}, vf[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
@@ -739,7 +740,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
         }
         __syncthreads();
         // ---- B: softmax + dS, one warp per query row (rows >= nq and keys >= Sk become zero) ----
-        for (int i = warp; i < QB; i += nw) {
+        for (int i = warp; i < nq4; i += nw) {
             if (i >= nq) {
                 for (int j = lane; j < KE; j += 32) { Ps[i * SP + j] = 0.f; dSs[i * SP + j] = 0.f; }
                 continue;
@@ -800,7 +801,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
 #pragma unroll
                 for (int b = 0; b < 4; ++b) { va[a][b] = 0.f; ka[a][b] = 0.f; }
 #pragma unroll 4
-            for (int i = 0; i < QB; ++i) {
+            for (int i = 0; i < nq4; ++i) {
                 const float4 pp = *reinterpret_cast<const float4*>(Ps + i * SP + tj * 4);
                 const float4 ss = *reinterpret_cast<const float4*>(dSs + i * SP + tj * 4);
                 const float4 oo = *reinterpret_cast<const float4*>(dOs + i * LD + td * 4);
@@ -829,33 +830,42 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(
                 }
             }
         }
-        // ---- D: dQ = dS K, 4 queries x 4 columns per thread ----
+        // ---- D: dQ = dS K from K^T, 4 queries x 4 columns {td, td+16, ..} per thread (consecutive K^T rows across the
+        // threads of a quarter-warp: conflict-free float4 loads with the KPT skew) ----
         float* dqb = dq + (q_row + q0) * ld_dq + h * DK;
-        for (int t = tid; t < (QB / 4) * (DK / 4); t += nthr) {
-            const int ti = t / (DK / 4), td = t - ti * (DK / 4);
+        constexpr int CG = DK / 4;  // column groups = threads per query tile
+        for (int t = tid; t < (nq4 / 4) * CG; t += nthr) {
+            const int ti = t / CG, td = t - ti * CG;
             float acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
             const float* sr = dSs + (ti * 4) * SP;
-#pragma unroll 4
-            for (int j = 0; j < KE; ++j) {
-                const float4 kk = *reinterpret_cast<const float4*>(Ks + j * LD + td * 4);
-                const float kf[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll 2
+            for (int j = 0; j < KE; j += 4) {
+                float4 sv[4], kv4[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const float sd = sr[a * SP + j];
+                for (int a = 0; a < 4; ++a) sv[a] = *reinterpret_cast<const float4*>(sr + a * SP + j);
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(sd, kf[b], acc[a][b]);
-                }
+                for (int b = 0; b < 4; ++b) kv4[b] = *reinterpret_cast<const float4*>(Kt + (td + CG * b) * KPT + j);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        acc[a][b] = fmaf(sv[a].x, kv4[b].x, acc[a][b]);
+                        acc[a][b] = fmaf(sv[a].y, kv4[b].y, acc[a][b]);
+                        acc[a][b] = fmaf(sv[a].z, kv4[b].z, acc[a][b]);
+                        acc[a][b] = fmaf(sv[a].w, kv4[b].w, acc[a][b]);
+                    }
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int i = ti * 4 + a;
-                if (i < nq)
-                    *reinterpret_cast<float4*>(dqb + (size_t)i * ld_dq + td * 4) =
-                        make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                if (i < nq) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dqb[(size_t)i * ld_dq + td + CG * b] = acc[a][b];
+                }
             }
         }
     }
