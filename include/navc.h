@@ -238,6 +238,29 @@ int navc_vocab_partials_tc_dyn(int mode, const uint16_t* h_hi, const uint16_t* h
                                int M, int V, int K, const int32_t* m_dev, float* part_max, float* part_sum,
                                int32_t* part_idx, void* stream);
 
+/* ---- autoregressive beam search on the device (models/Translator.py:94-161, models/Beam.py) ----
+ * One new position per beam row and step.  k_cache / v_cache: [T, N, D] fp32 per layer, written at step position
+ * `pos` by the row that computed it; anc [N, T] int32: anc[r, j] = the row that cached position j of r's prefix
+ * (beams are re-ordered by re-gathering this table, never the cache); hist [N, T] int64: r's tokens
+ * (hist[r, 0] = BOS), used for the key padding mask.  qkv [N, ld >= 3D] fp32 = the new position's projections. */
+int navc_self_attention_step(const float* qkv, int ld, float* k_cache, float* v_cache, const int32_t* anc,
+                             const int64_t* hist, int N, int T, int D, int H, int pos, int watch, float* ctx_f32,
+                             uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream);
+/* Top-K over beam x vocab of (beam score + log_softmax(logits row)) per video, straight from the logits
+ * [B*K, ld] (Translator.py:113-114, Beam.py:68-83): beams whose last token hist[r, pos] is EOS contribute -1e20,
+ * at the first step (first != 0) only beam 0 counts.  best_scores / best_ids [B, K] descending; id = beam * V + word;
+ * K <= 8; ties -> lowest id. */
+int navc_beam_topk(const float* logits, int ld, int B, int K, int V, const float* scores, const int64_t* hist, int T,
+                   int pos, int first, float* best_scores, int64_t* best_ids, void* stream);
+/* Beam.advance (Beam.py:68-117) for all B videos after step t (1-based): best_scores / best_ids [B, K] = top-K of
+ * (beam score + log-prob) over beam x vocab; re-gathers hist / anc (in -> out, distinct buffers), updates the
+ * beam scores, records hypotheses that emitted EOS (fin_*: [B, cap] score / length, [B, cap, T] tokens without
+ * BOS), marks a video done after `want` finished hypotheses or at t + 1 == max_len, counts them in n_done. */
+int navc_beam_advance(const float* best_scores, const int64_t* best_ids, int B, int K, int V, int t, int max_len,
+                      int want, int T, const int64_t* hist_in, int64_t* hist_out, const int32_t* anc_in,
+                      int32_t* anc_out, float* scores, int32_t* done, int32_t* fin_count, float* fin_score,
+                      int32_t* fin_len, int64_t* fin_tok, int cap, int32_t* n_done, void* stream);
+
 /* ---- iterative refinement (decoding/na_generate.py, decoding/algorithms.py) ----------------- */
 /* Length beam + canvas (na_generate.py:33-50, 116-135): beam[b,:] = clamp(top-lbs indices of
  * pred_length[b,:] + length_bias, 4, max_len-1) (descending value, lowest index on ties);

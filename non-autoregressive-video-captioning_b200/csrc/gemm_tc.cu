@@ -684,7 +684,9 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
         const int mt = (M + TBM - 1) / TBM;
         const int t256 = mt * ((N + 255) / 256) * epi.split_k, t128 = mt * ((N + 127) / 128) * epi.split_k;
         const int forced = epi.dbg >= 128 ? epi.dbg : 0;  // profiling aid: reserved = 128 / 256 forces a tile width
-        const bool narrow = forced ? forced == 128 : (N <= 128 || tile_waste_pct(t256, sms) >= tile_waste_pct(t128, sms) + 8);
+        // (fewer 256-wide tiles than SMs: the narrow tiling doubles the CTAs that share the operand streaming)
+        const bool narrow = forced ? forced == 128
+                                   : (N <= 128 || (t256 < sms && t128 > t256) || tile_waste_pct(t256, sms) >= tile_waste_pct(t128, sms) + 8);
         if constexpr (kEpi == kEpiPair) {
             // a bf16 hi/lo residual is prefetched by TMA (128-wide tiles only: the boxes need 64 KB of the ring)
             // (plain bf16 only: the split mode cannot spare two of its three 64 KB stages' worth of ring)

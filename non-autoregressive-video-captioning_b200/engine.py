@@ -489,6 +489,53 @@ class Engine:
             self.join_f32(x)
         return x, attns
 
+    def decoder_step(self, hist: torch.Tensor, anc: torch.Tensor, pos: int, caches, mem: dict, group: int,
+                     category: Optional[torch.Tensor], decoding_type: str = "ARFormer") -> Act:
+        """The causal BertDecoder for ONE new position per row (autoregressive beam search, decoding/ar_beam.py):
+        position `pos` of every row's prefix, self-attention over the K/V cache (include/navc.h
+        navc_self_attention_step) -> hidden Act [N, D].  Equals row `pos` of ``decoder_pass`` over the whole
+        prefix (models/Decoder.py:96-178 with the causal mask): earlier positions never see later ones."""
+        P, D, H = self.P, self.D, self.H
+        N, T = hist.shape
+        E = mem["E"]
+        assert N == mem["B"] * group and decoding_type != "NARFormer"
+        tokens = hist[:, pos].contiguous()  # this step's input token of every row
+        emb = P["emb"]
+        pair = self.tc and D % 64 == 0 and P["layers"][0]["f1"].N % 64 == 0 and \
+            all(lw[k] is None for lw in P["layers"] for k in ("so_ln", "co_ln", "f2_ln"))
+        x = self._new(N, D, not pair, True, lo=pair)
+        # S = 1 with the position table offset to row `pos`
+        L.call("navc_embed_ln", L.ptr(tokens), L.ptr(category), L.ptr(emb["word"]), emb["pos"][pos:].data_ptr(), L.ptr(emb["cat"]),
+               None, group, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), self.eps, N, 1, D, L.ptr(x.f32), L.ptr(x.hi), L.ptr(x.lo),
+               L.stream())
+        kv = mem["kv"]
+        # (one query row per beam: a 128-row tcgen05 tile holds only `group` rows, still 4x faster here than the
+        # fp32 tile kernel -- 32 vs 128 us at 640 rows)
+        tc_attn = self.tc_attention_ok(1, E) and kv.hi is not None
+        watch = int(self.opt.get("watch", 0)) if decoding_type == "ARFormer" else 0
+        for l, lw in enumerate(P["layers"]):
+            qkv = self.linear(x, lw["qkv"], f32=True, bf=False)
+            ctx = self._new(N, D, not self.tc, True)
+            kc, vc = caches[l]
+            L.call("navc_self_attention_step", L.ptr(qkv.f32), 3 * D, L.ptr(kc), L.ptr(vc), L.ptr(anc), L.ptr(hist), N, T, D, H,
+                   pos, watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.stream())
+            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tokens, pair)
+            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn)
+            ctx2 = self._new(N, D, not self.tc, True)
+            if tc_attn:
+                off = l * 2 * D
+                L.call("navc_cross_attention_tc", self.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D,
+                       kv.hi[:, off:].data_ptr(), kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N,
+                       N, 1, E, D, H, group, L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.stream())
+            else:
+                kv_l = self._kv_f32(mem)[:, l * 2 * D:]
+                L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, 1, E, D, H, group,
+                       L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), None, L.stream())
+            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tokens, pair)
+            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True)
+            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tokens, pair)
+        return x
+
     # ------------------------------------------------------------------------------------------
     # vocabulary projection
     # ------------------------------------------------------------------------------------------

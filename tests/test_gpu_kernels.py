@@ -594,3 +594,31 @@ def test_cross_attention_tc_packed(mode, tol, B, group, S, E):
         worst = max(worst, (ctx[r0:r0 + ln].cpu() - ref).abs().max().item() / max(1.0, ref.abs().max().item()))
     assert worst < tol, worst
     assert ctx[R:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,K,V,first", [(7, 5, 10547, 0), (3, 3, 300, 0), (4, 5, 1000, 1), (2, 8, 57, 0), (5, 1, 200, 0)])
+def test_beam_topk_matches_torch(B, K, V, first):
+    """navc_beam_topk == topk(masked_fill(log_softmax(logits) + beam score, last == EOS, -1e20)) (Beam.py:68-83)."""
+    T, pos = 12, 4
+    gen = torch.Generator().manual_seed(91)
+    ld = V + 3
+    logits = torch.randn(B * K, ld, generator=gen) * 3
+    scores = -torch.rand(B, K, generator=gen) * 10
+    hist = torch.randint(4, 50, (B * K, T), generator=gen)
+    if K > 1:
+        hist[1, pos] = 3  # an EOS-terminated beam
+        hist[K, pos] = 3
+    logp = torch.log_softmax(logits[:, :V], -1).view(B, K, V)
+    if first:
+        lk = logp[:, 0, :]
+    else:
+        lk = logp + scores.unsqueeze(-1)
+        lk = lk.masked_fill(hist[:, pos].view(B, K, 1).eq(3), -1e20).view(B, K * V)
+    want_s, want_i = lk.topk(K, dim=1)
+    d_logits, d_scores, d_hist = logits.to(DEV), scores.to(DEV), hist.to(DEV)
+    bs = torch.empty(B, K, device=DEV)
+    bi = torch.empty(B, K, dtype=torch.int64, device=DEV)
+    L.call("navc_beam_topk", L.ptr(d_logits), ld, B, K, V, L.ptr(d_scores), L.ptr(d_hist), T, pos, first, L.ptr(bs), L.ptr(bi),
+           L.stream())
+    assert torch.allclose(bs.cpu(), want_s, atol=2e-5, rtol=1e-6)
+    assert torch.equal(bi.cpu(), want_i)

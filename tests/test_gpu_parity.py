@@ -209,10 +209,13 @@ def test_graph_replay_matches_eager(precision):
     assert not model.engine.graphs
 
 
+@pytest.mark.parametrize("host_beam", [False, True], ids=["device", "host"])
+@pytest.mark.parametrize("heads", [8, 2], ids=["dk16", "dk64"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
-def test_ar_beam_search_matches_oracle(precision):
-    """Translator.translate_batch for an ARFormer model (beam search; reference Translator.py:94-161)."""
-    opt = cases.small("ARB", beam_size=3, topk=2, beam_alpha=1.0)
+def test_ar_beam_search_matches_oracle(precision, heads, host_beam):
+    """Translator.translate_batch for an ARFormer model (beam search; reference Translator.py:94-161): the
+    device-side search (K/V cache + navc_beam_advance) and the host-side cross-check implementation."""
+    opt = cases.small("ARB", beam_size=3, topk=2, beam_alpha=1.0, num_attention_heads=heads, navc_ar_host_beam=host_beam)
     torch.manual_seed(0)
     model = navc_b200.get_model(opt)
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
@@ -233,6 +236,103 @@ def test_ar_beam_search_matches_oracle(precision):
             assert abs(scores[b][n] - o_s[b][n]) < 2e-3, (b, n, scores[b][n], o_s[b][n])
             if gap > 1e-2:  # ranking decided by a clear margin -> identical token ids
                 assert hyps[b][n] == o_h[b][n], (b, n)
+
+
+@pytest.mark.parametrize("beam,topk,alpha,max_len", [(5, 1, 1.0, 16), (4, 3, 0.7, 9), (2, 4, 1.35, 12)])
+def test_ar_beam_device_equals_host_implementation(beam, topk, alpha, max_len):
+    """Same model, same inputs: the device-side beam search returns what the host-side (reference-shaped)
+    implementation returns -- token ids identical, scores to fp32 rounding -- across beam sizes, n-best > beam,
+    length penalties and videos that finish at different steps."""
+    out = {}
+    for host in (True, False):
+        opt = cases.small("ARB", beam_size=beam, topk=topk, beam_alpha=alpha, max_len=max_len, num_attention_heads=2,
+                          navc_ar_host_beam=host)
+        torch.manual_seed(0)
+        model = navc_b200.get_model(opt)
+        model.load_state_dict(cases.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 9))
+        model.to(DEV).eval()
+        model.set_precision("bf16x3")
+        feats, category = cases.synth_inputs(opt, 7, seed=77)
+        tr = navc_b200.Translator(model, opt, device=DEV)
+        with torch.no_grad():
+            out[host] = tr.translate_batch(model.encode(feats=to_dev(feats)), category.to(DEV), None, {})
+    (h_hyp, h_sc), (d_hyp, d_sc) = out[True], out[False]
+    assert len(h_hyp) == len(d_hyp) == 7
+    for b in range(7):
+        assert len(h_hyp[b]) == len(d_hyp[b]) >= 1
+        for n in range(len(h_hyp[b])):
+            assert abs(h_sc[b][n] - d_sc[b][n]) < 1e-3, (b, n, h_sc[b][n], d_sc[b][n])
+            nxt = abs(h_sc[b][n] - h_sc[b][n + 1]) if n + 1 < len(h_sc[b]) else 1.0
+            prv = abs(h_sc[b][n] - h_sc[b][n - 1]) if n > 0 else 1.0
+            if min(nxt, prv) > 5e-3:
+                assert h_hyp[b][n] == d_hyp[b][n], (b, n)
+
+
+def test_ar_beam_graph_replay_matches_eager():
+    """First call per shape runs eagerly, the second records one CUDA graph per step, later calls replay them:
+    same hypotheses, also for new inputs of the same shape."""
+    from navc_b200.decoding import ar_beam
+    opt = cases.small("ARB", beam_size=3, topk=2, beam_alpha=1.0, num_attention_heads=2)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt)
+    model.load_state_dict(cases.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 5))
+    model.to(DEV).eval()
+    model.set_precision("bf16x3")
+    tr = navc_b200.Translator(model, opt, device=DEV)
+    tr_eager = navc_b200.Translator(model, dict(opt, navc_graphs=False, navc_ar_host_beam=True), device=DEV)
+
+    def run(t, seed):
+        feats, category = cases.synth_inputs(opt, 6, seed=seed)
+        with torch.no_grad():
+            return t.translate_batch(model.encode(feats=to_dev(feats)), category.to(DEV), None, {})
+
+    first = run(tr, 1)
+    assert not ar_beam.beam_search.last_stats["graph"]
+    second = run(tr, 1)
+    assert ar_beam.beam_search.last_stats["graph"] and ar_beam.beam_search.last_stats["launches_per_step"] > 10
+    third = run(tr, 1)
+    assert first[0] == second[0] == third[0]
+    assert first[1] == second[1] == third[1]          # same kernels, same inputs: bit-identical scores
+    other = run(tr, 2)                                # new inputs through the recorded graphs
+    ref = run(tr_eager, 2)
+    assert other[0] != first[0]
+    for b in range(6):
+        for n in range(len(ref[0][b])):
+            assert abs(other[1][b][n] - ref[1][b][n]) < 1e-3
+            gap = abs(ref[1][b][0] - ref[1][b][1]) if len(ref[1][b]) > 1 else 1.0
+            if gap > 5e-3:
+                assert other[0][b][n] == ref[0][b][n], (b, n)
+
+
+def test_decoder_step_equals_last_row_of_full_pass():
+    """Engine.decoder_step over a K/V cache == the last position of decoder_pass over the whole prefix."""
+    opt = cases.small("ARB", num_attention_heads=2, max_len=12)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt)
+    model.load_state_dict(cases.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 4))
+    model.to(DEV).eval()
+    model.set_precision("bf16x3")
+    eng = model.engine
+    B, K, T = 3, 2, 12
+    N = B * K
+    feats, category = cases.synth_inputs(opt, B)
+    with torch.no_grad():
+        enc = model.encode(feats=to_dev(feats))
+        mem = eng.memory(enc["enc_output"].contiguous().float(), enc.get("_navc"))
+        gen = torch.Generator().manual_seed(3)
+        hist = torch.randint(6, opt["vocab_size"], (N, T), generator=gen)
+        hist[:, 0] = 2
+        hist[1, 3] = 0  # a PAD inside a prefix masks that key (and zeroes that row at its own step)
+        hist = hist.to(DEV)
+        anc = torch.arange(N, dtype=torch.int32, device=DEV).view(N, 1).repeat(1, T).contiguous()  # no re-ordering
+        caches = [(torch.zeros(T, N, eng.D, device=DEV), torch.zeros(T, N, eng.D, device=DEV)) for _ in eng.P["layers"]]
+        cat = category.to(DEV)
+        for pos in range(6):
+            step = eng.join_f32(eng.decoder_step(hist, anc, pos, caches, mem, K, cat, "ARFormer")).clone()
+            full, _ = eng.decoder_pass(hist[:, :pos + 1].contiguous(), mem, K, cat, "ARFormer", want_f32=True)
+            want = full.f32.view(N, pos + 1, -1)[:, -1, :]
+            err = (step - want).abs().max().item()
+            assert err < 2e-4 * max(1.0, want.abs().max().item()), (pos, err)
 
 
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
