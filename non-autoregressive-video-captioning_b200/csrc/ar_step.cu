@@ -176,7 +176,7 @@ __global__ void beam_advance_kernel(const float* __restrict__ best_scores, const
 // Beams whose last token is EOS contribute -1e20 (Beam.py:71-74); at the first step only beam 0 counts
 // (Beam.py:75-76).  Ties: lowest flat index first.
 constexpr int kBeamMaxK = 8;
-constexpr int kTopkThreads = 256;
+constexpr int kTopkThreads = 1024;  // one block per video: the whole SM works on its beam x vocab candidates
 
 __global__ void __launch_bounds__(kTopkThreads)
 beam_topk_kernel(const float* __restrict__ logits, int ld, int V, int K, const float* __restrict__ scores,
