@@ -51,16 +51,52 @@ def peaks():
 
 
 class ClockSampler:
-    """One `nvidia-smi -lms` process sampling clocks / throttle reasons during the timed regions."""
+    """SM clocks / throttle reasons sampled during the timed regions: an NVML thread in this process (a few
+    cheap driver queries every 50 ms); `nvidia-smi -lms` as a separate process when NVML is not importable or
+    $NAVC_SAMPLER=smi (heavier: every poll re-enters the driver through a fresh query of all fields)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.thread, self.stop_flag = index, [], None, None, False
+
+    def _nvml_loop(self, nv, handle):
+        R = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+             "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+             "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+             "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                watts = nv.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                bits = int(get(handle))
+                self.samples.append([str(mhz), str(mx), "%.2f" % watts] +
+                                    ["Active" if bits & R[n] else "Not Active"
+                                     for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def start(self):
         if os.environ.get("NAVC_NO_SAMPLER"):
             return
+        if os.environ.get("NAVC_SAMPLER", "nvml") != "smi":
+            try:
+                import threading
+                import pynvml as nv
+                nv.nvmlInit()
+                # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
+                phys = ids[self.index] if ids and self.index < len(ids) else self.index
+                handle = nv.nvmlDeviceGetHandleByIndex(phys)
+                self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -69,6 +105,10 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return
         if self.proc is None:
             return
         self.proc.terminate()
@@ -91,7 +131,8 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
                 "samples": len(self.samples), "samples_under_load": len(busy),
-                "power_w_max": max(float(s[2]) for s in self.samples)}
+                "power_w_max": max(float(s[2]) for s in self.samples),
+                "sampler": "nvml thread, 50 ms" if self.thread is not None else "nvidia-smi -lms 200"}
 
 
 def cpu_oracle_run(opt, batch, steps, warmup):

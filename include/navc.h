@@ -102,6 +102,14 @@ int navc_wgrad_tc(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld
 /* Data gradient dX[rows, k_in] = dY[rows, n_out] W[n_out, k_in] (+ e->residual) on the tensor cores, straight from
  * the forward's row-major bf16 weight copies (B operand consumed MN-major: no transposed weights).  fp32 output
  * (e->out_f32, e->ld_out), optional fp32 residual; dY pad columns [n_out, ld_dy) must be finite. */
+/* Tail split of navc_linear_tc (pair epilogue, K >= 1024): the tiles of the last, partly filled wave of the
+ * persistent grid are split along K across the idle SMs; the finishing CTA sums the partner CTAs' partial
+ * accumulators (handed over through an L2-resident workspace) before its epilogue.  Measured slower than leaving the
+ * SMs idle, so it is OFF unless $NAVC_STREAMK=1 or navc_set_streamk(1) (returns the previous
+ * setting).  navc_streamk_error: 1 if a finishing CTA ever gave up waiting for its partners (never expected), 0
+ * otherwise, -1 before navc_init; synchronises the device. */
+int navc_set_streamk(int on);
+int navc_streamk_error(void);
 int navc_dgrad_tc(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld_dy, const uint16_t* w_hi,
                   const uint16_t* w_lo, int ld_w, int rows, int n_out, int k_in, const navc_epilogue_t* e,
                   void* stream);

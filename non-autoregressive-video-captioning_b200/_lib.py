@@ -89,6 +89,8 @@ _PROTOS = {
     "navc_layernorm_bwd": [vp, vp, vp, f32, vp, i32, i32, vp, vp, vp, vp],
     "navc_embed_ln_bwd": [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
     "navc_self_attention_step": [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_streamk_error": [],
+    "navc_set_streamk": [i32],
     "navc_beam_topk": [vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp],
     "navc_beam_advance": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp],
     "navc_self_attention_tc_rows": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],

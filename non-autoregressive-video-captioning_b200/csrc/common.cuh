@@ -113,6 +113,10 @@ struct EpiParams {
     const uint16_t* res_hi;  // bf16 hi/lo residual (tcgen05 pair epilogue)
     const uint16_t* res_lo;
     const int* m_dev;        // device-side row count (tcgen05 path)
+    // split-K of the tiles of the last, partly filled wave of the persistent grid (set by the launcher, pair epilogue):
+    float* sk_ws;            // partial accumulator tiles [slot][128][TBN] fp32, NULL = off
+    int* sk_cnt;             // [2 * grid] arrival / departure counters, all zero between launches
+    int* sk_err;             // set to 1 if a finisher gave up waiting (never observed; keeps a bug from hanging the GPU)
 };
 static inline EpiParams to_params(const navc_epilogue_t* e) {
     EpiParams p;
@@ -125,6 +129,7 @@ static inline EpiParams to_params(const navc_epilogue_t* e) {
     p.res_hi = e->res_hi;
     p.res_lo = e->res_lo;
     p.m_dev = e->m_dev;
+    p.sk_ws = nullptr; p.sk_cnt = nullptr; p.sk_err = nullptr;
     return p;
 }
 

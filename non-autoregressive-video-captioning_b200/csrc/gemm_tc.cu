@@ -106,6 +106,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int split = kVocab ? 1 : epi.split_k;
     const int kpb = (k_blocks + split - 1) / split;  // k-blocks per split (host guarantees every split is non-empty)
     const int n_tiles = m_blocks * n_blocks * split;
+    // Tail split ("stream-K lite", pair epilogue): the tiles of the last, partly filled wave of the persistent grid are
+    // cut into sk_parts K-ranges so that every SM works during that wave; part 0 of a tile adds the other parts'
+    // partial accumulators (handed over through sk_ws) in its epilogue.  Derived in-kernel because M may be device-side.
+    int sk_full = n_tiles, sk_tail = 0, sk_parts = 1, sk_per = k_blocks;
+    if (kEpi == kEpiPair && epi.sk_ws != nullptr && split == 1) {
+        const int G = (int)gridDim.x;
+        sk_full = (n_tiles / G) * G;
+        sk_tail = n_tiles - sk_full;
+        // a part must keep >= 8 k-blocks (the hand-over costs about as much as 4-6 k-blocks of MMA) and the finishing
+        // CTA sums at most 3 partner tiles
+        int p = sk_tail > 0 ? min(min(G / sk_tail, k_blocks / 8), 4) : 1;
+        if (p >= 2) {
+            sk_per = (k_blocks + p - 1) / p;
+            sk_parts = (k_blocks + sk_per - 1) / sk_per;
+        }
+        if (sk_parts < 2) { sk_full = n_tiles; sk_tail = 0; sk_parts = 1; sk_per = k_blocks; }
+    }
+    struct Unit { int mn, kb0, kb1, part, tl; };
+    auto get_unit = [&](int it, Unit& u) -> bool {
+        const int t = (int)blockIdx.x + it * (int)gridDim.x;
+        if (sk_parts > 1) {
+            if (t < sk_full) { u.mn = t; u.kb0 = 0; u.kb1 = k_blocks; u.part = -1; u.tl = 0; return true; }
+            const int x = t - sk_full;
+            if (x >= sk_tail * sk_parts) return false;
+            u.tl = x / sk_parts;
+            u.part = x - u.tl * sk_parts;
+            u.mn = sk_full + u.tl;
+            u.kb0 = u.part * sk_per;
+            u.kb1 = min(k_blocks, u.kb0 + sk_per);
+            return true;
+        }
+        if (t >= n_tiles) return false;
+        u.mn = t / split;
+        u.kb0 = (t % split) * kpb;
+        u.kb1 = min(k_blocks, u.kb0 + kpb);
+        u.part = -1;
+        u.tl = 0;
+        return true;
+    };
 
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
@@ -131,10 +170,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int ks = tile % split, mn = tile / split;
+            Unit u;
+            for (int it = 0; get_unit(it, u); ++it) {
+                const int mn = u.mn;
                 const int mb = mn / n_blocks, nb = mn % n_blocks;
-                const int kb0 = ks * kpb, kb1 = min(k_blocks, kb0 + kpb);
+                const int kb0 = u.kb0, kb1 = u.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -172,11 +212,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            Unit u;
+            for (int it = 0; get_unit(it, u); ++it) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TBN);
-                const int kb0 = (tile % split) * kpb, kb1 = min(k_blocks, kb0 + kpb);
+                const int kb0 = u.kb0, kb1 = u.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -216,8 +257,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         uint32_t acc_phase = 0;
         uint32_t rstep = 0;  // residual boxes consumed so far by this warp (kEpi == 3)
         (void)rstep;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int mn = tile / split;
+        Unit u;
+        for (int it = 0; get_unit(it, u); ++it) {
+            const int mn = u.mn;
             const int mb = mn / n_blocks, nb = mn % n_blocks;
             const int row0 = mb * TBM + quarter * 32;
             const int row = row0 + lane;
@@ -251,6 +293,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + grp * GW);
+                // tail split: this thread's row of the partial tiles, [slot][128 rows][TBN] fp32
+                float* sk_row = nullptr;
+                if (u.part >= 0)
+                    sk_row = epi.sk_ws + ((size_t)(u.tl * (sk_parts - 1) + (u.part > 0 ? u.part - 1 : 0)) * TBM + quarter * 32 + lane) * TBN + grp * GW;
+                if (u.part > 0) {
+                    // a partner part: park the raw accumulators, signal, done
+#pragma unroll 1
+                    for (int c = 0; c < GW / 16; ++c) {
+                        if (ng0 + c * 16 >= N) break;
+                        uint32_t r[16];
+                        tc_ld16(t_row + (uint32_t)(c * 16), r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            __stcg(reinterpret_cast<uint4*>(sk_row + c * 16 + i * 4), make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]));
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(epi.sk_cnt + u.tl, 1);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+                    continue;
+                }
+                if (u.part == 0) {
+                    // the finishing part: all warps of all partners must have parked their partials.  Every unit of the
+                    // tail wave owns a CTA of the (fully resident) grid, so the partners are running; the wait is bounded
+                    // anyway so that a bug shows up as a flagged wrong result, not as a hung GPU.
+                    if (lane == 0) {
+                        const int want = (sk_parts - 1) * kPairEpiWarps;
+                        int* cnt = epi.sk_cnt + u.tl;
+                        unsigned spins = 0;
+                        while (atomicAdd(cnt, 0) < want) {   // read through L2, where the partners' increments land
+                            __nanosleep(64);
+                            if (++spins > (1u << 24)) { *epi.sk_err = 1; break; }
+                        }
+                    }
+                    __syncwarp();
+                    __threadfence();
+                }
 #pragma unroll 1
                 for (int c = 0; c < GW / 16; ++c) {
                     const int col0 = ng0 + c * 16;
@@ -292,6 +375,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         ++rstep;
                     }
                     tc_wait_ld();
+                    if (u.part == 0) {
+                        // add the partners' partial accumulators (parked in L2): all loads in flight, then the adds
+                        float4 w[3][4];
+#pragma unroll
+                        for (int p = 0; p < 3; ++p)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                w[p][i] = (p + 1 < sk_parts) ? __ldcg(reinterpret_cast<const float4*>(sk_row + (size_t)p * TBM * TBN + c * 16 + i * 4))
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int p = 0; p < 3; ++p)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                r[i * 4 + 0] = __float_as_uint(__uint_as_float(r[i * 4 + 0]) + w[p][i].x);
+                                r[i * 4 + 1] = __float_as_uint(__uint_as_float(r[i * 4 + 1]) + w[p][i].y);
+                                r[i * 4 + 2] = __float_as_uint(__uint_as_float(r[i * 4 + 2]) + w[p][i].z);
+                                r[i * 4 + 3] = __float_as_uint(__uint_as_float(r[i * 4 + 3]) + w[p][i].w);
+                            }
+                    }
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -349,6 +451,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         tma_store_2d(&map_o_hi, stg_s, col0, row0);
                         if (epi.out_lo) tma_store_2d(&map_o_lo, stg_s + 1024u, col0, row0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                if (u.part == 0 && lane == 0) {
+                    // the last finishing warp to leave re-arms the counters for the next launch
+                    if (atomicAdd(epi.sk_cnt + gridDim.x + u.tl, 1) == kPairEpiWarps - 1) {
+                        epi.sk_cnt[u.tl] = 0;
+                        epi.sk_cnt[gridDim.x + u.tl] = 0;
+                        __threadfence();
                     }
                 }
             } else if constexpr (!kVocab) {
@@ -549,6 +659,22 @@ bool pdl_enabled() {
 static bool g_tc_ready = false;
 bool tc_ready() { return g_tc_ready; }
 
+// tail split workspace: (#SMs) partial tiles of 128 x 256 fp32 + 2 counters per CTA + an error flag, allocated once
+static float* g_sk_ws = nullptr;
+static int* g_sk_cnt = nullptr;
+static int g_sk_slots = 0;
+static int g_sk_on = -1;
+static bool sk_enabled() {
+    if (g_sk_on < 0) {
+        // measured (round 1): config-2 step 14.59 ms with, 14.19 ms without; AR beam batch 33.5 vs 30.5 ms -- the
+        // hand-over through L2 and the partner -> finisher serialisation cost more than the idle SMs of the last
+        // wave.  Off unless NAVC_STREAMK=1 / navc_set_streamk(1).
+        const char* e = getenv("NAVC_STREAMK");
+        g_sk_on = (e && (e[0] == '1' || e[0] == 'y' || e[0] == 't')) ? 1 : 0;
+    }
+    return g_sk_on != 0 && g_sk_ws != nullptr;
+}
+
 int tc_init() {
     if (g_tc_ready) return 0;
     void* fn = nullptr;
@@ -556,6 +682,14 @@ int tc_init() {
     NAVC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     NAVC_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "navc_init: cuTensorMapEncodeTiled not available");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (!g_sk_ws) {
+        int sms = navc_sm_count();
+        if (sms <= 0) sms = 148;
+        g_sk_slots = sms;
+        NAVC_CUDA(cudaMalloc(&g_sk_ws, (size_t)g_sk_slots * TBM * 256 * sizeof(float)));
+        NAVC_CUDA(cudaMalloc(&g_sk_cnt, (size_t)(2 * g_sk_slots + 1) * sizeof(int)));
+        NAVC_CUDA(cudaMemset(g_sk_cnt, 0, (size_t)(2 * g_sk_slots + 1) * sizeof(int)));
+    }
 #define NAVC_TC_ATTR(X3, EPI, BN) \
     NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<X3, EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<X3, BN, EPI>::kSmemBytes))
     NAVC_TC_ATTR(false, kEpiGeneric, 256); NAVC_TC_ATTR(true, kEpiGeneric, 256);
@@ -655,13 +789,21 @@ static int launch_tc_bn(int mode, const uint16_t* x_hi, const uint16_t* x_lo, in
     const int tiles = ((M + TBM - 1) / TBM) * ((N + TBN - 1) / TBN) * epi.split_k;
     int sms = navc_sm_count();
     if (sms <= 0) sms = 148;
-    const int grid = tiles < sms ? tiles : sms;
+    int grid = tiles < sms ? tiles : sms;
+    EpiParams epi_sk = epi;
+    if (kEpi == kEpiPair && epi.split_k == 1 && sk_enabled() && sms <= g_sk_slots && (K + TBK - 1) / TBK >= 16) {
+        // tail split: needs the whole grid resident (one CTA per SM) -- the finishing part waits for its partners
+        grid = sms;
+        epi_sk.sk_ws = g_sk_ws;
+        epi_sk.sk_cnt = g_sk_cnt;
+        epi_sk.sk_err = g_sk_cnt + 2 * g_sk_slots;
+    }
     if (mode == NAVC_TC_BF16X3) {
         NAVC_CUDA(launch_pdl(gemm_tc_kernel<true, kEpi, TBN>, dim3(grid), dim3(tc_threads(kEpi)), TcCfg<true, TBN, kEpi>::kSmemBytes, st,
-                             ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, mr_hi, mr_lo, M, N, K, epi, vep));
+                             ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, mr_hi, mr_lo, M, N, K, epi_sk, vep));
     } else {
         NAVC_CUDA(launch_pdl(gemm_tc_kernel<false, kEpi, TBN>, dim3(grid), dim3(tc_threads(kEpi)), TcCfg<false, TBN, kEpi>::kSmemBytes, st,
-                             ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, mr_hi, mr_lo, M, N, K, epi, vep));
+                             ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, mr_hi, mr_lo, M, N, K, epi_sk, vep));
     }
     return check_launch(what);
 }
@@ -712,6 +854,21 @@ static int launch_tc_dgrad(int mode, const uint16_t* dy_hi, const uint16_t* dy_l
 }  // namespace navc
 
 using namespace navc;
+
+// 1 if a finishing CTA of a tail split ever gave up waiting for its partners (a bug; results of that launch are
+// wrong), else 0; -1 without the workspace.  Synchronises the device: tests only.
+extern "C" int navc_set_streamk(int on) {
+    const int prev = g_sk_on > 0 ? 1 : 0;
+    g_sk_on = on ? 1 : 0;
+    return prev;
+}
+
+extern "C" int navc_streamk_error(void) {
+    if (!g_sk_cnt) return -1;
+    int flag = 0;
+    if (cudaMemcpy(&flag, g_sk_cnt + 2 * g_sk_slots, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return flag;
+}
 
 extern "C" int navc_vocab_tile(int tc) { return tc ? kVocabBN / 2 : 128; }
 

@@ -352,7 +352,10 @@ class Engine:
             results["pred_length"] = pred
         else:
             L.call("navc_length_head", L.ptr(enc.f32), B, E, D, None, None, None, None, 0, L.ptr(enc_mean), None, L.stream())
-        results["enc_output"] = enc.f32
+        # the tensor handed to the caller is an ALIAS of enc.f32: Seq2Seq.encode hangs the cache below on it
+        # (enc_output._navc_cache); with the same object that would be a reference cycle (tensor -> cache -> Act ->
+        # tensor) and every batch's encoder memory + K|V projections (~440 MB at B = 128) would wait for the cyclic GC
+        results["enc_output"] = enc.f32.detach()
         results["enc_hidden"] = enc_hidden
         results["_navc"] = dict(enc=enc, enc_mean=enc_mean, B=B, E=E, owner=id(self))
         return results

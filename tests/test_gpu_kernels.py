@@ -622,3 +622,44 @@ def test_beam_topk_matches_torch(B, K, V, first):
            L.stream())
     assert torch.allclose(bs.cpu(), want_s, atol=2e-5, rtol=1e-6)
     assert torch.equal(bi.cpu(), want_i)
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("M,N,K", [(640, 512, 512), (640, 512, 2048), (640, 2048, 512), (10478, 512, 2048), (10478, 1536, 512),
+                                   (4736, 512, 512), (19000, 512, 512), (130, 256, 64), (7, 128, 128), (5000, 2048, 512)])
+def test_linear_pair_epilogue_tail_split(mode, tol, M, N, K):
+    """Pair epilogue (bf16 hi/lo outputs, bias, gelu, bf16-pair residual, row mask) over grids whose last wave is
+    partly filled: those tiles are split along K across the idle SMs and summed by the finishing CTA.  Launched
+    three times in a row (the arrival counters must re-arm themselves)."""
+    x = torch.randn(M, K, generator=g(50))
+    w = torch.randn(N, K, generator=g(51)) / math.sqrt(K)
+    b = torch.randn(N, generator=g(52))
+    res = torch.randn(M, N, generator=g(53))
+    toks = torch.randint(0, 4, (M,), generator=g(54))
+    xh, xl = [t.to(DEV) for t in split(x)]
+    wh, wl = [t.to(DEV) for t in split(w)]
+    rh, rl = [t.to(DEV) for t in split(res)]
+    bd, td = b.to(DEV), toks.to(DEV)
+    x3 = mode == "bf16x3"
+    y = x.double() @ w.double().t() + b.double()
+    y = O.activation("gelu_new")(y.float()).double()
+    y = (y + (rh.float() + (rl.float() if x3 else 0)).cpu().double()) * toks.ne(0).double().unsqueeze(1)
+    prev = L._lib.navc_set_streamk(1)  # opt-in feature (slower than idle SMs in practice): switched on for this test
+    try:
+        _tail_split_runs(mode, tol, M, N, K, x3, xh, xl, wh, wl, rh, rl, bd, td, y)
+    finally:
+        L._lib.navc_set_streamk(prev)
+    assert L._lib.navc_streamk_error() == 0
+
+
+def _tail_split_runs(mode, tol, M, N, K, x3, xh, xl, wh, wl, rh, rl, bd, td, y):
+    for rep in range(3):
+        ohi = torch.full((M, N), 9.0, dtype=torch.bfloat16, device=DEV)
+        olo = torch.full((M, N), 9.0, dtype=torch.bfloat16, device=DEV) if x3 else None
+        ep = L.Epilogue(L.ptr(bd), None, L.ptr(td), L.ACT["gelu_new"], N, None, L.ptr(ohi), L.ptr(olo), N, 0, 1, 0,
+                        L.ptr(rh), L.ptr(rl) if x3 else None, None)
+        L.call("navc_linear_tc", L.TC_BF16X3 if x3 else L.TC_BF16, L.ptr(xh), L.ptr(xl) if x3 else None, K, L.ptr(wh),
+               L.ptr(wl) if x3 else None, K, M, N, K, ep, L.stream())
+        got = (ohi.float() + (olo.float() if x3 else 0)).cpu().double()
+        err = (got - y).abs().max().item()
+        assert err < tol * max(1.0, y.abs().max().item()), (rep, err)
