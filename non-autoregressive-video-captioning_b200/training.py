@@ -464,12 +464,14 @@ def plan_packing(eng: Engine, token_sets, E: int, between=None):
             todo.append((t, nonpad, lens, torch.stack([lens.sum().to(torch.int32), suffix.to(torch.int32), lens.min()])))
         else:
             plans[_plan_key(t)] = None
-    stats = torch.stack([x[3] for x in todo]).to("cpu", non_blocking=True) if todo else None
+    dev_stats = torch.stack([x[3] for x in todo]) if todo else None
+    stats = dev_stats.to("cpu", non_blocking=True) if todo else None
     if between is not None:
         between()
     if not todo:
         return plans
-    torch.cuda.current_stream().synchronize()
+    if dev_stats.is_cuda:
+        torch.cuda.current_stream().synchronize()
     for (t, nonpad, lens, _), (total, ok, shortest) in zip(todo, stats.tolist()):  # the host read
         N, S = t.shape
         pk = None

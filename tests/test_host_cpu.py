@@ -96,3 +96,38 @@ def test_golden_inventory_loads_into_product_model():
     # teacher remap used by misc/run.py:275-279 of the reference: decoder.bert.* <- decoder.*
     tk = set(teacher.state_dict())
     assert all(k.replace("decoder.bert.", "decoder.") in tk for k in model.state_dict() if k.startswith("decoder.bert."))
+
+
+def test_training_packing_plan_decisions():
+    """training.plan_packing (host logic): packs only when PAD is a suffix of every row, no row is empty and enough
+    rows are PAD; one plan per token tensor, keyed so that a sliced view (AR input tokens[:, :-1]) finds its own."""
+    import torch
+    from navc_b200 import training as T
+
+    class FakeEngine:
+        opt = {}
+
+        def tc_attention_ok(self, S, E):
+            return True
+
+        def pack_rows(self, lens, S):
+            N = lens.numel()
+            rowmap = torch.tensor([n * S + s for n in range(N) for s in range(int(lens[n]))], dtype=torch.int32)
+            return dict(seq_off=None, rowmap=torch.cat([rowmap, torch.zeros(N * S - rowmap.numel(), dtype=torch.int32)]), N=N, S=S)
+
+    eng = FakeEngine()
+    t = torch.tensor([[5, 6, 0, 0], [7, 0, 0, 0], [1, 2, 3, 0]])
+    called = []
+    plans = T.plan_packing(eng, [t, t[:, :-1]], 10, between=lambda: called.append(1))
+    assert called == [1]
+    pk = plans[T._plan_key(t)]
+    assert pk["rows"] == 6 and pk["rowmap"].tolist() == [0, 1, 4, 8, 9, 10] and pk["pad_rows"].tolist() == [2, 3, 5, 6, 7, 11]
+    pk2 = plans[T._plan_key(t[:, :-1])]
+    assert pk2["rows"] == 6 and pk2["pad_rows"].tolist() == [2, 4, 5]
+    # PAD in the middle of a row, an empty row, (almost) no PAD at all -> padded path
+    for bad in (torch.tensor([[5, 0, 6, 0], [7, 0, 0, 0]]), torch.tensor([[5, 6, 0, 0], [0, 0, 0, 0]]),
+                torch.tensor([[5, 6, 7, 8], [1, 2, 3, 4]])):
+        assert list(T.plan_packing(eng, [bad], 10).values()) == [None]
+    # switched off
+    eng.opt = {"navc_train_packed": 0}
+    assert list(T.plan_packing(eng, [t], 10).values()) == [None]
