@@ -103,3 +103,30 @@ def test_shard_bounds_cover_and_balance():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_gradient_sink_follows_grad_ownership():
+    """GradientAllReduce.sink (what the backward kernels accumulate into in place): the flat-buffer view while
+    p.grad IS that view, nothing once an optimizer detached it, the view again after attach() / zero_grad();
+    the engine of the model points at it and keeps doing so across set_precision()."""
+    opt = cases.config1()
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt)
+    dp = parallel.GradientAllReduce(model, broadcast=False)
+    assert model.engine.grad_sink == dp.sink
+    p0, v0 = dp.params[0], dp.views[0]
+    assert dp.sink(p0) is v0
+    assert dp.sink(torch.nn.Parameter(torch.zeros(3))) is None            # not one of this model's parameters
+    model.zero_grad(set_to_none=True)
+    assert dp.sink(p0) is None                                            # detached: kernels must not write behind autograd
+    dp.attach()
+    assert dp.sink(p0) is v0
+    p0.grad = torch.ones_like(p0)
+    assert dp.sink(p0) is None
+    dp.zero_grad()
+    assert dp.sink(p0) is v0 and float(v0.abs().sum()) == 0.0
+    model.set_precision("fp32")
+    assert model.engine.grad_sink == dp.sink
+    # offsets are 256-byte aligned (vectorised / TMA operands) and the views tile the buffer without overlap
+    assert all(o % parallel.ALIGN == 0 for o in dp.offsets)
+    assert all(o2 >= o1 + p.numel() for o1, o2, p in zip(dp.offsets, dp.offsets[1:], dp.params))
