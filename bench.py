@@ -12,12 +12,19 @@ d_model 512, vocab 10547).  Metric: captions/s (one caption = one video's final 
   e2e          same metric through the public API with HOST inputs: per step the pinned-host ->
                device copy of the features/category and the device -> host read of the token ids
                are inside the timed region.
-  roofline     dominant kernel (tcgen05 GEMM, FFN up-projection launches) timed live with CUDA
-               events inside the timed region; achieved = algorithmic FLOPs / mean duration.
-  cpu_baseline the oracle port (torch fp32 restatement of the reference) on the host cores, on a
-               bounded sample of the same workload (N=1, rank 0 only).
-  --impl reference   times that CPU implementation alone (rank 0 only under torchrun).
-Multi-GPU: videos are independent -> each rank decodes its own B=128 batch (weak scaling), no
+  roofline     every launch class of the decoder layer (qkv, self, so, cq, cross, co, f1, f2, vocab, ...)
+               timed live with CUDA events on the launching stream in an eager re-run of the same steps;
+               `classes` holds {us, share, flops / bytes, frac_useful, frac_issued} per class and the
+               top-level fields describe the class with the largest time share.
+  parity       token ids of the GPU path (fp32 mode and the timed mode, through the replayed CUDA graph)
+               against the CPU reference's ids on the same 16 videos, video by video, with the oracle's
+               decision margins (N=1 only).
+  cpu_baseline the UNMODIFIED reference (baseline/_ref or /root/reference; else the oracle port) on the
+               host cores, on a bounded sample of the same workload (N=1, rank 0 only).
+  extra.train  data-parallel training (BASELINE configs 3 and 5): samples/s with the single NCCL gradient
+               all-reduce inside the timed step; config 5 = NACF global batch 1024 split over the N ranks.
+  --impl reference   times the reference's CPU implementation alone (rank 0 only under torchrun).
+Multi-GPU inference: videos are independent -> each rank decodes its own B=128 batch (weak scaling), no
 data-path collective; time = max over ranks.
 """
 import argparse
@@ -29,7 +36,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden"), os.path.join(ROOT, "tools")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -40,6 +47,9 @@ import cases  # noqa: E402
 METRIC = "captions/sec (NACF, max_len=30, n_frames=60)"
 UNIT = "captions/s"
 WORKLOAD = "NACF 6-layer d512 h8, feats 2x60x2048, vocab 10547, B=128/GPU, mask-predict T=5 + CT (6 passes), lbs=6"
+CONFIG = {"workload": WORKLOAD}   # identical in both arms; run details live under "details"
+PARITY_B = 16                     # videos of the parity / cpu_baseline sample
+MARGIN = {"fp32": 2e-5, "bf16x3": 1e-4, "tf32": 5e-3, "bf16": 2e-2}   # log-unit error bound of each mode (tests/test_gpu_parity.py)
 
 
 def peaks():
@@ -135,39 +145,84 @@ class ClockSampler:
                 "sampler": "nvml thread, 50 ms" if self.thread is not None else "nvidia-smi -lms 200"}
 
 
-def cpu_oracle_run(opt, batch, steps, warmup):
-    """Oracle port (= CPU restatement of the reference path) timed with perf_counter on all cores."""
-    from oracle import navc_oracle as O
+# ------------------------------------------------------------------------------------------------------
+# CPU side: the unmodified reference (preferred) or the oracle port
+# ------------------------------------------------------------------------------------------------------
+def reference_kind():
+    """'reference' when the unmodified reference is importable (from /root/reference, or from baseline/_ref with every
+    file matching the digests recorded at install time), else 'port' (the oracle restatement)."""
+    import refutil
+    if not refutil.reference_available():
+        return "port"
+    if os.path.realpath(refutil.REF_ROOT) == os.path.realpath(refutil.INSTALLED):
+        import install_reference
+        return "reference" if install_reference.verify() else "port"
+    return "reference"
+
+
+def cpu_run(opt, batch, steps, warmup, kind):
+    """encode + Translator.translate_batch on the host cores (all threads), perf_counter timed
+    (misc/run.py:130-141 drives the reference exactly so).  Returns (captions/s, s/step, ids [B, Smax])."""
     torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    import navc_b200
-    model = navc_b200.get_model(opt)  # parameter container only (same seeded init as the reference factory)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     feats, category = cases.synth_inputs(opt, batch)
-    for _ in range(warmup):
-        O.translate(sd, opt, feats, category)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        hyp = O.translate(sd, opt, feats, category)
-    dt = time.perf_counter() - t0
+    if kind == "reference":
+        import refutil
+        model = refutil.ref_get_model(opt, seed=0)   # models.get_model(opt) under torch.manual_seed(0), .eval()
+        vocab = {i: "w%d" % i for i in range(opt["vocab_size"])}
+        with refutil.reference_on_path():
+            from models.Translator import Translator
+            tr = Translator(model, dict(opt), device=torch.device("cpu"), teacher_model=None)
+
+            def once():
+                with torch.no_grad():
+                    enc = model.encode(feats=list(feats))
+                    hyp, _ = tr.translate_batch(enc, category, None, vocab)
+                return hyp
+
+            for _ in range(warmup):
+                once()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                hyp = once()
+            dt = time.perf_counter() - t0
+    else:
+        from oracle import navc_oracle as O
+        import navc_b200
+        torch.manual_seed(0)
+        model = navc_b200.get_model(opt)  # parameter container only (same seeded init as the reference factory)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        for _ in range(warmup):
+            O.translate(sd, opt, feats, category)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            hyp = O.translate(sd, opt, feats, category)
+        dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps, hyp
 
 
 def run_reference(args, opt, rank):
     if rank != 0:
         return
-    # bounded sample: probe B=4 once, then size the sample so the whole run ends within ~2.5 min
-    _, t4, _ = cpu_oracle_run(opt, 4, 1, 0)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    batch = 16 if t4 * 4 <= budget else (8 if t4 * 2 <= budget else 4)
-    value, sec, _ = cpu_oracle_run(opt, batch, args.steps, args.warmup)
+    kind = reference_kind()
+    # bounded sample: probe B=4 once, then the largest batch for which the whole run ends within ~4 min
+    _, t4, _ = cpu_run(opt, 4, 1, 0, kind)
+    budget = 240.0 / max(1, args.steps + args.warmup)
+    batch = 4
+    for cand in (128, 64, 32, 16, 8):
+        if t4 * cand / 4.0 * 1.15 <= budget:
+            batch = cand
+            break
+    value, sec, _ = cpu_run(opt, batch, args.steps, args.warmup, kind)
     cores = torch.get_num_threads()
-    sample = "B=%d videos per step of the B=128 workload (same model/opts/seeds), %d steps + %d warm-up" % (batch, args.steps, args.warmup)
+    sample = "B=%d videos per step of the B=128 workload (same model, opts, seeds), %d steps + %d warm-up, %.2f s/step" % (
+        batch, args.steps, args.warmup, sec)
+    what = "unmodified reference (models.get_model + Seq2Seq.encode + Translator.translate_batch, fp32, %d threads)" % cores \
+        if kind == "reference" else "oracle port (CPU restatement; the reference is not installed on this box)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(CONFIG),
+            "details": {"sample": sample, "code": what},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -195,6 +250,66 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+# ------------------------------------------------------------------------------------------------------
+# roofline table of the launch classes
+# ------------------------------------------------------------------------------------------------------
+def class_table(prof, samples, opt, precision, B, step_ms, pk):
+    """prof: Engine.prof of the eager profiling steps; samples: per profiled step {"R", "sq", "N", "S"}."""
+    D, I, L_, E = opt["dim_hidden"], opt["intermediate_size"], opt["num_hidden_layers_decoder"], 2 * opt["n_frames"]
+    V, F_, din = opt["vocab_size"], opt["n_frames"], opt["dim_i"]
+    n = len(samples)
+    R = sum(s["R"] for s in samples) / n          # decoder rows per launch (packed: sum of candidate lengths)
+    SQ = sum(s["sq"] for s in samples) / n        # sum over candidates of len^2
+    b = {"bf16x3": 4, "bf16": 2, "fp32": 4, "tf32": 4}[precision]   # operand bytes per element (hi + lo pairs in bf16x3)
+    mult = {"bf16x3": 3.0, "bf16": 1.0, "tf32": 2.0, "fp32": 0.0}[precision]   # bf16-MMA time units issued per useful product
+    peak_tf, peak_gb = pk["bf16_tflops_sustained"], pk["hbm_gbs"]
+    vocab_rows = [int(x) for x in torch.stack(prof.get("vocab_rows", [])).flatten().tolist()] if prof.get("vocab_rows") else []
+    rv = (sum(vocab_rows) / len(vocab_rows)) if vocab_rows else R
+    spec = {   # class: (flops per launch, algorithmic bytes per launch, bound, shape string)
+        "qkv": (2.0 * R * D * 3 * D, R * D * b + 3 * D * D * b + R * 3 * D * b, "tensor", "M=%d N=%d K=%d" % (R, 3 * D, D)),
+        "so": (2.0 * R * D * D, 3 * R * D * b + D * D * b, "tensor", "M=%d N=%d K=%d +residual" % (R, D, D)),
+        "cq": (2.0 * R * D * D, 2 * R * D * b + D * D * b, "tensor", "M=%d N=%d K=%d" % (R, D, D)),
+        "co": (2.0 * R * D * D, 3 * R * D * b + D * D * b, "tensor", "M=%d N=%d K=%d +residual" % (R, D, D)),
+        "f1": (2.0 * R * D * I, R * D * b + D * I * b + R * I * b, "tensor", "M=%d N=%d K=%d +gelu" % (R, I, D)),
+        "f2": (2.0 * R * D * I, R * I * b + D * I * b + 2 * R * D * b, "tensor", "M=%d N=%d K=%d +residual" % (R, D, I)),
+        "self": (4.0 * SQ * D, R * 3 * D * b + R * D * b, "hbm", "sum(len^2)=%d, 8 heads, dk 64" % SQ),
+        "cross": (4.0 * R * E * D, 2 * R * D * b + B * E * 2 * D * b, "hbm", "rows=%d x E=%d keys, 8 heads" % (R, E)),
+        "vocab": (2.0 * rv * D * V, rv * D * b + V * D * b + rv * ((V + 127) // 128) * 12, "tensor", "M=%d (mean) N=%d K=%d, softmax statistics epilogue" % (rv, V, D)),
+        "kv": (2.0 * B * E * D * L_ * 2 * D, B * E * D * b + L_ * 2 * D * D * b + B * E * L_ * 2 * D * b, "tensor", "M=%d N=%d K=%d (once per batch)" % (B * E, L_ * 2 * D, D)),
+        "enc0": (2.0 * B * F_ * din * D, B * F_ * din * b + din * D * b + B * F_ * D * (4 + b), "tensor", "M=%d N=%d K=%d" % (B * F_, D, din)),
+        "enc12": (2.0 * B * F_ * D * 2 * D, B * F_ * D * b + 2 * D * D * b + B * F_ * 2 * D * 4, "tensor", "M=%d N=%d K=%d" % (B * F_, 2 * D, D)),
+    }
+    ncu = None
+    path = os.path.join(ROOT, "profiles", "r2_ncu_classes_%s.json" % precision)
+    if os.path.isfile(path) and B == 128:
+        ncu = json.load(open(path))
+    total_us = 0.0
+    rows = {}
+    for tag, (flops, nbytes, bound, shape) in spec.items():
+        ev = prof.get(tag)
+        if not ev:
+            continue
+        durs = [a.elapsed_time(b_) * 1e3 for a, b_ in ev]
+        us = sum(durs) / len(durs)
+        per_step = sum(durs) / n
+        total_us += per_step
+        tf = flops / us / 1e6
+        gb = nbytes / us / 1e3
+        row = {"us": round(us, 2), "launches_per_step": len(durs) // n, "us_per_step": round(per_step, 1), "bound": bound,
+               "shape": shape, "flops": flops, "bytes": nbytes, "tflops": round(tf, 1), "gbs": round(gb, 1),
+               "frac_useful": round(tf / peak_tf, 4), "frac_issued": round(tf * mult / peak_tf, 4) if mult else None,
+               "frac_hbm": round(gb / peak_gb, 4)}
+        if ncu and tag in ncu.get("classes", {}):
+            row["traffic"] = ncu["classes"][tag].get("dram_bytes")
+            row["tensor_pipe_pct"] = ncu["classes"][tag].get("tensor_pct")
+        rows[tag] = row
+    for tag, row in rows.items():
+        row["share_of_profiled"] = round(row["us_per_step"] / total_us, 4)
+        row["share_of_step"] = round(row["us_per_step"] / (step_ms * 1e3), 4)
+    top = max(rows, key=lambda t: rows[t]["us_per_step"]) if rows else None
+    return rows, top, total_us, (ncu or {}).get("source")
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -205,6 +320,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("NAVC_PRECISION", "bf16x3"))
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra.train legs (configs 3 and 5)")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -286,7 +403,7 @@ def main():
 
     step_ms = {}
 
-    def timed(fn, steps):
+    def timed(fn, steps, name=None):
         for i in range(3):  # untimed settle steps of this very loop (PCIe / copy engine / clocks after the idle gap)
             fn(-3 + i)
         pending.clear()
@@ -300,7 +417,7 @@ def main():
             marks[i + 1].record()
         barrier()
         ms = marks[0].elapsed_time(marks[steps])
-        step_ms[fn.__name__] = [round(marks[i].elapsed_time(marks[i + 1]), 2) for i in range(steps)]
+        step_ms[name or fn.__name__] = [round(marks[i].elapsed_time(marks[i + 1]), 2) for i in range(steps)]
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -318,78 +435,161 @@ def main():
         sampler.start()
         # ---- timed region 1: resident inputs (kernel-side throughput) ----
         launches0 = L.launches
-        ms, hyp = timed(step_resident, args.steps)
+        ms, hyp = timed(step_resident, args.steps, "resident")
         launches = L.launches - launches0
         stats = dict(navc_b200.generate.last_stats)
-        step_ms["resident"] = step_ms.pop("step_resident")
         # ---- timed region 2: end to end from host buffers ----
         pending.clear()
         torch.cuda.synchronize()
-        ms_e2e, hyp_host = timed(step_e2e, args.steps)
+        ms_e2e, hyp_host = timed(step_e2e, args.steps, "e2e")
         pending.clear()
-        # ---- region 3: the same steps launched eagerly (graph replay off) with CUDA events around
-        # every FFN up-projection GEMM launch: per-launch duration of the dominant kernel ----
+        sampler.stop()
+        # ---- region 3 (not part of `value`): the same steps launched eagerly (graph replay off) with CUDA events
+        # around every launch class of the decoder layer ----
         tr.opt = dict(opt, navc_graphs=False)
         step_resident(0)
-        model.engine.profile_tag, model.engine.profile_events = "f1", []
-        timed(step_resident, min(args.steps, 5))
-        events = model.engine.profile_events
-        model.engine.profile_tag = None
+        model.engine.prof = {}
+        samples = []
+        for i in range(min(args.steps, 4)):
+            step_resident(i)
+            st = navc_b200.generate.last_stats
+            packed = bool(st.get("packed"))
+            samples.append({"R": st["rows_real"] if packed else st["N"] * st["S"],
+                            "sq": st["rows_sq"] if packed else st["N"] * st["S"] * st["S"], "N": st["N"], "S": st["S"]})
+        torch.cuda.synchronize()
+        prof = model.engine.prof
+        model.engine.prof = None
         tr.opt = opt
-        sampler.stop()
     d2h = hyp_host.numel() * 8
 
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
-    # roofline of the dominant kernel: tcgen05 GEMM, FFN up-projection launches (M=N_rows*S, N=2048, K=512)
     pk, pk_src = peaks()
     roof = None
-    if events:
-        durs = [a.elapsed_time(b) for a, b in events]
-        mean_ms = sum(durs) / len(durs)
-        # rows the launch really computes: sum of the candidate lengths when the rows are packed
-        R = stats["rows_real"] if stats.get("packed") else stats["N"] * stats["S"]
-        flops = 2.0 * R * opt["dim_hidden"] * opt["intermediate_size"]
-        achieved = flops / (mean_ms / 1e3) / 1e12
-        peak = pk["bf16_tflops_sustained"]
-        mma_mult = {"bf16x3": 3.0, "bf16": 1.0}.get(args.precision, 0.0)
-        # DRAM bytes of this launch from the committed `ncu --set full` capture (profiles/r1i_ncu_table_layer_*_packed.txt,
-        # same B=128 workload; dram__bytes_read.sum + dram__bytes_write.sum): below the algorithmic operand + result
-        # bytes because the bf16 results stay in the 126 MB L2 until the down-projection consumes them
-        traffic = {"bf16x3": 62.9e6, "bf16": 13.7e6}.get(args.precision) if (stats.get("packed") and B == 128) else None
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)", "kernel": "gemm_tc_kernel (FFN up-projection, M=%d N=%d K=%d)" % (R, opt["intermediate_size"], opt["dim_hidden"]),
-                "launches_timed": len(durs), "timed_in": "eager re-run of the same steps (graph replay off), CUDA events on the launching stream", "mean_us": mean_ms * 1e3, "peak_source": pk_src + " (sustained cuBLAS bf16)",
-                "algorithmic_flops_per_launch": flops,
-                "issued_mma_frac": achieved * mma_mult / peak if mma_mult else None,
-                "note": "achieved counts useful (fp32-equivalent) FLOPs; %s mode issues %.0fx as many bf16 MMAs" % (args.precision, mma_mult or 0)}
+    if prof:
+        rows, top, total_us, ncu_src = class_table(prof, samples, opt, args.precision, B, ms / args.steps, pk)
+        t = rows[top]
+        tensor = t["bound"] == "tensor"
+        roof = {"bound": t["bound"], "achieved": t["tflops"] if tensor else t["gbs"],
+                "peak": pk["bf16_tflops_sustained"] if tensor else pk["hbm_gbs"], "unit": "TFLOP/s" if tensor else "GB/s",
+                "frac": t["frac_useful"] if tensor else t["frac_hbm"], "traffic": t.get("traffic"),
+                "traffic_source": ncu_src, "kernel": "%s (%s)" % (top, t["shape"]), "mean_us": t["us"],
+                "issued_mma_frac": t["frac_issued"], "share_of_step": t["share_of_step"],
+                "peak_source": pk_src + (" (sustained cuBLAS bf16, MEASURED_PEAKS.json)" if tensor else " (copy bandwidth, MEASURED_PEAKS.json)"),
+                "timed_in": "eager re-run of %d steps (graph replay off), CUDA events on the launching stream around every launch" % len(samples),
+                "profiled_us_per_step": round(total_us, 1),
+                "note": "frac = useful (fp32-equivalent) FLOPs / measured sustained bf16 peak; %s issues %.0fx as many bf16-MMA time "
+                        "units per product (frac_issued)" % (args.precision, {"bf16x3": 3, "bf16": 1, "tf32": 2}.get(args.precision, 0)),
+                "classes": rows}
 
-    cpu = None
+    # ---- CPU baseline + parity on the same PARITY_B videos (N = 1 only) ----
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = 16
-        v, sec, hyp_cpu = cpu_oracle_run(opt, cb, 2, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "B=%d videos of the same workload, 2 timed repetitions + 1 warm-up (%.1f s each)" % (cb, sec)}
+        kind = reference_kind()
+        v, sec, hyp_cpu = cpu_run(opt, PARITY_B, 2, 1, kind)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+               "sample": "B=%d videos of the same workload (same model, opts, seeds), 2 timed repetitions + 1 warm-up (%.1f s each)" % (PARITY_B, sec)}
+        if not args.no_parity:
+            parity = parity_block(opt, model, dev, args.precision, hyp_cpu, kind)
+
+    # ---- data-parallel training (BASELINE configs 3 and 5): the single NCCL all-reduce inside the timed step ----
+    train = None
+    if not args.no_train:
+        del tr
+        model.engine.graphs.clear()
+        gc.unfreeze()
+        gc.collect()
+        torch.cuda.empty_cache()
+        train = train_block(args, world, rank, dev)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"bf16x3": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate; fp32-equivalent)",
-                          "bf16": "bf16", "fp32": "f32"}[args.precision],
-                "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "precision": args.precision, "passes": stats.get("passes"),
-                           "S": stats.get("S"), "rows": stats.get("N"), "cuda_graph": bool(stats.get("graph")),
-                           "packed_rows": bool(stats.get("packed")), "positions_real": stats.get("rows_real"),
-                           "positions_padded": (stats.get("N") or 0) * (stats.get("S") or 0),
-                           "l2": "inputs rotate over %d distinct batches (%d MB of features > 126 MB L2)" % (n_rot, n_rot * h2d >> 20)},
+                          "bf16": "bf16", "fp32": "f32", "tf32": "tf32"}[args.precision],
+                "data": "synthetic", "config": dict(CONFIG),
+                "details": {"batch_per_gpu": B, "precision": args.precision, "passes": stats.get("passes"),
+                            "S": stats.get("S"), "rows": stats.get("N"), "cuda_graph": bool(stats.get("graph")),
+                            "packed_rows": bool(stats.get("packed")), "positions_real": stats.get("rows_real"),
+                            "positions_padded": (stats.get("N") or 0) * (stats.get("S") or 0),
+                            "l2": "inputs rotate over %d distinct batches (%d MB of features > 126 MB L2)" % (n_rot, n_rot * h2d >> 20)},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
-                "per_step_ms": {"resident": step_ms.get("resident"), "e2e": step_ms.get("step_e2e")}}
+                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+                "extra": {"train": train},
+                "per_step_ms": {"resident": step_ms.get("resident"), "e2e": step_ms.get("e2e")}}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_block(opt, model, dev, precision, hyp_cpu, kind):
+    """GPU ids (fp32 mode and the timed mode; third call of the shape = replayed CUDA graph) against the CPU
+    reference's ids on the same PARITY_B videos, video by video.  A video counts as a real mismatch only when
+    every decision that reaches its ids clears the mode's arithmetic error (the oracle's `video_margin`, log units)."""
+    import navc_b200
+    from oracle import navc_oracle as O
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    feats, category = cases.synth_inputs(opt, PARITY_B)
+    hyp_o, det = O.translate(sd, opt, feats, category, return_details=True)
+    vm = det["video_margin"]
+    out = {"against": "unmodified reference on the host" if kind == "reference" else "oracle port on the host",
+           "sample": "the %d videos of the cpu_baseline leg (config 2 model, opts, seeds)" % PARITY_B,
+           "reference_equals_oracle": bool(hyp_cpu.shape == hyp_o.shape and torch.equal(hyp_cpu, hyp_o)),
+           "video_margin_log_units": {"min": float(vm.min()), "median": float(vm.median()), "max": float(vm.max())},
+           "modes": {}}
+    feats_d, cat_d = [f.to(dev) for f in feats], category.to(dev)
+    ref = hyp_cpu if hyp_cpu.shape == hyp_o.shape else hyp_o
+    for mode in dict.fromkeys(("fp32", precision)):
+        model.set_precision(mode)
+        tr = navc_b200.Translator(model, opt, device=dev)
+        with torch.no_grad():
+            for _ in range(3):  # eager, capture, replay
+                hyp, _ = tr.translate_batch(model.encode(feats=feats_d), cat_d, None, {})
+        st = navc_b200.generate.last_stats
+        hyp = hyp.cpu()
+        if hyp.shape != ref.shape:
+            out["modes"][mode] = {"error": "shape %s vs %s" % (tuple(hyp.shape), tuple(ref.shape))}
+            continue
+        eq = (hyp == ref).all(1)
+        above = vm > MARGIN[mode]
+        out["modes"][mode] = {
+            "videos": PARITY_B, "videos_equal": int(eq.sum()), "tokens_equal": float((hyp == ref).float().mean()),
+            "margin_threshold": MARGIN[mode], "videos_above_margin": int(above.sum()),
+            "videos_above_margin_equal": int((eq & above).sum()), "mismatch_above_margin": int((~eq & above).sum()),
+            "differing_videos": [{"video": int(b), "margin": float(vm[b])} for b in (~eq).nonzero().flatten().tolist()],
+            "passes_equal": st["passes"] == det["passes"],
+            "path": "%s, %s" % ("CUDA graph replay" if st.get("graph") else "eager", "packed rows" if st.get("packed") else "padded rows")}
+    model.set_precision(precision)
+    return out
+
+
+def train_block(args, world, rank, dev):
+    """extra.train: config 3 (ARB / NAB, B=256 per GPU; N=1 only) and config 5 (NACF, global batch 1024 split over the
+    ranks: strong scaling) through tools/train_bench.measure -- forward + loss + backward + ONE gradient all-reduce +
+    fused clip/Adam per step; plus the unmodified reference's train step on the host cores at B=32 (N=1)."""
+    import train_bench as tb
+    out = {"config5_nacf_global1024": None, "config3": None, "cpu_reference": None}
+    steps = max(4, min(args.steps, 10))
+    r = tb.measure("NACF", 1024 // world, steps, 3, args.precision, dev=dev)
+    r.pop("_step"), r.pop("_model")
+    r["scaling"] = "strong (global batch 1024 fixed, %d per GPU)" % (1024 // world)
+    out["config5_nacf_global1024"] = r
+    if world == 1:
+        gc.collect()
+        torch.cuda.empty_cache()
+        c3 = {}
+        for m in ("ARB", "NAB"):
+            x = tb.measure(m, 256, steps, 3, args.precision, dev=dev)
+            x.pop("_step"), x.pop("_model")
+            c3[m] = x
+            gc.collect()
+            torch.cuda.empty_cache()
+        out["config3"] = c3
+        if rank == 0 and not args.no_cpu_baseline:
+            out["cpu_reference"] = {m: tb.reference_train_cpu(m, 32, 1, 1) for m in ("NACF", "NAB", "ARB")}
+    return out if rank == 0 else None
 
 
 if __name__ == "__main__":

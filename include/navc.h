@@ -152,6 +152,12 @@ int navc_highway_bn(const float* x, const float* yg, int gate, int B, int F, int
                     const float* bn_w, const float* bn_b, float bn_eps, float* enc_hidden,
                     float* enc_out, uint16_t* enc_hi, uint16_t* enc_lo, void* stream);
 
+/* Same with the norm_type='ln' encoder norm (models/joint_representation.py:20, 46-47): nn.LayerNorm(D) over the
+ * features of every frame row (eps 1e-5, biased variance) instead of the BatchNorm affine.  D <= 1024. */
+int navc_highway_ln(const float* x, const float* yg, int gate, int B, int F, int D, int E, int slot,
+                    int n_modalities, int accumulate, const float* ln_w, const float* ln_b, float ln_eps,
+                    float* enc_hidden, float* enc_out, uint16_t* enc_hi, uint16_t* enc_lo, void* stream);
+
 /* Length head (models/Predictor.py:23-30) + the frame mean reused by enhance_input=2
  * (models/Decoder.py:137): enc_mean[b,:] = mean_e enc_out[b,e,:];
  * pred_length[b,:] = log_softmax(W2 relu(W1 enc_mean + b1) + b2).  w1 may be NULL (mean only). */

@@ -54,6 +54,7 @@ _PROTOS = {
     "navc_log_softmax": [vp, vp, i32, i32, i32, vp],
     "navc_log_softmax_ld": [vp, i32, vp, i32, i32, i32, vp],
     "navc_highway_bn": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp],
+    "navc_highway_ln": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp],
     "navc_length_head": [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp],
     "navc_embed_ln": [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp],
     "navc_layernorm": [vp, vp, vp, f32, vp, i32, i32, vp, vp, vp, vp],

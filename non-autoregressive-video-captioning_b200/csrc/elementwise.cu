@@ -85,6 +85,73 @@ __global__ void highway_bn_kernel(const float* __restrict__ x, const float* __re
     }
 }
 
+// norm_type='ln' variant (models/joint_representation.py:20, 46-47): LayerNorm over the D features of every frame
+// row instead of the BatchNorm affine.  One block per video, one warp per frame row (strided); enc_hidden (the
+// frame mean of the UN-normalised highway output) is accumulated through shared memory.  D <= 1024.
+__global__ void highway_ln_kernel(const float* __restrict__ x, const float* __restrict__ yg, int gate, int F,
+                                  int D, int E, int slot, float inv_fm, int accumulate,
+                                  const float* __restrict__ lw, const float* __restrict__ lb, float eps,
+                                  float* __restrict__ enc_hidden, float* __restrict__ enc_out,
+                                  uint16_t* __restrict__ enc_hi, uint16_t* __restrict__ enc_lo) {
+    extern __shared__ float hsum[];  // [D]
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int ldy = gate ? 2 * D : D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) hsum[d] = 0.f;
+    __syncthreads();
+    for (int f = warp; f < F; f += nw) {
+        const size_t r = (size_t)b * F + f;
+        float o[32];  // D / 32 values per lane
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int d = lane + i * 32;
+            o[i] = 0.f;
+            if (d < D) {
+                const float xv = x[r * D + d];
+                const float y = tanhf(yg[r * ldy + d]);
+                if (gate) {
+                    const float g = 1.0f / (1.0f + expf(-yg[r * ldy + D + d]));
+                    o[i] = g * xv + (1.0f - g) * y;
+                } else {
+                    o[i] = xv + y;
+                }
+                s += o[i];
+                atomicAdd(&hsum[d], o[i]);
+            }
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float v2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int d = lane + i * 32;
+            if (d < D) v2 += (o[i] - mean) * (o[i] - mean);
+        }
+        const float istd = 1.0f / sqrtf(warp_sum(v2) / (float)D + eps);   // biased variance, as nn.LayerNorm
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int d = lane + i * 32;
+            if (d < D) {
+                const float v = (o[i] - mean) * istd * lw[d] + lb[d];
+                const size_t oi = ((size_t)b * E + (size_t)slot * F + f) * D + d;
+                enc_out[oi] = v;
+                if (enc_hi) {
+                    uint16_t h, l;
+                    split_bf16(v, h, l);
+                    enc_hi[oi] = h;
+                    if (enc_lo) enc_lo[oi] = l;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (enc_hidden)
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const float hv = hsum[d] * inv_fm;
+            const size_t hi_ = (size_t)b * D + d;
+            enc_hidden[hi_] = accumulate ? enc_hidden[hi_] + hv : hv;
+        }
+}
+
 // ------------------------------------------------------------------------------------------------
 // one block (256 threads) per video.  dynamic smem: mean[D] + h1[D] + logits[max_len]
 __global__ void length_head_kernel(const float* __restrict__ enc_out, int E, int D,
@@ -342,6 +409,17 @@ extern "C" int navc_highway_bn(const float* x, const float* yg, int gate, int B,
                                                             bn_rm, bn_rv, bn_w, bn_b, bn_eps, enc_hidden, enc_out,
                                                             enc_hi, enc_lo);
     return check_launch("navc_highway_bn");
+}
+
+extern "C" int navc_highway_ln(const float* x, const float* yg, int gate, int B, int F, int D, int E, int slot,
+                               int n_modalities, int accumulate, const float* ln_w, const float* ln_b, float ln_eps,
+                               float* enc_hidden, float* enc_out, uint16_t* enc_hi, uint16_t* enc_lo, void* stream) {
+    NAVC_REQUIRE(x && yg && enc_out && ln_w && ln_b, "navc_highway_ln: null pointer");
+    NAVC_REQUIRE(B > 0 && F > 0 && D > 0 && D <= 1024 && (slot + 1) * F <= E, "navc_highway_ln: bad shape (D <= 1024)");
+    highway_ln_kernel<<<B, 256, (size_t)D * sizeof(float), as_stream(stream)>>>(
+        x, yg, gate, F, D, E, slot, 1.0f / ((float)F * (float)n_modalities), accumulate, ln_w, ln_b, ln_eps, enc_hidden,
+        enc_out, enc_hi, enc_lo);
+    return check_launch("navc_highway_ln");
 }
 
 extern "C" int navc_length_head(const float* enc_out, int B, int E, int D, const float* w1, const float* b1,

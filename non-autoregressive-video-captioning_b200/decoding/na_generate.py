@@ -117,7 +117,8 @@ def generate(opt, model, teacher_model, encoder_outputs, teacher_encoder_outputs
     beam = torch.empty((B, lbs), dtype=torch.int32, device=dev)
     smax = torch.zeros((1,), dtype=torch.int32, device=dev)
     L.call("navc_length_beam", L.ptr(pred_length), B, max_len, lbs, int(length_bias), L.ptr(beam), L.ptr(smax), L.stream())
-    S, rows_real = torch.cat([smax, beam.sum().to(torch.int32).view(1)]).tolist()  # ONE host read: Smax and sum(len)
+    # ONE host read: Smax, sum(len) and sum(len^2) (the last two only feed the statistics bench.py reports)
+    S, rows_real, rows_sq = torch.cat([smax, beam.sum().to(torch.int32).view(1), (beam * beam).sum().to(torch.int32).view(1)]).tolist()
 
     mem = eng.enc_inputs(encoder_outputs["enc_output"], encoder_outputs.get("_navc"))
     tmem = None
@@ -149,12 +150,12 @@ def generate(opt, model, teacher_model, encoder_outputs, teacher_encoder_outputs
                     del eng.graphs[k]
                 entry = eng.graphs[key] = _DecodeGraph(_run, opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping)
             hyp = entry.replay(mem, tmem, cat, beam)
-            generate.last_stats = dict(entry.stats, graph=True, rows_real=rows_real)
+            generate.last_stats = dict(entry.stats, graph=True, rows_real=rows_real, rows_sq=rows_sq)
             return hyp, None
         eng.graphs[key] = "warm"  # first call: run eagerly (also warms up lazily initialised kernels)
 
     hyp, stats = _run(opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping)
-    generate.last_stats = dict(stats, graph=False, rows_real=rows_real)
+    generate.last_stats = dict(stats, graph=False, rows_real=rows_real, rows_sq=rows_sq)
     return hyp, None
 
 

@@ -73,10 +73,9 @@ class Engine:
         self.grad_sink = None   # set by parallel.GradientAllReduce: parameter -> its p.grad view, for in-place accumulation
         self.device = None
         self.P: Dict[str, object] = {}
-        # optional live timing of one class of launches (bench.py roofline): CUDA events recorded on
-        # the launching stream around every `linear(..., tag=profile_tag)` call
-        self.profile_tag = None
-        self.profile_events = []
+        # optional live timing of the launch classes (bench.py roofline): when `prof` is a dict, CUDA events are
+        # recorded on the launching stream around every tagged launch: prof[tag] = [(start, stop), ...]
+        self.prof = None
         self.pack_id = 0
         self.graphs: Dict[tuple, object] = {}  # CUDA graphs of the decode loop (decoding/na_generate.py)
 
@@ -89,7 +88,9 @@ class Engine:
         load_state_dict / .to() / optimizer steps; after replacing one (``m.weight = nn.Parameter(..)``) call
         ``invalidate(structure=True)``."""
         if self._members is None:
-            self._members = (list(self.model.named_parameters()),
+            # remove_duplicate=False: with opt['tie_weights'] the vocabulary projection shares the word-embedding
+            # Parameter (seq2seq.py:30-33) and both state_dict names must resolve
+            self._members = (list(self.model.named_parameters(remove_duplicate=False)),
                              [(n, b) for n, b in self.model.named_buffers() if not n.endswith("num_batches_tracked")])
         return self._members
 
@@ -108,6 +109,10 @@ class Engine:
         """(Re)pack weights if any parameter changed (optimizer step, load_state_dict, .to())."""
         dev = self.members()[0][0][1].device
         L.ensure_init(dev)
+        if dev.type == "cuda" and dev.index is not None and torch.cuda.current_device() != dev.index:
+            # every launch goes to the CURRENT device's current stream: a model on cuda:1 driven while cuda:0 is
+            # current would launch on device 0 against device-1 pointers
+            torch.cuda.set_device(dev)
         sig = self._signature()
         if sig == self._sig and dev == self.device:
             return
@@ -274,10 +279,7 @@ class Engine:
         ep = L.Epilogue(L.ptr(lin.b), L.ptr(res32), L.ptr(row_tokens), act, ld_res,
                         L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), N, 0, 1, 0, L.ptr(res_hi), L.ptr(res_lo),
                         m_dev.data_ptr() if m_dev is not None else None)
-        timed = tag is not None and tag == self.profile_tag
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+        e0 = self._t0(tag)
         if use_tc:
             L.call("navc_linear_tc", self.tc_mode, L.ptr(x.hi), L.ptr(x.lo), K, L.ptr(lin.w_hi), L.ptr(lin.w_lo), K,
                    M, N, K, ep, L.stream())
@@ -285,10 +287,21 @@ class Engine:
             if x.f32 is None:
                 raise L.NavcError("fp32 GEMM path needs an fp32 activation (K=%d not a multiple of 64?)" % K)
             L.call("navc_linear_f32", L.ptr(x.f32), K, L.ptr(lin.w), K, M, N, K, ep, L.stream())
-        if timed:
-            e1.record()
-            self.profile_events.append((e0, e1))
+        self._t1(tag, e0)
         return out
+
+    def _t0(self, tag):
+        if self.prof is None or tag is None:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def _t1(self, tag, e0):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.prof.setdefault(tag, []).append((e0, e1))
 
     def layernorm(self, x: Act, ln, row_tokens, f32=True, bf=True) -> Act:
         out = self._new(x.M, x.N, f32 or not self.tc, bf)
@@ -296,12 +309,12 @@ class Engine:
                L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), L.stream())
         return out
 
-    def _proj_res(self, x: Act, lin, ln, residual: Act, row_tokens, pair=False, m_dev=None) -> Act:
+    def _proj_res(self, x: Act, lin, ln, residual: Act, row_tokens, pair=False, m_dev=None, tag=None) -> Act:
         """dense -> (+residual) -> [LayerNorm] -> * non_pad_mask   (models/bert.py:192-200, 240-247, 271-299).
         pair: the residual stream lives as bf16 hi/lo pairs only (tensor-core modes without LayerNorm)."""
         if ln is None:
-            return self.linear(x, lin, residual=residual, row_tokens=row_tokens, f32=not pair, bf=True, lo=pair, m_dev=m_dev)
-        y = self.linear(x, lin, residual=residual, row_tokens=None, f32=True, bf=False)
+            return self.linear(x, lin, residual=residual, row_tokens=row_tokens, f32=not pair, bf=True, lo=pair, m_dev=m_dev, tag=tag)
+        y = self.linear(x, lin, residual=residual, row_tokens=None, f32=True, bf=False, tag=tag)
         return self.layernorm(y, ln, row_tokens)
 
     # ------------------------------------------------------------------------------------------
@@ -329,11 +342,15 @@ class Engine:
             if len(set(frames)) != 1:
                 raise NotImplementedError("modalities with different frame counts")
             x_in = self.from_f32(f.reshape(B * F_, f.shape[2]).to(dev))
-            x = self.linear(x_in, st["l0"], f32=True, bf=True)
-            yg = self.linear(x, st["l12"], f32=True, bf=False)
+            x = self.linear(x_in, st["l0"], f32=True, bf=True, tag="enc0")
+            yg = self.linear(x, st["l12"], f32=True, bf=False, tag="enc12")
             norm = None if no_norm else P["norms"][i]
             if norm is not None and norm[0] == "ln":
-                raise NotImplementedError("norm_type='ln' encoder norm")
+                L.call("navc_highway_ln", L.ptr(x.f32), L.ptr(yg.f32), st["gate"], B, F_, D, E, i, len(feats), int(i > 0),
+                       L.ptr(norm[1]), L.ptr(norm[2]), 1e-5, L.ptr(enc_hidden), L.ptr(enc.f32), L.ptr(enc.hi), L.ptr(enc.lo),
+                       L.stream())
+                row0 += F_
+                continue
             rm = rv = bw = bb = None
             if norm is not None:
                 _, rm, rv, bw, bb = norm
@@ -357,7 +374,7 @@ class Engine:
         # tensor) and every batch's encoder memory + K|V projections (~440 MB at B = 128) would wait for the cyclic GC
         results["enc_output"] = enc.f32.detach()
         results["enc_hidden"] = enc_hidden
-        results["_navc"] = dict(enc=enc, enc_mean=enc_mean, B=B, E=E, owner=id(self))
+        results["_navc"] = dict(enc=enc, enc_mean=enc_mean, B=B, E=E, owner=id(self), pack_id=self.pack_id)
         return results
 
     # ------------------------------------------------------------------------------------------
@@ -367,13 +384,17 @@ class Engine:
         """Encoder memory in the operand formats of this engine (fp32 + bf16 hi/lo copies) and the
         frame mean used by enhance_input=2; reuses what ``encode`` already produced."""
         self.sync_weights()
-        if cache is not None and cache.get("owner") == id(self) and cache["enc"].f32.data_ptr() == enc_output.data_ptr():
+        if cache is not None and cache.get("owner") == id(self) and cache["enc"].f32.data_ptr() == enc_output.data_ptr() \
+                and cache["enc"].f32.numel() == enc_output.numel():   # (a batch slice shares data_ptr with the full tensor)
+            if cache.get("pack_id", self.pack_id) != self.pack_id:
+                cache.pop("kv", None)       # K|V were projected with weights that have since changed
+            cache["pack_id"] = self.pack_id
             return cache
         Bv, E, D = enc_output.shape
         enc = self.from_f32(enc_output.reshape(Bv * E, D))
         enc_mean = torch.empty((Bv, D), dtype=torch.float32, device=self.device)
         L.call("navc_length_head", L.ptr(enc.f32), Bv, E, D, None, None, None, None, 0, L.ptr(enc_mean), None, L.stream())
-        return dict(enc=enc, enc_mean=enc_mean, B=Bv, E=E, owner=id(self))
+        return dict(enc=enc, enc_mean=enc_mean, B=Bv, E=E, owner=id(self), pack_id=self.pack_id)
 
     def memory(self, enc_output: torch.Tensor, cache: Optional[dict] = None):
         """Per-video decoder memory: cross-attention K|V of every layer (computed once)
@@ -381,7 +402,7 @@ class Engine:
         cache = self.enc_inputs(enc_output, cache)
         if "kv" not in cache:
             tc_attn = self.tc_attention_ok(32, cache["E"])
-            cache["kv"] = self.linear(cache["enc"], self.P["kv_all"], f32=not tc_attn, bf=tc_attn)  # [Bv*E, L*2D]
+            cache["kv"] = self.linear(cache["enc"], self.P["kv_all"], f32=not tc_attn, bf=tc_attn, tag="kv")  # [Bv*E, L*2D]
         return cache
 
     def tc_attention_ok(self, S, E):
@@ -450,9 +471,10 @@ class Engine:
         tc_attn = self.tc_attention_ok(S, E) and not want_attn and kv.hi is not None
         watch = int(self.opt.get("watch", 0))
         for l, lw in enumerate(P["layers"]):
-            qkv = self.linear(x, lw["qkv"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev)
+            qkv = self.linear(x, lw["qkv"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="qkv")
             ctx = self._new(R, D, not self.tc, True)
             p_self = p_cross = None
+            e0 = self._t0("self")
             if packed is not None:
                 L.call("navc_self_attention_tc_packed", self.tc_mode, L.ptr(qkv.hi), L.ptr(qkv.lo), 3 * D, L.ptr(tokens),
                        L.ptr(packed["seq_off"]), N, S, D, H, mask_kind, watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo),
@@ -464,9 +486,11 @@ class Engine:
                 p_self = torch.empty((H, N, S, S), dtype=torch.float32, device=self.device) if want_attn else None
                 L.call("navc_self_attention", L.ptr(qkv.f32), 3 * D, L.ptr(tokens), N, S, D, H, mask_kind,
                        watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.ptr(p_self), L.stream())
-            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tok_flat, pair, m_dev)
-            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev)
+            self._t1("self", e0)
+            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tok_flat, pair, m_dev, tag="so")
+            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="cq")
             ctx2 = self._new(R, D, not self.tc, True)
+            e0 = self._t0("cross")
             if packed is not None:
                 off = l * 2 * D
                 L.call("navc_cross_attention_tc_packed", self.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D,
@@ -483,9 +507,10 @@ class Engine:
                 kv_l = self._kv_f32(mem)[:, l * 2 * D:]
                 L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, S, E, D, H, group,
                        L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
-            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair, m_dev)
+            self._t1("cross", e0)
+            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair, m_dev, tag="co")
             h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1", m_dev=m_dev)
-            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair, m_dev)
+            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair, m_dev, tag="f2")
             if want_attn:
                 attns.append((p_self, p_cross))
         if want_f32:
@@ -554,6 +579,9 @@ class Engine:
         ps = torch.empty((R, nt), dtype=torch.float32, device=dev)
         pi = torch.empty((R, nt), dtype=torch.int32, device=dev)
         tl = torch.empty((R,), dtype=torch.float32, device=dev) if target is not None else None
+        e0 = self._t0("vocab")
+        if self.prof is not None and m_dev is not None:
+            self.prof.setdefault("vocab_rows", []).append(m_dev.clone())  # device-side row count of this launch
         if m_dev is not None:
             assert use_tc and target is None
             L.call("navc_vocab_partials_tc_dyn", self.tc_mode, L.ptr(hidden.hi), L.ptr(hidden.lo), K, L.ptr(lin.w_hi),
@@ -565,6 +593,7 @@ class Engine:
         else:
             L.call("navc_vocab_partials_f32", L.ptr(hidden.f32), K, L.ptr(lin.w), K, L.ptr(lin.b), R, V, K,
                    L.ptr(pm), L.ptr(ps), L.ptr(pi), L.ptr(target), L.ptr(tl), L.stream())
+        self._t1("vocab", e0)
         return pm, ps, pi, nt, tl
 
     def logits(self, hidden2d: torch.Tensor) -> torch.Tensor:

@@ -9,7 +9,9 @@ independent units (videos), so
   streams stay rank-local exactly as in plain DDP) and the gradients are averaged
   with ONE all-reduce over a flat fp32 buffer per step (``GradientAllReduce``).  The loss of the
   reference is a token sum divided by the LOCAL batch size (misc/crit.py:40-46), so the mean of
-  the per-rank gradients over equal shards is the global-batch gradient.
+  the per-rank gradients over EQUAL shards is the global-batch gradient (``shard_bounds`` gives the
+  first ``n % world`` ranks one extra unit when the batch does not divide: pass
+  ``GradientAllReduce.allreduce(weight=local_batch / global_batch * world)`` to weight the ranks).
 
 ``torch.distributed`` (NCCL over NVLink on the GPUs, gloo in the CPU tests) is the transport.
 """
@@ -121,7 +123,9 @@ class GradientAllReduce:
         """(Re)point p.grad at the flat buffer (optimizers' zero_grad(set_to_none=True) detaches it)."""
         for p, v in zip(self.params, self.views):
             if p.grad is not v:
-                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                if p.grad is None:
+                    v.zero_()   # detached by zero_grad(set_to_none=True): no gradient this step, not last step's
+                elif p.grad.data_ptr() != v.data_ptr():
                     v.copy_(p.grad)
                 p.grad = v
 
@@ -130,10 +134,13 @@ class GradientAllReduce:
         for p, v in zip(self.params, self.views):
             p.grad = v
 
-    def allreduce(self):
-        """Average the gradients over the ranks: one collective on the whole buffer."""
+    def allreduce(self, weight: Optional[float] = None):
+        """Average the gradients over the ranks: one collective on the whole buffer.  ``weight`` scales this
+        rank's gradients first (unequal shards: local_batch * world / global_batch)."""
         self.attach()
         w = world()
+        if weight is not None and weight != 1.0:
+            self.flat.mul_(float(weight))
         if w == 1:
             return self.flat
         if dist.get_backend() == "nccl":

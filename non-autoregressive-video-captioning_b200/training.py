@@ -119,6 +119,14 @@ def _split_k(out_rows, out_cols, k):
     return max(1, min(kb, (2 * 148) // max(tiles, 1)))
 
 
+def _check_pack(eng, st):
+    """The backward kernels read the packed weights (eng.P) of the forward pass: a repack in between (an optimizer
+    step or load_state_dict between forward and backward) would silently mix weight versions."""
+    if st.get("pack_id", eng.pack_id) != eng.pack_id:
+        raise RuntimeError("navc: the model's weights changed between forward and backward (packed weights %d -> %d)"
+                           % (st["pack_id"], eng.pack_id))
+
+
 class Grads:
     """Gradient accumulator keyed by state_dict name."""
 
@@ -372,6 +380,7 @@ class EncodeFn(torch.autograd.Function):
     def backward(ctx, d_enc, d_hidden, *rest):
         model, st = ctx.model, ctx.state
         eng: Engine = model.engine
+        _check_pack(eng, st)
         P, D = eng.P, eng.D
         B, F_, E = st["B"], st["F"], st["E"]
         dev = eng.device
@@ -524,6 +533,9 @@ class DecoderFn(torch.autograd.Function):
         cat = category.contiguous() if category is not None else None
         seeds = Seeds()
         p = float(opt["hidden_dropout_prob"])
+        if float(opt.get("attention_probs_dropout_prob", 0.0) or 0.0) > 0.0:
+            raise NotImplementedError("attention_probs_dropout_prob > 0 in training (models/bert.py:135,169; the method "
+                                      "presets use 0.0): the attention cores take no dropout seed")
         enc = eng.from_f32(enc_output.detach().reshape(Bv * E, D))
         extra = None
         if decoding_type == "NARFormer":
@@ -601,7 +613,7 @@ class DecoderFn(torch.autograd.Function):
             layers.append(sv)
             x = xn
         ctx.model, ctx.keys = model, keys
-        ctx.state = dict(tokens=tokens, tok_flat=tok_flat, cat=cat, enc=enc, extra=extra, kv=kv.f32, layers=layers,
+        ctx.state = dict(pack_id=eng.pack_id, tokens=tokens, tok_flat=tok_flat, cat=cat, enc=enc, extra=extra, kv=kv.f32, layers=layers,
                          seed_e=seed_e, p=p, N=N, S=S, E=E, Bv=Bv, mask_kind=mask_kind, watch=watch, decoding_type=decoding_type,
                          pk=pk)
         ctx.pk = pk
@@ -616,6 +628,7 @@ class DecoderFn(torch.autograd.Function):
     def backward(ctx, d_hidden):
         model, st = ctx.model, ctx.state
         eng: Engine = model.engine
+        _check_pack(eng, st)
         P, D, H = eng.P, eng.D, eng.H
         dev = eng.device
         N, S, E, Bv = st["N"], st["S"], st["E"], st["Bv"]
@@ -758,7 +771,7 @@ class VocabFn(torch.autograd.Function):
             else:
                 out.copy_(logits[:, :V])
         ctx.model, ctx.log_probs = model, log_probs
-        ctx.state = dict(h=h, out=out if log_probs else None, R=R, V=V, Vp=Vp, shape=shape, n_params=len(params), pk=pk,
+        ctx.state = dict(pack_id=eng.pack_id, h=h, out=out if log_probs else None, R=R, V=V, Vp=Vp, shape=shape, n_params=len(params), pk=pk,
                          R_all=R_all, const_lp=const_lp)
         return out.view(*shape[:-1], V)
 
@@ -766,6 +779,7 @@ class VocabFn(torch.autograd.Function):
     def backward(ctx, d_out):
         model, st = ctx.model, ctx.state
         eng: Engine = model.engine
+        _check_pack(eng, st)
         lin = eng.P["vocab"]
         dev = eng.device
         R, V, Vp, pk = st["R"], st["V"], st["Vp"], st["pk"]
@@ -858,7 +872,7 @@ class FusedCEFn(torch.autograd.Function):
         L.call("navc_ce_stats", L.ptr(pm), L.ptr(ps), L.ptr(pi), nt, L.ptr(tl), L.ptr(lab), R, L.ptr(lse), L.ptr(nll), L.ptr(arg), L.stream())
         lazy.stats = (nll.view(labels.shape), arg.view(labels.shape))
         ctx.lazy, ctx.n_params = lazy, len(params)
-        ctx.state = dict(h=h, lse=lse, lab=lab, shape=hidden.shape)
+        ctx.state = dict(pack_id=eng.pack_id, h=h, lse=lse, lab=lab, shape=hidden.shape)
         return nll.sum()
 
     @staticmethod
@@ -866,6 +880,7 @@ class FusedCEFn(torch.autograd.Function):
         model = ctx.lazy.model
         eng: Engine = model.engine
         st = ctx.state
+        _check_pack(eng, st)
         lin = eng.P["vocab"]
         dev = eng.device
         h, lse, lab = st["h"], st["lse"], st["lab"]

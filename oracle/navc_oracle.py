@@ -326,9 +326,19 @@ class Decoder:
         self.passes = 0
         self.min_top2_gap = float("inf")
         self.min_select_gap = float("inf")
+        # per candidate row, in log units (logit / log-prob differences): the smallest margin of any decision
+        # whose outcome reaches the row's final tokens -- the argmax of a position that is merged, and the
+        # k-th / (k+1)-th boundary of every selection.  Parity reports use it to tell a real mismatch from a
+        # decision that sits inside the arithmetic error of the mode under test.
+        self.row_margin = None
+
+    def _row_min(self, values, valid):
+        """row_margin[n] = min(row_margin[n], min over valid positions of values[n, :])."""
+        v = values.masked_fill(~valid, float("inf")).min(dim=1)[0]
+        self.row_margin = v if self.row_margin is None else torch.minimum(self.row_margin, v)
 
     # algorithms.py:7-15, 143-167
-    def na_pass(self, tokens, enc_output, category, pad_mask):
+    def na_pass(self, tokens, enc_output, category, pad_mask, used=None):
         h, _, _ = decoder_forward(self.sd, self.opt, tokens, enc_output, category, output_attentions=False)
         logits = vocab_logits(self.sd, h)
         probs = torch.softmax(logits, dim=-1)
@@ -336,9 +346,11 @@ class Decoder:
         top2 = logits.topk(2, dim=-1)[0]
         # positions whose *input* token is PAD have an all-zero hidden state => all logits equal;
         # first-index argmax (= PAD) is the defined result there, so they are not counted as ties.
-        gap = (top2[..., 0] - top2[..., 1])[~(pad_mask | tokens.eq(PAD))]
+        live = ~(pad_mask | tokens.eq(PAD))
+        gap = (top2[..., 0] - top2[..., 1])[live]
         if gap.numel():
             self.min_top2_gap = min(self.min_top2_gap, gap.min().item())
+        self._row_min(top2[..., 0] - top2[..., 1], live if used is None else (live & used))
         idx = idx.masked_fill(pad_mask, PAD)
         p = p.masked_fill(pad_mask, 1.0)
         self.passes += 1
@@ -372,6 +384,8 @@ class Decoder:
 
     def _select_worst(self, probs, k):
         self.min_select_gap = min(self.min_select_gap, boundary_gap_smallest(probs, k).min().item())
+        lg = boundary_gap_smallest(probs.clamp_min(1e-38).log(), k)
+        self.row_margin = lg if self.row_margin is None else torch.minimum(self.row_margin, lg)
         return k_smallest_mask(probs, k)
 
     # algorithms.py:231-273
@@ -394,7 +408,7 @@ class Decoder:
                 k = (lens.float() * ratio).long()
                 mask = self._select_worst(prob * pt, k)
             tok = tok.masked_fill(mask, MASK)
-            ntok, nprob = self.na_pass(tok, enc_output, category, pad_mask)
+            ntok, nprob = self.na_pass(tok, enc_output, category, pad_mask, used=mask)
             tok = torch.where(mask, ntok, tok)
             prob = torch.where(mask, nprob, prob)
         pt = self.teacher_probs(tok, t_enc_output, category, pad_mask, is_last=True)
@@ -411,7 +425,7 @@ class Decoder:
                 k = (lens.float() * ratio).long()
                 mask = self._select_worst(prob, k)
             tok = tok.masked_fill(mask, MASK)
-            ntok, nprob = self.na_pass(tok, enc_output, category, pad_mask)
+            ntok, nprob = self.na_pass(tok, enc_output, category, pad_mask, used=mask)
             tok = torch.where(mask, ntok, tok)
             prob = torch.where(mask, nprob, prob)
         return tok, prob
@@ -439,14 +453,19 @@ class Decoder:
             if remain == 0 or remain == prev:
                 break
             prev = remain
-            ntok, nprob = self.na_pass(tok, enc_output, category, pad_mask)
+            ntok, nprob = self.na_pass(tok, enc_output, category, pad_mask, used=mask)
             cand = nprob.masked_fill(~mask, 0.0)
             k = mask.sum(1).clamp(max=q)
             # boundary-gap bookkeeping for the k largest
             srt = torch.sort(cand, dim=1, descending=True)[0]
             s = cand.shape[1]
             kk = k.clamp(min=1)
-            gap = (srt.gather(1, (kk - 1).unsqueeze(1)) - srt.gather(1, kk.clamp(max=s - 1).unsqueeze(1))).abs().squeeze(1)
+            hi_, lo_ = srt.gather(1, (kk - 1).unsqueeze(1)).squeeze(1), srt.gather(1, kk.clamp(max=s - 1).unsqueeze(1)).squeeze(1)
+            gap = (hi_ - lo_).abs()
+            # per row, in log units; rows that commit every remaining position (k == remaining) decide nothing
+            lg = (hi_.clamp_min(1e-38).log() - lo_.clamp_min(1e-38).log()).abs()
+            lg[(k == 0) | (k >= mask.sum(1)) | (k >= s)] = float("inf")
+            self.row_margin = lg if self.row_margin is None else torch.minimum(self.row_margin, lg)
             gap = gap[(k > 0) & (k < s)]
             if gap.numel():
                 self.min_select_gap = min(self.min_select_gap, gap.min().item())
@@ -473,7 +492,7 @@ class Decoder:
             if int(mask.sum()) == 0:
                 break
             tok = tok.masked_fill(mask, MASK)
-            ntok, nprob = self.na_pass(tok, enc_output, category, pad_mask)
+            ntok, nprob = self.na_pass(tok, enc_output, category, pad_mask, used=mask)
             tok = torch.where(mask, ntok, tok)
             prob = torch.where(mask, nprob, prob)
         tok, prob = self._refine_tail(tok, prob, lens, visual, enc_output, category, pad_mask)
@@ -508,10 +527,17 @@ def generate(sd, opt, encoder_outputs, category, teacher=None, teacher_encoder_o
         # lengths after clamping give identical candidates, which are not ties that matter)
         same = (tok == hyp.unsqueeze(1)).all(-1)
         other = score.masked_fill(same, float("-inf")).max(-1)[0]
-        cand_gap = (score.max(-1)[0] - other).min().item()
+        cand_gaps = score.max(-1)[0] - other
+        cand_gap = cand_gaps.min().item()
+        # per video, in log units: every decision of every candidate row, the candidate choice, and the boundary
+        # of the length beam (k-th vs (k+1)-th most likely length; a different beam changes the whole video)
+        srt = pred_length.sort(dim=1, descending=True)[0]
+        beam_gap = (srt[:, lbs - 1] - srt[:, lbs]) if srt.shape[1] > lbs else torch.full((bsz,), float("inf"))
+        video_margin = torch.minimum(torch.minimum(dec.row_margin.view(bsz, lbs).min(1)[0], cand_gaps), beam_gap)
         return hyp, {"beam": beam, "tokens": tok, "lprobs": lprobs, "score": score, "best": best,
                      "passes": dec.passes, "min_top2_gap": dec.min_top2_gap,
-                     "min_select_gap": dec.min_select_gap, "min_candidate_gap": cand_gap}
+                     "min_select_gap": dec.min_select_gap, "min_candidate_gap": cand_gap,
+                     "video_margin": video_margin, "beam_gap": beam_gap}
     return hyp
 
 

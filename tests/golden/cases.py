@@ -56,6 +56,20 @@ def small(method="NACF", **kw):
     return make_opt(method, **base)
 
 
+# dk = 64 variants (the head size of BASELINE configs 2-5): small with two heads, and a D=512 / 8-head "wide" model
+def dk64(method="NACF", **kw):
+    base = dict(num_attention_heads=2)
+    base.update(kw)
+    return small(method, **base)
+
+
+def wide(method="NACF", **kw):
+    base = dict(dim_hidden=512, num_attention_heads=8, num_hidden_layers_decoder=2, intermediate_size=1024, dim_i=256,
+                dim_m=384, n_frames=20, max_len=30, vocab_size=2000, length_beam_size=5)
+    base.update(kw)
+    return make_opt(method, **base)
+
+
 # BASELINE config 2 (headline): NACF 6-layer d512
 def config2(**kw):
     base = dict(dim_hidden=512, num_hidden_layers_decoder=6, intermediate_size=2048, dim_i=2048,
@@ -108,10 +122,11 @@ def seeded_state_dict(model_ctor, opt, seed=0):
     return model
 
 
-def synth_state_dict(shapes, seed=7):
+def synth_state_dict(shapes, seed=7, scale=1.0):
     """Reference-independent seeded weights for a {name: shape} inventory (golden fixtures store the
     inventory, not the weights).  Matrices ~N(0, 0.08), biases ~N(0, 0.05), norm weights ~1+N(0,0.1),
-    BN running_var in [0.5, 1.5]; embedding row PAD is zero as nn.Embedding(padding_idx=0) keeps it."""
+    BN running_var in [0.5, 1.5]; embedding row PAD is zero as nn.Embedding(padding_idx=0) keeps it.
+    ``scale`` multiplies the matrix standard deviation (wide models: keeps the softmax away from saturation)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for name in sorted(shapes):
@@ -132,5 +147,5 @@ def synth_state_dict(shapes, seed=7):
                 w[0].zero_()
             sd[name] = w
         else:
-            sd[name] = 0.08 * torch.randn(shape, generator=g)
+            sd[name] = (0.08 * scale) * torch.randn(shape, generator=g)
     return sd

@@ -24,10 +24,10 @@ import refutil  # noqa: E402
 from oracle import navc_oracle as O  # noqa: E402
 
 
-def build(opt, wseed):
+def build(opt, wseed, wscale=1.0):
     model = refutil.ref_get_model(opt)
     shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
-    sd = cases.synth_state_dict(shapes, wseed)
+    sd = cases.synth_state_dict(shapes, wseed, wscale)
     model.load_state_dict(sd)
     model.eval()
     return model, shapes, sd
@@ -73,13 +73,13 @@ def forward_case(name, opt, batch, wseed=7):
     print("wrote", name, "loss", float(loss.detach()))
 
 
-def decode_case(name, base_opt, batch, grid, teacher_opt=None, wseed=7):
-    out = {"kind": "decode", "opt": base_opt, "wseed": wseed, "batch": batch, "runs": []}
-    model, shapes, sd = build(base_opt, wseed)
+def decode_case(name, base_opt, batch, grid, teacher_opt=None, wseed=7, wscale=1.0):
+    out = {"kind": "decode", "opt": base_opt, "wseed": wseed, "wscale": wscale, "batch": batch, "runs": []}
+    model, shapes, sd = build(base_opt, wseed, wscale)
     out["shapes"] = shapes
     teacher = tsd = None
     if teacher_opt is not None:
-        teacher, tshapes, tsd = build(teacher_opt, wseed + 1)
+        teacher, tshapes, tsd = build(teacher_opt, wseed + 1, wscale)
         out["teacher_opt"], out["teacher_shapes"] = teacher_opt, tshapes
     feats, category = cases.synth_inputs(base_opt, batch)
     for kw in grid:
@@ -93,14 +93,27 @@ def decode_case(name, base_opt, batch, grid, teacher_opt=None, wseed=7):
         assert tie_free, (name, kw, det["min_select_gap"], det["min_top2_gap"], det["min_candidate_gap"])
         out["runs"].append({"kw": kw, "hyp": hyp.clone(), "passes": det["passes"],
                             "min_top2_gap": det["min_top2_gap"], "min_select_gap": det["min_select_gap"],
-                            "min_candidate_gap": det["min_candidate_gap"], "beam": det["beam"].clone()})
+                            "min_candidate_gap": det["min_candidate_gap"], "beam": det["beam"].clone(),
+                            "video_margin": det["video_margin"].clone()})
         print(name, kw, "passes", det["passes"], "gaps %.2e %.2e %.2e" % (
             det["min_top2_gap"], det["min_select_gap"], det["min_candidate_gap"]))
     torch.save(out, os.path.join(HERE, name + ".pt"))
 
 
+WIDE_SCALE = float(os.environ.get("WIDE_SCALE", "0.4"))   # D = 512: matrices ~N(0, 0.032)
+
+
 def main():
     assert refutil.reference_available(), "run in the build container (needs /root/reference)"
+    only = set(sys.argv[1:])
+
+    def want(name):
+        return not only or name in only
+
+    global forward_case, decode_case
+    _fwd, _dec = forward_case, decode_case
+    forward_case = lambda name, *a, **k: _fwd(name, *a, **k) if want(name) else None
+    decode_case = lambda name, *a, **k: _dec(name, *a, **k) if want(name) else None
     forward_case("fwd_config1_nab", cases.config1(), 4)
     forward_case("fwd_small_nacf", cases.small("NACF"), 5)
     forward_case("fwd_small_nacf_ln", cases.small("NACF", with_layernorm=True), 5)
@@ -116,6 +129,21 @@ def main():
                  dict(paradigm="ef", use_ct=True), dict(paradigm="l2r", use_ct=False),
                  dict(paradigm="mp", use_ct=False, no_candidate_decision=True)],
                 teacher_opt=cases.small("ARB"))
+    # ---- dk = 64 (the head size of BASELINE configs 2-5): the cases on which the product runs its tcgen05
+    # attention cores, packed rows, the second-level vocabulary packing and (mask-predict) CUDA-graph replay ----
+    forward_case("fwd_dk64_nacf", cases.dk64("NACF"), 5)
+    forward_case("fwd_dk64_arb", cases.dk64("ARB"), 5)
+    decode_case("dec_dk64_nacf", cases.dk64("NACF"), 6, grid)
+    decode_case("dec_dk64_nacf_teacher", cases.dk64("NACF"), 6,
+                [dict(paradigm="mp", use_ct=True), dict(paradigm="mp", use_ct=True, masking_decision=True),
+                 dict(paradigm="ef", use_ct=True, q=2), dict(paradigm="l2r", use_ct=False)],
+                teacher_opt=cases.dk64("ARB"))
+    wide_grid = [dict(paradigm="mp", use_ct=True), dict(paradigm="mp", use_ct=False), dict(paradigm="mp", use_ct=True, iterations=3),
+                 dict(paradigm="ef", use_ct=True, q=2), dict(paradigm="ef", use_ct=False, q=3), dict(paradigm="l2r", use_ct=True, q=2)]
+    decode_case("dec_wide_nacf", cases.wide("NACF"), 8, wide_grid, wscale=WIDE_SCALE)
+    decode_case("dec_wide_nacf_teacher", cases.wide("NACF"), 8,
+                [dict(paradigm="mp", use_ct=True), dict(paradigm="mp", use_ct=False, masking_decision=True)],
+                teacher_opt=cases.wide("ARB"), wscale=WIDE_SCALE)
 
 
 if __name__ == "__main__":

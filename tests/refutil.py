@@ -1,7 +1,10 @@
-"""Helpers to import the UNMODIFIED reference from /root/reference (build container only).
+"""Helpers to import the UNMODIFIED reference: from /root/reference in the build container, else from
+baseline/_ref/ (the git-ignored, digest-checked install made by tools/install_reference.py, which travels to
+the GPU box with gpurun).
 
-The reference is never copied; it is imported in place to pin the oracle and to generate golden
-vectors.  On the GPU box /root/reference does not exist and everything here reports "absent".
+The reference is never part of the product: it is imported only to pin the oracle, to generate golden vectors,
+as the CPU baseline / reference arm of bench.py, and by the boundary test that drives the reference's own
+Translator over a navc model.
 """
 from __future__ import annotations
 
@@ -10,7 +13,21 @@ import io
 import os
 import sys
 
-REF_ROOT = os.environ.get("NAVC_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+INSTALLED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")  # tools/install_reference.py (unmodified copy, git-ignored)
+
+
+def _pick_root():
+    env = os.environ.get("NAVC_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", INSTALLED):
+        if os.path.isfile(os.path.join(cand, "models", "seq2seq.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _pick_root()
 
 
 def reference_available() -> bool:

@@ -27,9 +27,9 @@ TOL = {"fp32": 2e-4, "bf16x3": 5e-4, "bf16": 1.5e-1}
 MARGIN = {"fp32": 2e-5, "bf16x3": 1e-4, "bf16": 2e-2}
 
 
-def build(opt, shapes, wseed, precision):
+def build(opt, shapes, wseed, precision, wscale=1.0):
     model = navc_b200.get_model(opt)
-    model.load_state_dict(cases.synth_state_dict(shapes, wseed))
+    model.load_state_dict(cases.synth_state_dict(shapes, wseed, wscale))
     model.to(DEV).eval()
     model.set_precision(precision)
     return model
@@ -69,10 +69,11 @@ def test_forward_matches_golden(path, precision):
 @pytest.mark.parametrize("path", DEC, ids=[os.path.basename(p)[:-3] for p in DEC])
 def test_translate_ids_match_golden(path, precision):
     g = torch.load(path, weights_only=False)
-    model = build(g["opt"], g["shapes"], g["wseed"], precision)
+    sc = g.get("wscale", 1.0)
+    model = build(g["opt"], g["shapes"], g["wseed"], precision, sc)
     teacher = None
     if "teacher_opt" in g:
-        teacher = build(g["teacher_opt"], g["teacher_shapes"], g["wseed"] + 1, precision)
+        teacher = build(g["teacher_opt"], g["teacher_shapes"], g["wseed"] + 1, precision, sc)
     feats, category = cases.synth_inputs(g["opt"], g["batch"])
     feats, category = to_dev(feats), category.to(DEV)
     vocab = {i: "w%d" % i for i in range(g["opt"]["vocab_size"])}
@@ -85,8 +86,24 @@ def test_translate_ids_match_golden(path, precision):
             t_enc = teacher.encode(feats=feats) if teacher is not None else None
             hyp, _ = tr.translate_batch(enc, category, None, vocab, teacher_encoder_outputs=t_enc)
         stats = navc_b200.generate.last_stats
+        expect_tc = g["opt"]["dim_hidden"] == 64 * g["opt"]["num_attention_heads"] and precision != "fp32"
+        if expect_tc:  # the dk = 64 fixtures must exercise the timed configuration: packed rows (+ graph replay for mp)
+            assert stats["packed"], (run["kw"], stats)
         margin = min(run["min_top2_gap"], run["min_select_gap"], run["min_candidate_gap"])
         same = torch.equal(hyp.cpu(), run["hyp"])
+        if "video_margin" in run:
+            # per-video margins in log units (oracle `video_margin`): every video whose decisions all clear the mode's
+            # error must reproduce the reference's ids exactly; a differing video below it is printed, never hidden
+            vm = run["video_margin"]
+            bad = (hyp.cpu() != run["hyp"]).any(1)
+            for b in bad.nonzero().flatten().tolist():
+                if vm[b].item() > MARGIN[precision]:
+                    problems.append((run["kw"], "video %d differs with margin %.2e" % (b, vm[b].item())))
+                else:
+                    print("NOTE video %d: sub-margin decision (%.2e) flipped for %s" % (b, vm[b].item(), run["kw"]))
+            if stats["passes"] != run["passes"] and vm.min().item() > MARGIN[precision]:
+                problems.append((run["kw"], "passes %d != %d" % (stats["passes"], run["passes"])))
+            continue
         if stats["passes"] != run["passes"] and margin > MARGIN[precision]:
             problems.append((run["kw"], "passes %d != %d" % (stats["passes"], run["passes"])))
         if not same:
@@ -95,6 +112,38 @@ def test_translate_ids_match_golden(path, precision):
             else:
                 print("NOTE sub-margin decision (%.2e) flipped for %s" % (margin, run["kw"]))
     assert not problems, problems
+
+
+@pytest.mark.parametrize("path", [p for p in DEC if "dk64" in p or "wide" in p], ids=lambda p: os.path.basename(p)[:-3])
+def test_translate_goldens_through_graph_replay(path):
+    """Same dk = 64 goldens through the path bench.py times: the third call of a (batch, Smax) shape replays the
+    captured CUDA graph of the whole mask-predict loop (packed rows, tcgen05 attention cores, second-level vocabulary
+    packing) -- ids must equal the reference's on every video whose margin clears the mode's error."""
+    g = torch.load(path, weights_only=False)
+    sc = g.get("wscale", 1.0)
+    model = build(g["opt"], g["shapes"], g["wseed"], "bf16x3", sc)
+    teacher = build(g["teacher_opt"], g["teacher_shapes"], g["wseed"] + 1, "bf16x3", sc) if "teacher_opt" in g else None
+    feats, category = cases.synth_inputs(g["opt"], g["batch"])
+    feats, category = to_dev(feats), category.to(DEV)
+    problems, replays = [], 0
+    for run in g["runs"]:
+        if run["kw"].get("paradigm", "mp") != "mp":
+            continue
+        opt = dict(g["opt"], **run["kw"])
+        tr = navc_b200.Translator(model, opt, device=DEV, teacher_model=teacher)
+        for rep in range(3):
+            with torch.no_grad():
+                enc = model.encode(feats=feats)
+                t_enc = teacher.encode(feats=feats) if teacher is not None else None
+                hyp, _ = tr.translate_batch(enc, category, None, {}, teacher_encoder_outputs=t_enc)
+        stats = navc_b200.generate.last_stats
+        assert stats["graph"] and stats["packed"], stats
+        replays += 1
+        vm = run["video_margin"]
+        for b in (hyp.cpu() != run["hyp"]).any(1).nonzero().flatten().tolist():
+            if vm[b].item() > MARGIN["bf16x3"]:
+                problems.append((run["kw"], "video %d differs with margin %.2e" % (b, vm[b].item())))
+    assert replays > 0 and not problems, problems
 
 
 def test_decoder_and_vocab_attributes_match_oracle():
@@ -139,42 +188,57 @@ def test_midsize_translate_matches_oracle(precision):
     with torch.no_grad():
         enc = model.encode(feats=to_dev(feats))
         hyp, _ = tr.translate_batch(enc, category.to(DEV), None, {})
-    margin = min(det["min_top2_gap"], det["min_select_gap"], det["min_candidate_gap"])
-    rows_equal = (hyp.cpu() == hyp_o).all(1).float().mean().item()
-    print("margin %.2e rows equal %.3f" % (margin, rows_equal))
-    if margin > MARGIN[precision]:
-        assert torch.equal(hyp.cpu(), hyp_o)
-    else:
-        assert rows_equal >= 0.9
+    n_eq, n_above = check_against_oracle(hyp, hyp_o, det["video_margin"], precision, "midsize")
+    print("midsize [%s]: %d/24 videos equal the oracle, %d/24 clear the margin" % (precision, n_eq, n_above))
+    assert n_above >= 12, det["video_margin"].tolist()
 
 
-def test_full_size_properties():
-    """BASELINE config 2 shape (B=32 here): size-independent properties of the decode --
-    (i) deterministic / idempotent, (ii) PAD beyond each chosen length and no MASK-only rows,
-    (iii) fp32 and bf16x3 modes agree on >= 99% of tokens, (iv) the candidate picked maximises the
-    length-normalised score."""
+def check_against_oracle(hyp, hyp_o, video_margin, precision, what):
+    """Every video whose smallest decision margin (oracle `video_margin`, log units) clears the mode's error must carry
+    the oracle's ids exactly; every differing video is printed with its margin.  Returns (#equal, #above margin)."""
+    hyp = hyp.cpu()
+    assert hyp.shape == hyp_o.shape, (what, hyp.shape, hyp_o.shape)
+    equal = (hyp == hyp_o).all(1)
+    above = video_margin > MARGIN[precision]
+    problems = []
+    for b in (~equal).nonzero().flatten().tolist():
+        line = "%s [%s] video %d differs, margin %.2e (mode error bound %.0e)" % (what, precision, b, video_margin[b].item(), MARGIN[precision])
+        print(line)
+        if above[b]:
+            problems.append(line)
+    assert not problems, problems
+    return int(equal.sum()), int(above.sum())
+
+
+def test_full_size_ids_match_oracle():
+    """BASELINE config 2 (the shape and options bench.py times; B=16 here so the CPU oracle finishes in seconds):
+    fp32 and bf16x3 ids against the oracle's, video by video, through eager launches AND the replayed CUDA graph;
+    plus size-independent properties (deterministic, 6 passes, packed rows on the tensor-core path)."""
     opt = cases.config2()
     torch.manual_seed(0)
-    model = navc_b200.get_model(opt).to(DEV).eval()
-    feats, category = cases.synth_inputs(opt, 32)
+    model = navc_b200.get_model(opt)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.to(DEV).eval()
+    feats, category = cases.synth_inputs(opt, 16)
+    hyp_o, det = O.translate(sd, opt, feats, category, return_details=True)
+    vm = det["video_margin"]
     feats, category = to_dev(feats), category.to(DEV)
-    out = {}
     for precision in ("fp32", "bf16x3"):
         model.set_precision(precision)
         tr = navc_b200.Translator(model, opt, device=DEV)
-        with torch.no_grad():
-            enc = model.encode(feats=feats)
-            h1, _ = tr.translate_batch(enc, category, None, {})
-            enc = model.encode(feats=feats)
-            h2, _ = tr.translate_batch(enc, category, None, {})
-        assert torch.equal(h1, h2)
-        assert navc_b200.generate.last_stats["passes"] == 6
-        out[precision] = h1.cpu()
-    a, b = out["fp32"], out["bf16x3"]
-    assert a.shape == b.shape and a.shape[0] == 32
-    assert (a == b).float().mean().item() >= 0.99
-    # PAD is a suffix or an interior predicted <pad>; every row has at least 4 non-pad positions
-    assert ((a != 0).sum(1) >= 1).all()
+        hyps = []
+        for rep in range(3):  # eager, capture, replay
+            with torch.no_grad():
+                enc = model.encode(feats=feats)
+                h, _ = tr.translate_batch(enc, category, None, {})
+            hyps.append(h.cpu())
+        st = navc_b200.generate.last_stats
+        assert st["passes"] == det["passes"] == 6 and st["graph"]
+        assert st["packed"] == (precision != "fp32")
+        assert torch.equal(hyps[0], hyps[1]) and torch.equal(hyps[1], hyps[2])   # eager == captured == replayed
+        n_eq, n_above = check_against_oracle(hyps[2], hyp_o, vm, precision, "config 2")
+        print("config 2 [%s]: %d/16 videos equal the oracle, %d/16 clear the margin" % (precision, n_eq, n_above))
+        assert n_above >= 6, "margins too small for this check to mean anything: %s" % vm.tolist()
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
@@ -371,17 +435,19 @@ def test_decoder_step_equals_last_row_of_full_pass():
 
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 def test_packed_rows_match_padded_layout(precision):
-    """Packed-row decoding (only the sum(len) real positions are decoder rows; include/navc.h
-    "packed rows") returns the ids of the padded [N, S] layout it replaces, for mask-predict with and
-    without coarse-grained templates and for easy-first, at the headline head size (dk = 64)."""
+    """Packed-row decoding (only the sum(len) real positions are decoder rows; include/navc.h "packed rows") and the
+    padded [N, S] layout it replaces, both against the ORACLE's ids video by video (not against each other), for
+    mask-predict with and without coarse-grained templates and for easy-first, at the headline head size (dk = 64)."""
     for kw in (dict(paradigm="mp", use_ct=True), dict(paradigm="mp", use_ct=False), dict(paradigm="ef", use_ct=True, q=2)):
-        opt = cases.small("NACF", dim_hidden=512, num_attention_heads=8, intermediate_size=1024, max_len=30,
-                          length_beam_size=5, navc_graphs=False, **kw)
-        torch.manual_seed(0)
-        model = navc_b200.get_model(opt).to(DEV).eval()
+        opt = cases.wide("NACF", navc_graphs=False, **kw)
+        model = navc_b200.get_model(opt)
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        sd = cases.synth_state_dict(shapes, 11, 0.5)
+        model.load_state_dict(sd)
+        model.to(DEV).eval()
         model.set_precision(precision)
         feats, category = cases.synth_inputs(opt, 9)
-        outs = {}
+        hyp_o, det = O.translate(sd, opt, feats, category, return_details=True)
         for packed in (0, 1):
             tr = navc_b200.Translator(model, dict(opt, navc_packed=packed), device=DEV)
             with torch.no_grad():
@@ -389,8 +455,6 @@ def test_packed_rows_match_padded_layout(precision):
                 hyp, _ = tr.translate_batch(enc, category.to(DEV), None, {})
             st = navc_b200.generate.last_stats
             assert st["packed"] == bool(packed) and st["rows_real"] <= st["N"] * st["S"]
-            outs[packed] = hyp.cpu()
-        agree = (outs[0] == outs[1]).float().mean().item()
-        # same arithmetic per row up to the accumulation order of the tile a row lands in (~1e-5 on the
-        # hidden states): ids agree except on near-tied decisions
-        assert agree > 0.97, (kw, agree)
+            n_eq, n_above = check_against_oracle(hyp, hyp_o, det["video_margin"], precision, "%s packed=%d" % (kw, packed))
+            if precision == "bf16x3":
+                assert n_above >= 5, det["video_margin"].tolist()

@@ -843,3 +843,79 @@ def test_wgrad_tc_mn_major(mode, tol, rows, n_out, k_in, split):
            rows, n_out, k_in, ep, L.stream())
     ref = base.double() + dy.double().t() @ x.double()
     close(out, ref, tol, "wgrad")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_tied_vocabulary_projection_forward_and_gradients(precision):
+    """opt['tie_weights'] (models/seq2seq.py:30-33): tgt_word_prj shares the word-embedding Parameter (and gains a
+    bias).  The engine must resolve both state_dict names, and the shared Parameter's gradient is the SUM of the
+    embedding-lookup and the projection contributions."""
+    opt = cases.small("NAB", hidden_dropout_prob=0.0, encoder_dropout=0.0, tie_weights=True, num_attention_heads=2)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt)
+    emb_key = "decoder.embedding.word_embeddings.weight"
+    assert model.tgt_word_prj.weight is dict(model.named_parameters())[emb_key]
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(cases.synth_state_dict(shapes, 13))
+    with torch.no_grad():
+        model.tgt_word_prj.bias.normal_(0.0, 0.05, generator=torch.Generator().manual_seed(5))
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.to(DEV)
+    model.set_precision(precision)
+    feats, category = cases.synth_inputs(opt, 6)
+    toks = cases.synth_tokens(opt, 6, kind="nar")
+    dev = lambda t: [x.to(DEV) for x in t] if isinstance(t, (list, tuple)) else t.to(DEV)
+    # eval forward
+    model.eval()
+    with torch.no_grad():
+        res = model(feats=dev(feats), tgt_tokens=toks["tokens"].to(DEV), category=category.to(DEV))
+        ref = O.model_forward(sd0, opt, feats, toks["tokens"], category)
+    assert (res["tgt_word_logprobs"][0].cpu() - ref["tgt_word_logprobs"][0]).abs().max().item() < 5e-4
+    # training forward / backward
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd0.items()}
+    sd["tgt_word_prj.weight"] = sd[emb_key]   # one leaf behind both names
+    bn_state = {}
+    ref = O.model_forward(sd, opt, feats, toks["tokens"], category, training=True, bn_state=bn_state)
+    ref_loss = O.criterion(opt, ref, toks["labels"], toks["length_target"])
+    ref_loss.backward()
+    model.train()
+    res = model(feats=dev(feats), tgt_tokens=toks["tokens"].to(DEV), category=category.to(DEV))
+    loss = O.criterion(opt, res, toks["labels"].to(DEV), toks["length_target"].to(DEV))
+    loss.backward()
+    tol = GRAD_TOL[precision]
+    assert abs(loss.item() - ref_loss.item()) < tol * max(1.0, abs(ref_loss.item()))
+    checked = 0
+    for name, p in model.named_parameters():
+        rg = sd[name].grad
+        if rg is None or rg.abs().max().item() == 0:
+            continue
+        assert p.grad is not None, name
+        close(p.grad, rg, tol, name, atol=2e-7)
+        checked += 1
+    assert checked > 15 and model.tgt_word_prj.bias.grad is not None
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_layernorm_encoder_norm_matches_oracle(precision):
+    """norm_type='ln' (models/joint_representation.py:20, 46-47): nn.LayerNorm per frame row instead of BatchNorm1d."""
+    opt = cases.small("NACF", norm_type="ln", num_attention_heads=2, use_ct=True)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert "joint_representation_learner.ln0.weight" in shapes
+    sd = cases.synth_state_dict(shapes, 17)
+    model.load_state_dict(sd)
+    model.to(DEV).eval()
+    model.set_precision(precision)
+    feats, category = cases.synth_inputs(opt, 6)
+    with torch.no_grad():
+        enc = model.encode(feats=[f.to(DEV) for f in feats])
+        ref = O.encode(sd, opt, feats)
+    tol = 1e-4 if precision == "fp32" else 5e-4
+    for k in ("enc_output", "enc_hidden", "pred_length"):
+        assert (enc[k].cpu() - ref[k]).abs().max().item() < tol, k
+    hyp_o, det = O.translate(sd, opt, feats, category, return_details=True)
+    with torch.no_grad():
+        hyp, _ = navc_b200.Translator(model, opt, device=DEV).translate_batch(enc, category.to(DEV), None, {})
+    for b in (hyp.cpu() != hyp_o).any(1).nonzero().flatten().tolist():
+        assert det["video_margin"][b].item() <= 1e-4, (b, det["video_margin"][b].item())

@@ -79,10 +79,11 @@ def test_gradient_golden(path):
 @pytest.mark.parametrize("path", DEC, ids=[os.path.basename(p)[:-3] for p in DEC])
 def test_decode_golden(path):
     g = load(path)
-    sd = cases.synth_state_dict(g["shapes"], g["wseed"])
+    sc = g.get("wscale", 1.0)
+    sd = cases.synth_state_dict(g["shapes"], g["wseed"], sc)
     teacher = None
     if "teacher_opt" in g:
-        teacher = (cases.synth_state_dict(g["teacher_shapes"], g["wseed"] + 1), g["teacher_opt"])
+        teacher = (cases.synth_state_dict(g["teacher_shapes"], g["wseed"] + 1, sc), g["teacher_opt"])
     feats, category = cases.synth_inputs(g["opt"], g["batch"])
     for run in g["runs"]:
         opt = dict(g["opt"], **run["kw"])
@@ -90,6 +91,8 @@ def test_decode_golden(path):
         assert det["passes"] == run["passes"], run["kw"]
         assert torch.equal(det["beam"], run["beam"]), run["kw"]
         assert torch.equal(hyp, run["hyp"]), run["kw"]
+        if "video_margin" in run:
+            torch.testing.assert_close(det["video_margin"], run["video_margin"], rtol=1e-3, atol=1e-6)
 
 
 def test_tie_break_is_lowest_index_first():

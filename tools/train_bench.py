@@ -78,6 +78,146 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+def train_opt(method, fused_ce=False):
+    """BASELINE configs 3 / 5: the config-2 model shape in training."""
+    kw = dict(dim_hidden=512, num_hidden_layers_decoder=6, intermediate_size=2048, dim_i=2048, dim_m=2048,
+              n_frames=60, max_len=30, vocab_size=10547)
+    opt = cases.make_opt(method, **kw)
+    opt["navc_fused_ce"] = bool(fused_ce)
+    nar = opt["decoding_type"] == "NARFormer"
+    opt.update(crit_key=[("tgt_word_logprobs", "tgt_word_labels")] + ([("pred_length", "tgt_length")] if nar else []),
+               crit_name=["Cap Loss"] + (["Length Loss"] if nar else []), crit_scale=[1.0] + ([1.0] if nar else []),
+               optim="adam", learning_rate=5e-4, minimum_learning_rate=5e-5, decay=0.9, weight_decay=5e-4, grad_clip=5)
+    return opt
+
+
+def measure(method, B, steps, warmup, precision="bf16x3", fused_ce=False, torch_optim=False, dev=None, seed_rank=0):
+    """Time `steps` training steps of `method` at B samples on THIS rank (torch.distributed, if initialised, supplies
+    the ONE gradient all-reduce per step and the max-over-ranks time).  Returns a dict (every rank)."""
+    import torch.distributed as dist
+    import navc_b200
+    from navc_b200 import _lib as L, parallel
+    from navc_b200.misc import crit as ncrit
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dev = dev or torch.device("cuda", torch.cuda.current_device())
+    opt = train_opt(method, fused_ce)
+    crit = ncrit.get_criterion(opt)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt).to(dev)
+    model.set_precision(precision)
+    model.train()
+    dp = parallel.GradientAllReduce(model)
+    if torch_optim:
+        optim = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-4)
+    else:
+        from navc_b200 import optim as nopt
+        optim = nopt.get_optimizer(opt, model, grads=dp)
+    n_rot = 3
+    batches = [make_batch(opt, B, 1234 + 31 * r + 1000 * (rank + seed_rank), dev) for r in range(n_rot)]
+
+    def step(i):
+        b = batches[i % n_rot]
+        dp.zero_grad()
+        res = model(feats=b["feats"], tgt_tokens=b["tgt"], category=b["category"])
+        if not fused_ce:
+            loss = reference_loss(opt, res, b["labels"], b["lt"])
+        else:
+            res["tgt_word_labels"], res["tgt_length"] = b["labels"], b["lt"]
+            loss = crit.get_loss(res)
+        loss.backward()
+        dp.allreduce()
+        if torch_optim:
+            torch.nn.utils.clip_grad_value_(model.parameters(), 5)
+        optim.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(warmup, 3)):
+        loss = step(i)
+    barrier()
+    l0 = L.launches
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    marks[0].record()
+    for i in range(steps):
+        loss = step(i)
+        marks[i + 1].record()
+    barrier()
+    ms = marks[0].elapsed_time(marks[-1])
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    out = {"method": method, "samples_per_s": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps,
+           "batch_per_gpu": B, "global_batch": B * world, "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+           "precision": precision, "gpu_launches": L.launches - l0, "final_loss": float(loss.item()),
+           "allreduce_bytes": dp.nbytes if world > 1 else 0, "params": sum(p.numel() for p in model.parameters()),
+           "per_step_ms": {"min": round(per_step[0], 3), "median": round(per_step[len(per_step) // 2], 3),
+                           "max": round(per_step[-1], 3)},
+           "rows": "%d of %d decoder rows (packed)" % model.engine.last_train_rows
+                   if getattr(model.engine, "last_train_rows", None) else None,
+           "step": "fwd (dropout 0.5, BN batch stats) + loss + bwd + %s + %s" % (
+               "one NCCL all-reduce (AVG) of the flat fp32 gradient buffer" if world > 1 else "no collective (1 rank)",
+               "torch clip_grad_value_ + Adam" if torch_optim else "fused clip + Adam (navc_clip_adam, one launch)")}
+    out["_step"], out["_model"] = step, model
+    return out
+
+
+def reference_train_cpu(method, B, steps, warmup):
+    """The reference's OWN training step (misc/run.py:254-261: model(**batch) -> Criterion.get_loss -> backward ->
+    clip_grad_value_ -> Adam) on the host cores, unmodified code from /root/reference or baseline/_ref; None if the
+    reference is not installed."""
+    import contextlib
+    import io
+    import warnings
+    import refutil
+    if not refutil.reference_available():
+        return None
+    opt = train_opt(method)
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = make_batch(opt, B, 1234, torch.device("cpu"))
+    with refutil.reference_on_path(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from models import get_model
+        from misc.crit import get_criterion
+        from misc.optim import get_optimizer
+        from torch.nn.utils import clip_grad_value_
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = get_model(dict(opt))
+        model.train()
+        crit = get_criterion(opt)
+        crit.reset_loss_recorder()
+        optimizer = get_optimizer(opt, model)
+
+        def step():
+            optimizer.zero_grad()
+            res = model(feats=b["feats"], tgt_tokens=b["tgt"], category=b["category"], opt=opt, vocab=None)
+            res["tgt_word_labels"] = b["labels"]
+            if b["lt"] is not None:
+                res["tgt_length"] = b["lt"]
+            loss = crit.get_loss(res)
+            loss.backward()
+            clip_grad_value_(model.parameters(), opt["grad_clip"])
+            optimizer.step()
+            return loss
+
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = step()
+        dt = time.perf_counter() - t0
+    return {"method": method, "samples_per_s": B * steps / dt, "ms_per_step": dt / steps * 1e3, "batch": B,
+            "cores": torch.get_num_threads(), "kind": "reference", "final_loss": float(loss.item()),
+            "step": "unmodified reference: model(**batch), misc.crit.Criterion, backward, clip_grad_value_(5), Adam (misc/run.py:254-261)"}
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -92,13 +232,12 @@ def main():
                     "the logits and the criterion's meters add host syncs) instead of the reference's loss on materialised log-probs")
     ap.add_argument("--torch-optim", action="store_true", help="caller-side clip_grad_value_ + torch.optim.Adam instead of the fused navc_clip_adam step")
     ap.add_argument("--profile", action="store_true", help="print a per-kernel device-time breakdown of one step")
+    ap.add_argument("--cpu-reference", type=int, default=0, help="also time the unmodified reference's train step on the host cores at this batch")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import torch.distributed as dist
-    import navc_b200
-    from navc_b200 import _lib as L, parallel
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -107,84 +246,21 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version / debug lines off stdout (one JSON line)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     B = args.global_batch // world if args.global_batch else args.batch
-    kw = dict(dim_hidden=512, num_hidden_layers_decoder=6, intermediate_size=2048, dim_i=2048, dim_m=2048,
-              n_frames=60, max_len=30, vocab_size=10547)
-    opt = cases.make_opt(args.method, **kw)
-    opt["navc_fused_ce"] = bool(args.fused_ce)
-    nar = opt["decoding_type"] == "NARFormer"
-    opt.update(crit_key=[("tgt_word_logprobs", "tgt_word_labels")] + ([("pred_length", "tgt_length")] if nar else []),
-               crit_name=["Cap Loss"] + (["Length Loss"] if nar else []), crit_scale=[1.0] + ([1.0] if nar else []))
-    from navc_b200.misc import crit as ncrit
-    crit = ncrit.get_criterion(opt)
-    torch.manual_seed(0)
-    model = navc_b200.get_model(opt).to(dev)
-    model.set_precision(args.precision)
-    model.train()
-    dp = parallel.GradientAllReduce(model)
-    if args.torch_optim:
-        optim = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-4)
-    else:
-        from navc_b200 import optim as nopt
-        opt.update(optim="adam", learning_rate=5e-4, minimum_learning_rate=5e-5, decay=0.9, weight_decay=5e-4, grad_clip=5)
-        optim = nopt.get_optimizer(opt, model, grads=dp)
-    n_rot = 3
-    batches = [make_batch(opt, B, 1234 + 31 * r + 1000 * rank, dev) for r in range(n_rot)]
-
-    def step(i):
-        b = batches[i % n_rot]
-        dp.zero_grad()
-        res = model(feats=b["feats"], tgt_tokens=b["tgt"], category=b["category"])
-        if not args.fused_ce:
-            loss = reference_loss(opt, res, b["labels"], b["lt"])
-        else:
-            res["tgt_word_labels"], res["tgt_length"] = b["labels"], b["lt"]
-            loss = crit.get_loss(res)
-        loss.backward()
-        dp.allreduce()
-        if args.torch_optim:
-            torch.nn.utils.clip_grad_value_(model.parameters(), 5)
-        optim.step()
-        return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(args.warmup, 3)):
-        loss = step(i)
-    barrier()
-    l0 = L.launches
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    marks[0].record()
-    for i in range(args.steps):
-        loss = step(i)
-        marks[i + 1].record()
-    barrier()
-    ms = marks[0].elapsed_time(marks[-1])
-    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    launches = L.launches - l0
+    r = measure(args.method, B, args.steps, args.warmup, args.precision, args.fused_ce, args.torch_optim, dev)
+    step = r.pop("_step")
+    r.pop("_model")
     if rank == 0:
-        nparams = sum(p.numel() for p in model.parameters())
         line = {"metric": "training samples/sec (%s 6-layer d512, fwd+bwd+allreduce+clip+Adam)" % args.method,
-                "value": world * B * args.steps / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong" if args.global_batch else "weak", "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": "%s training step, feats 2x60x2048, max_len 30, vocab 10547, dropout 0.5" % args.method,
-                           "batch_per_gpu": B, "global_batch": B * world, "params": nparams,
-                           "optimizer": "torch clip_grad_value_ + Adam" if args.torch_optim else "fused navc_clip_adam (one launch)",
+                           "batch_per_gpu": B, "global_batch": B * world, "params": r["params"], "step": r["step"],
                            "loss": "torch log-probs + NLL" if not args.fused_ce else "fused cross-entropy (navc_b200.misc.crit, incl. its accuracy / perplexity meters)",
-                           "allreduce_bytes": dp.nbytes if world > 1 else 0,
-                           "l2": "inputs rotate over %d distinct batches" % n_rot},
-                "gpu_launches": launches, "final_loss": float(loss.item()),
-                "per_step_ms": {"min": round(per_step[0], 3), "median": round(per_step[len(per_step) // 2], 3),
-                                "max": round(per_step[-1], 3)},
-                "rows": "%d of %d decoder rows (packed)" % model.engine.last_train_rows
-                        if getattr(model.engine, "last_train_rows", None) else None}
+                           "allreduce_bytes": r["allreduce_bytes"], "l2": "inputs rotate over 3 distinct batches"},
+                "gpu_launches": r["gpu_launches"], "final_loss": r["final_loss"], "per_step_ms": r["per_step_ms"], "rows": r["rows"]}
+        if args.cpu_reference:
+            line["cpu_reference"] = reference_train_cpu(args.method, args.cpu_reference, 2, 1)
         emit(line)
     if args.profile and rank == 0:
         from torch.profiler import profile, ProfilerActivity
