@@ -11,6 +11,8 @@ from torch.profiler import profile, ProfilerActivity
 
 precision = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+# "range": only one step is visible to `ncu --profile-from-start off` (cudaProfilerStart/Stop around it), then exit
+RANGE = len(sys.argv) > 3 and sys.argv[3] == "range"
 dev = torch.device("cuda", 0)
 opt = cases.config2()
 torch.manual_seed(0)
@@ -26,6 +28,12 @@ with torch.no_grad():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    if RANGE:
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        sys.exit(0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); step(); e1.record(); torch.cuda.synchronize()
     print("step ms (events): %.2f" % e0.elapsed_time(e1))
