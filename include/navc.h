@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NAVC_VERSION 2
+#define NAVC_VERSION 3
 
 /* token ids, config/Constants.py:1-6 */
 #define NAVC_PAD 0
@@ -67,6 +67,9 @@ typedef struct {
     const uint16_t* res_lo;     /* NULL); needs bf16-only outputs (out_f32 == NULL, residual == NULL), N % 8 == 0 */
     const int32_t* m_dev;       /* tcgen05 path: optional DEVICE scalar; only the first min(M, *m_dev) rows are computed
                                    (packed-row decoding: the row count is known on the device only) */
+    int32_t m_hint;             /* optional HOST estimate of *m_dev (0 = none): only steers the tile shape / cluster choice
+                                   of the launch, never the result */
+    int32_t pad_;
 } navc_epilogue_t;
 
 int navc_version(void);

@@ -21,7 +21,8 @@ i32, i64, u64, f32, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
 class Epilogue(C.Structure):
     _fields_ = [("bias", vp), ("residual", vp), ("row_tokens", vp), ("act", i32), ("ld_res", i32),
                 ("out_f32", vp), ("out_hi", vp), ("out_lo", vp), ("ld_out", i32), ("reserved", i32),
-                ("split_k", i32), ("accumulate", i32), ("res_hi", vp), ("res_lo", vp), ("m_dev", vp)]
+                ("split_k", i32), ("accumulate", i32), ("res_hi", vp), ("res_lo", vp), ("m_dev", vp),
+                ("m_hint", i32), ("pad_", i32)]
 
 
 class Step(C.Structure):

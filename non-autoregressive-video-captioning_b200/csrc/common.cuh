@@ -113,6 +113,7 @@ struct EpiParams {
     const uint16_t* res_hi;  // bf16 hi/lo residual (tcgen05 pair epilogue)
     const uint16_t* res_lo;
     const int* m_dev;        // device-side row count (tcgen05 path)
+    int m_hint;              // host estimate of *m_dev (tile-shape choice only; 0 = none)
     // split-K of the tiles of the last, partly filled wave of the persistent grid (set by the launcher, pair epilogue):
     float* sk_ws;            // partial accumulator tiles [slot][128][TBN] fp32, NULL = off
     int* sk_cnt;             // [2 * grid] arrival / departure counters, all zero between launches
@@ -129,6 +130,7 @@ static inline EpiParams to_params(const navc_epilogue_t* e) {
     p.res_hi = e->res_hi;
     p.res_lo = e->res_lo;
     p.m_dev = e->m_dev;
+    p.m_hint = e->m_hint;
     p.sk_ws = nullptr; p.sk_cnt = nullptr; p.sk_err = nullptr;
     return p;
 }

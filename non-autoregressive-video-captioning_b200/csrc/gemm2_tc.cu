@@ -1,0 +1,422 @@
+// tcgen05 GEMM of the inference hot path, second generation:  Y = epilogue(X[M,K] * W[N,K]^T), bf16 hi(/lo) outputs.
+//
+// Same pipeline as gemm_tc.cu (TMA 128B swizzle -> shared-memory ring -> tcgen05.mma 128xNx16, fp32 accumulators in
+// TMEM, double buffered -> tcgen05.ld -> fused "pair" epilogue: bias / activation / bf16 hi+lo residual / non-pad row
+// mask / bf16 hi+lo split, TMA stores), rebuilt around what the round-2 measurements showed (profiles/r2a_*): in the
+// split-bf16 mode every projection GEMM of the decoder layer was bound by the L2 -> shared-memory operand stream
+// (96 KB per k-block and CTA for a 128x256 tile: 8.5-9.3 TB/s over 148 SMs), not by the tensor pipe, and the
+// N = 512 GEMMs additionally lost a third of their last wave.
+//
+//  * Thread-block clusters of 2 CTAs along M share the B (weight) tile: each CTA loads half of it and TMA-multicasts
+//    it into both CTAs' rings (`.multicast::cluster`), so a CTA pulls 64 KB instead of 96 KB per k-block from L2.
+//    The ring's "slot free" barriers count the MMA commits of BOTH CTAs (tcgen05.commit ... multicast::cluster),
+//    because a CTA's TMA writes into its partner's slot.
+//  * Tail split along N: the tiles of the last, partly filled wave of the persistent grid are cut into 2 or 4 column
+//    parts (UMMA N = TBN/2, TBN/4) that run on the otherwise idle SMs.  Unlike a split along K (gemm_tc.cu's tail
+//    split, measured slower) no partial sums have to be handed over: every part owns its output columns.
+//  * The bf16 hi/lo residual of the first epilogue step is requested BEFORE the accumulator barrier is awaited and
+//    every later step's residual one step ahead, so its L2 latency overlaps the main loop / the previous step.
+//
+// Warp roles (576 threads, persistent, one CTA per SM): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
+// warps 2..17 epilogue (warp = TMEM lane quarter x column group of TBN/4; lane = row; 16-column steps).
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace navc {
+
+constexpr int G2_BM = 128, G2_BK = 64;
+constexpr int G2_EPI_WARPS = 16;
+constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
+constexpr int G2_ACC = 2;            // TMEM accumulator stages (2 x TBN columns)
+constexpr int G2_TILE_A = G2_BM * G2_BK * 2;   // 16 KB
+
+template <bool kX3, int TBN> struct G2Cfg {
+    static constexpr int kTileB = TBN * G2_BK * 2;
+    static constexpr int kStageBytes = (kX3 ? 2 : 1) * (G2_TILE_A + kTileB);
+    static constexpr int kStages = 196608 / kStageBytes;           // 2 (x3, 256) / 3 (x3, 128) / 4 (bf16, 256) / 6 (bf16, 128)
+    static constexpr int kRingBytes = kStages * kStageBytes;
+    static constexpr int kStgBytes = G2_EPI_WARPS * 2048;          // per warp: hi box (1 KB) + lo box (1 KB)
+    static constexpr int kSmemBytes = kRingBytes + kStgBytes + 1024 /*align*/ + 512 /*barriers*/;
+    static_assert(kStages >= 2, "operand ring needs at least two stages");
+};
+
+struct G2Unit { int mb, n0, w; bool valid; };
+
+template <bool kX3, int TBN, int kCl>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+                int M_max, int N, int K, EpiParams epi) {
+    using Cfg = G2Cfg<kX3, TBN>;
+    constexpr int kTileB = Cfg::kTileB;
+    const int M = epi.m_dev ? min(M_max, __ldg(epi.m_dev)) : M_max;   // device-side row count (packed rows)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint8_t* stg_all = smem_gen + Cfg::kRingBytes;
+    const uint32_t bar_off = Cfg::kRingBytes + Cfg::kStgBytes;
+    const uint32_t bar_base = smem_base + bar_off;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + G2_ACC + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + bar_off + 8 * (2 * Cfg::kStages + 2 * G2_ACC));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = kCl > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = (int)blockIdx.x / kCl, G = (int)gridDim.x / kCl;   // cluster index, clusters in the grid
+
+    // ---- schedule: a unit = one (row group of kCl m-blocks, column block) tile per cluster; the units of the last,
+    //      partly filled wave are cut into p column parts of TBN / p columns ----
+    const int m_blocks = (M + G2_BM - 1) / G2_BM, n_blocks = (N + TBN - 1) / TBN;
+    const int k_blocks = (K + G2_BK - 1) / G2_BK;   // TMA zero-fills the K tail
+    const int n_units = ((m_blocks + kCl - 1) / kCl) * n_blocks;
+    const int full = (n_units / G) * G, rem = n_units - full;
+    int parts = 1;
+    if (rem > 0 && epi.dbg != 7) {
+        const int q = G / rem;
+        parts = q >= 4 ? 4 : (q >= 2 ? 2 : 1);
+        if (parts > TBN / 64) parts = TBN / 64;     // parts keep >= 64 columns
+    }
+    const int total = full + rem * parts;
+    auto get_unit = [&](int it, G2Unit& u) -> bool {
+        const int t = cid + it * G;
+        if (t >= total) return false;
+        int ui, part = 0;
+        u.w = TBN;
+        if (t < full) {
+            ui = t;
+        } else {
+            const int x = t - full;
+            ui = full + x / parts;
+            part = x - (x / parts) * parts;
+            u.w = TBN / parts;
+        }
+        const int mg = ui / n_blocks, nb = ui - mg * n_blocks;   // column block fastest: concurrent clusters share the A rows in L2
+        u.mb = mg * kCl + crank;
+        u.n0 = nb * TBN + part * u.w;
+        u.valid = u.mb < m_blocks && u.n0 < N;
+        return true;
+    };
+
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kCl); }
+        for (int s = 0; s < G2_ACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), G2_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (kCl > 1) cluster_sync_all();   // the partner's barriers must be initialised before anything of ours can reach them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            G2Unit u;
+            for (int it = 0; get_unit(it, u); ++it) {
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);   // both CTAs' MMAs are done with this slot (in both CTAs)
+                    const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                    mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * G2_BK, u.mb * G2_BM);
+                    if (kX3) tma_load_2d(sa + G2_TILE_A + kTileB, &map_a_lo, full_bar(stage), kb * G2_BK, u.mb * G2_BM);
+                    if constexpr (kCl > 1) {
+                        // my half of the B rows, delivered to both CTAs of the cluster
+                        const int brow = u.n0 + crank * (TBN / 2);
+                        const uint32_t off = (uint32_t)(crank * (TBN / 2) * 128);
+                        tma_load_2d_mc(sa + G2_TILE_A + off, &map_b_hi, full_bar(stage), kb * G2_BK, brow, (uint16_t)0x3);
+                        if (kX3) tma_load_2d_mc(sa + 2 * G2_TILE_A + kTileB + off, &map_b_lo, full_bar(stage), kb * G2_BK, brow, (uint16_t)0x3);
+                    } else {
+                        tma_load_2d(sa + G2_TILE_A, &map_b_hi, full_bar(stage), kb * G2_BK, u.n0);
+                        if (kX3) tma_load_2d(sa + 2 * G2_TILE_A + kTileB, &map_b_lo, full_bar(stage), kb * G2_BK, u.n0);
+                    }
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            G2Unit u;
+            for (int it = 0; get_unit(it, u); ++it) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TBN);
+                const uint32_t idesc = make_idesc(G2_BM, u.w);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                    const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sa + G2_TILE_A);
+                    const uint64_t da_lo = make_smem_desc(sa + G2_TILE_A + kTileB), db_lo = make_smem_desc(sa + 2 * G2_TILE_A + kTileB);
+#pragma unroll
+                    for (int k = 0; k < G2_BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        if (kX3) {
+                            // small cross terms first, the dominant hi*hi product last
+                            tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
+                        } else {
+                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    if constexpr (kCl > 1) tc_commit_mc(empty_bar(stage), (uint16_t)0x3); else tc_commit(empty_bar(stage));
+                    if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..17) =====================
+        constexpr int GW = TBN / 4, STEPS = GW / 16;
+        const int ew = warp - 2;
+        const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+        const int grp = ew >> 2;        // column group [grp * GW, grp * GW + GW) of the tile
+        uint8_t* stg = stg_all + ew * 2048;   // hi box at +0, lo box at +1024
+        const uint32_t stg_s = smem_u32(stg);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        G2Unit u;
+        for (int it = 0; get_unit(it, u); ++it) {
+            const int row0 = u.mb * G2_BM + quarter * 32;
+            const int rowp = row0 + lane;
+            const bool row_ok = u.valid && rowp < M;
+            const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[rowp] == NAVC_PAD) : false;
+            const int cl0 = grp * GW;                       // first tile-local column of this warp
+            const bool active = u.valid && cl0 < u.w && u.n0 + cl0 < N && row0 < M;   // warp-uniform
+            // residual of one 16-column step: 2 x 16 bytes of hi (+ lo) per row
+            uint4 rh[2][2], rl[2][2];
+            auto load_res = [&](int c, uint4 (&h)[2], uint4 (&l)[2]) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    h[i] = make_uint4(0u, 0u, 0u, 0u);
+                    l[i] = make_uint4(0u, 0u, 0u, 0u);
+                    const int col = u.n0 + cl0 + c * 16 + i * 8;
+                    if (epi.res_hi && row_ok && cl0 + c * 16 < u.w && col < N) {
+                        const size_t ro = (size_t)rowp * epi.ld_res + col;
+                        h[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
+                        if (epi.res_lo) l[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
+                    }
+                }
+            };
+            if (active) load_res(0, rh[0], rl[0]);          // overlaps the main loop of this tile
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            if (active) {
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + cl0);
+#pragma unroll
+                for (int c = 0; c < STEPS; ++c) {
+                    const int cl = cl0 + c * 16;
+                    const int col0 = u.n0 + cl;
+                    if (cl >= u.w || col0 >= N) break;      // warp-uniform
+                    uint32_t r[16];
+                    tc_ld16(t_row + (uint32_t)(c * 16), r);
+                    if (c + 1 < STEPS) load_res(c + 1, rh[(c + 1) & 1], rl[(c + 1) & 1]);   // one step ahead
+                    float4 bv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (epi.bias && col0 + i * 4 < N) bv[i] = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + i * 4));
+                    }
+                    tc_wait_ld();
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[i * 4 + 0] = __uint_as_float(r[i * 4 + 0]) + bv[i].x;
+                        v[i * 4 + 1] = __uint_as_float(r[i * 4 + 1]) + bv[i].y;
+                        v[i * 4 + 2] = __uint_as_float(r[i * 4 + 2]) + bv[i].z;
+                        v[i * 4 + 3] = __uint_as_float(r[i * 4 + 3]) + bv[i].w;
+                    }
+                    if (epi.act == NAVC_ACT_GELU_NEW) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], NAVC_ACT_GELU_NEW);
+                    } else if (epi.act != NAVC_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], epi.act);
+                    }
+                    if (epi.res_hi) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const uint4 h4 = rh[c & 1][i], l4 = rl[c & 1][i];
+                            const uint32_t hw_[4] = {h4.x, h4.y, h4.z, h4.w};
+                            const uint32_t lw_[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                v[i * 8 + q * 2 + 0] += __uint_as_float(hw_[q] << 16) + __uint_as_float(lw_[q] << 16);
+                                v[i * 8 + q * 2 + 1] += __uint_as_float(hw_[q] & 0xffff0000u) + __uint_as_float(lw_[q] & 0xffff0000u);
+                            }
+                        }
+                    }
+                    if (rz) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    }
+                    uint32_t hw[8], lw[8];
+                    if (epi.out_lo) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            hw[j] = *reinterpret_cast<const uint32_t*>(&hb);
+                        }
+                    }
+                    // the previous step's TMA stores must have finished reading the staging boxes
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    *reinterpret_cast<uint4*>(stg + lane * 32) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(stg + lane * 32 + 16) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                    if (epi.out_lo) {
+                        *reinterpret_cast<uint4*>(stg + 1024 + lane * 32) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        *reinterpret_cast<uint4*>(stg + 1024 + lane * 32 + 16) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_o_hi, stg_s, col0, row0);
+                        if (epi.out_lo) tma_store_2d(&map_o_lo, stg_s + 1024u, col0, row0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging stays valid until read
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (kCl > 1) cluster_sync_all();   // no CTA leaves while its partner may still multicast into it / arrive on its barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+int tc_make_store_map16(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld);   // gemm_tc.cu
+
+static bool g_g2_ready = false;
+static int g2_init() {
+    if (g_g2_ready) return 0;
+#define NAVC_G2_ATTR(X3, BN, CL) \
+    NAVC_CUDA(cudaFuncSetAttribute(gemm2_tc_kernel<X3, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<X3, BN>::kSmemBytes))
+    NAVC_G2_ATTR(false, 128, 1); NAVC_G2_ATTR(false, 256, 1); NAVC_G2_ATTR(true, 128, 1); NAVC_G2_ATTR(true, 256, 1);
+    NAVC_G2_ATTR(false, 128, 2); NAVC_G2_ATTR(false, 256, 2); NAVC_G2_ATTR(true, 128, 2); NAVC_G2_ATTR(true, 256, 2);
+#undef NAVC_G2_ATTR
+    g_g2_ready = true;
+    return 0;
+}
+
+// cost (in units of a 128-column tile time) of the persistent schedule the kernel derives, for choosing TBN
+static float g2_cost(int m_blocks, int N, int tbn, int cl, int sms) {
+    const int units = ((m_blocks + cl - 1) / cl) * ((N + tbn - 1) / tbn);
+    int G = sms / cl;
+    if (G > units) G = units;
+    const int full = units / G, rem = units % G;
+    int parts = 1;
+    if (rem > 0) {
+        const int q = G / rem;
+        parts = q >= 4 ? 4 : (q >= 2 ? 2 : 1);
+        if (parts > tbn / 64) parts = tbn / 64;
+    }
+    // a part re-streams the whole A tile for 1/parts of the columns: charge it 30 % more than its share
+    const float tail = rem > 0 ? (parts > 1 ? 1.3f / parts : 1.0f) : 0.0f;
+    return (full + tail) * (tbn / 128.0f) * (tbn == 256 ? 0.92f : 1.0f);   // 256-wide tiles stream fewer operand bytes per flop
+}
+
+template <bool kX3, int TBN, int kCl>
+static int g2_launch(const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi, const uint16_t* w_lo, int ldw,
+                     int M, int N, int K, const EpiParams& epi, int sms, cudaStream_t st) {
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo;
+    const int bbox = kCl > 1 ? TBN / 2 : TBN;
+    if (tc_make_map(&ma_hi, x_hi, M, K, ldx, G2_BM) || tc_make_map(&mb_hi, w_hi, N, K, ldw, bbox)) return 1;
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+    if (kX3) {
+        if (tc_make_map(&ma_lo, x_lo, M, K, ldx, G2_BM) || tc_make_map(&mb_lo, w_lo, N, K, ldw, bbox)) return 1;
+    }
+    if (tc_make_store_map16(&mo_hi, epi.out_hi, M, N, epi.ld_out)) return 1;
+    mo_lo = mo_hi;
+    if (epi.out_lo && tc_make_store_map16(&mo_lo, epi.out_lo, M, N, epi.ld_out)) return 1;
+    const int m_blocks = (M + G2_BM - 1) / G2_BM;
+    const int units = ((m_blocks + kCl - 1) / kCl) * ((N + TBN - 1) / TBN);
+    int clusters = sms / kCl;
+    if (clusters > units * (TBN / 64)) clusters = units * (TBN / 64);   // small problems: room for the column parts
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * kCl);
+    cfg.blockDim = dim3(G2_THREADS);
+    cfg.dynamicSmemBytes = G2Cfg<kX3, TBN>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = kCl;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = kCl > 1 ? 2 : 1;
+    NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<kX3, TBN, kCl>, ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi));
+    return check_launch("navc_linear_tc (gemm2)");
+}
+
+static int g_g2_on = -1;
+bool g2_enabled() {
+    if (g_g2_on < 0) {
+        const char* e = getenv("NAVC_GEMM2");   // NAVC_GEMM2=0: the first-generation kernel (gemm_tc.cu) for A/B runs
+        g_g2_on = (e && (e[0] == '0' || e[0] == 'n' || e[0] == 'f')) ? 0 : 1;
+    }
+    return g_g2_on != 0;
+}
+
+// Pair-epilogue GEMM (bf16 hi(/lo) outputs only): called by navc_linear_tc once the arguments are validated.
+int g2_linear(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi, const uint16_t* w_lo, int ldw,
+              int M, int N, int K, const EpiParams& epi, cudaStream_t st) {
+    NAVC_REQUIRE(tc_ready(), "navc_linear_tc: navc_init() has not been called");
+    if (g2_init()) return 2;
+    int sms = navc_sm_count();
+    if (sms <= 0) sms = 148;
+    // rows the launch is expected to compute (packed rows: the device-side count; the host passes its estimate)
+    const int m_est = (epi.m_hint > 0 && epi.m_hint < M) ? epi.m_hint : M;
+    const int mbe = (m_est + G2_BM - 1) / G2_BM;
+    const char* ecl = getenv("NAVC_GEMM2_CLUSTER");
+    int cl = (mbe >= 8 && sms % 2 == 0) ? 2 : 1;     // tiny M (AR beam steps): nothing to share
+    if (ecl) cl = ecl[0] == '1' ? 1 : 2;
+    int tbn = (N > 128 && g2_cost(mbe, N, 256, cl, sms) <= g2_cost(mbe, N, 128, cl, sms)) ? 256 : 128;
+    if (epi.dbg == 128 || epi.dbg == 256) tbn = epi.dbg;   // profiling aid: force a tile width
+    const bool x3 = mode == NAVC_TC_BF16X3;
+#define NAVC_G2_GO(X3, BN, CL) return g2_launch<X3, BN, CL>(x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, sms, st)
+    if (x3) {
+        if (tbn == 256) { if (cl == 2) NAVC_G2_GO(true, 256, 2); NAVC_G2_GO(true, 256, 1); }
+        if (cl == 2) NAVC_G2_GO(true, 128, 2);
+        NAVC_G2_GO(true, 128, 1);
+    }
+    if (tbn == 256) { if (cl == 2) NAVC_G2_GO(false, 256, 2); NAVC_G2_GO(false, 256, 1); }
+    if (cl == 2) NAVC_G2_GO(false, 128, 2);
+    NAVC_G2_GO(false, 128, 1);
+#undef NAVC_G2_GO
+}
+
+}  // namespace navc

@@ -733,6 +733,13 @@ static int tc_make_store_map(CUtensorMap* map, const uint16_t* ptr, int rows, in
     return 0;
 }
 
+int tc_make_store_map16(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld) {   // gemm2_tc.cu
+    return tc_make_store_map(map, ptr, rows, cols, ld);
+}
+int g2_linear(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi, const uint16_t* w_lo, int ldw,
+              int M, int N, int K, const EpiParams& epi, cudaStream_t st);   // gemm2_tc.cu
+bool g2_enabled();
+
 static thread_local int g_dgrad_w_rows = 0;  // true row count of the dgrad B operand (launch_tc_dgrad)
 
 static int tile_waste_pct(int tiles, int sms) {  // idle share of the last wave of a persistent grid, in percent
@@ -893,6 +900,16 @@ extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_
                       (!p.res_hi || (p.ld_res % 8 == 0 && ((((uintptr_t)p.res_hi) | ((uintptr_t)p.res_lo)) & 15) == 0));
     NAVC_REQUIRE(pair || !p.res_hi, "navc_linear_tc: a bf16 hi/lo residual needs bf16-only outputs (no out_f32 / fp32 residual), "
                                     "N %% 8 == 0 and 16-byte aligned operands");
+    if (pair && g2_enabled() && !sk_enabled() && (p.dbg == 0 || p.dbg == 7 || p.dbg == 128 || p.dbg == 256)) {
+        // second-generation kernel (gemm2_tc.cu): cluster multicast of the weight tile, tail split along N
+        NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "navc_linear_tc: bad mode %d", mode);
+        NAVC_REQUIRE(x_hi && w_hi && (mode == NAVC_TC_BF16 || (x_lo && w_lo)), "navc_linear_tc: null operand");
+        NAVC_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0,
+                     "navc_linear_tc: need K%%8==0 and ld%%8==0 (M=%d N=%d K=%d ldx=%d ldw=%d)", M, N, K, ldx, ldw);
+        NAVC_REQUIRE((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0,
+                     "navc_linear_tc: operands must be 16-byte aligned");
+        return g2_linear(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, as_stream(stream));
+    }
     if (pair) return launch_tc<kEpiPair>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
     return launch_tc<kEpiGeneric>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
 }

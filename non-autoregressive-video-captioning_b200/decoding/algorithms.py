@@ -19,7 +19,7 @@ from ..config import Constants
 
 
 class Refiner:
-    def __init__(self, opt, model, teacher_model, mem, teacher_mem, category, beam, S, dict_mapping=None):
+    def __init__(self, opt, model, teacher_model, mem, teacher_mem, category, beam, S, dict_mapping=None, rows_hint=0):
         self.opt, self.model, self.teacher = opt, model, teacher_model
         self.eng = model.engine
         self.mem, self.tmem = mem, teacher_mem
@@ -42,7 +42,7 @@ class Refiner:
         want = opt.get("navc_packed", os.environ.get("NAVC_PACKED", "1"))
         self.packed = None
         if str(want).lower() not in ("0", "false", "no", "off") and self.eng.can_pack(S, mem["E"]):
-            self.packed = self.eng.pack_rows(self.lens, S)
+            self.packed = self.eng.pack_rows(self.lens, S, rows_hint)
         # second-level packing of the vocabulary projection: logits only at the positions the previous step
         # re-masked (double-buffered row lists / slot maps; counts are device scalars)
         self.vsel = None       # (rows, count, slot) written by the last selecting step

@@ -49,7 +49,7 @@ class _DecodeGraph:
     the candidate selection) for a fixed (batch, Smax) shape.  Inputs are copied into graph-owned
     buffers, the graph is replayed, the hypotheses are cloned out: one launch per call."""
 
-    def __init__(self, run, opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping):
+    def __init__(self, run, opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping, rows_hint=0):
         eng = model.engine
         self.pack_ids = (eng.pack_id, teacher_model.engine.pack_id if teacher_model is not None else -1)
         self.mem = _clone_inputs(mem)
@@ -62,7 +62,7 @@ class _DecodeGraph:
         torch.cuda.synchronize()
         n0 = L.launches
         with torch.cuda.graph(self.graph):
-            self.hyp, self.stats = run(opt, model, teacher_model, self.mem, self.tmem, self.cat, self.beam, S, dict_mapping)
+            self.hyp, self.stats = run(opt, model, teacher_model, self.mem, self.tmem, self.cat, self.beam, S, dict_mapping, rows_hint)
         self.n_launches = L.launches - n0  # kernels of ours inside the graph (replayed on every call)
 
     def load(self, mem, tmem, cat, beam):
@@ -82,14 +82,14 @@ class _DecodeGraph:
         return self.hyp.clone()
 
 
-def _run(opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping):
+def _run(opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping, rows_hint=0):
     """K|V projection of the encoder memory, the refinement algorithm, the candidate selection."""
     eng = model.engine
     B, lbs = beam.shape
     mem = eng.memory(mem["enc"].f32, mem)
     if tmem is not None:
         tmem = teacher_model.engine.memory(tmem["enc"].f32, tmem)
-    ref = Refiner(opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping)
+    ref = Refiner(opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping, rows_hint)
     tokens, lprobs = ALGORITHMS[opt.get("paradigm", "mp")](ref)
     hyp = torch.empty((B, S), dtype=torch.int64, device=beam.device)
     L.call("navc_select_best", L.ptr(tokens), L.ptr(lprobs), L.ptr(ref.lens), B, lbs, S,
@@ -148,13 +148,13 @@ def generate(opt, model, teacher_model, encoder_outputs, teacher_encoder_outputs
                 live = [k for k, v in eng.graphs.items() if isinstance(v, _DecodeGraph)]
                 for k in live[:max(0, len(live) - (_MAX_GRAPHS - 1))]:  # each graph owns its activations: keep a few shapes
                     del eng.graphs[k]
-                entry = eng.graphs[key] = _DecodeGraph(_run, opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping)
+                entry = eng.graphs[key] = _DecodeGraph(_run, opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping, rows_real)
             hyp = entry.replay(mem, tmem, cat, beam)
             generate.last_stats = dict(entry.stats, graph=True, rows_real=rows_real, rows_sq=rows_sq)
             return hyp, None
         eng.graphs[key] = "warm"  # first call: run eagerly (also warms up lazily initialised kernels)
 
-    hyp, stats = _run(opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping)
+    hyp, stats = _run(opt, model, teacher_model, mem, tmem, cat, beam, S, dict_mapping, rows_real)
     generate.last_stats = dict(stats, graph=False, rows_real=rows_real, rows_sq=rows_sq)
     return hyp, None
 

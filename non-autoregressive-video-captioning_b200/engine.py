@@ -257,7 +257,7 @@ class Engine:
         return a
 
     def linear(self, x: Act, lin: PackedLinear, act=0, residual=None,
-               row_tokens: Optional[torch.Tensor] = None, f32=True, bf=True, tag=None, lo=False, m_dev=None) -> Act:
+               row_tokens: Optional[torch.Tensor] = None, f32=True, bf=True, tag=None, lo=False, m_dev=None, m_hint=0) -> Act:
         """nn.Linear + fused epilogue (include/navc.h navc_epilogue_t).  ``residual`` is an fp32 tensor
         or an Act; an Act without an fp32 copy is passed as its bf16 hi/lo pair (tcgen05 pair epilogue)."""
         M, N, K = x.M, lin.N, lin.K
@@ -278,7 +278,7 @@ class Engine:
             res32, ld_res = residual, residual.shape[-1]
         ep = L.Epilogue(L.ptr(lin.b), L.ptr(res32), L.ptr(row_tokens), act, ld_res,
                         L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), N, 0, 1, 0, L.ptr(res_hi), L.ptr(res_lo),
-                        m_dev.data_ptr() if m_dev is not None else None)
+                        m_dev.data_ptr() if m_dev is not None else None, int(m_hint), 0)
         e0 = self._t0(tag)
         if use_tc:
             L.call("navc_linear_tc", self.tc_mode, L.ptr(x.hi), L.ptr(x.lo), K, L.ptr(lin.w_hi), L.ptr(lin.w_lo), K,
@@ -309,11 +309,12 @@ class Engine:
                L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), L.stream())
         return out
 
-    def _proj_res(self, x: Act, lin, ln, residual: Act, row_tokens, pair=False, m_dev=None, tag=None) -> Act:
+    def _proj_res(self, x: Act, lin, ln, residual: Act, row_tokens, pair=False, m_dev=None, tag=None, m_hint=0) -> Act:
         """dense -> (+residual) -> [LayerNorm] -> * non_pad_mask   (models/bert.py:192-200, 240-247, 271-299).
         pair: the residual stream lives as bf16 hi/lo pairs only (tensor-core modes without LayerNorm)."""
         if ln is None:
-            return self.linear(x, lin, residual=residual, row_tokens=row_tokens, f32=not pair, bf=True, lo=pair, m_dev=m_dev, tag=tag)
+            return self.linear(x, lin, residual=residual, row_tokens=row_tokens, f32=not pair, bf=True, lo=pair, m_dev=m_dev, tag=tag,
+                               m_hint=m_hint)
         y = self.linear(x, lin, residual=residual, row_tokens=None, f32=True, bf=False, tag=tag)
         return self.layernorm(y, ln, row_tokens)
 
@@ -414,14 +415,15 @@ class Engine:
             mem["kv"].f32 = self.linear(mem["enc"], self.P["kv_all"], f32=True, bf=False).f32
         return mem["kv"].f32
 
-    def pack_rows(self, lens: torch.Tensor, S: int):
+    def pack_rows(self, lens: torch.Tensor, S: int, hint: int = 0):
         """Packed-row bookkeeping for a fixed set of candidate lengths (include/navc.h "packed rows"):
-        seq_off [N+1] (seq_off[N] = row count, device side), rowmap [N*S]."""
+        seq_off [N+1] (seq_off[N] = row count, device side), rowmap [N*S].  ``hint``: the host's estimate of the row
+        count (navc_epilogue_t.m_hint: steers tile shapes only)."""
         N = lens.numel()
         seq_off = torch.empty((N + 1,), dtype=torch.int32, device=self.device)
         rowmap = torch.zeros((N * S,), dtype=torch.int32, device=self.device)
         L.call("navc_pack_rows", L.ptr(lens), N, S, L.ptr(seq_off), L.ptr(rowmap), L.stream())
-        return dict(seq_off=seq_off, rowmap=rowmap, count=seq_off[N:], N=N, S=S)
+        return dict(seq_off=seq_off, rowmap=rowmap, count=seq_off[N:], N=N, S=S, hint=int(hint))
 
     def can_pack(self, S, E):
         """Packed rows need the all-tensor-core layer (pair epilogues + tcgen05 attention cores)."""
@@ -451,11 +453,11 @@ class Engine:
         pair = self.tc and D % 64 == 0 and P["layers"][0]["f1"].N % 64 == 0 and \
             all(lw[k] is None for lw in P["layers"] for k in ("so_ln", "co_ln", "f2_ln"))
         x = self._new(R, D, not pair, True, lo=pair)
-        m_dev = None
+        m_dev, mh = None, 0
         if packed is not None:
             # only the sum(len) real positions are rows (R stays the launch maximum, the count is device side)
             assert pair and not want_attn and packed["N"] == N and packed["S"] == S
-            m_dev = packed["count"]
+            m_dev, mh = packed["count"], packed.get("hint", 0)
             tok_flat = torch.empty((R,), dtype=torch.int64, device=self.device)  # token id of every packed row
             L.call("navc_embed_ln_packed", L.ptr(tokens), L.ptr(category), L.ptr(emb["word"]), L.ptr(emb["pos"]),
                    L.ptr(emb["cat"]), L.ptr(extra), group, L.ptr(emb["ln_w"]), L.ptr(emb["ln_b"]), self.eps, N, S, D,
@@ -471,7 +473,7 @@ class Engine:
         tc_attn = self.tc_attention_ok(S, E) and not want_attn and kv.hi is not None
         watch = int(self.opt.get("watch", 0))
         for l, lw in enumerate(P["layers"]):
-            qkv = self.linear(x, lw["qkv"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="qkv")
+            qkv = self.linear(x, lw["qkv"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="qkv", m_hint=mh)
             ctx = self._new(R, D, not self.tc, True)
             p_self = p_cross = None
             e0 = self._t0("self")
@@ -487,8 +489,8 @@ class Engine:
                 L.call("navc_self_attention", L.ptr(qkv.f32), 3 * D, L.ptr(tokens), N, S, D, H, mask_kind,
                        watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.ptr(p_self), L.stream())
             self._t1("self", e0)
-            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tok_flat, pair, m_dev, tag="so")
-            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="cq")
+            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tok_flat, pair, m_dev, tag="so", m_hint=mh)
+            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="cq", m_hint=mh)
             ctx2 = self._new(R, D, not self.tc, True)
             e0 = self._t0("cross")
             if packed is not None:
@@ -508,9 +510,9 @@ class Engine:
                 L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, S, E, D, H, group,
                        L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
             self._t1("cross", e0)
-            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair, m_dev, tag="co")
-            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1", m_dev=m_dev)
-            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair, m_dev, tag="f2")
+            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair, m_dev, tag="co", m_hint=mh)
+            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1", m_dev=m_dev, m_hint=mh)
+            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair, m_dev, tag="f2", m_hint=mh)
             if want_attn:
                 attns.append((p_self, p_cross))
         if want_f32:
