@@ -36,8 +36,8 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_struct_layout_matches_header():
     import ctypes
     navc = _navc()
-    # navc_epilogue_t: 3 pointers, 2 int32, 3 pointers, 2 int32 ; navc_step_t per include/navc.h
-    assert ctypes.sizeof(navc._lib.Epilogue) == 3 * 8 + 8 + 3 * 8 + 8 + 8 + 16 + 8
+    # navc_epilogue_t: 3 pointers, 2 int32, 3 pointers, 4 int32, 3 pointers, 2 int32 ; navc_step_t per include/navc.h
+    assert ctypes.sizeof(navc._lib.Epilogue) == 3 * 8 + 8 + 3 * 8 + 8 + 8 + 16 + 8 + 8
     assert ctypes.sizeof(navc._lib.Step) == 3 * 8 + 8 * 4 + 16 * 8
 
 
