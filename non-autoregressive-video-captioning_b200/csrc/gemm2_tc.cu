@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
-                int M_max, int N, int K, EpiParams epi) {
+                int M_max, int N, int K, EpiParams epi, int direct) {
+    // direct != 0: the epilogue writes its rows with 256-bit global stores (row = lane: 32 contiguous bytes per tensor
+    // and step) instead of staging 32 x 16 boxes in shared memory for TMA stores; 2 = addresses are 32-byte aligned
     using Cfg = G2Cfg<kX3, TBN>;
     constexpr int kTileB = Cfg::kTileB;
     const int M = epi.m_dev ? min(M_max, __ldg(epi.m_dev)) : M_max;   // device-side row count (packed rows)
@@ -279,6 +281,24 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             hw[j] = *reinterpret_cast<const uint32_t*>(&hb);
                         }
                     }
+                    if (direct) {
+                        if (row_ok) {
+                            uint16_t* oh = epi.out_hi + (size_t)rowp * epi.ld_out + col0;
+                            uint16_t* ol = epi.out_lo ? epi.out_lo + (size_t)rowp * epi.ld_out + col0 : nullptr;
+                            if (direct == 2 && col0 + 16 <= N) {
+                                st_global_256(oh, hw);
+                                if (ol) st_global_256(ol, lw);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 2; ++i)
+                                    if (col0 + i * 8 < N) {
+                                        *reinterpret_cast<uint4*>(oh + i * 8) = make_uint4(hw[i * 4], hw[i * 4 + 1], hw[i * 4 + 2], hw[i * 4 + 3]);
+                                        if (ol) *reinterpret_cast<uint4*>(ol + i * 8) = make_uint4(lw[i * 4], lw[i * 4 + 1], lw[i * 4 + 2], lw[i * 4 + 3]);
+                                    }
+                            }
+                        }
+                        continue;
+                    }
                     // the previous step's TMA stores must have finished reading the staging boxes
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
@@ -378,7 +398,16 @@ static int g2_launch(const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const 
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = kCl > 1 ? 2 : 1;
-    NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<kX3, TBN, kCl>, ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi));
+    // epilogue stores: 256-bit global stores by default (measured: the 32 x 16 TMA store boxes, 32-byte rows, were what
+    // paced the epilogue -- and with it the whole tile); NAVC_GEMM2_STORE=tma restores the staged TMA stores
+    static int store_mode = -1;
+    if (store_mode < 0) {
+        const char* e = getenv("NAVC_GEMM2_STORE");
+        store_mode = (e && e[0] == 't') ? 0 : 1;
+    }
+    int direct = store_mode;
+    if (direct && epi.ld_out % 16 == 0 && ((((uintptr_t)epi.out_hi) | ((uintptr_t)epi.out_lo)) & 31) == 0) direct = 2;
+    NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<kX3, TBN, kCl>, ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, direct));
     return check_launch("navc_linear_tc (gemm2)");
 }
 
