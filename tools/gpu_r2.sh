@@ -23,5 +23,10 @@ classes)
       python tools/profile_step.py bf16x3 128 range > gpurun_out/${TAG}_ncu_layer.log 2>&1
   python tools/ncu_table.py /tmp/ncu/prof_layer.ncu-rep > gpurun_out/${TAG}_ncu_table_layer_bf16x3.txt
   python tools/ncu_classes.py /tmp/ncu/prof_layer.ncu-rep bf16x3 gpurun_out/${TAG}_ncu_classes_bf16x3.json > /dev/null ;;
+gemmprof)
+  # full capture (with source correlation) of the first decoder layer's GEMMs of one eager step; the report travels back
+  NAVC_GRAPHS=0 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gemm" -s 5 -c 6 -f \
+      -o gpurun_out/${TAG}_prof_gemm python tools/profile_step.py bf16x3 128 range > gpurun_out/${TAG}_ncu_gemm.log 2>&1
+  python tools/ncu_metrics.py gpurun_out/${TAG}_prof_gemm.ncu-rep > gpurun_out/${TAG}_ncu_gemm_metrics.txt ;;
 esac; done
 ls -la gpurun_out | tail -20
