@@ -7,10 +7,14 @@
 // (96 KB per k-block and CTA for a 128x256 tile: 8.5-9.3 TB/s over 148 SMs), not by the tensor pipe, and the
 // N = 512 GEMMs additionally lost a third of their last wave.
 //
-//  * Thread-block clusters of 2 CTAs along M share the B (weight) tile: each CTA loads half of it and TMA-multicasts
-//    it into both CTAs' rings (`.multicast::cluster`), so a CTA pulls 64 KB instead of 96 KB per k-block from L2.
-//    The ring's "slot free" barriers count the MMA commits of BOTH CTAs (tcgen05.commit ... multicast::cluster),
-//    because a CTA's TMA writes into its partner's slot.
+//  * CTA pairs (`tcgen05.mma.cta_group::2`, clusters of 2 CTAs on one TPC) compute 256-row tiles: each CTA stages its
+//    own 128 A rows and only HALF of the B (weight) rows of the tile, the leader CTA issues UMMA 256 x N x 16 and the
+//    tensor cores read the other half from the partner's shared memory -- 64 KB instead of 96 KB per k-block enter
+//    each SM for a 128 x 256 share of the tile.  (What was measured first: the k-block time of every variant followed
+//    bytes-into-the-SM / ~40 B/clk, the chip-wide L2 -> SM cap; TMA multicast inside a 2-CTA cluster brought nothing,
+//    the bytes still enter both SMs.)  TMA loads of both CTAs complete on the leader's barrier, the leader's
+//    tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs, the partner's epilogue warps arrive
+//    remotely on the leader's "accumulator drained" barrier.
 //  * Tail split along N: the tiles of the last, partly filled wave of the persistent grid are cut into 2 or 4 column
 //    parts (UMMA N = TBN/2, TBN/4) that run on the otherwise idle SMs.  Unlike a split along K (gemm_tc.cu's tail
 //    split, measured slower) no partial sums have to be handed over: every part owns its output columns.
@@ -31,10 +35,11 @@ constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
 constexpr int G2_ACC = 2;            // TMEM accumulator stages (2 x TBN columns)
 constexpr int G2_TILE_A = G2_BM * G2_BK * 2;   // 16 KB
 
-template <bool kX3, int TBN> struct G2Cfg {
-    static constexpr int kTileB = TBN * G2_BK * 2;
+template <bool kX3, int TBN, int kCl = 1> struct G2Cfg {
+    static constexpr int kTileB = (TBN / kCl) * G2_BK * 2;         // a CTA of a pair stages half of the B rows
     static constexpr int kStageBytes = (kX3 ? 2 : 1) * (G2_TILE_A + kTileB);
-    static constexpr int kStages = 196608 / kStageBytes;           // 2 (x3, 256) / 3 (x3, 128) / 4 (bf16, 256) / 6 (bf16, 128)
+    static constexpr int kStagesRaw = 196608 / kStageBytes;        // 1 CTA: 2 (x3, 256) / 3 (x3, 128) / 4 (bf16, 256) / 6 (bf16, 128)
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw; // pair:  3 (x3, 256) / 4 (x3, 128) / 6 (bf16, 256) / 8 (bf16, 128)
     static constexpr int kRingBytes = kStages * kStageBytes;
     static constexpr int kStgBytes = G2_EPI_WARPS * 2048;          // per warp: hi box (1 KB) + lo box (1 KB)
     static constexpr int kSmemBytes = kRingBytes + kStgBytes + 1024 /*align*/ + 512 /*barriers*/;
@@ -51,8 +56,9 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 int M_max, int N, int K, EpiParams epi, int direct) {
     // direct != 0: the epilogue writes its rows with 256-bit global stores (row = lane: 32 contiguous bytes per tensor
     // and step) instead of staging 32 x 16 boxes in shared memory for TMA stores; 2 = addresses are 32-byte aligned
-    using Cfg = G2Cfg<kX3, TBN>;
+    using Cfg = G2Cfg<kX3, TBN, kCl>;
     constexpr int kTileB = Cfg::kTileB;
+    constexpr bool kPair = kCl == 2;
     const int M = epi.m_dev ? min(M_max, __ldg(epi.m_dev)) : M_max;   // device-side row count (packed rows)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -105,17 +111,26 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kCl); }
-        for (int s = 0; s < G2_ACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), G2_EPI_WARPS); }
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        // pair: the leader's MMA thread waits for the epilogue warps of BOTH CTAs
+        for (int s = 0; s < G2_ACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kCl * G2_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (kPair) {
+        __syncthreads();
+        cluster_sync_all();   // both CTAs' barriers are initialised before anything can reach them; both are present for the alloc
+    }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (kPair) {   // the same warp of both CTAs allocates the pair's columns
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (kCl > 1) cluster_sync_all();   // the partner's barriers must be initialised before anything of ours can reach them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
@@ -128,20 +143,27 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             G2Unit u;
             for (int it = 0; get_unit(it, u); ++it) {
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);   // both CTAs' MMAs are done with this slot (in both CTAs)
+                    mbar_wait(empty_bar(stage), phase ^ 1u);   // the MMAs reading this slot (of this CTA) have retired
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                    mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                    tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * G2_BK, u.mb * G2_BM);
-                    if (kX3) tma_load_2d(sa + G2_TILE_A + kTileB, &map_a_lo, full_bar(stage), kb * G2_BK, u.mb * G2_BM);
-                    if constexpr (kCl > 1) {
-                        // my half of the B rows, delivered to both CTAs of the cluster
-                        const int brow = u.n0 + crank * (TBN / 2);
-                        const uint32_t off = (uint32_t)(crank * (TBN / 2) * 128);
-                        tma_load_2d_mc(sa + G2_TILE_A + off, &map_b_hi, full_bar(stage), kb * G2_BK, brow, (uint16_t)0x3);
-                        if (kX3) tma_load_2d_mc(sa + 2 * G2_TILE_A + kTileB + off, &map_b_lo, full_bar(stage), kb * G2_BK, brow, (uint16_t)0x3);
+                    if constexpr (kPair) {
+                        // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
+                        const uint32_t fb = mapa_u32(full_bar(stage), 0);
+                        if (crank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                        const int brow = u.n0 + crank * (u.w / 2);   // my half of the tile's B rows (UMMA N = u.w)
+                        tma_load_2d_2cta(sa, &map_a_hi, fb, kb * G2_BK, u.mb * G2_BM);
+                        tma_load_2d_2cta(sa + G2_TILE_A, &map_b_hi, fb, kb * G2_BK, brow);
+                        if (kX3) {
+                            tma_load_2d_2cta(sa + G2_TILE_A + kTileB, &map_a_lo, fb, kb * G2_BK, u.mb * G2_BM);
+                            tma_load_2d_2cta(sa + 2 * G2_TILE_A + kTileB, &map_b_lo, fb, kb * G2_BK, brow);
+                        }
                     } else {
+                        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                        tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * G2_BK, u.mb * G2_BM);
                         tma_load_2d(sa + G2_TILE_A, &map_b_hi, full_bar(stage), kb * G2_BK, u.n0);
-                        if (kX3) tma_load_2d(sa + 2 * G2_TILE_A + kTileB, &map_b_lo, full_bar(stage), kb * G2_BK, u.n0);
+                        if (kX3) {
+                            tma_load_2d(sa + G2_TILE_A + kTileB, &map_a_lo, full_bar(stage), kb * G2_BK, u.mb * G2_BM);
+                            tma_load_2d(sa + 2 * G2_TILE_A + kTileB, &map_b_lo, full_bar(stage), kb * G2_BK, u.n0);
+                        }
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -149,7 +171,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && crank == 0) {   // pair: only the leader CTA issues
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -159,7 +181,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TBN);
-                const uint32_t idesc = make_idesc(G2_BM, u.w);
+                const uint32_t idesc = make_idesc(kCl * G2_BM, u.w);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -169,7 +191,15 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
                     for (int k = 0; k < G2_BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-                        if (kX3) {
+                        if constexpr (kPair) {
+                            if (kX3) {
+                                tc_mma_bf16_2cta(d_tmem, da_lo + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                                tc_mma_bf16_2cta(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+                                tc_mma_bf16_2cta(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
+                            } else {
+                                tc_mma_bf16_2cta(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                            }
+                        } else if (kX3) {
                             // small cross terms first, the dominant hi*hi product last
                             tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
                             tc_mma_bf16(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
@@ -178,8 +208,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
                         }
                     }
-                    if constexpr (kCl > 1) tc_commit_mc(empty_bar(stage), (uint16_t)0x3); else tc_commit(empty_bar(stage));
-                    if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));
+                    if constexpr (kPair) {
+                        tc_commit_2cta_mc(empty_bar(stage), (uint16_t)0x3);               // slot free, in both CTAs
+                        if (kb == k_blocks - 1) tc_commit_2cta_mc(tfull_bar(acc), (uint16_t)0x3);   // accumulators ready, in both CTAs
+                    } else {
+                        tc_commit(empty_bar(stage));
+                        if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                 }
                 if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
@@ -319,7 +354,10 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+                if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0));   // the leader's MMA thread waits for both CTAs
+                else mbar_arrive(tempty_bar(acc));
+            }
             if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging stays valid until read
@@ -327,10 +365,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (kCl > 1) cluster_sync_all();   // no CTA leaves while its partner may still multicast into it / arrive on its barriers
+    if (kPair) cluster_sync_all();   // no CTA leaves (or frees TMEM) while the pair's MMAs / barrier arrivals can still reach it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if constexpr (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -341,7 +382,7 @@ static bool g_g2_ready = false;
 static int g2_init() {
     if (g_g2_ready) return 0;
 #define NAVC_G2_ATTR(X3, BN, CL) \
-    NAVC_CUDA(cudaFuncSetAttribute(gemm2_tc_kernel<X3, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<X3, BN>::kSmemBytes))
+    NAVC_CUDA(cudaFuncSetAttribute(gemm2_tc_kernel<X3, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<X3, BN, CL>::kSmemBytes))
     NAVC_G2_ATTR(false, 128, 1); NAVC_G2_ATTR(false, 256, 1); NAVC_G2_ATTR(true, 128, 1); NAVC_G2_ATTR(true, 256, 1);
     NAVC_G2_ATTR(false, 128, 2); NAVC_G2_ATTR(false, 256, 2); NAVC_G2_ATTR(true, 128, 2); NAVC_G2_ATTR(true, 256, 2);
 #undef NAVC_G2_ATTR
@@ -350,7 +391,7 @@ static int g2_init() {
 }
 
 // cost (in units of a 128-column tile time) of the persistent schedule the kernel derives, for choosing TBN
-static float g2_cost(int m_blocks, int N, int tbn, int cl, int sms) {
+static float g2_cost(int m_blocks, int N, int tbn, int cl, int sms, bool x3) {
     const int units = ((m_blocks + cl - 1) / cl) * ((N + tbn - 1) / tbn);
     int G = sms / cl;
     if (G > units) G = units;
@@ -363,7 +404,11 @@ static float g2_cost(int m_blocks, int N, int tbn, int cl, int sms) {
     }
     // a part re-streams the whole A tile for 1/parts of the columns: charge it 30 % more than its share
     const float tail = rem > 0 ? (parts > 1 ? 1.3f / parts : 1.0f) : 0.0f;
-    return (full + tail) * (tbn / 128.0f) * (tbn == 256 ? 0.92f : 1.0f);   // 256-wide tiles stream fewer operand bytes per flop
+    // bytes entering an SM per k-block and 128 x tbn share of the tile: A rows + (pair: half of) the B rows; the k-block
+    // time follows that stream (~40 B/clk) or the MMAs, whichever is longer
+    // (units: the MMA time of a 128-column k-block -- 768 cycles split-bf16, 256 plain; stream at 40 B/clk)
+    const float mma = tbn / 128.0f, stream = (128.0f + (float)tbn / cl) / (x3 ? 120.0f : 80.0f);
+    return (full + tail) * (mma > stream ? mma : stream);
 }
 
 template <bool kX3, int TBN, int kCl>
@@ -387,7 +432,7 @@ static int g2_launch(const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * kCl);
     cfg.blockDim = dim3(G2_THREADS);
-    cfg.dynamicSmemBytes = G2Cfg<kX3, TBN>::kSmemBytes;
+    cfg.dynamicSmemBytes = G2Cfg<kX3, TBN, kCl>::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -431,11 +476,11 @@ int g2_linear(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, con
     const int m_est = (epi.m_hint > 0 && epi.m_hint < M) ? epi.m_hint : M;
     const int mbe = (m_est + G2_BM - 1) / G2_BM;
     const char* ecl = getenv("NAVC_GEMM2_CLUSTER");
-    int cl = (mbe >= 8 && sms % 2 == 0) ? 2 : 1;     // tiny M (AR beam steps): nothing to share
+    int cl = (mbe >= 8 && sms % 2 == 0) ? 2 : 1;     // tiny M (AR beam steps): more, smaller tiles instead of CTA pairs
     if (ecl) cl = ecl[0] == '1' ? 1 : 2;
-    int tbn = (N > 128 && g2_cost(mbe, N, 256, cl, sms) <= g2_cost(mbe, N, 128, cl, sms)) ? 256 : 128;
-    if (epi.dbg == 128 || epi.dbg == 256) tbn = epi.dbg;   // profiling aid: force a tile width
     const bool x3 = mode == NAVC_TC_BF16X3;
+    int tbn = (N > 128 && g2_cost(mbe, N, 256, cl, sms, x3) <= g2_cost(mbe, N, 128, cl, sms, x3)) ? 256 : 128;
+    if (epi.dbg == 128 || epi.dbg == 256) tbn = epi.dbg;   // profiling aid: force a tile width
 #define NAVC_G2_GO(X3, BN, CL) return g2_launch<X3, BN, CL>(x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, sms, st)
     if (x3) {
         if (tbn == 256) { if (cl == 2) NAVC_G2_GO(true, 256, 2); NAVC_G2_GO(true, 256, 1); }
