@@ -145,6 +145,11 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);   // the MMAs reading this slot (of this CTA) have retired
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                    if (epi.dbg == 15) {   // profiling aid: no operand loads (ring handshake only)
+                        if (!kPair || crank == 0) mbar_arrive(full_bar(stage));
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     if constexpr (kPair) {
                         // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
                         const uint32_t fb = mapa_u32(full_bar(stage), 0);
@@ -191,6 +196,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
                     for (int k = 0; k < G2_BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        if (epi.dbg == 14 && (kb | k)) continue;   // profiling aid: one MMA per tile
                         if constexpr (kPair) {
                             if (kX3) {
                                 tc_mma_bf16_2cta(d_tmem, da_lo + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
@@ -237,7 +243,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const bool row_ok = u.valid && rowp < M;
             const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[rowp] == NAVC_PAD) : false;
             const int cl0 = grp * GW;                       // first tile-local column of this warp
-            const bool active = u.valid && cl0 < u.w && u.n0 + cl0 < N && row0 < M;   // warp-uniform
+            const bool active = u.valid && cl0 < u.w && u.n0 + cl0 < N && row0 < M && epi.dbg != 11;   // warp-uniform
             // residual of one 16-column step: 2 x 16 bytes of hi (+ lo) per row
             uint4 rh[2][2], rl[2][2];
             auto load_res = [&](int c, uint4 (&h)[2], uint4 (&l)[2]) {
@@ -246,7 +252,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     h[i] = make_uint4(0u, 0u, 0u, 0u);
                     l[i] = make_uint4(0u, 0u, 0u, 0u);
                     const int col = u.n0 + cl0 + c * 16 + i * 8;
-                    if (epi.res_hi && row_ok && cl0 + c * 16 < u.w && col < N) {
+                    if (epi.res_hi && row_ok && cl0 + c * 16 < u.w && col < N && epi.dbg != 13) {
                         const size_t ro = (size_t)rowp * epi.ld_res + col;
                         h[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
                         if (epi.res_lo) l[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
@@ -316,6 +322,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             hw[j] = *reinterpret_cast<const uint32_t*>(&hb);
                         }
                     }
+                    if (epi.dbg == 12) continue;   // profiling aid: no stores
                     if (direct) {
                         if (row_ok) {
                             uint16_t* oh = epi.out_hi + (size_t)rowp * epi.ld_out + col0;
