@@ -40,12 +40,22 @@ for mode, mname in modes:
             for i in range(3):
                 run(i)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # device time per launch: 30 launches captured in one CUDA graph (no host launch cost between them), replayed
             reps = 30
-            e0.record()
-            for i in range(reps):
-                run(i)
-            e1.record(); torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / reps
+            st = torch.cuda.Stream()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(st):
+                with torch.cuda.graph(graph, stream=st):
+                    for i in range(reps):
+                        run(i)
+                graph.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                graph.replay()
+                graph.replay()
+                e1.record(st)
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (2 * reps)
             line += " dbg%-3d %6.1f us" % (dbg, us)
         print(line)
