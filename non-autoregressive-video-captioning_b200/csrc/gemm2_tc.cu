@@ -48,6 +48,20 @@ template <bool kX3, int TBN, int kCl = 1> struct G2Cfg {
 
 struct G2Unit { int mb, n0, w; bool valid; };
 
+// Optional in-kernel timeline (tools/gemm2_trace.py): when navc_debug_trace() has installed a buffer, the producer
+// lane, the MMA lane and lane 0 of epilogue warp 2 of every CTA record (tag, clock64) pairs -- 3 roles x 64 events.
+__device__ unsigned long long* g2_trace_buf = nullptr;
+struct G2Trace {
+    unsigned long long* p;
+    int n;
+    __device__ G2Trace(int role) : p(nullptr), n(0) {
+        if (g2_trace_buf) p = g2_trace_buf + ((size_t)blockIdx.x * 3 + role) * 64;
+    }
+    __device__ __forceinline__ void ev(unsigned tag) {
+        if (p && n < 64) p[n++] = ((unsigned long long)tag << 56) | ((unsigned long long)clock64() & 0x00ffffffffffffffull);
+    }
+};
+
 template <bool kX3, int TBN, int kCl>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -141,9 +155,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             G2Unit u;
+            G2Trace tr(0);
+            tr.ev(1);   // prologue done
             for (int it = 0; get_unit(it, u); ++it) {
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);   // the MMAs reading this slot (of this CTA) have retired
+                    if (kb == 0) tr.ev(2);                     // first load of a unit issued
+                    if (kb == k_blocks - 1) tr.ev(3);          // last load of a unit issued
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     if (epi.dbg == 15) {   // profiling aid: no operand loads (ring handshake only)
                         if (!kPair || crank == 0) mbar_arrive(full_bar(stage));
@@ -182,14 +200,18 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             int acc = 0;
             uint32_t acc_phase = 0;
             G2Unit u;
+            G2Trace tr(1);
             for (int it = 0; get_unit(it, u); ++it) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
+                tr.ev(4);   // accumulator stage free
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TBN);
                 const uint32_t idesc = make_idesc(kCl * G2_BM, u.w);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
+                    if (kb == 0) tr.ev(5);                  // first operands of the unit landed
+                    if (kb == k_blocks - 1) tr.ev(6);       // last operands landed
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sa + G2_TILE_A);
                     const uint64_t da_lo = make_smem_desc(sa + G2_TILE_A + kTileB), db_lo = make_smem_desc(sa + 2 * G2_TILE_A + kTileB);
@@ -237,6 +259,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         int acc = 0;
         uint32_t acc_phase = 0;
         G2Unit u;
+        G2Trace tr(2);
+        if (ew != 0 || lane != 0) tr.p = nullptr;
         for (int it = 0; get_unit(it, u); ++it) {
             const int row0 = u.mb * G2_BM + quarter * 32;
             const int rowp = row0 + lane;
@@ -262,6 +286,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (active) load_res(0, rh[0], rl[0]);          // overlaps the main loop of this tile
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            tr.ev(7);   // accumulators of the unit ready
             if (active) {
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + cl0);
 #pragma unroll
@@ -359,6 +384,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                 }
             }
+            tr.ev(8);   // epilogue of the unit issued
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -368,6 +394,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging stays valid until read
+        tr.ev(9);       // stores drained
     }
 
     tc_fence_before();
@@ -384,6 +411,14 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
 // ---- host side ------------------------------------------------------------------------------------
 int tc_make_store_map16(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld);   // gemm_tc.cu
+
+}  // namespace navc
+// Debug: install (or remove, buf == NULL) the in-kernel timeline buffer: 3 x 64 uint64 per CTA of the grid.
+extern "C" int navc_debug_trace(void* buf) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+    return cudaMemcpyToSymbol(navc::g2_trace_buf, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
+}
+namespace navc {
 
 static bool g_g2_ready = false;
 static int g2_init() {
