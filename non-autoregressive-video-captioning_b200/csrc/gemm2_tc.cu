@@ -1,25 +1,29 @@
 // tcgen05 GEMM of the inference hot path, second generation:  Y = epilogue(X[M,K] * W[N,K]^T), bf16 hi(/lo) outputs.
 //
-// Same pipeline as gemm_tc.cu (TMA 128B swizzle -> shared-memory ring -> tcgen05.mma 128xNx16, fp32 accumulators in
+// Same building blocks as gemm_tc.cu (TMA 128B swizzle -> shared-memory ring -> tcgen05.mma, fp32 accumulators in
 // TMEM, double buffered -> tcgen05.ld -> fused "pair" epilogue: bias / activation / bf16 hi+lo residual / non-pad row
-// mask / bf16 hi+lo split, TMA stores), rebuilt around what the round-2 measurements showed (profiles/r2a_*): in the
-// split-bf16 mode every projection GEMM of the decoder layer was bound by the L2 -> shared-memory operand stream
-// (96 KB per k-block and CTA for a 128x256 tile: 8.5-9.3 TB/s over 148 SMs), not by the tensor pipe, and the
-// N = 512 GEMMs additionally lost a third of their last wave.
+// mask / bf16 hi+lo split, TMA stores), rebuilt around an in-kernel timeline of the round-1 kernel
+// (navc_debug_trace / tools/gemm2_trace.py, profiles/r2f_*):
 //
 //  * CTA pairs (`tcgen05.mma.cta_group::2`, clusters of 2 CTAs on one TPC) compute 256-row tiles: each CTA stages its
 //    own 128 A rows and only HALF of the B (weight) rows of the tile, the leader CTA issues UMMA 256 x N x 16 and the
-//    tensor cores read the other half from the partner's shared memory -- 64 KB instead of 96 KB per k-block enter
-//    each SM for a 128 x 256 share of the tile.  (What was measured first: the k-block time of every variant followed
-//    bytes-into-the-SM / ~40 B/clk, the chip-wide L2 -> SM cap; TMA multicast inside a 2-CTA cluster brought nothing,
-//    the bytes still enter both SMs.)  TMA loads of both CTAs complete on the leader's barrier, the leader's
-//    tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs, the partner's epilogue warps arrive
-//    remotely on the leader's "accumulator drained" barrier.
+//    tensor cores read the other half from the partner's shared memory: 64 KB instead of 96 KB per k-block enter each
+//    SM for its 128 x 256 share of the tile (three ring stages instead of two).  TMA loads of both CTAs complete on
+//    the leader's barrier, the leader's tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs, the
+//    partner's epilogue warps arrive remotely on the leader's "accumulator drained" barrier.
+//    (Tried first and dropped: TMA multicast of the B tile inside a 2-CTA cluster -- no gain, the bytes still enter
+//    both SMs -- and 256-bit global stores instead of TMA store boxes -- the row-per-lane stores cost ~120 cycles each.)
+//  * The residual is PRELOADED INTO THE ACCUMULATOR: while a tile's MMAs run, the epilogue warps fetch the bf16 hi/lo
+//    residual of the tile that will use the other TMEM stage next, join it to fp32 and `tcgen05.st` it there; the MMAs
+//    of that tile then accumulate onto it.  The timeline showed 2.5 us per 16-column epilogue step with the residual
+//    loaded in the epilogue (exposed L2 latency under the operand stream) against 1.3 us without: 10 us per tile against
+//    a 6.6 us main loop.  Preloaded, the residual's latency hides behind a whole main loop and costs no registers.
+//  * Epilogue steps are software pipelined: the tcgen05.ld of step c+1 is issued before step c is computed, and the hi
+//    and lo boxes leave as separate bulk groups (`cp.async.bulk.wait_group.read 1`), so a staging box is only waited
+//    for when the store issued a full half-step earlier has not drained yet.
 //  * Tail split along N: the tiles of the last, partly filled wave of the persistent grid are cut into 2 or 4 column
-//    parts (UMMA N = TBN/2, TBN/4) that run on the otherwise idle SMs.  Unlike a split along K (gemm_tc.cu's tail
-//    split, measured slower) no partial sums have to be handed over: every part owns its output columns.
-//  * The bf16 hi/lo residual of the first epilogue step is requested BEFORE the accumulator barrier is awaited and
-//    every later step's residual one step ahead, so its L2 latency overlaps the main loop / the previous step.
+//    parts (UMMA N = TBN/2, TBN/4; B arrives as 32-row boxes so a part loads only its own weight rows) that run on the
+//    otherwise idle SMs.  Unlike a split along K (gemm_tc.cu's tail split, measured slower) nothing is handed over.
 //
 // Warp roles (576 threads, persistent, one CTA per SM): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
 // warps 2..17 epilogue (warp = TMEM lane quarter x column group of TBN/4; lane = row; 16-column steps).
@@ -34,6 +38,7 @@ constexpr int G2_EPI_WARPS = 16;
 constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
 constexpr int G2_ACC = 2;            // TMEM accumulator stages (2 x TBN columns)
 constexpr int G2_TILE_A = G2_BM * G2_BK * 2;   // 16 KB
+constexpr int G2_PBOX = 32;          // rows of the B boxes used by the column parts of the tail wave
 
 template <bool kX3, int TBN, int kCl = 1> struct G2Cfg {
     static constexpr int kTileB = (TBN / kCl) * G2_BK * 2;         // a CTA of a pair stages half of the B rows
@@ -66,14 +71,15 @@ template <bool kX3, int TBN, int kCl>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const __grid_constant__ CUtensorMap map_p_hi, const __grid_constant__ CUtensorMap map_p_lo,
                 const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
-                int M_max, int N, int K, EpiParams epi, int direct) {
-    // direct != 0: the epilogue writes its rows with 256-bit global stores (row = lane: 32 contiguous bytes per tensor
-    // and step) instead of staging 32 x 16 boxes in shared memory for TMA stores; 2 = addresses are 32-byte aligned
+                int M_max, int N, int K, EpiParams epi) {
     using Cfg = G2Cfg<kX3, TBN, kCl>;
     constexpr int kTileB = Cfg::kTileB;
     constexpr bool kPair = kCl == 2;
+    constexpr int kParts = kX3 ? 2 : 1;
     const int M = epi.m_dev ? min(M_max, __ldg(epi.m_dev)) : M_max;   // device-side row count (packed rows)
+    const bool pre = epi.res_hi != nullptr;                           // residual preloaded into the accumulators
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -87,11 +93,11 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + bar_off + 8 * (2 * Cfg::kStages + 2 * G2_ACC));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int crank = kCl > 1 ? (int)cluster_ctarank() : 0;
+    const int crank = kPair ? (int)cluster_ctarank() : 0;
     const int cid = (int)blockIdx.x / kCl, G = (int)gridDim.x / kCl;   // cluster index, clusters in the grid
 
     // ---- schedule: a unit = one (row group of kCl m-blocks, column block) tile per cluster; the units of the last,
-    //      partly filled wave are cut into p column parts of TBN / p columns ----
+    //      partly filled wave are cut into `parts` column parts of TBN / parts columns ----
     const int m_blocks = (M + G2_BM - 1) / G2_BM, n_blocks = (N + TBN - 1) / TBN;
     const int k_blocks = (K + G2_BK - 1) / G2_BK;   // TMA zero-fills the K tail
     const int n_units = ((m_blocks + kCl - 1) / kCl) * n_blocks;
@@ -158,34 +164,35 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             G2Trace tr(0);
             tr.ev(1);   // prologue done
             for (int it = 0; get_unit(it, u); ++it) {
+                // a column part loads only its own B rows, as 32-row boxes
+                const bool part = u.w < TBN;
+                const int brows = u.w / kCl;                         // B rows this CTA stages
+                const uint32_t bytes = (uint32_t)(kParts * (G2_TILE_A + brows * 128));
+                const int brow0 = u.n0 + crank * brows;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);   // the MMAs reading this slot (of this CTA) have retired
                     if (kb == 0) tr.ev(2);                     // first load of a unit issued
-                    if (kb == k_blocks - 1) tr.ev(3);          // last load of a unit issued
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     if (epi.dbg == 15) {   // profiling aid: no operand loads (ring handshake only)
                         if (!kPair || crank == 0) mbar_arrive(full_bar(stage));
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                         continue;
                     }
-                    if constexpr (kPair) {
-                        // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
-                        const uint32_t fb = mapa_u32(full_bar(stage), 0);
-                        if (crank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-                        const int brow = u.n0 + crank * (u.w / 2);   // my half of the tile's B rows (UMMA N = u.w)
-                        tma_load_2d_2cta(sa, &map_a_hi, fb, kb * G2_BK, u.mb * G2_BM);
-                        tma_load_2d_2cta(sa + G2_TILE_A, &map_b_hi, fb, kb * G2_BK, brow);
-                        if (kX3) {
-                            tma_load_2d_2cta(sa + G2_TILE_A + kTileB, &map_a_lo, fb, kb * G2_BK, u.mb * G2_BM);
-                            tma_load_2d_2cta(sa + 2 * G2_TILE_A + kTileB, &map_b_lo, fb, kb * G2_BK, brow);
-                        }
+                    // pair: both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
+                    const uint32_t fb = kPair ? mapa_u32(full_bar(stage), 0) : full_bar(stage);
+                    if (crank == 0) mbar_expect_tx(full_bar(stage), kCl * bytes);
+                    auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
+                        if constexpr (kPair) tma_load_2d_2cta(dst, map, fb, c0, c1); else tma_load_2d(dst, map, fb, c0, c1);
+                    };
+                    load(sa, &map_a_hi, kb * G2_BK, u.mb * G2_BM);
+                    if (kX3) load(sa + G2_TILE_A + kTileB, &map_a_lo, kb * G2_BK, u.mb * G2_BM);
+                    if (!part) {
+                        load(sa + G2_TILE_A, &map_b_hi, kb * G2_BK, brow0);
+                        if (kX3) load(sa + 2 * G2_TILE_A + kTileB, &map_b_lo, kb * G2_BK, brow0);
                     } else {
-                        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                        tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * G2_BK, u.mb * G2_BM);
-                        tma_load_2d(sa + G2_TILE_A, &map_b_hi, full_bar(stage), kb * G2_BK, u.n0);
-                        if (kX3) {
-                            tma_load_2d(sa + G2_TILE_A + kTileB, &map_a_lo, full_bar(stage), kb * G2_BK, u.mb * G2_BM);
-                            tma_load_2d(sa + 2 * G2_TILE_A + kTileB, &map_b_lo, full_bar(stage), kb * G2_BK, u.n0);
+                        for (int j = 0; j < brows / G2_PBOX; ++j) {
+                            load(sa + G2_TILE_A + j * (G2_PBOX * 128), &map_p_hi, kb * G2_BK, brow0 + j * G2_PBOX);
+                            if (kX3) load(sa + 2 * G2_TILE_A + kTileB + j * (G2_PBOX * 128), &map_p_lo, kb * G2_BK, brow0 + j * G2_PBOX);
                         }
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
@@ -202,7 +209,9 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             G2Unit u;
             G2Trace tr(1);
             for (int it = 0; get_unit(it, u); ++it) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                // residual preloaded: phase k of the barrier = "stage ready for its k-th use" (drained AND preloaded),
+                // the first use included; otherwise the first use of a stage passes immediately
+                mbar_wait(tempty_bar(acc), pre ? acc_phase : (acc_phase ^ 1u));
                 tc_fence_after();
                 tr.ev(4);   // accumulator stage free
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TBN);
@@ -211,7 +220,6 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     if (kb == 0) tr.ev(5);                  // first operands of the unit landed
-                    if (kb == k_blocks - 1) tr.ev(6);       // last operands landed
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sa + G2_TILE_A);
                     const uint64_t da_lo = make_smem_desc(sa + G2_TILE_A + kTileB), db_lo = make_smem_desc(sa + 2 * G2_TILE_A + kTileB);
@@ -219,21 +227,22 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     for (int k = 0; k < G2_BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
                         if (epi.dbg == 14 && (kb | k)) continue;   // profiling aid: one MMA per tile
+                        const uint32_t first = (pre || (kb | k)) ? 1u : 0u;   // accumulate onto the preloaded residual
                         if constexpr (kPair) {
                             if (kX3) {
-                                tc_mma_bf16_2cta(d_tmem, da_lo + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                                tc_mma_bf16_2cta(d_tmem, da_lo + koff, db_hi + koff, idesc, first);
                                 tc_mma_bf16_2cta(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
                                 tc_mma_bf16_2cta(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
                             } else {
-                                tc_mma_bf16_2cta(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                                tc_mma_bf16_2cta(d_tmem, da_hi + koff, db_hi + koff, idesc, first);
                             }
                         } else if (kX3) {
                             // small cross terms first, the dominant hi*hi product last
-                            tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, first);
                             tc_mma_bf16(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
                             tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
                         } else {
-                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, first);
                         }
                     }
                     if constexpr (kPair) {
@@ -243,6 +252,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         tc_commit(empty_bar(stage));
                         if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));
                     }
+                    if (kb == k_blocks - 1) tr.ev(6);       // last MMAs of the unit issued
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                 }
                 if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
@@ -254,49 +264,86 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int ew = warp - 2;
         const int quarter = warp & 3;   // TMEM lane quarter this warp may access
         const int grp = ew >> 2;        // column group [grp * GW, grp * GW + GW) of the tile
+        const int cl0 = grp * GW;       // first tile-local column of this warp
         uint8_t* stg = stg_all + ew * 2048;   // hi box at +0, lo box at +1024
         const uint32_t stg_s = smem_u32(stg);
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        G2Unit u;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         G2Trace tr(2);
         if (ew != 0 || lane != 0) tr.p = nullptr;
+
+        auto arrive_drained = [&](int a) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(tempty_bar(a), 0));   // the leader's MMA thread waits for both CTAs
+                else mbar_arrive(tempty_bar(a));
+            }
+        };
+        // residual of unit `v` -> accumulator stage `a` (fp32 = hi + lo), zeros for rows / columns outside the output
+        auto preload = [&](const G2Unit& v, int a) {
+            if (!(v.valid && cl0 < v.w && v.n0 + cl0 < N)) return;   // warp-uniform: the MMAs do not touch these columns
+            const int rowp = v.mb * G2_BM + quarter * 32 + lane;
+            const bool row_ok = rowp < M;
+            uint4 h[STEPS][2], l[STEPS][2];
+#pragma unroll
+            for (int c = 0; c < STEPS; ++c)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    h[c][i] = make_uint4(0u, 0u, 0u, 0u);
+                    l[c][i] = make_uint4(0u, 0u, 0u, 0u);
+                    const int col = v.n0 + cl0 + c * 16 + i * 8;
+                    if (row_ok && cl0 + c * 16 < v.w && col < N) {
+                        const size_t ro = (size_t)rowp * epi.ld_res + col;
+                        h[c][i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
+                        if (epi.res_lo) l[c][i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
+                    }
+                }
+#pragma unroll
+            for (int c = 0; c < STEPS; ++c) {
+                if (cl0 + c * 16 >= v.w) break;   // warp-uniform
+                uint32_t f[16];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t hw_[4] = {h[c][i].x, h[c][i].y, h[c][i].z, h[c][i].w};
+                    const uint32_t lw_[4] = {l[c][i].x, l[c][i].y, l[c][i].z, l[c][i].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        f[i * 8 + q * 2 + 0] = __float_as_uint(__uint_as_float(hw_[q] << 16) + __uint_as_float(lw_[q] << 16));
+                        f[i * 8 + q * 2 + 1] = __float_as_uint(__uint_as_float(hw_[q] & 0xffff0000u) + __uint_as_float(lw_[q] & 0xffff0000u));
+                    }
+                }
+                tc_st16(t_lane + (uint32_t)(a * TBN + cl0 + c * 16), f);
+            }
+            tc_wait_st();
+        };
+
+        G2Unit u;
+        if (pre) {   // the first use of both accumulator stages
+            for (int a = 0; a < G2_ACC; ++a) {
+                if (get_unit(a, u)) preload(u, a);
+                arrive_drained(a);
+            }
+        }
+        int acc = 0;
+        uint32_t acc_phase = 0;
         for (int it = 0; get_unit(it, u); ++it) {
             const int row0 = u.mb * G2_BM + quarter * 32;
             const int rowp = row0 + lane;
             const bool row_ok = u.valid && rowp < M;
             const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[rowp] == NAVC_PAD) : false;
-            const int cl0 = grp * GW;                       // first tile-local column of this warp
             const bool active = u.valid && cl0 < u.w && u.n0 + cl0 < N && row0 < M && epi.dbg != 11;   // warp-uniform
-            // residual of one 16-column step: 2 x 16 bytes of hi (+ lo) per row
-            uint4 rh[2][2], rl[2][2];
-            auto load_res = [&](int c, uint4 (&h)[2], uint4 (&l)[2]) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    h[i] = make_uint4(0u, 0u, 0u, 0u);
-                    l[i] = make_uint4(0u, 0u, 0u, 0u);
-                    const int col = u.n0 + cl0 + c * 16 + i * 8;
-                    if (epi.res_hi && row_ok && cl0 + c * 16 < u.w && col < N && epi.dbg != 13) {
-                        const size_t ro = (size_t)rowp * epi.ld_res + col;
-                        h[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
-                        if (epi.res_lo) l[i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
-                    }
-                }
-            };
-            if (active) load_res(0, rh[0], rl[0]);          // overlaps the main loop of this tile
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             tr.ev(7);   // accumulators of the unit ready
             if (active) {
-                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TBN + cl0);
+                const uint32_t t_row = t_lane + (uint32_t)(acc * TBN + cl0);
+                uint32_t r[2][16];
+                tc_ld16(t_row, r[0]);
 #pragma unroll
                 for (int c = 0; c < STEPS; ++c) {
                     const int cl = cl0 + c * 16;
                     const int col0 = u.n0 + cl;
                     if (cl >= u.w || col0 >= N) break;      // warp-uniform
-                    uint32_t r[16];
-                    tc_ld16(t_row + (uint32_t)(c * 16), r);
-                    if (c + 1 < STEPS) load_res(c + 1, rh[(c + 1) & 1], rl[(c + 1) & 1]);   // one step ahead
                     float4 bv[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -304,13 +351,16 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         if (epi.bias && col0 + i * 4 < N) bv[i] = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + i * 4));
                     }
                     tc_wait_ld();
+                    // the next step's accumulators travel while this step is computed and stored
+                    if (c + 1 < STEPS && cl + 16 < u.w && col0 + 16 < N) tc_ld16(t_row + (uint32_t)((c + 1) * 16), r[(c + 1) & 1]);
+                    tr.ev(20 + c);
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        v[i * 4 + 0] = __uint_as_float(r[i * 4 + 0]) + bv[i].x;
-                        v[i * 4 + 1] = __uint_as_float(r[i * 4 + 1]) + bv[i].y;
-                        v[i * 4 + 2] = __uint_as_float(r[i * 4 + 2]) + bv[i].z;
-                        v[i * 4 + 3] = __uint_as_float(r[i * 4 + 3]) + bv[i].w;
+                        v[i * 4 + 0] = __uint_as_float(r[c & 1][i * 4 + 0]) + bv[i].x;
+                        v[i * 4 + 1] = __uint_as_float(r[c & 1][i * 4 + 1]) + bv[i].y;
+                        v[i * 4 + 2] = __uint_as_float(r[c & 1][i * 4 + 2]) + bv[i].z;
+                        v[i * 4 + 3] = __uint_as_float(r[c & 1][i * 4 + 3]) + bv[i].w;
                     }
                     if (epi.act == NAVC_ACT_GELU_NEW) {
 #pragma unroll
@@ -318,19 +368,6 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     } else if (epi.act != NAVC_ACT_NONE) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], epi.act);
-                    }
-                    if (epi.res_hi) {
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const uint4 h4 = rh[c & 1][i], l4 = rl[c & 1][i];
-                            const uint32_t hw_[4] = {h4.x, h4.y, h4.z, h4.w};
-                            const uint32_t lw_[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                v[i * 8 + q * 2 + 0] += __uint_as_float(hw_[q] << 16) + __uint_as_float(lw_[q] << 16);
-                                v[i * 8 + q * 2 + 1] += __uint_as_float(hw_[q] & 0xffff0000u) + __uint_as_float(lw_[q] & 0xffff0000u);
-                            }
-                        }
                     }
                     if (rz) {
 #pragma unroll
@@ -347,50 +384,45 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             hw[j] = *reinterpret_cast<const uint32_t*>(&hb);
                         }
                     }
+                    tr.ev(30 + c);
                     if (epi.dbg == 12) continue;   // profiling aid: no stores
-                    if (direct) {
-                        if (row_ok) {
-                            uint16_t* oh = epi.out_hi + (size_t)rowp * epi.ld_out + col0;
-                            uint16_t* ol = epi.out_lo ? epi.out_lo + (size_t)rowp * epi.ld_out + col0 : nullptr;
-                            if (direct == 2 && col0 + 16 <= N) {
-                                st_global_256(oh, hw);
-                                if (ol) st_global_256(ol, lw);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 2; ++i)
-                                    if (col0 + i * 8 < N) {
-                                        *reinterpret_cast<uint4*>(oh + i * 8) = make_uint4(hw[i * 4], hw[i * 4 + 1], hw[i * 4 + 2], hw[i * 4 + 3]);
-                                        if (ol) *reinterpret_cast<uint4*>(ol + i * 8) = make_uint4(lw[i * 4], lw[i * 4 + 1], lw[i * 4 + 2], lw[i * 4 + 3]);
-                                    }
-                            }
-                        }
-                        continue;
+                    // hi box: its previous store (one bulk group before the most recent one) must have read the staging box
+                    if (lane == 0) {
+                        if (epi.out_lo) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
-                    // the previous step's TMA stores must have finished reading the staging boxes
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
                     *reinterpret_cast<uint4*>(stg + lane * 32) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     *reinterpret_cast<uint4*>(stg + lane * 32 + 16) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-                    if (epi.out_lo) {
-                        *reinterpret_cast<uint4*>(stg + 1024 + lane * 32) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                        *reinterpret_cast<uint4*>(stg + 1024 + lane * 32 + 16) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
                         tma_store_2d(&map_o_hi, stg_s, col0, row0);
-                        if (epi.out_lo) tma_store_2d(&map_o_lo, stg_s + 1024u, col0, row0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    if (epi.out_lo) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the previous lo box
+                        __syncwarp();
+                        *reinterpret_cast<uint4*>(stg + 1024 + lane * 32) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        *reinterpret_cast<uint4*>(stg + 1024 + lane * 32 + 16) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&map_o_lo, stg_s + 1024u, col0, row0);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                    tr.ev(50 + c);
                 }
             }
             tr.ev(8);   // epilogue of the unit issued
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0));   // the leader's MMA thread waits for both CTAs
-                else mbar_arrive(tempty_bar(acc));
+            if (pre) {
+                // this stage's next user (two units ahead): its residual goes in before the stage is handed back
+                G2Unit nx;
+                tc_fence_before();   // our tcgen05.ld of this stage are complete (wait::ld) before the tcgen05.st below
+                if (get_unit(it + G2_ACC, nx)) preload(nx, acc);
             }
+            arrive_drained(acc);
             if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging stays valid until read
@@ -432,7 +464,7 @@ static int g2_init() {
     return 0;
 }
 
-// cost (in units of a 128-column tile time) of the persistent schedule the kernel derives, for choosing TBN
+// cost of the persistent schedule the kernel derives, for choosing TBN (units: the MMA time of a 128-column k-block)
 static float g2_cost(int m_blocks, int N, int tbn, int cl, int sms, bool x3) {
     const int units = ((m_blocks + cl - 1) / cl) * ((N + tbn - 1) / tbn);
     int G = sms / cl;
@@ -444,25 +476,28 @@ static float g2_cost(int m_blocks, int N, int tbn, int cl, int sms, bool x3) {
         parts = q >= 4 ? 4 : (q >= 2 ? 2 : 1);
         if (parts > tbn / 64) parts = tbn / 64;
     }
-    // a part re-streams the whole A tile for 1/parts of the columns: charge it 30 % more than its share
-    const float tail = rem > 0 ? (parts > 1 ? 1.3f / parts : 1.0f) : 0.0f;
-    // bytes entering an SM per k-block and 128 x tbn share of the tile: A rows + (pair: half of) the B rows; the k-block
-    // time follows that stream (~40 B/clk) or the MMAs, whichever is longer
-    // (units: the MMA time of a 128-column k-block -- 768 cycles split-bf16, 256 plain; stream at 40 B/clk)
-    const float mma = tbn / 128.0f, stream = (128.0f + (float)tbn / cl) / (x3 ? 120.0f : 80.0f);
-    return (full + tail) * (mma > stream ? mma : stream);
+    // bytes entering an SM per k-block: the A rows + (pair: half of) the B rows; a k-block takes the longer of its
+    // MMAs (768 cycles split-bf16 / 256 plain per 128 columns) and that stream at ~40 B/clk
+    auto kblock = [&](float cols) {
+        const float mma = cols / 128.0f, stream = (128.0f + cols / cl) / (x3 ? 120.0f : 80.0f);
+        return mma > stream ? mma : stream;
+    };
+    return full * kblock((float)tbn) + (rem > 0 ? kblock((float)tbn / parts) : 0.0f);
 }
 
 template <bool kX3, int TBN, int kCl>
 static int g2_launch(const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi, const uint16_t* w_lo, int ldw,
                      int M, int N, int K, const EpiParams& epi, int sms, cudaStream_t st) {
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo;
-    const int bbox = kCl > 1 ? TBN / 2 : TBN;
-    if (tc_make_map(&ma_hi, x_hi, M, K, ldx, G2_BM) || tc_make_map(&mb_hi, w_hi, N, K, ldw, bbox)) return 1;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mp_hi, mp_lo, mo_hi, mo_lo;
+    const int bbox = TBN / kCl;
+    if (tc_make_map(&ma_hi, x_hi, M, K, ldx, G2_BM) || tc_make_map(&mb_hi, w_hi, N, K, ldw, bbox) ||
+        tc_make_map(&mp_hi, w_hi, N, K, ldw, G2_PBOX)) return 1;
     ma_lo = ma_hi;
     mb_lo = mb_hi;
+    mp_lo = mp_hi;
     if (kX3) {
-        if (tc_make_map(&ma_lo, x_lo, M, K, ldx, G2_BM) || tc_make_map(&mb_lo, w_lo, N, K, ldw, bbox)) return 1;
+        if (tc_make_map(&ma_lo, x_lo, M, K, ldx, G2_BM) || tc_make_map(&mb_lo, w_lo, N, K, ldw, bbox) ||
+            tc_make_map(&mp_lo, w_lo, N, K, ldw, G2_PBOX)) return 1;
     }
     if (tc_make_store_map16(&mo_hi, epi.out_hi, M, N, epi.ld_out)) return 1;
     mo_lo = mo_hi;
@@ -485,16 +520,7 @@ static int g2_launch(const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const 
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = kCl > 1 ? 2 : 1;
-    // epilogue stores: 256-bit global stores by default (measured: the 32 x 16 TMA store boxes, 32-byte rows, were what
-    // paced the epilogue -- and with it the whole tile); NAVC_GEMM2_STORE=tma restores the staged TMA stores
-    static int store_mode = -1;
-    if (store_mode < 0) {
-        const char* e = getenv("NAVC_GEMM2_STORE");
-        store_mode = (e && e[0] == 't') ? 0 : 1;
-    }
-    int direct = store_mode;
-    if (direct && epi.ld_out % 16 == 0 && ((((uintptr_t)epi.out_hi) | ((uintptr_t)epi.out_lo)) & 31) == 0) direct = 2;
-    NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<kX3, TBN, kCl>, ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, M, N, K, epi, direct));
+    NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<kX3, TBN, kCl>, ma_hi, ma_lo, mb_hi, mb_lo, mp_hi, mp_lo, mo_hi, mo_lo, M, N, K, epi));
     return check_launch("navc_linear_tc (gemm2)");
 }
 

@@ -35,11 +35,14 @@ torch.cuda.synchronize()
 fn(None)
 print("kernel %.1f us (events)" % (e0.elapsed_time(e1) * 1e3))
 t = buf.cpu().view(148, 3, 64)
-NAMES = {1: "prologue", 2: "ld0", 3: "ldN", 4: "accfree", 5: "op0", 6: "opN", 7: "accrdy", 8: "epi", 9: "drain"}
+NAMES = {**{20 + c: "ld%d" % c for c in range(4)}, **{30 + c: "cmp%d" % c for c in range(4)}, **{40 + c: "free%d" % c for c in range(4)},
+         **{50 + c: "st%d" % c for c in range(4)}}
+NAMES.update({1: "prologue", 2: "ld0", 3: "ldN", 4: "accfree", 5: "op0", 6: "opN", 7: "accrdy", 8: "epi", 9: "drain"})
 GHZ = float(os.environ.get("GHZ", "1.9"))
-for cta in (0, 1, 2, 75, 146, 147):
+ROLES = [int(x) for x in os.environ.get("ROLES", "0,1,2").split(",")]
+for cta in (0, 1, 75, 146):
     ev = []
-    for role in range(3):
+    for role in ROLES:
         for x in t[cta, role].tolist():
             if x:
                 ev.append((x & ((1 << 56) - 1), (x >> 56) & 0xff, role))
