@@ -284,35 +284,41 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (!(v.valid && cl0 < v.w && v.n0 + cl0 < N)) return;   // warp-uniform: the MMAs do not touch these columns
             const int rowp = v.mb * G2_BM + quarter * 32 + lane;
             const bool row_ok = rowp < M;
-            uint4 h[STEPS][2], l[STEPS][2];
+            // two 16-column steps at a time: 32 registers of loads in flight (the latency is hidden behind a main loop anyway)
+            constexpr int PS = STEPS < 2 ? STEPS : 2;
 #pragma unroll
-            for (int c = 0; c < STEPS; ++c)
+            for (int c0 = 0; c0 < STEPS; c0 += PS) {
+                if (cl0 + c0 * 16 >= v.w) break;   // warp-uniform
+                uint4 h[PS][2], l[PS][2];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    h[c][i] = make_uint4(0u, 0u, 0u, 0u);
-                    l[c][i] = make_uint4(0u, 0u, 0u, 0u);
-                    const int col = v.n0 + cl0 + c * 16 + i * 8;
-                    if (row_ok && cl0 + c * 16 < v.w && col < N) {
-                        const size_t ro = (size_t)rowp * epi.ld_res + col;
-                        h[c][i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
-                        if (epi.res_lo) l[c][i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
+                for (int c = 0; c < PS; ++c)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        h[c][i] = make_uint4(0u, 0u, 0u, 0u);
+                        l[c][i] = make_uint4(0u, 0u, 0u, 0u);
+                        const int col = v.n0 + cl0 + (c0 + c) * 16 + i * 8;
+                        if (row_ok && cl0 + (c0 + c) * 16 < v.w && col < N) {
+                            const size_t ro = (size_t)rowp * epi.ld_res + col;
+                            h[c][i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
+                            if (epi.res_lo) l[c][i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
+                        }
                     }
-                }
 #pragma unroll
-            for (int c = 0; c < STEPS; ++c) {
-                if (cl0 + c * 16 >= v.w) break;   // warp-uniform
-                uint32_t f[16];
+                for (int c = 0; c < PS; ++c) {
+                    if (cl0 + (c0 + c) * 16 >= v.w) break;   // warp-uniform
+                    uint32_t f[16];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const uint32_t hw_[4] = {h[c][i].x, h[c][i].y, h[c][i].z, h[c][i].w};
-                    const uint32_t lw_[4] = {l[c][i].x, l[c][i].y, l[c][i].z, l[c][i].w};
+                    for (int i = 0; i < 2; ++i) {
+                        const uint32_t hw_[4] = {h[c][i].x, h[c][i].y, h[c][i].z, h[c][i].w};
+                        const uint32_t lw_[4] = {l[c][i].x, l[c][i].y, l[c][i].z, l[c][i].w};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        f[i * 8 + q * 2 + 0] = __float_as_uint(__uint_as_float(hw_[q] << 16) + __uint_as_float(lw_[q] << 16));
-                        f[i * 8 + q * 2 + 1] = __float_as_uint(__uint_as_float(hw_[q] & 0xffff0000u) + __uint_as_float(lw_[q] & 0xffff0000u));
+                        for (int q = 0; q < 4; ++q) {
+                            f[i * 8 + q * 2 + 0] = __float_as_uint(__uint_as_float(hw_[q] << 16) + __uint_as_float(lw_[q] << 16));
+                            f[i * 8 + q * 2 + 1] = __float_as_uint(__uint_as_float(hw_[q] & 0xffff0000u) + __uint_as_float(lw_[q] & 0xffff0000u));
+                        }
                     }
+                    tc_st16(t_lane + (uint32_t)(a * TBN + cl0 + (c0 + c) * 16), f);
                 }
-                tc_st16(t_lane + (uint32_t)(a * TBN + cl0 + c * 16), f);
             }
             tc_wait_st();
         };
