@@ -33,7 +33,10 @@ def _init():
     os.environ.pop("NAVC_GEMM2_CLUSTER", None)
 
 
-def run(mode, M, N, K, cluster, force=0, cnt=None, epilogue=True, seed=60):
+def run(mode, M, N, K, cluster, force=0, cnt=None, epilogue=True, seed=60, act="none"):
+    """epilogue=True: bias + `act` + bf16-pair residual + row mask (act='none' is what the decoder layer's residual
+    GEMMs use and what gemm2 serves: the residual is preloaded into the accumulators; an activation together with a
+    residual goes to the first-generation kernel)."""
     x = torch.randn(M, K, generator=g(seed))
     w = torch.randn(N, K, generator=g(seed + 1)) / math.sqrt(K)
     b = torch.randn(N, generator=g(seed + 2))
@@ -48,7 +51,9 @@ def run(mode, M, N, K, cluster, force=0, cnt=None, epilogue=True, seed=60):
     we = wh.float().cpu().double() + (wl.float().cpu().double() if x3 else 0)
     y = xe @ we.t()
     if epilogue:
-        y = O.activation("gelu_new")((y + b.double()).float()).double()
+        y = y + b.double()
+        if act != "none":
+            y = O.activation(act)(y.float()).double()
         y = (y + (rh.float() + (rl.float() if x3 else 0)).cpu().double()) * toks.ne(0).double().unsqueeze(1)
     if cluster:
         os.environ["NAVC_GEMM2_CLUSTER"] = str(cluster)
@@ -56,7 +61,7 @@ def run(mode, M, N, K, cluster, force=0, cnt=None, epilogue=True, seed=60):
     olo = torch.full((M, N), 9.0, dtype=torch.bfloat16, device=DEV) if x3 else None
     m_dev = torch.tensor([cnt], dtype=torch.int32, device=DEV) if cnt is not None else None
     if epilogue:
-        ep = L.Epilogue(L.ptr(bd), None, L.ptr(td), L.ACT["gelu_new"], N, None, L.ptr(ohi), L.ptr(olo), N, force, 1, 0,
+        ep = L.Epilogue(L.ptr(bd), None, L.ptr(td), L.ACT[act], N, None, L.ptr(ohi), L.ptr(olo), N, force, 1, 0,
                         L.ptr(rh), L.ptr(rl) if x3 else None, L.ptr(m_dev), cnt or 0, 0)
     else:
         ep = L.Epilogue(None, None, None, 0, 0, None, L.ptr(ohi), L.ptr(olo), N, force, 1, 0, None, None, L.ptr(m_dev), cnt or 0, 0)
@@ -80,6 +85,31 @@ def run(mode, M, N, K, cluster, force=0, cnt=None, epilogue=True, seed=60):
                                    (3000, 520, 200), (129, 1024, 64), (7777, 264, 1032), (40000, 512, 128)])
 def test_gemm2_matches_reference(mode, cluster, M, N, K):
     run(mode, M, N, K, cluster)
+    run(mode, M, N, K, cluster, act="gelu_new", seed=70)
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("act", ["gelu_new", "relu"])
+def test_gemm2_activation_without_residual(mode, act):
+    """bias + activation, no residual (the FFN up-projection): gemm2's plain epilogue."""
+    M, N, K = 10478, 2048, 512
+    x = torch.randn(M, K, generator=g(80))
+    w = torch.randn(N, K, generator=g(81)) / math.sqrt(K)
+    b = torch.randn(N, generator=g(82))
+    x3 = mode == "bf16x3"
+    xh, xl = [t.to(DEV) for t in split(x)]
+    wh, wl = [t.to(DEV) for t in split(w)]
+    xe = xh.float().cpu().double() + (xl.float().cpu().double() if x3 else 0)
+    we = wh.float().cpu().double() + (wl.float().cpu().double() if x3 else 0)
+    y = O.activation(act)((xe @ we.t() + b.double()).float()).double()
+    ohi = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
+    olo = torch.empty((M, N), dtype=torch.bfloat16, device=DEV) if x3 else None
+    bd = b.to(DEV)
+    ep = L.Epilogue(L.ptr(bd), None, None, L.ACT[act], 0, None, L.ptr(ohi), L.ptr(olo), N, 0, 1, 0, None, None, None, 0, 0)
+    L.call("navc_linear_tc", L.TC_BF16X3 if x3 else L.TC_BF16, L.ptr(xh), L.ptr(xl) if x3 else None, K, L.ptr(wh),
+           L.ptr(wl) if x3 else None, K, M, N, K, ep, L.stream())
+    got = (ohi.float() + (olo.float() if x3 else 0)).cpu().double()
+    assert (got - y).abs().max().item() < (3e-5 if x3 else 1.2e-2) * max(1.0, y.abs().max().item())
 
 
 @pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
