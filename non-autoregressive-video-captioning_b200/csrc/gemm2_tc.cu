@@ -13,11 +13,11 @@
 //    partner's epilogue warps arrive remotely on the leader's "accumulator drained" barrier.
 //    (Tried first and dropped: TMA multicast of the B tile inside a 2-CTA cluster -- no gain, the bytes still enter
 //    both SMs -- and 256-bit global stores instead of TMA store boxes -- the row-per-lane stores cost ~120 cycles each.)
-//  * The residual is PRELOADED INTO THE ACCUMULATOR: while a tile's MMAs run, the epilogue warps fetch the bf16 hi/lo
-//    residual of the tile that will use the other TMEM stage next, join it to fp32 and `tcgen05.st` it there; the MMAs
-//    of that tile then accumulate onto it.  The timeline showed 2.5 us per 16-column epilogue step with the residual
-//    loaded in the epilogue (exposed L2 latency under the operand stream) against 1.3 us without: 10 us per tile against
-//    a 6.6 us main loop.  Preloaded, the residual's latency hides behind a whole main loop and costs no registers.
+//  * The bf16 hi/lo residual is read with 256-bit loads (a row-per-lane access costs the LSU per distinct line, not
+//    per byte), the first step's before the accumulator barrier is awaited and every later step's one step ahead.
+//    (Tried and dropped: preloading the residual into the TMEM accumulators with tcgen05.st so that the MMAs add onto
+//    it -- correct, but the two preloads ahead of a CTA's first MMA cost 10 us at kernel start, and with 1-2 tiles per
+//    CTA at the config-2 shapes there is no steady state to win it back: so 29.8 vs 30.8 us, f2 65.6 vs 61.2 us.)
 //  * Epilogue steps are software pipelined: the tcgen05.ld of step c+1 is issued before step c is computed, and the hi
 //    and lo boxes leave as separate bulk groups (`cp.async.bulk.wait_group.read 1`), so a staging box is only waited
 //    for when the store issued a full half-step earlier has not drained yet.
@@ -67,7 +67,7 @@ struct G2Trace {
     }
 };
 
-template <bool kX3, int TBN, int kCl>
+template <bool kX3, int TBN, int kCl, bool kRes>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -79,7 +79,6 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     constexpr bool kPair = kCl == 2;
     constexpr int kParts = kX3 ? 2 : 1;
     const int M = epi.m_dev ? min(M_max, __ldg(epi.m_dev)) : M_max;   // device-side row count (packed rows)
-    const bool pre = epi.res_hi != nullptr;                           // residual preloaded into the accumulators
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -209,9 +208,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             G2Unit u;
             G2Trace tr(1);
             for (int it = 0; get_unit(it, u); ++it) {
-                // residual preloaded: phase k of the barrier = "stage ready for its k-th use" (drained AND preloaded),
-                // the first use included; otherwise the first use of a stage passes immediately
-                mbar_wait(tempty_bar(acc), pre ? acc_phase : (acc_phase ^ 1u));
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // the first use of a stage passes immediately
                 tc_fence_after();
                 tr.ev(4);   // accumulator stage free
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TBN);
@@ -227,7 +224,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     for (int k = 0; k < G2_BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
                         if (epi.dbg == 14 && (kb | k)) continue;   // profiling aid: one MMA per tile
-                        const uint32_t first = (pre || (kb | k)) ? 1u : 0u;   // accumulate onto the preloaded residual
+                        const uint32_t first = (kb | k) ? 1u : 0u;
                         if constexpr (kPair) {
                             if (kX3) {
                                 tc_mma_bf16_2cta(d_tmem, da_lo + koff, db_hi + koff, idesc, first);
@@ -279,57 +276,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 else mbar_arrive(tempty_bar(a));
             }
         };
-        // residual of unit `v` -> accumulator stage `a` (fp32 = hi + lo), zeros for rows / columns outside the output
-        auto preload = [&](const G2Unit& v, int a) {
-            if (!(v.valid && cl0 < v.w && v.n0 + cl0 < N)) return;   // warp-uniform: the MMAs do not touch these columns
-            const int rowp = v.mb * G2_BM + quarter * 32 + lane;
-            const bool row_ok = rowp < M;
-            // two 16-column steps at a time: 32 registers of loads in flight (the latency is hidden behind a main loop anyway)
-            constexpr int PS = STEPS < 2 ? STEPS : 2;
-#pragma unroll
-            for (int c0 = 0; c0 < STEPS; c0 += PS) {
-                if (cl0 + c0 * 16 >= v.w) break;   // warp-uniform
-                uint4 h[PS][2], l[PS][2];
-#pragma unroll
-                for (int c = 0; c < PS; ++c)
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        h[c][i] = make_uint4(0u, 0u, 0u, 0u);
-                        l[c][i] = make_uint4(0u, 0u, 0u, 0u);
-                        const int col = v.n0 + cl0 + (c0 + c) * 16 + i * 8;
-                        if (row_ok && cl0 + (c0 + c) * 16 < v.w && col < N) {
-                            const size_t ro = (size_t)rowp * epi.ld_res + col;
-                            h[c][i] = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro));
-                            if (epi.res_lo) l[c][i] = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro));
-                        }
-                    }
-#pragma unroll
-                for (int c = 0; c < PS; ++c) {
-                    if (cl0 + (c0 + c) * 16 >= v.w) break;   // warp-uniform
-                    uint32_t f[16];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const uint32_t hw_[4] = {h[c][i].x, h[c][i].y, h[c][i].z, h[c][i].w};
-                        const uint32_t lw_[4] = {l[c][i].x, l[c][i].y, l[c][i].z, l[c][i].w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            f[i * 8 + q * 2 + 0] = __float_as_uint(__uint_as_float(hw_[q] << 16) + __uint_as_float(lw_[q] << 16));
-                            f[i * 8 + q * 2 + 1] = __float_as_uint(__uint_as_float(hw_[q] & 0xffff0000u) + __uint_as_float(lw_[q] & 0xffff0000u));
-                        }
-                    }
-                    tc_st16(t_lane + (uint32_t)(a * TBN + cl0 + (c0 + c) * 16), f);
-                }
-            }
-            tc_wait_st();
-        };
-
         G2Unit u;
-        if (pre) {   // the first use of both accumulator stages
-            for (int a = 0; a < G2_ACC; ++a) {
-                if (get_unit(a, u)) preload(u, a);
-                arrive_drained(a);
-            }
-        }
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int it = 0; get_unit(it, u); ++it) {
@@ -338,12 +285,42 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const bool row_ok = u.valid && rowp < M;
             const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[rowp] == NAVC_PAD) : false;
             const bool active = u.valid && cl0 < u.w && u.n0 + cl0 < N && row0 < M && epi.dbg != 11;   // warp-uniform
+            // residual of one 16-column step: 32 bytes of hi (+ lo) per row
+            const bool res_wide = (epi.ld_res % 16 == 0) && ((((uintptr_t)epi.res_hi) | ((uintptr_t)epi.res_lo)) & 31) == 0;
+            uint32_t rh[kRes ? 2 : 1][8], rl[kRes ? 2 : 1][8];
+            auto load_res = [&](int c, uint32_t (&h)[8], uint32_t (&l)[8]) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { h[j] = 0u; l[j] = 0u; }
+                const int col = u.n0 + cl0 + c * 16;
+                if (row_ok && cl0 + c * 16 < u.w && col < N) {
+                    const size_t ro = (size_t)rowp * epi.ld_res + col;
+                    if (res_wide && col + 16 <= N) {
+                        ld_global_nc_256(epi.res_hi + ro, h);
+                        if (epi.res_lo) ld_global_nc_256(epi.res_lo + ro, l);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            if (col + i * 8 < N) {
+                                const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro + i * 8));
+                                h[i * 4] = a4.x; h[i * 4 + 1] = a4.y; h[i * 4 + 2] = a4.z; h[i * 4 + 3] = a4.w;
+                                if (epi.res_lo) {
+                                    const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro + i * 8));
+                                    l[i * 4] = b4.x; l[i * 4 + 1] = b4.y; l[i * 4 + 2] = b4.z; l[i * 4 + 3] = b4.w;
+                                }
+                            }
+                    }
+                }
+            };
+            if (kRes && active) load_res(0, rh[0], rl[0]);   // overlaps the main loop of this tile
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             tr.ev(7);   // accumulators of the unit ready
             if (active) {
                 const uint32_t t_row = t_lane + (uint32_t)(acc * TBN + cl0);
-                uint32_t r[2][16];
+                // without a residual the accumulator registers are double buffered (the next step's tcgen05.ld travels
+                // while this step is computed); with one, the registers go to the residual's one-step lookahead instead
+                constexpr int RB = kRes ? 1 : 2;
+                uint32_t r[RB][16];
                 tc_ld16(t_row, r[0]);
 #pragma unroll
                 for (int c = 0; c < STEPS; ++c) {
@@ -357,23 +334,32 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         if (epi.bias && col0 + i * 4 < N) bv[i] = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + i * 4));
                     }
                     tc_wait_ld();
-                    // the next step's accumulators travel while this step is computed and stored
-                    if (c + 1 < STEPS && cl + 16 < u.w && col0 + 16 < N) tc_ld16(t_row + (uint32_t)((c + 1) * 16), r[(c + 1) & 1]);
+                    const bool more = c + 1 < STEPS && cl + 16 < u.w && col0 + 16 < N;
+                    if (!kRes && more) tc_ld16(t_row + (uint32_t)((c + 1) * 16), r[(c + 1) % RB]);
+                    if (kRes && more) load_res(c + 1, rh[(c + 1) & 1], rl[(c + 1) & 1]);   // one step ahead
                     tr.ev(20 + c);
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        v[i * 4 + 0] = __uint_as_float(r[c & 1][i * 4 + 0]) + bv[i].x;
-                        v[i * 4 + 1] = __uint_as_float(r[c & 1][i * 4 + 1]) + bv[i].y;
-                        v[i * 4 + 2] = __uint_as_float(r[c & 1][i * 4 + 2]) + bv[i].z;
-                        v[i * 4 + 3] = __uint_as_float(r[c & 1][i * 4 + 3]) + bv[i].w;
+                        v[i * 4 + 0] = __uint_as_float(r[c % RB][i * 4 + 0]) + bv[i].x;
+                        v[i * 4 + 1] = __uint_as_float(r[c % RB][i * 4 + 1]) + bv[i].y;
+                        v[i * 4 + 2] = __uint_as_float(r[c % RB][i * 4 + 2]) + bv[i].z;
+                        v[i * 4 + 3] = __uint_as_float(r[c % RB][i * 4 + 3]) + bv[i].w;
                     }
+                    if (kRes && more) tc_ld16(t_row + (uint32_t)((c + 1) * 16), r[0]);   // r[0] is free again
                     if (epi.act == NAVC_ACT_GELU_NEW) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], NAVC_ACT_GELU_NEW);
                     } else if (epi.act != NAVC_ACT_NONE) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], epi.act);
+                    }
+                    if constexpr (kRes) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            v[q * 2 + 0] += __uint_as_float(rh[c & 1][q] << 16) + __uint_as_float(rl[c & 1][q] << 16);
+                            v[q * 2 + 1] += __uint_as_float(rh[c & 1][q] & 0xffff0000u) + __uint_as_float(rl[c & 1][q] & 0xffff0000u);
+                        }
                     }
                     if (rz) {
 #pragma unroll
@@ -422,12 +408,6 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 }
             }
             tr.ev(8);   // epilogue of the unit issued
-            if (pre) {
-                // this stage's next user (two units ahead): its residual goes in before the stage is handed back
-                G2Unit nx;
-                tc_fence_before();   // our tcgen05.ld of this stage are complete (wait::ld) before the tcgen05.st below
-                if (get_unit(it + G2_ACC, nx)) preload(nx, acc);
-            }
             arrive_drained(acc);
             if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
         }
@@ -462,7 +442,8 @@ static bool g_g2_ready = false;
 static int g2_init() {
     if (g_g2_ready) return 0;
 #define NAVC_G2_ATTR(X3, BN, CL) \
-    NAVC_CUDA(cudaFuncSetAttribute(gemm2_tc_kernel<X3, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<X3, BN, CL>::kSmemBytes))
+    NAVC_CUDA(cudaFuncSetAttribute(gemm2_tc_kernel<X3, BN, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<X3, BN, CL>::kSmemBytes)); \
+    NAVC_CUDA(cudaFuncSetAttribute(gemm2_tc_kernel<X3, BN, CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<X3, BN, CL>::kSmemBytes))
     NAVC_G2_ATTR(false, 128, 1); NAVC_G2_ATTR(false, 256, 1); NAVC_G2_ATTR(true, 128, 1); NAVC_G2_ATTR(true, 256, 1);
     NAVC_G2_ATTR(false, 128, 2); NAVC_G2_ATTR(false, 256, 2); NAVC_G2_ATTR(true, 128, 2); NAVC_G2_ATTR(true, 256, 2);
 #undef NAVC_G2_ATTR
@@ -526,7 +507,10 @@ static int g2_launch(const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const 
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = kCl > 1 ? 2 : 1;
-    NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<kX3, TBN, kCl>, ma_hi, ma_lo, mb_hi, mb_lo, mp_hi, mp_lo, mo_hi, mo_lo, M, N, K, epi));
+    if (epi.res_hi)
+        NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<kX3, TBN, kCl, true>, ma_hi, ma_lo, mb_hi, mb_lo, mp_hi, mp_lo, mo_hi, mo_lo, M, N, K, epi));
+    else
+        NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<kX3, TBN, kCl, false>, ma_hi, ma_lo, mb_hi, mb_lo, mp_hi, mp_lo, mo_hi, mo_lo, M, N, K, epi));
     return check_launch("navc_linear_tc (gemm2)");
 }
 

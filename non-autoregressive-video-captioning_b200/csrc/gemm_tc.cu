@@ -900,8 +900,7 @@ extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_
                       (!p.res_hi || (p.ld_res % 8 == 0 && ((((uintptr_t)p.res_hi) | ((uintptr_t)p.res_lo)) & 15) == 0));
     NAVC_REQUIRE(pair || !p.res_hi, "navc_linear_tc: a bf16 hi/lo residual needs bf16-only outputs (no out_f32 / fp32 residual), "
                                     "N %% 8 == 0 and 16-byte aligned operands");
-    // (gemm2 preloads the residual into the accumulators, which only commutes with the identity activation)
-    if (pair && g2_enabled() && !sk_enabled() && !(p.res_hi && p.act != NAVC_ACT_NONE) && (p.dbg == 0 || p.dbg == 7 || (p.dbg >= 11 && p.dbg <= 15) || p.dbg == 128 || p.dbg == 256)) {
+    if (pair && g2_enabled() && !sk_enabled() && (p.dbg == 0 || p.dbg == 7 || (p.dbg >= 11 && p.dbg <= 15) || p.dbg == 128 || p.dbg == 256)) {
         // second-generation kernel (gemm2_tc.cu): cluster multicast of the weight tile, tail split along N
         NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "navc_linear_tc: bad mode %d", mode);
         NAVC_REQUIRE(x_hi && w_hi && (mode == NAVC_TC_BF16 || (x_lo && w_lo)), "navc_linear_tc: null operand");
