@@ -514,14 +514,16 @@ static int g2_launch(const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const 
     return check_launch("navc_linear_tc (gemm2)");
 }
 
-static int g_g2_on = -1;
+static int g_g2_on = -1;   // 0 off, 1 on (split-bf16 mode), 2 forced (every mode)
 bool g2_enabled() {
     if (g_g2_on < 0) {
-        const char* e = getenv("NAVC_GEMM2");   // NAVC_GEMM2=0: the first-generation kernel (gemm_tc.cu) for A/B runs
-        g_g2_on = (e && (e[0] == '0' || e[0] == 'n' || e[0] == 'f')) ? 0 : 1;
+        // NAVC_GEMM2=0: the first-generation kernel (gemm_tc.cu) for A/B runs; NAVC_GEMM2=force: also in plain bf16
+        const char* e = getenv("NAVC_GEMM2");
+        g_g2_on = (e && (e[0] == '0' || e[0] == 'n')) ? 0 : ((e && e[0] == 'f') ? 2 : 1);
     }
     return g_g2_on != 0;
 }
+bool g2_forced() { return g2_enabled() && g_g2_on == 2; }
 
 // Pair-epilogue GEMM (bf16 hi(/lo) outputs only): called by navc_linear_tc once the arguments are validated.
 int g2_linear(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi, const uint16_t* w_lo, int ldw,

@@ -739,6 +739,7 @@ int tc_make_store_map16(CUtensorMap* map, const uint16_t* ptr, int rows, int col
 int g2_linear(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w_hi, const uint16_t* w_lo, int ldw,
               int M, int N, int K, const EpiParams& epi, cudaStream_t st);   // gemm2_tc.cu
 bool g2_enabled();
+bool g2_forced();
 
 static thread_local int g_dgrad_w_rows = 0;  // true row count of the dgrad B operand (launch_tc_dgrad)
 
@@ -900,7 +901,10 @@ extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_
                       (!p.res_hi || (p.ld_res % 8 == 0 && ((((uintptr_t)p.res_hi) | ((uintptr_t)p.res_lo)) & 15) == 0));
     NAVC_REQUIRE(pair || !p.res_hi, "navc_linear_tc: a bf16 hi/lo residual needs bf16-only outputs (no out_f32 / fp32 residual), "
                                     "N %% 8 == 0 and 16-byte aligned operands");
-    if (pair && g2_enabled() && !sk_enabled() && (p.dbg == 0 || p.dbg == 7 || (p.dbg >= 11 && p.dbg <= 15) || p.dbg == 128 || p.dbg == 256)) {
+    // second-generation kernel (CTA pairs, tail split along N) in the split-bf16 mode, where it measured faster (config-2
+    // step 13.98 vs 14.10 ms); plain bf16 keeps the first-generation kernel with its TMA-prefetched residual boxes
+    // (7.87 vs 9.19 ms) unless NAVC_GEMM2=force
+    if (pair && g2_enabled() && (mode == NAVC_TC_BF16X3 || g2_forced()) && !sk_enabled() && (p.dbg == 0 || p.dbg == 7 || (p.dbg >= 11 && p.dbg <= 15) || p.dbg == 128 || p.dbg == 256)) {
         // second-generation kernel (gemm2_tc.cu): cluster multicast of the weight tile, tail split along N
         NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "navc_linear_tc: bad mode %d", mode);
         NAVC_REQUIRE(x_hi && w_hi && (mode == NAVC_TC_BF16 || (x_lo && w_lo)), "navc_linear_tc: null operand");

@@ -12,6 +12,7 @@ import navc_b200
 from navc_b200 import _lib as L
 from oracle import navc_oracle as O
 
+os.environ["NAVC_GEMM2"] = "force"   # read once by the library: gemm2 also in plain bf16 mode (the product uses it for bf16x3)
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda", 0)
 
