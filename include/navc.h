@@ -236,6 +236,21 @@ int navc_cross_attention_tc_packed(int mode, const uint16_t* q_hi, const uint16_
                                    const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv,
                                    const int32_t* seq_off, int N, int S, int E, int D, int H, int group,
                                    float* ctx_f32, uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream);
+/* Second-generation attention cores over packed rows (csrc/attention2_tc.cu): ONE persistent, warp-specialised,
+ * two-stage pipelined kernel per launch (TMA producer / MMA issuer / two alternating softmax + epilogue groups).
+ * Self-attention tiles are 96-row windows of the packed row space: navc_pack_tiles fills tile_seq[0..n_tiles] (first
+ * sequence of every window; n_tiles = ceil(max rows / navc_attention_window())) once per set of candidate lengths.
+ * Same arithmetic contract as navc_self_attention / navc_cross_attention (models/bert.py:139-179); bf16 hi(/lo) outputs. */
+int navc_attention_window(void);
+int navc_pack_tiles(const int32_t* seq_off, int N, int32_t* tile_seq, int n_tiles, void* stream);
+int navc_self_attention_tc_tiles(int mode, const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld,
+                                 const int64_t* tokens, const int32_t* seq_off, const int32_t* tile_seq,
+                                 int n_tiles, int rows, int N, int S, int D, int H, int mask_kind, int watch,
+                                 uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream);
+int navc_cross_attention_tc_tiles(int mode, const uint16_t* q_hi, const uint16_t* q_lo, int ldq,
+                                  const uint16_t* kv_hi, const uint16_t* kv_lo, int ldkv,
+                                  const int32_t* seq_off, int rows, int N, int S, int E, int D, int H, int group,
+                                  uint16_t* ctx_hi, uint16_t* ctx_lo, void* stream);
 /* The same with the row count of the packed buffers given explicitly (`rows` >= seq_off[N]; the _packed entry
  * points assume buffers of N*S rows): the training path sizes its buffers to the real positions. */
 int navc_self_attention_tc_rows(int mode, const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld,

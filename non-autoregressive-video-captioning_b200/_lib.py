@@ -67,6 +67,10 @@ _PROTOS = {
     "navc_embed_ln_packed": [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
     "navc_self_attention_tc_packed": [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
     "navc_cross_attention_tc_packed": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_attention_window": [],
+    "navc_pack_tiles": [vp, i32, vp, i32, vp],
+    "navc_self_attention_tc_tiles": [i32, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp],
+    "navc_cross_attention_tc_tiles": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp],
     "navc_gather_rows": [vp, vp, i32, vp, vp, i32, vp, vp, vp],
     "navc_vocab_partials_tc_dyn": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp],
     "navc_length_beam": [vp, i32, i32, i32, i32, vp, vp, vp],

@@ -423,7 +423,14 @@ class Engine:
         seq_off = torch.empty((N + 1,), dtype=torch.int32, device=self.device)
         rowmap = torch.zeros((N * S,), dtype=torch.int32, device=self.device)
         L.call("navc_pack_rows", L.ptr(lens), N, S, L.ptr(seq_off), L.ptr(rowmap), L.stream())
-        return dict(seq_off=seq_off, rowmap=rowmap, count=seq_off[N:], N=N, S=S, hint=int(hint))
+        pk = dict(seq_off=seq_off, rowmap=rowmap, count=seq_off[N:], N=N, S=S, hint=int(hint))
+        if os.environ.get("NAVC_ATTN2", "1") not in ("0", "no", "off"):
+            # second-generation attention cores: 96-row windows of the packed row space (navc_pack_tiles)
+            n_tiles = (N * S + L._lib.navc_attention_window() - 1) // L._lib.navc_attention_window()
+            tile_seq = torch.empty((n_tiles + 1,), dtype=torch.int32, device=self.device)
+            L.call("navc_pack_tiles", L.ptr(seq_off), N, L.ptr(tile_seq), n_tiles, L.stream())
+            pk.update(tile_seq=tile_seq, n_tiles=n_tiles)
+        return pk
 
     def can_pack(self, S, E):
         """Packed rows need the all-tensor-core layer (pair epilogues + tcgen05 attention cores)."""
@@ -477,7 +484,11 @@ class Engine:
             ctx = self._new(R, D, not self.tc, True)
             p_self = p_cross = None
             e0 = self._t0("self")
-            if packed is not None:
+            if packed is not None and "tile_seq" in packed:
+                L.call("navc_self_attention_tc_tiles", self.tc_mode, L.ptr(qkv.hi), L.ptr(qkv.lo), 3 * D, L.ptr(tokens),
+                       L.ptr(packed["seq_off"]), L.ptr(packed["tile_seq"]), packed["n_tiles"], R, N, S, D, H, mask_kind, watch,
+                       L.ptr(ctx.hi), L.ptr(ctx.lo), L.stream())
+            elif packed is not None:
                 L.call("navc_self_attention_tc_packed", self.tc_mode, L.ptr(qkv.hi), L.ptr(qkv.lo), 3 * D, L.ptr(tokens),
                        L.ptr(packed["seq_off"]), N, S, D, H, mask_kind, watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo),
                        L.stream())
@@ -493,7 +504,12 @@ class Engine:
             q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="cq", m_hint=mh)
             ctx2 = self._new(R, D, not self.tc, True)
             e0 = self._t0("cross")
-            if packed is not None:
+            if packed is not None and "tile_seq" in packed:
+                off = l * 2 * D
+                L.call("navc_cross_attention_tc_tiles", self.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D,
+                       kv.hi[:, off:].data_ptr(), kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N,
+                       L.ptr(packed["seq_off"]), R, N, S, E, D, H, group, L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.stream())
+            elif packed is not None:
                 off = l * 2 * D
                 L.call("navc_cross_attention_tc_packed", self.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D,
                        kv.hi[:, off:].data_ptr(), kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N,
