@@ -360,6 +360,18 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                         *reinterpret_cast<uint4*>(panel_hi + 2 * A2_TILE + ch) = make_uint4(lo_w[i * 4], lo_w[i * 4 + 1], lo_w[i * 4 + 2], lo_w[i * 4 + 3]);
                 }
             }
+            // key rows beyond the item's keys that a box brought in anyway hold whatever follows in memory (rows past the
+            // packed count are never written: possibly NaN bit patterns): P is 0 there, but 0 * NaN would poison O, so
+            // those V rows are cleared (a key row = one 128-byte swizzled row of the hi / lo tile)
+            if (r >= g.nkeys) {
+                mbar_wait(bar_v(s), par);
+                uint8_t* vrow = gP + Cfg::kQK + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    *reinterpret_cast<uint4*>(vrow + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    if (kX3) *reinterpret_cast<uint4*>(vrow + A2_TILE + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             __syncwarp();

@@ -63,7 +63,8 @@ def test_self_attention_tiles(mode, tol, kind, N, S, lo):
     lens, off = packing(N, S, 46, lo)
     R = int(off[-1])
     gen = g(47)
-    qkv = torch.randn(N * S, 3 * D, generator=gen)          # packed rows first, garbage (finite) beyond
+    qkv = torch.randn(N * S, 3 * D, generator=gen)          # packed rows first, NaN beyond (rows past the count are never written)
+    qkv[R:] = float("nan")
     toks = torch.zeros(N, S, dtype=torch.int64)
     for n in range(N):
         toks[n, :lens[n]] = torch.randint(1, 50, (int(lens[n]),), generator=gen)
@@ -106,6 +107,7 @@ def test_cross_attention_tiles(mode, tol, B, group, S, E, lo):
     R = int(off[-1])
     gen = g(49)
     q = torch.randn(N * S, D, generator=gen)
+    q[R:] = float("nan")                                     # rows past the packed count are never written
     kv = torch.randn(B * E, 2 * D, generator=gen)
     qh, ql = split(q)
     kh, kl_ = split(kv)
