@@ -42,6 +42,19 @@ template <bool kX3> struct A2Cfg {
     static constexpr int kSmemBytes = 2 * kStage + kStg + kTail + 1024 /*align*/;
 };
 
+// optional in-kernel timeline (navc_debug_trace_attn, tools/attn2_trace.py): roles 0 producer, 1 MMA issuer, 2 softmax group 0
+__device__ unsigned long long* a2_trace_buf = nullptr;
+struct A2Trace {
+    unsigned long long* p;
+    int n;
+    __device__ A2Trace(int role) : p(nullptr), n(0) {
+        if (a2_trace_buf) p = a2_trace_buf + ((size_t)blockIdx.x * 3 + role) * 64;
+    }
+    __device__ __forceinline__ void ev(unsigned tag) {
+        if (p && n < 64) p[n++] = ((unsigned long long)tag << 56) | ((unsigned long long)clock64() & 0x00ffffffffffffffull);
+    }
+};
+
 struct A2Geom { int row0, nq, krow0, nkeys, h, s0, s1, pad_; };
 
 struct A2Params {
@@ -112,6 +125,8 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
         // ===================== producer =====================
         if (lane == 0) {
             int i = 0;
+            A2Trace tr(0);
+            tr.ev(1);
             const int total = p.n_tiles * p.H;
             for (int w = (int)blockIdx.x; w < total; w += (int)gridDim.x) {
                 const int tile = w / p.H, h = w - tile * p.H;   // head fastest: concurrent CTAs share a tile's rows in L2
@@ -136,7 +151,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                 }
                 if (g.nq <= 0) continue;
                 const int s = i & 1, k = i >> 1;
+                tr.ev(2);   // geometry of the item known
                 if (i >= 2) mbar_wait(bar_o(s), (uint32_t)((k - 1) & 1));   // the MMAs of item i-2 have retired: stage s is free
+                tr.ev(3);   // stage free: loads issued
                 geom[s] = g;
                 const int nbq = (g.nq + 31) >> 5, nbk = (g.nkeys + 31) >> 5;
                 const uint32_t sq = stage_s(s), sk = sq + P * A2_TILE, sv = sq + Cfg::kQK;
@@ -194,9 +211,11 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                 tc_commit(bar_o(s));
             };
             int pending = -1, stops = 0;
+            A2Trace tr(1);
             for (int i = 0; stops < 2; ++i) {
                 const int s = i & 1, k = i >> 1;
                 mbar_wait(bar_qk(s), (uint32_t)(k & 1));
+                tr.ev(4);   // Q / K landed
                 if (geom[s].nq == 0) {
                     if (pending >= 0) { do_pv(pending); pending = -1; }
                     mbar_arrive(bar_s(s));   // lets this stage's softmax group see its terminator
@@ -221,7 +240,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                     }
                 }
                 tc_commit(bar_s(s));
+                tr.ev(5);   // S issued
                 if (pending >= 0) do_pv(pending);   // O = P V of the previous item, while this item's softmax runs
+                tr.ev(6);   // previous item's PV issued
                 pending = i;
             }
         }
@@ -244,6 +265,8 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             const uint32_t upto_b = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
             return upto_b & ~((1u << a) - 1u);
         };
+        A2Trace tr(2);
+        if (warp != 2 || lane != 0) tr.p = nullptr;
         for (int k = 0;; ++k) {
             const uint32_t par = (uint32_t)(k & 1);
             const int item = 2 * k + grp;           // position in this CTA's item sequence
@@ -251,6 +274,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             const A2Geom g = geom[s];
             if (g.nq == 0) break;
             tc_fence_after();
+            tr.ev(7);   // S ready
             // ---- this row's visible keys [own_lo, own_hi) and, for self-attention, its position and the PAD keys ----
             int own_lo = 0, own_hi = g.nkeys, ipos = 0;
             if (p.is_self) {
@@ -300,6 +324,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             for (int c = 0; c < 4; ++c)
                 if (c >= c_lo && c <= c_hi) tc_ld32(tS + t_lane + (uint32_t)(c * 32), v[c]);
             tc_wait_ld();
+            tr.ev(8);   // S in registers
             float m = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -376,10 +401,12 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_p(s));
+            tr.ev(9);   // P written
 
             // ---- epilogue: O row * 1/sum -> staging rows -> full lines to global memory ----
             mbar_wait(bar_o(s), par);
             tc_fence_after();
+            tr.ev(10);  // O ready
             const float inv = sum > 0.f ? 1.0f / sum : 0.f;
             uint32_t o[2][32];
             tc_ld32(tS + t_lane, o[0]);
@@ -422,6 +449,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_stg(quarter));    // staging quarter free for the next item
+            tr.ev(11);  // context rows stored
         }
     }
 
@@ -489,6 +517,12 @@ static int launch_attn2(int mode, const uint16_t* q_hi, const uint16_t* q_lo, in
 using namespace navc;
 
 extern "C" int navc_attention_window(void) { return 96; }
+
+// Debug: install (or remove, buf == NULL) the in-kernel timeline buffer: 3 x 64 uint64 per CTA of the grid.
+extern "C" int navc_debug_trace_attn(void* buf) {
+    unsigned long long* q = reinterpret_cast<unsigned long long*>(buf);
+    return cudaMemcpyToSymbol(navc::a2_trace_buf, &q, sizeof(q)) == cudaSuccess ? 0 : 1;
+}
 
 extern "C" int navc_pack_tiles(const int32_t* seq_off, int N, int32_t* tile_seq, int n_tiles, void* stream) {
     NAVC_REQUIRE(seq_off && tile_seq && N > 0 && n_tiles > 0, "navc_pack_tiles: bad arguments");
