@@ -14,8 +14,9 @@
 //               only as many as the item has rows / keys)
 //   warp 1      MMA issuer: S = Q K^T (UMMA 128x128x16) of item i, then O = P V (UMMA 128x64x16, V consumed MN-major) of
 //               item i-1
-//   warps 2-5 / 6-9   two softmax + epilogue groups, alternating items: ONE pass over S (the row stays in registers:
-//               max, exp, sum), P -> shared memory (bf16 hi/lo, the A operand of the second product), then O * 1/sum
+//   warps 2-5 / 6-9   two softmax + epilogue groups, alternating items: row maximum, then exp / row sum over S
+//               (32-key chunks straight from tensor memory), P -> TENSOR memory (tcgen05.st, packed bf16 hi / lo: the
+//               A operand of the second product, which never touches shared memory), then O * 1/sum
 //               -> swizzled staging rows -> full 128-byte lines to global memory (4 rows per store instruction)
 // Self-attention tiles are 96-row windows of the packed row space (every sequence that STARTS in the window; at most
 // 127 rows): block-diagonal masks from the per-row sequence bounds, no slot padding.  Cross-attention tiles are a
@@ -35,7 +36,7 @@ constexpr float kMaskFill2 = -10e6f;    // models/bert.py:161
 
 template <bool kX3> struct A2Cfg {
     static constexpr int P = kX3 ? 2 : 1;
-    static constexpr int kQK = 2 * P * A2_TILE;               // [Q hi, (Q lo), K hi, (K lo)]; P panels alias it
+    static constexpr int kQK = 2 * P * A2_TILE;               // [Q hi, (Q lo), K hi, (K lo)]
     static constexpr int kStage = 3 * P * A2_TILE;            // + [V hi, (V lo)]: 96 KB (48 KB plain bf16)
     static constexpr int kStg = P * A2_TILE;                  // context staging rows, hi (+ lo)
     static constexpr int kTail = 1024;                        // barriers, tmem slot, geometry, pad-key words
@@ -92,9 +93,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
     auto bar_t = [&](int s) { return bar_base + 8u * (10 + s); };
     auto bar_stg = [&](int q) { return bar_base + 8u * (12 + q); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
-    A2Geom* geom = reinterpret_cast<A2Geom*>(tail + 192);             // [2]
-    uint32_t* padw_all = reinterpret_cast<uint32_t*>(tail + 256);     // [2 groups][4] PAD-key bits per 32-key chunk
-    uint8_t* keypad_all = tail + 320;                                  // [2 groups][128]
+    A2Geom* geom = reinterpret_cast<A2Geom*>(tail + 192);             // [4]: item i uses slot i & 3
+    uint32_t* padw_all = reinterpret_cast<uint32_t*>(tail + 320);     // [2 groups][4] PAD-key bits per 32-key chunk
+    uint8_t* keypad_all = tail + 384;                                  // [2 groups][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -111,7 +112,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill above, before any TMA write / UMMA read
@@ -152,9 +153,10 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                 if (g.nq <= 0) continue;
                 const int s = i & 1, k = i >> 1;
                 tr.ev(2);   // geometry of the item known
-                if (i >= 2) mbar_wait(bar_o(s), (uint32_t)((k - 1) & 1));   // the MMAs of item i-2 have retired: stage s is free
-                tr.ev(3);   // stage free: loads issued
-                geom[s] = g;
+                // Q / K of stage s are free as soon as the S = Q K^T of item i-2 has retired (P lives in tensor memory)
+                if (i >= 2) mbar_wait(bar_s(s), (uint32_t)((k - 1) & 1));
+                tr.ev(3);   // Q / K loads issued
+                geom[i & 3] = g;
                 const int nbq = (g.nq + 31) >> 5, nbk = (g.nkeys + 31) >> 5;
                 const uint32_t sq = stage_s(s), sk = sq + P * A2_TILE, sv = sq + Cfg::kQK;
                 mbar_expect_tx(bar_qk(s), (uint32_t)((nbq + nbk) * A2_BOX * P));
@@ -166,6 +168,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                     tma_load_2d(sk + b * A2_BOX, &map_kv_hi, bar_qk(s), p.k_col + h * 64, g.krow0 + b * 32);
                     if (kX3) tma_load_2d(sk + A2_TILE + b * A2_BOX, &map_kv_lo, bar_qk(s), p.k_col + h * 64, g.krow0 + b * 32);
                 }
+                if (i >= 2) mbar_wait(bar_o(s), (uint32_t)((k - 1) & 1));   // V of stage s: free once the P V of item i-2 has retired
                 mbar_expect_tx(bar_v(s), (uint32_t)(nbk * A2_BOX * P));
                 for (int b = 0; b < nbk; ++b) {
                     tma_load_2d(sv + b * A2_BOX, &map_kv_hi, bar_v(s), p.v_col + h * 64, g.krow0 + b * 32);
@@ -177,7 +180,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             for (int t = 0; t < 2; ++t, ++i) {
                 const int s = i & 1, k = i >> 1;
                 if (i >= 2) mbar_wait(bar_o(s), (uint32_t)((k - 1) & 1));
-                geom[s].nq = 0;
+                geom[i & 3].nq = 0;
                 mbar_arrive(bar_qk(s));
             }
         }
@@ -192,20 +195,18 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                 mbar_wait(bar_v(s), par);
                 mbar_wait(bar_p(s), par);
                 tc_fence_after();
-                const uint32_t sp = stage_s(s), sv = sp + Cfg::kQK;
-                const uint32_t tO = tmem_base + (uint32_t)(s * 128);
+                const uint32_t sv = stage_s(s) + Cfg::kQK;
+                const uint32_t tO = tmem_base + (uint32_t)(s * 256), tP = tO + 128u;   // P hi at +128, P lo at +192 (64 columns each)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    // A: P panel k/4 (64 keys each, 16 KB), 32 B per k-step inside the panel; B: V rows 16k..16k+15 (MN-major)
-                    const uint32_t pa = sp + (uint32_t)((k >> 2) * A2_TILE + (k & 3) * 32);
-                    const uint64_t dp_hi = make_smem_desc(pa), dp_lo = make_smem_desc(pa + 2 * A2_TILE);
+                    // A: P columns 8k..8k+7 (16 keys as packed bf16 pairs); B: V rows 16k..16k+15 (MN-major)
                     const uint64_t dv_hi = make_smem_desc_mn(sv + (uint32_t)(k * 2048)), dv_lo = make_smem_desc_mn(sv + A2_TILE + (uint32_t)(k * 2048));
                     if (kX3) {
-                        tc_mma_bf16(tO, dp_lo, dv_hi, idesc_o, k ? 1u : 0u);
-                        tc_mma_bf16(tO, dp_hi, dv_lo, idesc_o, 1u);
-                        tc_mma_bf16(tO, dp_hi, dv_hi, idesc_o, 1u);
+                        tc_mma_bf16_ts(tO, tP + 64u + (uint32_t)(k * 8), dv_hi, idesc_o, k ? 1u : 0u);
+                        tc_mma_bf16_ts(tO, tP + (uint32_t)(k * 8), dv_lo, idesc_o, 1u);
+                        tc_mma_bf16_ts(tO, tP + (uint32_t)(k * 8), dv_hi, idesc_o, 1u);
                     } else {
-                        tc_mma_bf16(tO, dp_hi, dv_hi, idesc_o, k ? 1u : 0u);
+                        tc_mma_bf16_ts(tO, tP + (uint32_t)(k * 8), dv_hi, idesc_o, k ? 1u : 0u);
                     }
                 }
                 tc_commit(bar_o(s));
@@ -216,7 +217,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                 const int s = i & 1, k = i >> 1;
                 mbar_wait(bar_qk(s), (uint32_t)(k & 1));
                 tr.ev(4);   // Q / K landed
-                if (geom[s].nq == 0) {
+                if (geom[i & 3].nq == 0) {
                     if (pending >= 0) { do_pv(pending); pending = -1; }
                     mbar_arrive(bar_s(s));   // lets this stage's softmax group see its terminator
                     ++stops;
@@ -225,7 +226,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                 if (i >= 2) mbar_wait(bar_t(s), (uint32_t)((k - 1) & 1));   // the epilogue of item i-2 has read its O: TMEM stage free
                 tc_fence_after();
                 const uint32_t sq = stage_s(s), sk = sq + P * A2_TILE;
-                const uint32_t tS = tmem_base + (uint32_t)(s * 128);
+                const uint32_t tS = tmem_base + (uint32_t)(s * 256);
                 const uint64_t dq_hi = make_smem_desc(sq), dq_lo = make_smem_desc(sq + A2_TILE);
                 const uint64_t dk_hi = make_smem_desc(sk), dk_lo = make_smem_desc(sk + A2_TILE);
 #pragma unroll
@@ -253,8 +254,8 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
         const int r = quarter * 32 + lane;          // tile row = TMEM lane
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
         const int s = grp;
-        uint8_t* gP = stage_g(s);
-        const uint32_t tS = tmem_base + (uint32_t)(s * 128);
+        uint8_t* gV = stage_g(s) + Cfg::kQK;
+        const uint32_t tS = tmem_base + (uint32_t)(s * 256), tP = tS + 128u;
         uint32_t* padw = padw_all + grp * 4;
         uint8_t* keypad = keypad_all + grp * 128;
         const float scale = 0.125f;                 // 1/sqrt(dk), dk = 64: exact power of two == the reference's division
@@ -271,7 +272,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             const uint32_t par = (uint32_t)(k & 1);
             const int item = 2 * k + grp;           // position in this CTA's item sequence
             mbar_wait(bar_s(s), par);
-            const A2Geom g = geom[s];
+            const A2Geom g = geom[item & 3];
             if (g.nq == 0) break;
             tc_fence_after();
             tr.ev(7);   // S ready
@@ -318,79 +319,72 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                     fm = f & vm;
                 }
             };
-            // ---- ONE pass over S: the row's chunks stay in registers ----
-            uint32_t v[4][32];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (c >= c_lo && c <= c_hi) tc_ld32(tS + t_lane + (uint32_t)(c * 32), v[c]);
-            tc_wait_ld();
-            tr.ev(8);   // S in registers
+            // ---- two passes over S, one 32-key chunk at a time.  The chunk loops are deliberately NOT unrolled: the first
+            // version kept the whole row in registers with everything unrolled (4 chunks x 3 mask specialisations) and spent
+            // 22 % of its issue slots waiting for instruction fetch (ncu: stall_no_inst) -- the code no longer fit the
+            // instruction caches.  Re-reading a chunk from tensor memory is far cheaper than that. ----
             float m = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c < c_lo || c > c_hi) continue;
+#pragma unroll 1
+            for (int c = c_lo; c <= c_hi; ++c) {
+                uint32_t v[32];
+                tc_ld32(tS + t_lane + (uint32_t)(c * 32), v);
                 uint32_t vis, fill;
                 chunk_masks(c, vis, fill);
                 const uint32_t vm = vis & ~fill;
+                tc_wait_ld();
                 float mc = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if ((vm >> j) & 1u) mc = fmaxf(mc, __uint_as_float(v[c][j]));
+                    if ((vm >> j) & 1u) mc = fmaxf(mc, __uint_as_float(v[j]));
                 m = fmaxf(m, mc * scale);               // scale > 0: max commutes with the scaling
                 if (fill) m = fmaxf(m, kMaskFill2);
             }
+            tr.ev(8);   // row maxima known
             float sum = 0.f;
-            const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
             const float m2 = m * kLog2e, sc2 = scale * kLog2e;
             const float e_fill = fast_exp2((kMaskFill2 - m) * kLog2e);  // 0 unless every visible key is filled
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < 4; ++c) {
-                uint8_t* panel_hi = gP + (c >> 1) * A2_TILE + row_off;
+                uint32_t hi_w[16], lo_w[16];
                 if (c < c_lo || c > c_hi) {  // warp-uniform: no visible key in this chunk for any row of the warp
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t ch = (uint32_t)(((c & 1) * 4 + i) ^ (r & 7)) * 16;
-                        *reinterpret_cast<uint4*>(panel_hi + ch) = make_uint4(0u, 0u, 0u, 0u);
-                        if (kX3) *reinterpret_cast<uint4*>(panel_hi + 2 * A2_TILE + ch) = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                    continue;
-                }
-                uint32_t vm, fm;
-                chunk_masks(c, vm, fm);
-                uint32_t hi_w[16], lo_w[16];
+                    for (int i = 0; i < 16; ++i) { hi_w[i] = 0u; lo_w[i] = 0u; }
+                } else {
+                    uint32_t v[32];
+                    tc_ld32(tS + t_lane + (uint32_t)(c * 32), v);
+                    uint32_t vm, fm;
+                    chunk_masks(c, vm, fm);
+                    tc_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float e2[2];
+                    for (int j = 0; j < 32; j += 2) {
+                        float e2[2];
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        float e = fast_exp2(fmaf(__uint_as_float(v[c][j + q]), sc2, -m2));
-                        if ((fm >> (j + q)) & 1u) e = e_fill;
-                        if (!((vm >> (j + q)) & 1u)) e = 0.f;
-                        e2[q] = e;
-                        sum += e;
-                    }
-                    if (kX3) {
-                        split_bf16x2(e2[0], e2[1], hi_w[j >> 1], lo_w[j >> 1]);
-                    } else {
-                        const __nv_bfloat162 hb = __floats2bfloat162_rn(e2[0], e2[1]);
-                        hi_w[j >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+                        for (int q = 0; q < 2; ++q) {
+                            float e = fast_exp2(fmaf(__uint_as_float(v[j + q]), sc2, -m2));
+                            if ((fm >> (j + q)) & 1u) e = e_fill;
+                            if (!((vm >> (j + q)) & 1u)) e = 0.f;
+                            e2[q] = e;
+                            sum += e;
+                        }
+                        if (kX3) {
+                            split_bf16x2(e2[0], e2[1], hi_w[j >> 1], lo_w[j >> 1]);
+                        } else {
+                            const __nv_bfloat162 hb = __floats2bfloat162_rn(e2[0], e2[1]);
+                            hi_w[j >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+                        }
                     }
                 }
-                // 32 keys = 64 B = four 16-byte chunks of panel c/2, chunk index (c%2)*4 + i
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t ch = (uint32_t)(((c & 1) * 4 + i) ^ (r & 7)) * 16;
-                    *reinterpret_cast<uint4*>(panel_hi + ch) = make_uint4(hi_w[i * 4], hi_w[i * 4 + 1], hi_w[i * 4 + 2], hi_w[i * 4 + 3]);
-                    if (kX3)
-                        *reinterpret_cast<uint4*>(panel_hi + 2 * A2_TILE + ch) = make_uint4(lo_w[i * 4], lo_w[i * 4 + 1], lo_w[i * 4 + 2], lo_w[i * 4 + 3]);
-                }
+                // 32 keys = 16 packed columns of this row's P (hi at tP, lo at tP + 64)
+                tc_st16(tP + t_lane + (uint32_t)(c * 16), hi_w);
+                if (kX3) tc_st16(tP + 64u + t_lane + (uint32_t)(c * 16), lo_w);
             }
+            tc_wait_st();
             // key rows beyond the item's keys that a box brought in anyway hold whatever follows in memory (rows past the
             // packed count are never written: possibly NaN bit patterns): P is 0 there, but 0 * NaN would poison O, so
             // those V rows are cleared (a key row = one 128-byte swizzled row of the hi / lo tile)
             if (r >= g.nkeys) {
                 mbar_wait(bar_v(s), par);
-                uint8_t* vrow = gP + Cfg::kQK + (r >> 3) * 1024 + (r & 7) * 128;
+                uint8_t* vrow = gV + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     *reinterpret_cast<uint4*>(vrow + i * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -416,7 +410,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_t(s));            // TMEM stage s may take the S of item i+2
             // this warp's quarter of the staging rows is shared with the other group's warp of the same quarter
+            tr.ev(12);  // O in registers
             if (item >= 1) mbar_wait(bar_stg(quarter), (uint32_t)((item - 1) & 1));
+            tr.ev(13);  // staging quarter ours
             uint8_t* srow = stg_g + r * 128;
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {   // 8 columns = one 16-byte chunk of the row; chunk j lives at j ^ (r & 7)
@@ -457,7 +453,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 

@@ -46,7 +46,7 @@ fn.argtypes = [ctypes.c_void_p]
 assert fn(buf.data_ptr()) == 0
 run(); torch.cuda.synchronize(); fn(None)
 t = buf.cpu().view(148, 3, 64)
-NAMES = {1: "start", 2: "geom", 3: "issue", 4: "qk", 5: "S", 6: "PV", 7: "Srdy", 8: "Sreg", 9: "P", 10: "Ordy", 11: "stored"}
+NAMES = {1: "start", 2: "geom", 3: "issue", 4: "qk", 5: "S", 6: "PV", 7: "Srdy", 8: "Sreg", 9: "P", 10: "Ordy", 11: "stored", 12: "Oreg", 13: "lock"}
 GHZ = float(os.environ.get("GHZ", "1.9"))
 for cta in (0, 77):
     for role in range(3):
