@@ -331,11 +331,17 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                 uint32_t vis, fill;
                 chunk_masks(c, vis, fill);
                 const uint32_t vm = vis & ~fill;
+                const bool plain = __all_sync(0xffffffffu, vm == 0xffffffffu);
                 tc_wait_ld();
                 float mc = -INFINITY;
+                if (plain) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if ((vm >> j) & 1u) mc = fmaxf(mc, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) mc = fmaxf(mc, __uint_as_float(v[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if ((vm >> j) & 1u) mc = fmaxf(mc, __uint_as_float(v[j]));
+                }
                 m = fmaxf(m, mc * scale);               // scale > 0: max commutes with the scaling
                 if (fill) m = fmaxf(m, kMaskFill2);
             }
@@ -354,23 +360,41 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                     tc_ld32(tS + t_lane + (uint32_t)(c * 32), v);
                     uint32_t vm, fm;
                     chunk_masks(c, vm, fm);
+                    // warp-uniform: every key of the chunk visible and unfilled for every row (cross-attention chunks below
+                    // E, interior chunks of long sequences): the per-key selects are half of the issue slots of this loop
+                    const bool plain = __all_sync(0xffffffffu, vm == 0xffffffffu && fm == 0u);
                     tc_wait_ld();
+                    if (plain) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float e2[2];
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            float e = fast_exp2(fmaf(__uint_as_float(v[j + q]), sc2, -m2));
-                            if ((fm >> (j + q)) & 1u) e = e_fill;
-                            if (!((vm >> (j + q)) & 1u)) e = 0.f;
-                            e2[q] = e;
-                            sum += e;
+                        for (int j = 0; j < 32; j += 2) {
+                            const float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sc2, -m2));
+                            const float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sc2, -m2));
+                            sum += e0 + e1;
+                            if (kX3) {
+                                split_bf16x2(e0, e1, hi_w[j >> 1], lo_w[j >> 1]);
+                            } else {
+                                const __nv_bfloat162 hb = __floats2bfloat162_rn(e0, e1);
+                                hi_w[j >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+                            }
                         }
-                        if (kX3) {
-                            split_bf16x2(e2[0], e2[1], hi_w[j >> 1], lo_w[j >> 1]);
-                        } else {
-                            const __nv_bfloat162 hb = __floats2bfloat162_rn(e2[0], e2[1]);
-                            hi_w[j >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float e2[2];
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                float e = fast_exp2(fmaf(__uint_as_float(v[j + q]), sc2, -m2));
+                                if ((fm >> (j + q)) & 1u) e = e_fill;
+                                if (!((vm >> (j + q)) & 1u)) e = 0.f;
+                                e2[q] = e;
+                                sum += e;
+                            }
+                            if (kX3) {
+                                split_bf16x2(e2[0], e2[1], hi_w[j >> 1], lo_w[j >> 1]);
+                            } else {
+                                const __nv_bfloat162 hb = __floats2bfloat162_rn(e2[0], e2[1]);
+                                hi_w[j >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+                            }
                         }
                     }
                 }
