@@ -100,9 +100,8 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     pdl_launch_dependents();
-    // stale shared memory must at least be finite: rows of a tile that no box covers still enter the products
-    for (int i = threadIdx.x; i < (2 * Cfg::kStage + Cfg::kStg) / 16; i += A2_THREADS)
-        reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // (stale shared memory: Q / K rows that no box covers only reach rows / key columns of S that are not stored resp.
+    // are masked by selects, never arithmetically; the V rows beyond an item's keys are cleared per item below)
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_qk(s), 1); mbar_init(bar_v(s), 1); mbar_init(bar_s(s), 1); mbar_init(bar_p(s), 4);
@@ -115,7 +114,6 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill above, before any TMA write / UMMA read
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -124,64 +122,88 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
 
     if (warp == 0) {
         // ===================== producer =====================
-        if (lane == 0) {
+        // The geometry of a work item hangs on two dependent global loads (~1 us each under load), and half of the
+        // enumerated cross-attention tiles are empty: looked up one item at a time this paced the whole kernel (timeline:
+        // 2.8 us between issues).  So the 32 lanes look up 32 consecutive items of this CTA at once, then lane 0 walks them.
+        {
             int i = 0;
             A2Trace tr(0);
+            if (lane != 0) tr.p = nullptr;
             tr.ev(1);
             const int total = p.n_tiles * p.H;
-            for (int w = (int)blockIdx.x; w < total; w += (int)gridDim.x) {
-                const int tile = w / p.H, h = w - tile * p.H;   // head fastest: concurrent CTAs share a tile's rows in L2
-                A2Geom g;
-                g.h = h;
-                if (p.is_self) {
-                    g.s0 = __ldg(p.tile_seq + tile);
-                    g.s1 = __ldg(p.tile_seq + tile + 1);
-                    if (g.s1 <= g.s0) continue;
-                    g.row0 = __ldg(p.seq_off + g.s0);
-                    g.nq = __ldg(p.seq_off + g.s1) - g.row0;
-                    g.krow0 = g.row0;
-                    g.nkeys = g.nq;
-                } else {
-                    const int v = tile / p.tiles_per_owner, z = tile - v * p.tiles_per_owner;
-                    const int r0 = __ldg(p.seq_off + v * p.group), r1 = __ldg(p.seq_off + min((v + 1) * p.group, p.n_seq));
-                    g.row0 = r0 + z * 128;
-                    g.nq = min(128, r1 - g.row0);
-                    g.krow0 = v * p.E;
-                    g.nkeys = p.E;
-                    g.s0 = g.s1 = 0;
+            bool done = false;
+            for (int base = 0; !done; base += 32) {
+                const int w = (int)blockIdx.x + (base + lane) * (int)gridDim.x;
+                A2Geom mine;
+                mine.row0 = mine.krow0 = mine.nkeys = mine.s0 = mine.s1 = mine.pad_ = 0;
+                mine.nq = w < total ? 0 : -1;   // -1: past the end
+                mine.h = 0;
+                if (w < total) {
+                    const int tile = w / p.H;   // head fastest: concurrent CTAs share a tile's rows in L2
+                    mine.h = w - tile * p.H;
+                    if (p.is_self) {
+                        mine.s0 = __ldg(p.tile_seq + tile);
+                        mine.s1 = __ldg(p.tile_seq + tile + 1);
+                        if (mine.s1 > mine.s0) {
+                            mine.row0 = __ldg(p.seq_off + mine.s0);
+                            mine.nq = __ldg(p.seq_off + mine.s1) - mine.row0;
+                            mine.krow0 = mine.row0;
+                            mine.nkeys = mine.nq;
+                        }
+                    } else {
+                        const int v = tile / p.tiles_per_owner, z = tile - v * p.tiles_per_owner;
+                        const int r0 = __ldg(p.seq_off + v * p.group), r1 = __ldg(p.seq_off + min((v + 1) * p.group, p.n_seq));
+                        mine.row0 = r0 + z * 128;
+                        mine.nq = max(0, min(128, r1 - mine.row0));
+                        mine.krow0 = v * p.E;
+                        mine.nkeys = p.E;
+                    }
                 }
-                if (g.nq <= 0) continue;
-                const int s = i & 1, k = i >> 1;
-                tr.ev(2);   // geometry of the item known
-                // Q / K of stage s are free as soon as the S = Q K^T of item i-2 has retired (P lives in tensor memory)
-                if (i >= 2) mbar_wait(bar_s(s), (uint32_t)((k - 1) & 1));
-                tr.ev(3);   // Q / K loads issued
-                geom[i & 3] = g;
-                const int nbq = (g.nq + 31) >> 5, nbk = (g.nkeys + 31) >> 5;
-                const uint32_t sq = stage_s(s), sk = sq + P * A2_TILE, sv = sq + Cfg::kQK;
-                mbar_expect_tx(bar_qk(s), (uint32_t)((nbq + nbk) * A2_BOX * P));
-                for (int b = 0; b < nbq; ++b) {
-                    tma_load_2d(sq + b * A2_BOX, &map_q_hi, bar_qk(s), p.q_col + h * 64, g.row0 + b * 32);
-                    if (kX3) tma_load_2d(sq + A2_TILE + b * A2_BOX, &map_q_lo, bar_qk(s), p.q_col + h * 64, g.row0 + b * 32);
+                for (int l = 0; l < 32; ++l) {
+                    A2Geom g;
+                    g.row0 = __shfl_sync(0xffffffffu, mine.row0, l); g.nq = __shfl_sync(0xffffffffu, mine.nq, l);
+                    g.krow0 = __shfl_sync(0xffffffffu, mine.krow0, l); g.nkeys = __shfl_sync(0xffffffffu, mine.nkeys, l);
+                    g.h = __shfl_sync(0xffffffffu, mine.h, l); g.s0 = __shfl_sync(0xffffffffu, mine.s0, l);
+                    g.s1 = __shfl_sync(0xffffffffu, mine.s1, l); g.pad_ = 0;
+                    if (g.nq < 0) { done = true; break; }
+                    if (g.nq == 0) continue;
+                    if (lane == 0) {
+                        const int s = i & 1, k = i >> 1, h = g.h;
+                        tr.ev(2);   // next item
+                        // Q / K of stage s are free as soon as the S = Q K^T of item i-2 has retired (P lives in tensor memory)
+                        if (i >= 2) mbar_wait_relaxed(bar_s(s), (uint32_t)((k - 1) & 1));
+                        tr.ev(3);   // Q / K loads issued
+                        geom[i & 3] = g;
+                        const int nbq = (g.nq + 31) >> 5, nbk = (g.nkeys + 31) >> 5;
+                        const uint32_t sq = stage_s(s), sk = sq + P * A2_TILE, sv = sq + Cfg::kQK;
+                        mbar_expect_tx(bar_qk(s), (uint32_t)((nbq + nbk) * A2_BOX * P));
+                        for (int b2 = 0; b2 < nbq; ++b2) {
+                            tma_load_2d(sq + b2 * A2_BOX, &map_q_hi, bar_qk(s), p.q_col + h * 64, g.row0 + b2 * 32);
+                            if (kX3) tma_load_2d(sq + A2_TILE + b2 * A2_BOX, &map_q_lo, bar_qk(s), p.q_col + h * 64, g.row0 + b2 * 32);
+                        }
+                        for (int b2 = 0; b2 < nbk; ++b2) {
+                            tma_load_2d(sk + b2 * A2_BOX, &map_kv_hi, bar_qk(s), p.k_col + h * 64, g.krow0 + b2 * 32);
+                            if (kX3) tma_load_2d(sk + A2_TILE + b2 * A2_BOX, &map_kv_lo, bar_qk(s), p.k_col + h * 64, g.krow0 + b2 * 32);
+                        }
+                        if (i >= 2) mbar_wait_relaxed(bar_o(s), (uint32_t)((k - 1) & 1));   // V of stage s: free once the P V of item i-2 has retired
+                        mbar_expect_tx(bar_v(s), (uint32_t)(nbk * A2_BOX * P));
+                        for (int b2 = 0; b2 < nbk; ++b2) {
+                            tma_load_2d(sv + b2 * A2_BOX, &map_kv_hi, bar_v(s), p.v_col + h * 64, g.krow0 + b2 * 32);
+                            if (kX3) tma_load_2d(sv + A2_TILE + b2 * A2_BOX, &map_kv_lo, bar_v(s), p.v_col + h * 64, g.krow0 + b2 * 32);
+                        }
+                    }
+                    ++i;
+                    __syncwarp();
                 }
-                for (int b = 0; b < nbk; ++b) {
-                    tma_load_2d(sk + b * A2_BOX, &map_kv_hi, bar_qk(s), p.k_col + h * 64, g.krow0 + b * 32);
-                    if (kX3) tma_load_2d(sk + A2_TILE + b * A2_BOX, &map_kv_lo, bar_qk(s), p.k_col + h * 64, g.krow0 + b * 32);
-                }
-                if (i >= 2) mbar_wait(bar_o(s), (uint32_t)((k - 1) & 1));   // V of stage s: free once the P V of item i-2 has retired
-                mbar_expect_tx(bar_v(s), (uint32_t)(nbk * A2_BOX * P));
-                for (int b = 0; b < nbk; ++b) {
-                    tma_load_2d(sv + b * A2_BOX, &map_kv_hi, bar_v(s), p.v_col + h * 64, g.krow0 + b * 32);
-                    if (kX3) tma_load_2d(sv + A2_TILE + b * A2_BOX, &map_kv_lo, bar_v(s), p.v_col + h * 64, g.krow0 + b * 32);
-                }
-                ++i;
             }
             // one terminator per stage (each softmax group and the MMA warp stop on theirs)
-            for (int t = 0; t < 2; ++t, ++i) {
-                const int s = i & 1, k = i >> 1;
-                if (i >= 2) mbar_wait(bar_o(s), (uint32_t)((k - 1) & 1));
-                geom[i & 3].nq = 0;
-                mbar_arrive(bar_qk(s));
+            if (lane == 0) {
+                for (int t = 0; t < 2; ++t, ++i) {
+                    const int s = i & 1, k = i >> 1;
+                    if (i >= 2) mbar_wait_relaxed(bar_o(s), (uint32_t)((k - 1) & 1));
+                    geom[i & 3].nq = 0;
+                    mbar_arrive(bar_qk(s));
+                }
             }
         }
     } else if (warp == 1) {
@@ -192,8 +214,8 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             auto do_pv = [&](int j) {
                 const int s = j & 1;
                 const uint32_t par = (uint32_t)((j >> 1) & 1);
-                mbar_wait(bar_v(s), par);
-                mbar_wait(bar_p(s), par);
+                mbar_wait_relaxed(bar_v(s), par);
+                mbar_wait_relaxed(bar_p(s), par);
                 tc_fence_after();
                 const uint32_t sv = stage_s(s) + Cfg::kQK;
                 const uint32_t tO = tmem_base + (uint32_t)(s * 256), tP = tO + 128u;   // P hi at +128, P lo at +192 (64 columns each)
@@ -215,7 +237,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
             A2Trace tr(1);
             for (int i = 0; stops < 2; ++i) {
                 const int s = i & 1, k = i >> 1;
-                mbar_wait(bar_qk(s), (uint32_t)(k & 1));
+                mbar_wait_relaxed(bar_qk(s), (uint32_t)(k & 1));
                 tr.ev(4);   // Q / K landed
                 if (geom[i & 3].nq == 0) {
                     if (pending >= 0) { do_pv(pending); pending = -1; }
@@ -223,7 +245,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_const
                     ++stops;
                     continue;
                 }
-                if (i >= 2) mbar_wait(bar_t(s), (uint32_t)((k - 1) & 1));   // the epilogue of item i-2 has read its O: TMEM stage free
+                if (i >= 2) mbar_wait_relaxed(bar_t(s), (uint32_t)((k - 1) & 1));   // the epilogue of item i-2 has read its O: TMEM stage free
                 tc_fence_after();
                 const uint32_t sq = stage_s(s), sk = sq + P * A2_TILE;
                 const uint32_t tS = tmem_base + (uint32_t)(s * 256);
