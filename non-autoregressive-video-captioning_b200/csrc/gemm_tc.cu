@@ -707,8 +707,36 @@ int tc_init() {
     return 0;
 }
 
+// Encoded tensor maps are pure functions of (pointer, shape, leading dimension, box): a small per-thread direct-mapped
+// cache saves the ~1 us driver call per map (a GEMM launch builds 6-8 of them: 10+ us of host time per launch, which
+// paced the eager paths -- training steps, the per-class timing of bench.py -- more than the kernels did).
+int tc_make_map_uncached(CUtensorMap* map, const uint16_t* ptr, int rows, int K, int ld, int box_rows);
+struct MapKey { const void* ptr; int rows, cols, ld, box, kind; };
+struct MapSlot { MapKey key; CUtensorMap map; bool used; };
+static thread_local MapSlot g_map_cache[512];
+static inline bool map_cache_get(const MapKey& k, CUtensorMap* out, MapSlot** slot) {
+    const uint64_t h = ((uint64_t)(uintptr_t)k.ptr >> 4) * 0x9E3779B97F4A7C15ull ^ ((uint64_t)k.rows * 1315423911u) ^ ((uint64_t)k.cols << 20) ^
+                       ((uint64_t)k.ld << 7) ^ ((uint64_t)k.box << 3) ^ (uint64_t)k.kind;
+    MapSlot* s = &g_map_cache[(h >> 17) & 511];
+    *slot = s;
+    if (s->used && s->key.ptr == k.ptr && s->key.rows == k.rows && s->key.cols == k.cols && s->key.ld == k.ld && s->key.box == k.box &&
+        s->key.kind == k.kind) {
+        *out = s->map;
+        return true;
+    }
+    return false;
+}
+
 // 2-D bf16 tensor map over a row-major [rows, K] matrix with leading dimension ld, box = [box_rows, 64].
 int tc_make_map(CUtensorMap* map, const uint16_t* ptr, int rows, int K, int ld, int box_rows) {
+    const MapKey key = {ptr, rows, K, ld, box_rows, 0};
+    MapSlot* slot;
+    if (map_cache_get(key, map, &slot)) return 0;
+    if (tc_make_map_uncached(map, ptr, rows, K, ld, box_rows)) return 1;
+    slot->key = key; slot->map = *map; slot->used = true;
+    return 0;
+}
+int tc_make_map_uncached(CUtensorMap* map, const uint16_t* ptr, int rows, int K, int ld, int box_rows) {
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
@@ -721,7 +749,16 @@ int tc_make_map(CUtensorMap* map, const uint16_t* ptr, int rows, int K, int ld, 
 }
 
 // 2-D bf16 tensor map for the epilogue's TMA stores: box = [32 rows, 16 columns], no swizzle.
+static int tc_make_store_map_uncached(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld);
 static int tc_make_store_map(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld) {
+    const MapKey key = {ptr, rows, cols, ld, 32, 1};
+    MapSlot* slot;
+    if (map_cache_get(key, map, &slot)) return 0;
+    if (tc_make_store_map_uncached(map, ptr, rows, cols, ld)) return 1;
+    slot->key = key; slot->map = *map; slot->used = true;
+    return 0;
+}
+static int tc_make_store_map_uncached(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld) {
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {16u, 32u};
