@@ -263,7 +263,7 @@ def class_table(prof, samples, opt, precision, B, step_ms, pk):
     b = {"bf16x3": 4, "bf16": 2, "fp32": 4, "tf32": 4}[precision]   # operand bytes per element (hi + lo pairs in bf16x3)
     mult = {"bf16x3": 3.0, "bf16": 1.0, "tf32": 2.0, "fp32": 0.0}[precision]   # bf16-MMA time units issued per useful product
     peak_tf, peak_gb = pk["bf16_tflops_sustained"], pk["hbm_gbs"]
-    vocab_rows = [int(x) for x in torch.stack(prof.get("vocab_rows", [])).flatten().tolist()] if prof.get("vocab_rows") else []
+    vocab_rows = prof.get("vocab_rows") or []
     rv = (sum(vocab_rows) / len(vocab_rows)) if vocab_rows else R
     spec = {   # class: (flops per launch, algorithmic bytes per launch, bound, shape string)
         "qkv": (2.0 * R * D * 3 * D, R * D * b + 3 * D * D * b + R * 3 * D * b, "tensor", "M=%d N=%d K=%d" % (R, 3 * D, D)),
@@ -289,7 +289,7 @@ def class_table(prof, samples, opt, precision, B, step_ms, pk):
         ev = prof.get(tag)
         if not ev:
             continue
-        durs = [a.elapsed_time(b_) * 1e3 for a, b_ in ev]
+        durs = list(ev)   # microseconds per launch
         us = sum(durs) / len(durs)
         per_step = sum(durs) / n
         total_us += per_step
@@ -444,22 +444,53 @@ def main():
         ms_e2e, hyp_host = timed(step_e2e, args.steps, "e2e")
         pending.clear()
         sampler.stop()
-        # ---- region 3 (not part of `value`): the same steps launched eagerly (graph replay off) with CUDA events
-        # around every launch class of the decoder layer ----
-        tr.opt = dict(opt, navc_graphs=False)
-        step_resident(0)
+        # ---- region 3 (not part of `value`): per-class device times from the REPLAYED graph.  The decode graphs are
+        # dropped and re-captured with CUDA events around every launch class recorded INTO the graph (external event
+        # nodes); each replay re-records them, so elapsed_time() is device time with no host launch latency inside ----
+        prof_mode = "graph replay with event-record nodes around every launch class"
+        samples, acc = [], {}
+        model.engine.graphs.clear()
         model.engine.prof = {}
-        samples = []
-        for i in range(min(args.steps, 4)):
-            step_resident(i)
-            st = navc_b200.generate.last_stats
-            packed = bool(st.get("packed"))
-            samples.append({"R": st["rows_real"] if packed else st["N"] * st["S"],
-                            "sq": st["rows_sq"] if packed else st["N"] * st["S"] * st["S"], "N": st["N"], "S": st["S"]})
-        torch.cuda.synchronize()
-        prof = model.engine.prof
+        try:
+            step_resident(0)                      # eager ("warm") call of this shape; its events are discarded
+            model.engine.prof = {}
+            step_resident(0)                      # capture: the events below are nodes of the graph
+            prof = model.engine.prof
+            if not navc_b200.generate.last_stats.get("graph"):
+                raise RuntimeError("no graph")
+            for i in range(6):
+                step_resident(0)                  # same batch shape -> replay of the captured graph
+                torch.cuda.synchronize()
+                st = navc_b200.generate.last_stats
+                packed = bool(st.get("packed"))
+                samples.append({"R": st["rows_real"] if packed else st["N"] * st["S"],
+                                "sq": st["rows_sq"] if packed else st["N"] * st["S"] * st["S"], "N": st["N"], "S": st["S"]})
+                for tag, ev in prof.items():
+                    if tag == "vocab_rows":
+                        acc.setdefault(tag, []).extend(int(x) for x in torch.stack(ev).flatten().tolist())
+                    else:
+                        acc.setdefault(tag, []).extend(a.elapsed_time(b_) * 1e3 for a, b_ in ev)
+        except Exception as exc:                  # e.g. a paradigm that does not replay graphs: eager timing instead
+            prof_mode = "eager re-run (graph replay unavailable: %s)" % type(exc).__name__
+            tr.opt = dict(opt, navc_graphs=False)
+            model.engine.prof = {}
+            samples, acc = [], {}
+            for i in range(min(args.steps, 4)):
+                step_resident(i)
+                st = navc_b200.generate.last_stats
+                packed = bool(st.get("packed"))
+                samples.append({"R": st["rows_real"] if packed else st["N"] * st["S"],
+                                "sq": st["rows_sq"] if packed else st["N"] * st["S"] * st["S"], "N": st["N"], "S": st["S"]})
+            torch.cuda.synchronize()
+            for tag, ev in model.engine.prof.items():
+                if tag == "vocab_rows":
+                    acc[tag] = [int(x) for x in torch.stack(ev).flatten().tolist()]
+                else:
+                    acc[tag] = [a.elapsed_time(b_) * 1e3 for a, b_ in ev]
+            tr.opt = opt
+        prof = acc
         model.engine.prof = None
-        tr.opt = opt
+        model.engine.graphs.clear()
     d2h = hyp_host.numel() * 8
 
     value = world * B * args.steps / (ms / 1e3)
@@ -477,7 +508,7 @@ def main():
                 "traffic_source": ncu_src, "kernel": "%s (%s)" % (top, t["shape"]), "mean_us": t["us"],
                 "issued_mma_frac": t["frac_issued"], "share_of_step": t["share_of_step"],
                 "peak_source": pk_src + (" (sustained cuBLAS bf16, MEASURED_PEAKS.json)" if tensor else " (copy bandwidth, MEASURED_PEAKS.json)"),
-                "timed_in": "eager re-run of %d steps (graph replay off), CUDA events on the launching stream around every launch" % len(samples),
+                "timed_in": "%s, %d steps" % (prof_mode, len(samples)),
                 "profiled_us_per_step": round(total_us, 1),
                 "note": "frac = useful (fp32-equivalent) FLOPs / measured sustained bf16 peak; %s issues %.0fx as many bf16-MMA time "
                         "units per product (frac_issued)" % (args.precision, {"bf16x3": 3, "bf16": 1, "tf32": 2}.get(args.precision, 0)),

@@ -293,13 +293,16 @@ class Engine:
     def _t0(self, tag):
         if self.prof is None or tag is None:
             return None
-        e0 = torch.cuda.Event(enable_timing=True)
+        # inside a stream capture the events become event-record NODES of the graph (external=True): every replay
+        # re-records them, so the per-class times come from the replayed graph itself, with no host gap between the
+        # start event and the launch (eager timing charges each launch the host's latency to issue it)
+        e0 = torch.cuda.Event(enable_timing=True, external=torch.cuda.is_current_stream_capturing())
         e0.record()
         return e0
 
     def _t1(self, tag, e0):
         if e0 is not None:
-            e1 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True, external=torch.cuda.is_current_stream_capturing())
             e1.record()
             self.prof.setdefault(tag, []).append((e0, e1))
 
