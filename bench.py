@@ -13,7 +13,8 @@ d_model 512, vocab 10547).  Metric: captions/s (one caption = one video's final 
                device copy of the features/category and the device -> host read of the token ids
                are inside the timed region.
   roofline     every launch class of the decoder layer (qkv, self, so, cq, cross, co, f1, f2, vocab, ...)
-               timed live with CUDA events on the launching stream in an eager re-run of the same steps;
+               timed live with CUDA events on the launching stream: the decode graph is re-captured with
+               event-record nodes around every launch class and replayed (device time, no host latency);
                `classes` holds {us, share, flops / bytes, frac_useful, frac_issued} per class and the
                top-level fields describe the class with the largest time share.
   parity       token ids of the GPU path (fp32 mode and the timed mode, through the replayed CUDA graph)
@@ -468,8 +469,12 @@ def main():
                 for tag, ev in prof.items():
                     if tag == "vocab_rows":
                         acc.setdefault(tag, []).extend(int(x) for x in torch.stack(ev).flatten().tolist())
-                    else:
+                    elif not tag.startswith("enc"):
                         acc.setdefault(tag, []).extend(a.elapsed_time(b_) * 1e3 for a, b_ in ev)
+            # the encoder runs outside the decode graph: its events are appended eagerly, once per call (7 calls here)
+            for tag, ev in prof.items():
+                if tag.startswith("enc"):
+                    acc[tag] = [a.elapsed_time(b_) * 1e3 for a, b_ in ev][len(ev) // 7:]
         except Exception as exc:                  # e.g. a paradigm that does not replay graphs: eager timing instead
             prof_mode = "eager re-run (graph replay unavailable: %s)" % type(exc).__name__
             tr.opt = dict(opt, navc_graphs=False)

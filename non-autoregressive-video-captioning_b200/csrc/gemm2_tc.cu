@@ -311,7 +311,19 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                 }
             };
-            if (kRes && active) load_res(0, rh[0], rl[0]);   // overlaps the main loop of this tile
+            if (kRes && active) {
+                // the unit's whole row segment -> L2 now (the layer input was written several launches ago and has
+                // mostly left L2): the later steps' loads, issued only one step ahead, then miss no further than L2
+                if (row_ok && epi.dbg != 13) {
+                    const size_t ro = (size_t)rowp * epi.ld_res + u.n0 + cl0;
+                    int wcols = u.w - cl0 < GW ? u.w - cl0 : GW;
+                    if (u.n0 + cl0 + wcols > N) wcols = N - u.n0 - cl0;
+                    prefetch_l2(epi.res_hi + ro);
+                    prefetch_l2(epi.res_hi + ro + wcols - 1);
+                    if (epi.res_lo) { prefetch_l2(epi.res_lo + ro); prefetch_l2(epi.res_lo + ro + wcols - 1); }
+                }
+                load_res(0, rh[0], rl[0]);   // overlaps the main loop of this tile
+            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             tr.ev(7);   // accumulators of the unit ready
@@ -536,10 +548,14 @@ int g2_linear(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, con
     const int m_est = (epi.m_hint > 0 && epi.m_hint < M) ? epi.m_hint : M;
     const int mbe = (m_est + G2_BM - 1) / G2_BM;
     const char* ecl = getenv("NAVC_GEMM2_CLUSTER");
-    int cl = (mbe >= 8 && sms % 2 == 0) ? 2 : 1;     // tiny M (AR beam steps): more, smaller tiles instead of CTA pairs
+    // out / query projections (N <= 512, K <= 512: 8 k-blocks per tile, 1-2 tiles per CTA): no steady state to win back a
+    // pair's start-up or a 256-wide tile's last, un-overlapped epilogue -- single CTAs, 128-wide tiles (isolated, M = 10 553:
+    // so 24.0 us against 29.6 (256 wide), 31.3 (pairs) and 27.4 (first-generation kernel); cq 21.1 / 22.0 / 23.1 / 21.9)
+    const bool small = N <= 512 && K <= 512;
+    int cl = (mbe >= 8 && sms % 2 == 0 && !small) ? 2 : 1;     // tiny M (AR beam steps): more, smaller tiles instead of CTA pairs
     if (ecl) cl = ecl[0] == '1' ? 1 : 2;
     const bool x3 = mode == NAVC_TC_BF16X3;
-    int tbn = (N > 128 && g2_cost(mbe, N, 256, cl, sms, x3) <= g2_cost(mbe, N, 128, cl, sms, x3)) ? 256 : 128;
+    int tbn = (N > 128 && !(small && !ecl) && g2_cost(mbe, N, 256, cl, sms, x3) <= g2_cost(mbe, N, 128, cl, sms, x3)) ? 256 : 128;
     if (epi.dbg == 128 || epi.dbg == 256) tbn = epi.dbg;   // profiling aid: force a tile width
 #define NAVC_G2_GO(X3, BN, CL) return g2_launch<X3, BN, CL>(x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, sms, st)
     if (x3) {

@@ -941,7 +941,10 @@ extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_
     // second-generation kernel (CTA pairs, tail split along N) in the split-bf16 mode, where it measured faster (config-2
     // step 13.98 vs 14.10 ms); plain bf16 keeps the first-generation kernel with its TMA-prefetched residual boxes
     // (7.87 vs 9.19 ms) unless NAVC_GEMM2=force
-    if (pair && g2_enabled() && (mode == NAVC_TC_BF16X3 || g2_forced()) && !sk_enabled() && (p.dbg == 0 || p.dbg == 7 || (p.dbg >= 11 && p.dbg <= 15) || p.dbg == 128 || p.dbg == 256)) {
+    // NAVC_GEMM2_SMALL=0 keeps the out / query projections (N <= 512, K <= 512) on the first-generation kernel (A/B runs)
+    static const bool g2_small = !(getenv("NAVC_GEMM2_SMALL") && getenv("NAVC_GEMM2_SMALL")[0] == '0');
+    const bool g2_shape = (N > 512 || K > 512) || g2_small || g2_forced();
+    if (pair && g2_enabled() && g2_shape && (mode == NAVC_TC_BF16X3 || g2_forced()) && !sk_enabled() && (p.dbg == 0 || p.dbg == 7 || (p.dbg >= 11 && p.dbg <= 15) || p.dbg == 128 || p.dbg == 256)) {
         // second-generation kernel (gemm2_tc.cu): cluster multicast of the weight tile, tail split along N
         NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "navc_linear_tc: bad mode %d", mode);
         NAVC_REQUIRE(x_hi && w_hi && (mode == NAVC_TC_BF16 || (x_lo && w_lo)), "navc_linear_tc: null operand");

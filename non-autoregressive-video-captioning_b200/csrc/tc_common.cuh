@@ -196,6 +196,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bmn(int m, int n) { return mak
 // Every tcgen05 kernel lets its successor launch early (its CTAs become resident as ours exit, during
 // the partially filled last wave) and runs its own prologue -- barrier init, TMEM allocation -- before
 // waiting for the predecessor's memory to be complete.  No-ops when launched without the attribute.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -112,6 +112,11 @@ class GradientAllReduce:
         eng = getattr(model, "engine", None)
         if eng is not None:
             eng.grad_sink = self.sink
+            eng.grads_final_hook = self.begin_early   # called by the encoder's backward before it launches anything
+        self.overlap = True       # all-reduce the finished part of the buffer under the encoder's backward
+        self.weight = 1.0         # this rank's weight (unequal shards), set BEFORE backward when overlap is on
+        self._early = None        # (split, work) of the collective in flight
+        self._split_of = {}
 
     def sink(self, p):
         """The flat-buffer view a backward kernel may accumulate into directly: only while p.grad IS that view
@@ -130,23 +135,62 @@ class GradientAllReduce:
                 p.grad = v
 
     def zero_grad(self):
+        if self._early is not None:   # a step was abandoned between backward() and allreduce()
+            self._early[1].wait()
+            self._early = None
         self.flat.zero_()
         for p, v in zip(self.params, self.views):
             p.grad = v
 
+    def _reduce(self, buf, async_op=False):
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(buf, op=dist.ReduceOp.AVG, async_op=async_op)  # sum and 1/world inside the collective
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=async_op)
+
+    def begin_early(self, outstanding: Sequence[torch.nn.Parameter]):
+        """Overlap: called (by the encoder's backward, the last autograd node of a step that produces parameter
+        gradients) when only the gradients of ``outstanding`` are still to come.  Everything behind the last of
+        those parameters in the flat buffer is final, so its all-reduce is launched now (asynchronously, on the
+        process group's stream, ordered after the kernels already queued) and runs under the rest of the backward
+        pass; ``allreduce()`` then reduces the head of the buffer and joins both."""
+        if not self.overlap or world() == 1 or self._early is not None:
+            return
+        key = tuple(id(p) for p in outstanding)
+        split = self._split_of.get(key)
+        if split is None:
+            ids = set(key)
+            split = 0
+            for p, o in zip(self.params, self.offsets):
+                if id(p) in ids:
+                    split = max(split, o + (p.numel() + ALIGN - 1) // ALIGN * ALIGN)
+            self._split_of[key] = split
+        if split >= self.numel or any(p.grad is not v for p, v in zip(self.params, self.views)):
+            return   # nothing behind the outstanding parameters, or some p.grad is not (yet) a view of the buffer
+        tail = self.flat[split:]
+        if self.weight != 1.0:
+            tail.mul_(float(self.weight))
+        self._early = (split, self._reduce(tail, async_op=True))
+
     def allreduce(self, weight: Optional[float] = None):
-        """Average the gradients over the ranks: one collective on the whole buffer.  ``weight`` scales this
-        rank's gradients first (unequal shards: local_batch * world / global_batch)."""
+        """Average the gradients over the ranks: one collective on the whole buffer (two when the tail of the buffer
+        went out early, ``begin_early``).  ``weight`` scales this rank's gradients first (unequal shards:
+        local_batch * world / global_batch); with overlap on, set ``self.weight`` before the backward pass instead."""
         self.attach()
         w = world()
-        if weight is not None and weight != 1.0:
-            self.flat.mul_(float(weight))
+        weight = self.weight if weight is None else float(weight)
+        early, self._early = self._early, None
+        if early is not None and weight != self.weight:
+            raise RuntimeError("GradientAllReduce: part of the buffer was reduced early with weight %g; set .weight before "
+                               "backward() (or .overlap = False) instead of passing weight=%g here" % (self.weight, weight))
+        head = self.flat if early is None else self.flat[:early[0]]
+        if weight != 1.0:
+            head.mul_(weight)
         if w == 1:
             return self.flat
-        if dist.get_backend() == "nccl":
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)  # sum and 1/world inside the collective
-        else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self._reduce(head)
+        if early is not None:
+            early[1].wait()
+        if dist.get_backend() != "nccl":
             self.flat.div_(w)
         return self.flat
 

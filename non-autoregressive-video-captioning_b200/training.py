@@ -386,6 +386,12 @@ class EncodeFn(torch.autograd.Function):
         dev = eng.device
         BF = B * F_
         grads = Grads(eng)
+        # every consumer of the encoder's outputs has run its backward: the gradients of all other parameters are
+        # final, and a data-parallel owner of p.grad may start reducing them under this node (parallel.begin_early)
+        hook = getattr(eng, "grads_final_hook", None)
+        if hook is not None:
+            named = eng.named_params()
+            hook([named[k] for k in ctx.keys if k is not None and k in named])
         feng = _F32Engine(eng)
         d_enc = torch.zeros((B, E, D), dtype=torch.float32, device=dev) if d_enc is None else d_enc.contiguous().clone()
         d_hidden = None if d_hidden is None else d_hidden.contiguous()

@@ -95,6 +95,82 @@ def test_flat_gradient_allreduce_and_sharding_world2():
     assert n_params <= res[0][5] < n_params + 64 * 200  # flat buffer = parameters + alignment padding
 
 
+def _worker_early(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        opt = cases.config1()
+        torch.manual_seed(3)
+        model = navc_b200.get_model(opt)
+        dp = parallel.GradientAllReduce(model)
+        assert model.engine.grads_final_hook == dp.begin_early
+        named = dict(model.named_parameters())
+        enc = [p for k, p in named.items() if not k.startswith(("decoder.", "tgt_word_prj."))]
+        late = set(id(p) for p in enc)
+        res = []
+        for weight in (1.0, 0.5 + rank):
+            dp.zero_grad()
+            dp.weight = weight
+            g = torch.Generator().manual_seed(11 + rank)
+            grads = [torch.randn(p.shape, generator=g) for p in dp.params]
+            for p, gr in zip(dp.params, grads):          # "decoder side" first, as the backward pass does
+                if id(p) not in late:
+                    p.grad.add_(gr)
+            dp.begin_early(enc)                          # what EncodeFn.backward calls before producing its own gradients
+            in_flight = dp._early is not None
+            split = dp._early[0] if in_flight else -1
+            for p, gr in zip(dp.params, grads):
+                if id(p) in late:
+                    p.grad.add_(gr)
+            flat = dp.allreduce().clone()
+            # the same step without overlap
+            dp.zero_grad()
+            dp.overlap = False
+            for p, gr in zip(dp.params, grads):
+                p.grad.add_(gr)
+            dp.begin_early(enc)
+            assert dp._early is None
+            ref = dp.allreduce().clone()
+            dp.overlap = True
+            res.append((in_flight, split, torch.allclose(flat, ref, atol=1e-6), float(ref.abs().sum())))
+        first_late = min(o for p, o in zip(dp.params, dp.offsets) if id(p) in late)
+        last_late = max(o for p, o in zip(dp.params, dp.offsets) if id(p) in late)
+        # passing a different weight at allreduce() time while a part is in flight must fail loudly
+        dp.zero_grad(); dp.weight = 1.0
+        dp.begin_early(enc)
+        try:
+            dp.allreduce(weight=2.0)
+            raised = False
+        except RuntimeError:
+            raised = True
+        q.put((rank, res, first_late, last_late, dp.numel, raised))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_early_allreduce_of_finished_gradients_world2():
+    """parallel.GradientAllReduce.begin_early: the tail of the flat buffer (every parameter behind the encoder's) is
+    reduced while the encoder's gradients are still being produced; the result equals the single collective."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_early, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res, first_late, last_late, numel, raised in out:
+        assert raised
+        for in_flight, split, same, norm in res:
+            assert in_flight and same and norm > 0
+            assert last_late < split < numel      # most of the buffer (the decoder) goes out early
+        assert first_late == 0                    # encoder parameters come first in the module tree
+
+
 def test_shard_bounds_cover_and_balance():
     for n in (0, 1, 7, 128, 1000):
         for w in (1, 2, 4, 8):
