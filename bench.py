@@ -266,15 +266,26 @@ def class_table(prof, samples, opt, precision, B, step_ms, pk):
     peak_tf, peak_gb = pk["bf16_tflops_sustained"], pk["hbm_gbs"]
     vocab_rows = prof.get("vocab_rows") or []
     rv = (sum(vocab_rows) / len(vocab_rows)) if vocab_rows else R
+    def layer_tail(r, sfx, note):   # everything behind the self-attention core, on r rows
+        return {
+            "so" + sfx: (2.0 * r * D * D, 3 * r * D * b + D * D * b, "tensor", "M=%d N=%d K=%d +residual%s" % (r, D, D, note)),
+            "cq" + sfx: (2.0 * r * D * D, 2 * r * D * b + D * D * b, "tensor", "M=%d N=%d K=%d%s" % (r, D, D, note)),
+            "co" + sfx: (2.0 * r * D * D, 3 * r * D * b + D * D * b, "tensor", "M=%d N=%d K=%d +residual%s" % (r, D, D, note)),
+            "f1" + sfx: (2.0 * r * D * I, r * D * b + D * I * b + r * I * b, "tensor", "M=%d N=%d K=%d +gelu%s" % (r, I, D, note)),
+            "f2" + sfx: (2.0 * r * D * I, r * I * b + D * I * b + 2 * r * D * b, "tensor", "M=%d N=%d K=%d +residual%s" % (r, D, I, note)),
+            "cross" + sfx: (4.0 * r * E * D, 2 * r * D * b + B * E * 2 * D * b, "hbm", "rows=%d x E=%d keys, 8 heads%s" % (r, E, note)),
+        }
+    # last layer of the passes that only merge re-masked positions: the compacted rows (the vocabulary GEMM's rows)
+    per = max(len(vocab_rows) // max(n, 1), 1)
+    kp = len(prof.get("so_p") or []) // max(n, 1)
+    pr = [v for j, v in enumerate(vocab_rows) if (j % per) >= per - kp]
+    rp = (sum(pr) / len(pr)) if pr else R
     spec = {   # class: (flops per launch, algorithmic bytes per launch, bound, shape string)
         "qkv": (2.0 * R * D * 3 * D, R * D * b + 3 * D * D * b + R * 3 * D * b, "tensor", "M=%d N=%d K=%d" % (R, 3 * D, D)),
-        "so": (2.0 * R * D * D, 3 * R * D * b + D * D * b, "tensor", "M=%d N=%d K=%d +residual" % (R, D, D)),
-        "cq": (2.0 * R * D * D, 2 * R * D * b + D * D * b, "tensor", "M=%d N=%d K=%d" % (R, D, D)),
-        "co": (2.0 * R * D * D, 3 * R * D * b + D * D * b, "tensor", "M=%d N=%d K=%d +residual" % (R, D, D)),
-        "f1": (2.0 * R * D * I, R * D * b + D * I * b + R * I * b, "tensor", "M=%d N=%d K=%d +gelu" % (R, I, D)),
-        "f2": (2.0 * R * D * I, R * I * b + D * I * b + 2 * R * D * b, "tensor", "M=%d N=%d K=%d +residual" % (R, D, I)),
         "self": (4.0 * SQ * D, R * 3 * D * b + R * D * b, "hbm", "sum(len^2)=%d, 8 heads, dk 64" % SQ),
-        "cross": (4.0 * R * E * D, 2 * R * D * b + B * E * 2 * D * b, "hbm", "rows=%d x E=%d keys, 8 heads" % (R, E)),
+        **layer_tail(R, "", ""),
+        **layer_tail(rp, "_p", " (last layer, re-masked rows only: mean M)"),
+        "gather": (0.0, 2 * 2 * rp * D * b, "hbm", "context + residual rows of the re-masked positions, %d rows (mean)" % rp),
         "vocab": (2.0 * rv * D * V, rv * D * b + V * D * b + rv * ((V + 127) // 128) * 12, "tensor", "M=%d (mean) N=%d K=%d, softmax statistics epilogue" % (rv, V, D)),
         "kv": (2.0 * B * E * D * L_ * 2 * D, B * E * D * b + L_ * 2 * D * D * b + B * E * L_ * 2 * D * b, "tensor", "M=%d N=%d K=%d (once per batch)" % (B * E, L_ * 2 * D, D)),
         "enc0": (2.0 * B * F_ * din * D, B * F_ * din * b + din * D * b + B * F_ * D * (4 + b), "tensor", "M=%d N=%d K=%d" % (B * F_, D, din)),

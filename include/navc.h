@@ -264,6 +264,16 @@ int navc_cross_attention_tc_rows(int mode, const uint16_t* q_hi, const uint16_t*
 /* out[k, :] = in[rows[k], :] for k < *count (bf16 hi / lo pairs, D % 8 == 0; lo may be NULL). */
 int navc_gather_rows(const uint16_t* in_hi, const uint16_t* in_lo, int D, const int32_t* rows,
                      const int32_t* count, int max_rows, uint16_t* out_hi, uint16_t* out_lo, void* stream);
+/* Ordered compaction of the positions navc_refine_step selected (its flag mode: sel_rows == NULL, sel_slot = 0/1 per real
+ * packed row).  In place: slot[r] := number of selected rows before r (the compact index of a selected row; slot has
+ * max_rows + 1 entries); rows[k] = k-th selected packed row, ascending; seq_off_c[n] = slot[seq_off[n]], n = 0..N: the
+ * packed offsets of the compacted row space -- the selected rows of a sequence (and of a video's candidates) stay
+ * contiguous, so the packed cross-attention core and the GEMMs run on them unchanged; *count = seq_off_c[N].
+ * Used for the LAST decoder layer of a refinement pass: only re-masked positions are read from that pass
+ * (decoding/algorithms.py:155-167 assigns tokens / probabilities at mask_ind only), so everything behind the last
+ * self-attention core runs on those rows alone. */
+int navc_compact_rows(int32_t* slot, const int32_t* seq_off, int N, int max_rows, int32_t* rows, int32_t* count,
+                      int32_t* seq_off_c, void* stream);
 /* navc_vocab_partials_tc over the first min(M, *m_dev) rows. */
 int navc_vocab_partials_tc_dyn(int mode, const uint16_t* h_hi, const uint16_t* h_lo, int ldh,
                                const uint16_t* w_hi, const uint16_t* w_lo, int ldw, const float* bias,
@@ -347,7 +357,8 @@ typedef struct {
     const int32_t* part_slot;  /* in, or NULL: partials of packed row r live in row part_slot[r] (a previous step's sel_slot) */
     int32_t* sel_rows;         /* out, or NULL: packed rows of the positions selected for re-masking, in any order */
     int32_t* sel_count;        /* out: their number (device scalar, atomicAdd; caller zeroes) */
-    int32_t* sel_slot;         /* out: [N*S] packed row -> index in sel_rows */
+    int32_t* sel_slot;         /* out: [N*S + 1] packed row -> index in sel_rows; with sel_rows == NULL: 0/1 selection flag of
+                                  every real packed row, to be ordered by navc_compact_rows */
 } navc_step_t;
 /* One launch per refinement iteration: combine the vocabulary partials into (argmax, max prob),
  * apply the pad rules, merge into the state, choose the next positions to re-mask, write the next

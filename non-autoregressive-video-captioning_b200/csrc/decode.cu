@@ -191,6 +191,8 @@ __global__ void refine_step_kernel(StepArgs a, int S) {
             const int k = atomicAdd(p.sel_count, 1);
             p.sel_rows[k] = prow;
             p.sel_slot[prow] = k;
+        } else if (!p.sel_rows && p.sel_slot && !pad) {
+            p.sel_slot[p.seq_off[n] + i] = sel ? 1 : 0;   // flags only: navc_compact_rows orders them
         }
         if (p.select == NAVC_SELECT_NONE && p.lprobs) p.lprobs[o] = logf(prob * tprob);
     }
@@ -283,6 +285,7 @@ extern "C" int navc_refine_step(const navc_step_t* p, int N, int S, void* stream
     NAVC_REQUIRE(p->merge != NAVC_MERGE_MASKED || p->upd_mask, "navc_refine_step: MERGE_MASKED needs upd_mask");
     NAVC_REQUIRE(!p->part_slot || (p->seq_off && p->merge == NAVC_MERGE_MASKED), "navc_refine_step: part_slot needs seq_off and MERGE_MASKED");
     NAVC_REQUIRE(!p->sel_rows || (p->seq_off && p->sel_count && p->sel_slot), "navc_refine_step: sel_rows needs seq_off, sel_count, sel_slot");
+    NAVC_REQUIRE(!p->sel_slot || p->seq_off, "navc_refine_step: sel_slot needs seq_off");
     NAVC_REQUIRE((p->select != NAVC_SELECT_GIVEN && p->select != NAVC_SELECT_WINDOW) || p->given,
                  "navc_refine_step: selection needs `given`");
     StepArgs a;
@@ -292,6 +295,65 @@ extern "C" int navc_refine_step(const navc_step_t* p, int N, int S, void* stream
     size_t smem = (size_t)S * 2 * (sizeof(float) + sizeof(int));
     refine_step_kernel<<<N, threads, smem, as_stream(stream)>>>(a, S);
     return check_launch("navc_refine_step");
+}
+
+// Ordered compaction of the selected packed rows (flags in `slot`, written by navc_refine_step without sel_rows): one block,
+// thread t owns a contiguous chunk of rows.  slot[r] becomes the number of selected rows before r (for a selected row: its
+// index in `rows`), rows[] the selected rows in ascending order, seq_off_c[n] = slot[seq_off[n]] the packed offsets of the
+// compacted row space (a sequence's / video's selected rows stay contiguous), count = seq_off_c[N].
+__global__ void compact_rows_kernel(int32_t* __restrict__ slot, const int32_t* __restrict__ seq_off, int N, int max_rows,
+                                    int32_t* __restrict__ rows, int32_t* __restrict__ count, int32_t* __restrict__ seq_off_c) {
+    __shared__ int wsum[32];
+    __shared__ int total_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int R = seq_off[N];
+    if (R > max_rows) R = max_rows;
+    const int per = (max_rows + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int lo = tid * per < R ? tid * per : R;
+    const int hi = lo + per < R ? lo + per : R;
+    int c = 0;
+    for (int r = lo; r < hi; ++r) c += slot[r] != 0;
+    int incl = c;
+#pragma unroll
+    for (int sh = 1; sh < 32; sh <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, sh);
+        if (lane >= sh) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int sh = 1; sh < 32; sh <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, sh);
+            if (lane >= sh) wi += v;
+        }
+        wsum[lane] = wi - w;                      // exclusive prefix of the warp totals
+        if (lane == 31) total_s = wi;
+    }
+    __syncthreads();
+    int base = wsum[warp] + incl - c;
+    for (int r = lo; r < hi; ++r) {
+        const int f = slot[r] != 0;
+        slot[r] = base;
+        if (f) rows[base] = r;
+        base += f;
+    }
+    const int total = total_s;
+    if (tid == 0) { count[0] = total; slot[R] = total; }
+    __syncthreads();
+    for (int n = tid; n <= N; n += blockDim.x) {
+        const int r = seq_off[n];
+        seq_off_c[n] = r >= R ? total : slot[r];
+    }
+}
+
+extern "C" int navc_compact_rows(int32_t* slot, const int32_t* seq_off, int N, int max_rows, int32_t* rows, int32_t* count,
+                                 int32_t* seq_off_c, void* stream) {
+    NAVC_REQUIRE(slot && seq_off && rows && count && seq_off_c && N > 0 && max_rows > 0, "navc_compact_rows: bad arguments");
+    compact_rows_kernel<<<1, 1024, 0, as_stream(stream)>>>(slot, seq_off, N, max_rows, rows, count, seq_off_c);
+    return check_launch("navc_compact_rows");
 }
 
 extern "C" int navc_teacher_probs(const float* part_max, const float* part_sum, int n_tiles,

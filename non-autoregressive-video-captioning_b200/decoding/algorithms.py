@@ -50,7 +50,12 @@ class Refiner:
         if self.packed is not None:
             R = N * S
             self.vbuf = [(torch.empty((R,), dtype=torch.int32, device=dev), torch.zeros((1,), dtype=torch.int32, device=dev),
-                          torch.zeros((R,), dtype=torch.int32, device=dev)) for _ in range(2)]
+                          torch.zeros((R + 1,), dtype=torch.int32, device=dev), torch.zeros((N + 1,), dtype=torch.int32, device=dev))
+                         for _ in range(2)]
+        # the LAST decoder layer of a pass that only merges re-masked positions runs on those rows alone (everything behind
+        # its self-attention core; include/navc.h navc_compact_rows); opt['navc_prune'] / $NAVC_PRUNE = 0: all rows + a gather
+        self.prune = str(opt.get("navc_prune", os.environ.get("NAVC_PRUNE", "1"))).lower() not in ("0", "false", "no", "off")
+        self.rows_hint = int(rows_hint)
         self.n_steps = 0
         self.passes = 0
         self.pending = None  # (partials, merge kind, is_ct) of the pass not yet merged
@@ -67,17 +72,24 @@ class Refiner:
 
     def run_pass(self, merge, is_ct=False):
         """decoder + vocabulary statistics on the current canvas (algorithms.py:143-167)."""
-        hid, _ = self.eng.decoder_pass(self.canvas, self.mem, self.group, self.category, "NARFormer", packed=self.packed)
+        sub_rows = merge == L.MERGE_MASKED and self.vsel is not None
+        prune = None
+        if sub_rows and self.prune:
+            rows, count, slot, seq_off_c = self.vsel
+            prune = dict(rows=rows, count=count, seq_off=seq_off_c, hint=self.rows_hint // 2)
+        hid, _ = self.eng.decoder_pass(self.canvas, self.mem, self.group, self.category, "NARFormer", packed=self.packed, prune=prune)
         m_dev = self.packed["count"] if self.packed is not None else None
         slot = None
-        if merge == L.MERGE_MASKED and self.vsel is not None:
+        if sub_rows:
             # only the re-masked positions are merged: project just their rows onto the vocabulary
-            rows, count, slot = self.vsel
-            from ..engine import Act
-            sub = Act(hid.M, hid.N, hi=torch.empty_like(hid.hi), lo=None if hid.lo is None else torch.empty_like(hid.lo))
-            L.call("navc_gather_rows", L.ptr(hid.hi), L.ptr(hid.lo), hid.N, L.ptr(rows), L.ptr(count), hid.M,
-                   L.ptr(sub.hi), L.ptr(sub.lo), L.stream())
-            hid, m_dev = sub, count
+            rows, count, slot, _ = self.vsel
+            if prune is None:
+                from ..engine import Act
+                sub = Act(hid.M, hid.N, hi=torch.empty_like(hid.hi), lo=None if hid.lo is None else torch.empty_like(hid.lo))
+                L.call("navc_gather_rows", L.ptr(hid.hi), L.ptr(hid.lo), hid.N, L.ptr(rows), L.ptr(count), hid.M,
+                       L.ptr(sub.hi), L.ptr(sub.lo), L.stream())
+                hid = sub
+            m_dev = count
         self.vsel = None
         self.pending = (self.eng.vocab_partials(hid, m_dev=m_dev), merge, is_ct, slot)
         self.passes += 1
@@ -108,11 +120,14 @@ class Refiner:
         st.masked0 = L.ptr(self.masked0) if emit_flags else None
         st.seq_off = L.ptr(self.packed["seq_off"]) if self.packed is not None else None
         if self.packed is not None and select in (L.SELECT_WORST, L.SELECT_MASKTOK, L.SELECT_GIVEN):
-            rows, count, slot_map = self.vbuf[self.n_steps % 2]
-            count.zero_()
-            st.sel_rows, st.sel_count, st.sel_slot = L.ptr(rows), L.ptr(count), L.ptr(slot_map)
-            self.vsel = (rows, count, slot_map)
+            rows, count, slot_map, seq_off_c = self.vbuf[self.n_steps % 2]
+            st.sel_rows, st.sel_count, st.sel_slot = None, L.ptr(count), L.ptr(slot_map)   # flag mode
+            self.vsel = (rows, count, slot_map, seq_off_c)
         L.call("navc_refine_step", st, self.N, self.S, L.stream())
+        if self.vsel is not None and st.sel_slot:
+            rows, count, slot_map, seq_off_c = self.vsel
+            L.call("navc_compact_rows", L.ptr(slot_map), L.ptr(self.packed["seq_off"]), self.N, self.N * self.S, L.ptr(rows),
+                   L.ptr(count), L.ptr(seq_off_c), L.stream())
         self.pending = None
         self.n_steps += 1
         return slot

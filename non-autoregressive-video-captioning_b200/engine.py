@@ -442,8 +442,12 @@ class Engine:
             all(lw[k] is None for lw in P["layers"] for k in ("so_ln", "co_ln", "f2_ln"))
 
     def decoder_pass(self, tokens: torch.Tensor, mem: dict, group: int, category: Optional[torch.Tensor],
-                     decoding_type: str, want_attn=False, want_f32=False, packed: Optional[dict] = None):
-        """One BertDecoder forward (models/Decoder.py:96-178) -> hidden Act [N*S, D] (+ attention probs)."""
+                     decoding_type: str, want_attn=False, want_f32=False, packed: Optional[dict] = None,
+                     prune: Optional[dict] = None):
+        """One BertDecoder forward (models/Decoder.py:96-178) -> hidden Act [N*S, D] (+ attention probs).
+        ``prune`` (packed rows only; rows / count / seq_off of navc_compact_rows): the caller reads the hidden states of
+        these rows only, so the last layer runs on them alone behind its self-attention core (which needs every row as
+        key / value) and the result is the COMPACTED Act: row k = hidden state of packed row rows[k]."""
         P, D, H = self.P, self.D, self.H
         N, S = tokens.shape
         R = N * S
@@ -482,6 +486,7 @@ class Engine:
         mask_kind = L.MASK_KIND[decoding_type]
         tc_attn = self.tc_attention_ok(S, E) and not want_attn and kv.hi is not None
         watch = int(self.opt.get("watch", 0))
+        sfx = ""
         for l, lw in enumerate(P["layers"]):
             qkv = self.linear(x, lw["qkv"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="qkv", m_hint=mh)
             ctx = self._new(R, D, not self.tc, True)
@@ -503,15 +508,27 @@ class Engine:
                 L.call("navc_self_attention", L.ptr(qkv.f32), 3 * D, L.ptr(tokens), N, S, D, H, mask_kind,
                        watch, L.ptr(ctx.f32), L.ptr(ctx.hi), L.ptr(ctx.lo), L.ptr(p_self), L.stream())
             self._t1("self", e0)
-            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tok_flat, pair, m_dev, tag="so", m_hint=mh)
-            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="cq", m_hint=mh)
+            seq_off = packed["seq_off"] if packed is not None else None
+            if prune is not None and l == len(P["layers"]) - 1:
+                assert packed is not None and "tile_seq" in packed
+                e0 = self._t0("gather")
+                ctx_c, x_c = self._new(R, D, False, True, lo=ctx.lo is not None), self._new(R, D, False, True, lo=x.lo is not None)
+                for src, dst in ((ctx, ctx_c), (x, x_c)):
+                    L.call("navc_gather_rows", L.ptr(src.hi), L.ptr(src.lo), D, L.ptr(prune["rows"]), L.ptr(prune["count"]), R,
+                           L.ptr(dst.hi), L.ptr(dst.lo), L.stream())
+                self._t1("gather", e0)
+                ctx, x, tok_flat = ctx_c, x_c, None          # (packed rows are never PAD: the row mask is a no-op)
+                m_dev, mh, seq_off = prune["count"], prune.get("hint", 0), prune["seq_off"]
+                sfx = "_p"                                   # profiling tags of the launches on the compacted rows
+            a = self._proj_res(ctx, lw["so"], lw["so_ln"], x, tok_flat, pair, m_dev, tag="so" + sfx, m_hint=mh)
+            q = self.linear(a, lw["cq"], f32=not tc_attn, bf=tc_attn, m_dev=m_dev, tag="cq" + sfx, m_hint=mh)
             ctx2 = self._new(R, D, not self.tc, True)
-            e0 = self._t0("cross")
+            e0 = self._t0("cross" + sfx)
             if packed is not None and "tile_seq" in packed:
                 off = l * 2 * D
                 L.call("navc_cross_attention_tc_tiles", self.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D,
                        kv.hi[:, off:].data_ptr(), kv.lo[:, off:].data_ptr() if kv.lo is not None else None, kv.N,
-                       L.ptr(packed["seq_off"]), R, N, S, E, D, H, group, L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.stream())
+                       L.ptr(seq_off), R, N, S, E, D, H, group, L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.stream())
             elif packed is not None:
                 off = l * 2 * D
                 L.call("navc_cross_attention_tc_packed", self.tc_mode, L.ptr(q.hi), L.ptr(q.lo), D,
@@ -528,10 +545,10 @@ class Engine:
                 kv_l = self._kv_f32(mem)[:, l * 2 * D:]
                 L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, S, E, D, H, group,
                        L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
-            self._t1("cross", e0)
-            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair, m_dev, tag="co", m_hint=mh)
-            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1", m_dev=m_dev, m_hint=mh)
-            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair, m_dev, tag="f2", m_hint=mh)
+            self._t1("cross" + sfx, e0)
+            c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair, m_dev, tag="co" + sfx, m_hint=mh)
+            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1" + sfx, m_dev=m_dev, m_hint=mh)
+            x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair, m_dev, tag="f2" + sfx, m_hint=mh)
             if want_attn:
                 attns.append((p_self, p_cross))
         if want_f32:

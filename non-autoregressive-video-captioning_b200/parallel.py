@@ -17,6 +17,7 @@ independent units (videos), so
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import torch
@@ -113,7 +114,8 @@ class GradientAllReduce:
         if eng is not None:
             eng.grad_sink = self.sink
             eng.grads_final_hook = self.begin_early   # called by the encoder's backward before it launches anything
-        self.overlap = True       # all-reduce the finished part of the buffer under the encoder's backward
+        # all-reduce the finished part of the buffer under the encoder's backward ($NAVC_DP_OVERLAP=0: one collective)
+        self.overlap = os.environ.get("NAVC_DP_OVERLAP", "1") not in ("0", "no", "off")
         self.weight = 1.0         # this rank's weight (unequal shards), set BEFORE backward when overlap is on
         self._early = None        # (split, work) of the collective in flight
         self._split_of = {}

@@ -458,3 +458,57 @@ def test_packed_rows_match_padded_layout(precision):
             n_eq, n_above = check_against_oracle(hyp, hyp_o, det["video_margin"], precision, "%s packed=%d" % (kw, packed))
             if precision == "bf16x3":
                 assert n_above >= 5, det["video_margin"].tolist()
+
+
+def test_compact_rows_orders_the_selected_positions():
+    """navc_compact_rows (include/navc.h): ordered compaction of refine_step's selection flags -- ascending row list,
+    packed row -> compact index, per-sequence offsets of the compacted row space, device-side count."""
+    g = torch.Generator().manual_seed(5)
+    for N, S in ((1, 7), (37, 28), (768, 28)):
+        lens = torch.randint(1, S + 1, (N,), generator=g, dtype=torch.int32)
+        seq_off = torch.zeros(N + 1, dtype=torch.int32)
+        seq_off[1:] = torch.cumsum(lens, 0)
+        R = int(seq_off[-1])
+        flags = (torch.rand(N * S + 1, generator=g) < 0.35).to(torch.int32)
+        flags[R:] = 7   # stale entries behind the real rows must not count
+        slot = flags.clone().to(DEV)
+        rows = torch.full((N * S,), -1, dtype=torch.int32, device=DEV)
+        count = torch.zeros(1, dtype=torch.int32, device=DEV)
+        seq_off_c = torch.full((N + 1,), -1, dtype=torch.int32, device=DEV)
+        L.call("navc_compact_rows", L.ptr(slot), L.ptr(seq_off.to(DEV)), N, N * S, L.ptr(rows), L.ptr(count), L.ptr(seq_off_c), L.stream())
+        sel = torch.nonzero(flags[:R]).flatten().to(torch.int32)
+        assert int(count) == sel.numel()
+        assert torch.equal(rows[:sel.numel()].cpu(), sel)
+        excl = torch.cumsum(flags[:R] != 0, 0) - (flags[:R] != 0).long()
+        assert torch.equal(slot[:R].cpu().long(), excl)
+        want_off = torch.tensor([int((flags[:int(seq_off[n])] != 0).sum()) for n in range(N + 1)], dtype=torch.int32)
+        assert torch.equal(seq_off_c.cpu(), want_off)
+
+
+@pytest.mark.parametrize("kw", [dict(paradigm="mp", use_ct=True), dict(paradigm="mp", use_ct=False),
+                                dict(paradigm="ef", use_ct=True, q=2), dict(paradigm="l2r", use_ct=True, q=1)])
+def test_last_layer_on_remasked_rows_only_is_exact(kw):
+    """Refinement passes that merge only re-masked positions run their LAST decoder layer on those rows alone
+    (opt['navc_prune'], default on).  Rows are independent behind the self-attention core, so token ids AND
+    probabilities must equal the all-rows pass bit for bit; both also match the oracle's ids."""
+    opt = cases.wide("NACF", **kw)
+    model = navc_b200.get_model(opt)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = cases.synth_state_dict(shapes, 11, 0.5)
+    model.load_state_dict(sd)
+    model.to(DEV).eval()
+    model.set_precision("bf16x3")
+    feats, category = cases.synth_inputs(opt, 9)
+    hyp_o, det = O.translate(sd, opt, feats, category, return_details=True)
+    outs = []
+    for prune in (1, 0):
+        tr = navc_b200.Translator(model, dict(opt, navc_prune=prune), device=DEV)
+        with torch.no_grad():
+            for _ in range(3):   # eager, capture, replay
+                enc = model.encode(feats=to_dev(feats))
+                hyp, scores = tr.translate_batch(enc, category.to(DEV), None, {})
+        outs.append((hyp.cpu(), scores.cpu() if torch.is_tensor(scores) else scores))
+        check_against_oracle(hyp, hyp_o, det["video_margin"], "bf16x3", "%s prune=%d" % (kw, prune))
+    assert torch.equal(outs[0][0], outs[1][0])
+    if torch.is_tensor(outs[0][1]):
+        assert torch.equal(outs[0][1], outs[1][1])
