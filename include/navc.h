@@ -461,6 +461,17 @@ int navc_self_attention_bwd_packed(const float* qkv, int ld, const int64_t* toke
 int navc_cross_attention_bwd_packed(const float* q, int ldq, const float* kv, int ldkv, const int32_t* seq_off, int N,
                                     int S, int E, int D, int H, const float* d_ctx, float* d_q, int ld_dq, float* d_kv,
                                     int ld_dkv, void* stream);
+/* The same two gradients on the tensor cores (csrc/attention_bwd_tc.cu; dk == 64, S <= 32, E <= 128, packed rows only): one
+ * CTA per (owner, head), five tcgen05 products (S, dP, dV, dK, dQ) on bf16 (mode NAVC_TC_BF16) or split-bf16
+ * (NAVC_TC_BF16X3) operands made in-kernel from the fp32 activations; softmax statistics, P and dS in fp32.
+ * Same arguments / results as navc_self_attention_bwd_packed / navc_cross_attention_bwd_packed (self: the PAD mask is
+ * implied by the packing, so no token ids are read), plus `ctx` [rows, D] fp32, the forward pass's context (or NULL):
+ * with it the softmax-gradient row term sum_j P_ij dP_ij is taken as dO_i . ctx_i, which saves a pass over dP. */
+int navc_self_attention_bwd_tc(int mode, const float* qkv, int ld, const int32_t* seq_off, int N, int S, int D, int H,
+                               int mask_kind, int watch, const float* d_ctx, const float* ctx, float* d_qkv, void* stream);
+int navc_cross_attention_bwd_tc(int mode, const float* q, int ldq, const float* kv, int ldkv, const int32_t* seq_off,
+                                int N, int S, int E, int D, int H, const float* d_ctx, const float* ctx, float* d_q,
+                                int ld_dq, float* d_kv, int ld_dkv, void* stream);
 int navc_embed_ln_bwd_packed(const float* dout, const int64_t* tokens, const int64_t* category, const float* word_emb,
                              const float* pos_emb, const float* cat_emb, const float* extra, int group,
                              const float* ln_w, float eps, int S, int D, const int32_t* rowmap, int rows,

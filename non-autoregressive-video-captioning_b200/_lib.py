@@ -104,6 +104,8 @@ _PROTOS = {
     "navc_cross_attention_tc_rows": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
     "navc_self_attention_bwd_packed": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
     "navc_cross_attention_bwd_packed": [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, vp],
+    "navc_self_attention_bwd_tc": [i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    "navc_cross_attention_bwd_tc": [i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, i32, vp],
     "navc_embed_ln_bwd_packed": [vp, vp, vp, vp, vp, vp, vp, i32, vp, f32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp],
     "navc_log_softmax_rows": [vp, i32, vp, i32, vp, i32, i32, vp],
     "navc_log_softmax_bwd_rows": [vp, vp, vp, i32, i32, i32, vp, i32, vp],

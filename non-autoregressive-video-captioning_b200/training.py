@@ -651,6 +651,14 @@ class DecoderFn(torch.autograd.Function):
             g = gp
         nl = len(P["layers"])
         d_kv = torch.empty((Bv * E, nl * 2 * D), dtype=torch.float32, device=dev)
+        # attention gradients on the tensor cores (csrc/attention_bwd_tc.cu: dk == 64, S <= 32, E <= 128, packed rows).
+        # opt['navc_attn_bwd_tc'] / $NAVC_ATTN_BWD_TC: 1 (default) text -> video attention only -- 535 vs 669 us per launch
+        # at 1024 videos; the token self-attention (<= 30 keys: one 32-key chunk of a 128-wide tile) measured 302 vs 288 us
+        # against the fp32 CUDA-core kernel and stays there; 2 = both on the tensor cores; 0 = neither
+        want = str(eng.opt.get("navc_attn_bwd_tc", os.environ.get("NAVC_ATTN_BWD_TC", "1"))).lower()
+        tc_ok = pk is not None and eng.tc and eng.tc_attention_ok(S, E)
+        tc_bwd = tc_ok and want not in ("0", "false", "no", "off")
+        tc_bwd_self = tc_ok and want in ("2", "all", "both")
         for l in range(nl - 1, -1, -1):
             lw, sv = P["layers"][l], st["layers"][l]
             d_f2, d_c_res = _post_bwd(eng, g, lw["f2_ln"], lw["f2_ln_key"], sv["s_f1"], p, sv["s_f2"], p, tok_flat, sv["f2"], grads)
@@ -662,7 +670,11 @@ class DecoderFn(torch.autograd.Function):
             d_ctx2 = lin_bwd(eng, sv["ctx2"], lw["co"], d_co, grads)
             d_q = torch.empty((R, D), dtype=torch.float32, device=dev)
             off = l * 2 * D
-            if pk is not None:
+            if pk is not None and tc_bwd:
+                L.call("navc_cross_attention_bwd_tc", eng.tc_mode, L.ptr(sv["q"]), D, st["kv"][:, off:].data_ptr(), st["kv"].shape[1],
+                       L.ptr(pk["seq_off"]), N, S, E, D, H, L.ptr(d_ctx2), L.ptr(sv["ctx2"].f32), L.ptr(d_q), D,
+                       d_kv[:, off:].data_ptr(), d_kv.shape[1], L.stream())
+            elif pk is not None:
                 L.call("navc_cross_attention_bwd_packed", L.ptr(sv["q"]), D, st["kv"][:, off:].data_ptr(), st["kv"].shape[1],
                        L.ptr(pk["seq_off"]), N, S, E, D, H, L.ptr(d_ctx2), L.ptr(d_q), D, d_kv[:, off:].data_ptr(),
                        d_kv.shape[1], L.stream())
@@ -673,7 +685,10 @@ class DecoderFn(torch.autograd.Function):
             d_so, d_x_res = _post_bwd(eng, d_a, lw["so_ln"], lw["so_ln_key"], sv["s_so"], p, 0, 0.0, tok_flat, sv["so"], grads)
             d_ctx1 = lin_bwd(eng, sv["ctx1"], lw["so"], d_so, grads)
             d_qkv = torch.empty((R, 3 * D), dtype=torch.float32, device=dev)
-            if pk is not None:
+            if pk is not None and tc_bwd_self:
+                L.call("navc_self_attention_bwd_tc", eng.tc_mode, L.ptr(sv["qkv"]), 3 * D, L.ptr(pk["seq_off"]), N, S, D, H,
+                       st["mask_kind"], st["watch"], L.ptr(d_ctx1), L.ptr(sv["ctx1"].f32), L.ptr(d_qkv), L.stream())
+            elif pk is not None:
                 L.call("navc_self_attention_bwd_packed", L.ptr(sv["qkv"]), 3 * D, L.ptr(st["tokens"]), L.ptr(pk["seq_off"]), N, S,
                        D, H, st["mask_kind"], st["watch"], L.ptr(d_ctx1), L.ptr(d_qkv), L.stream())
             else:

@@ -417,6 +417,78 @@ def test_cross_attention_backward_packed(D, H, S, E):
     close(d_kv.view(N, E, 2 * D), kv.grad, 2e-5, "packed cross attn dkv")
 
 
+@pytest.mark.parametrize("with_ctx", [True, False])
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("kind", ["NARFormer", "ARFormer", "SelfMask"])
+@pytest.mark.parametrize("D,H,S", [(128, 2, 11), (512, 8, 30), (64, 1, 32)])
+def test_self_attention_backward_tc(mode, kind, D, H, S, with_ctx):
+    """csrc/attention_bwd_tc.cu (tcgen05, dk = 64) against torch autograd, sequence by sequence; rows beyond the
+    packed count are NaN-poisoned and must neither be read into a result nor written."""
+    lens = [min(l, S) for l in (S, 1, S - 3, 5, 2, S - 1, 16, 17)]
+    N = len(lens)
+    seq_off, rowmap = _pack(lens, S)
+    Rp = int(seq_off[-1])
+    toks = torch.randint(1, 9, (N, S), generator=g(60))
+    for n, l in enumerate(lens):
+        toks[n, l:] = 0
+    qkv = torch.randn(Rp, 3 * D, generator=g(61)).requires_grad_(True)
+    d_ctx = torch.randn(Rp, D, generator=g(62))
+    ctx_rows = []
+    for n, l in enumerate(lens):
+        r0 = int(seq_off[n])
+        x = qkv[r0:r0 + l].unsqueeze(0)
+        mask = O.self_attention_mask(toks[n:n + 1, :l], kind, 0)
+        ctx = _mha_ref(x[..., :D], x[..., D:2 * D], x[..., 2 * D:], mask, H)
+        ctx.backward(d_ctx[r0:r0 + l].unsqueeze(0))
+        ctx_rows.append(ctx.detach()[0])
+    pad = 40   # poisoned rows behind the packed rows
+    ctx_d = torch.full((Rp + pad, D), float("nan"), device=DEV)
+    ctx_d[:Rp] = torch.cat(ctx_rows).to(DEV)
+    qkv_d = torch.full((Rp + pad, 3 * D), float("nan"), device=DEV)
+    qkv_d[:Rp] = qkv.detach().to(DEV)
+    dctx_d = torch.full((Rp + pad, D), float("nan"), device=DEV)
+    dctx_d[:Rp] = d_ctx.to(DEV)
+    d_qkv = torch.full((Rp + pad, 3 * D), 7.0, device=DEV)
+    L.call("navc_self_attention_bwd_tc", L.TC_BF16X3 if mode == "bf16x3" else L.TC_BF16, L.ptr(qkv_d), 3 * D, P(seq_off), N, S, D, H,
+           L.MASK_KIND[kind], 0, L.ptr(dctx_d), L.ptr(ctx_d) if with_ctx else None, L.ptr(d_qkv), L.stream())
+    close(d_qkv[:Rp], qkv.grad, 3e-5 if mode == "bf16x3" else 2e-2, "tc self attn bwd %s" % mode)
+    assert torch.all(d_qkv[Rp:] == 7.0)
+
+
+@pytest.mark.parametrize("with_ctx", [True, False])
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("D,H,S,E", [(128, 2, 9, 12), (512, 8, 30, 120), (64, 1, 32, 128)])
+def test_cross_attention_backward_tc(mode, D, H, S, E, with_ctx):
+    lens = [min(l, S) for l in (S, 1, S - 3, 5, 2, 16, 17)]
+    N = len(lens)
+    seq_off, _ = _pack(lens, S)
+    Rp = int(seq_off[-1])
+    q = torch.randn(Rp, D, generator=g(63)).requires_grad_(True)
+    kv = torch.randn(N, E, 2 * D, generator=g(64)).requires_grad_(True)
+    d_ctx = torch.randn(Rp, D, generator=g(65))
+    ctx_rows = []
+    for n, l in enumerate(lens):
+        r0 = int(seq_off[n])
+        ctx = _mha_ref(q[r0:r0 + l].unsqueeze(0), kv[n:n + 1, :, :D], kv[n:n + 1, :, D:], None, H)
+        ctx.backward(d_ctx[r0:r0 + l].unsqueeze(0))
+        ctx_rows.append(ctx.detach()[0])
+    pad = 40
+    ctx_d = torch.full((Rp + pad, D), float("nan"), device=DEV)
+    ctx_d[:Rp] = torch.cat(ctx_rows).to(DEV)
+    q_d = torch.full((Rp + pad, D), float("nan"), device=DEV)
+    q_d[:Rp] = q.detach().to(DEV)
+    dctx_d = torch.full((Rp + pad, D), float("nan"), device=DEV)
+    dctx_d[:Rp] = d_ctx.to(DEV)
+    d_q = torch.full((Rp + pad, D), 7.0, device=DEV)
+    d_kv = torch.full((N * E, 2 * D), float("nan"), device=DEV)
+    L.call("navc_cross_attention_bwd_tc", L.TC_BF16X3 if mode == "bf16x3" else L.TC_BF16, L.ptr(q_d), D, P(kv), 2 * D, P(seq_off),
+           N, S, E, D, H, L.ptr(dctx_d), L.ptr(ctx_d) if with_ctx else None, L.ptr(d_q), D, L.ptr(d_kv), 2 * D, L.stream())
+    tol = 3e-5 if mode == "bf16x3" else 2e-2
+    close(d_q[:Rp], q.grad, tol, "tc cross attn dq %s" % mode)
+    close(d_kv.view(N, E, 2 * D), kv.grad, tol, "tc cross attn dkv %s" % mode)
+    assert torch.all(d_q[Rp:] == 7.0)
+
+
 def test_packed_row_helpers():
     S, D, V = 7, 64, 301
     lens = [7, 2, 5, 1]
@@ -487,8 +559,11 @@ def test_packed_training_matches_oracle_and_padded_path(method, kw):
         if rg is None or rg.abs().max().item() == 0:
             assert p.grad is None or p.grad.abs().max().item() < 1e-6, name
             continue
-        close(p.grad, rg, tol, name, atol=2e-7)
-        close(p.grad, grads2[name].grad, 1e-4, name + " (packed vs padded)", atol=2e-7)
+        # atol: the key-bias gradients are analytically zero (softmax is invariant to a key bias); what is left is the
+        # rounding of dS -- 2^-17 relative per element through the split-bf16 operands of the tcgen05 backward
+        atol = 2e-7 + (1e-4 * sd[name.replace("key.bias", "key.weight")].grad.abs().max().item() if name.endswith("key.bias") else 0.0)
+        close(p.grad, rg, tol, name, atol=atol)
+        close(p.grad, grads2[name].grad, 1e-4, name + " (packed vs padded)", atol=atol)
         checked += 1
     assert checked > 20
 
@@ -513,7 +588,10 @@ def test_packed_vocab_bias_gradient_with_unmasked_loss():
         out[packed, "rows"] = model.engine.last_train_rows
     assert out[1, "rows"][0] < out[0, "rows"][0]
     for k, v in out[0].items():
-        close(out[1][k], v, 1e-4, k, atol=2e-6)  # atol: the key-bias gradients are analytically zero (rounding noise)
+        # atol: the key-bias gradients are analytically zero (softmax is invariant to a key bias): what is left is rounding
+        # noise of dS (2^-17 relative per element through the split-bf16 operands), measured against the key WEIGHT gradient
+        atol = 2e-6 + (1e-4 * out[0][k.replace("key.bias", "key.weight")].abs().max().item() if k.endswith("key.bias") else 0.0)
+        close(out[1][k], v, 1e-4, k, atol=atol)
 
 
 # ---------------------------------------------------------------------------------------------------
