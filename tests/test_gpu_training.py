@@ -47,6 +47,15 @@ def P(t):
     return L.ptr(t)
 
 
+def zero_atol(name, ref_grad_of, base=2e-7):
+    """Absolute slack for gradients that are analytically zero: softmax is invariant to a key bias, so what a kernel
+    returns for `*.key.bias` is rounding noise of dS (fp32 CUDA cores: ~1e-8; split-bf16 tcgen05 operands: 2^-17 relative
+    per element) -- judged against the scale of the key WEIGHT gradient of the same block."""
+    if name.endswith("key.bias"):
+        return base + 1e-4 * ref_grad_of(name.replace("key.bias", "key.weight")).abs().max().item()
+    return base
+
+
 def close(a, b, tol, what="", atol=0.0):
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     scale = max(b.abs().max().item(), 1e-6)
@@ -656,7 +665,7 @@ def test_gradients_match_oracle(method, kw, precision):
         assert p.grad is not None, name
         # atol: gradients that are analytically zero (softmax is invariant to the key bias) are pure
         # rounding noise (~1e-8) on both sides
-        close(p.grad, rg, tol, name, atol=2e-7)
+        close(p.grad, rg, tol, name, atol=zero_atol(name, lambda k: sd[k].grad))
         checked += 1
     assert checked > 20
     for k, v in bn_state.items():  # running statistics updated as nn.BatchNorm1d does
@@ -731,7 +740,7 @@ def test_direct_gradient_accumulation_matches_autograd():
         grads[direct] = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
     assert set(grads[True]) == set(grads[False])
     for k, v in grads[False].items():
-        close(grads[True][k], v, 2e-5, k, atol=2e-7)
+        close(grads[True][k], v, 2e-5, k, atol=zero_atol(k, lambda n: grads[False][n]))
 
 
 def test_training_with_dropout_runs_and_is_seed_reproducible():
@@ -892,7 +901,7 @@ def test_fused_cross_entropy_matches_oracle(precision):
         rg = sd[name].grad
         if rg is None or rg.abs().max().item() == 0:
             continue
-        close(p.grad, rg, tol, name, atol=2e-7)
+        close(p.grad, rg, tol, name, atol=zero_atol(name, lambda k: sd[k].grad))
     # meters: top-1 accuracy and perplexity from the fused statistics vs the oracle's log-probs
     names, info = crit.get_loss_info()
     lp = ref["tgt_word_logprobs"][1].detach()
@@ -968,7 +977,7 @@ def test_tied_vocabulary_projection_forward_and_gradients(precision):
         if rg is None or rg.abs().max().item() == 0:
             continue
         assert p.grad is not None, name
-        close(p.grad, rg, tol, name, atol=2e-7)
+        close(p.grad, rg, tol, name, atol=zero_atol(name, lambda k: sd[k].grad))
         checked += 1
     assert checked > 15 and model.tgt_word_prj.bias.grad is not None
 
