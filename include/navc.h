@@ -95,6 +95,13 @@ int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx
                    const uint16_t* w_hi, const uint16_t* w_lo, int ldw, int M, int N, int K,
                    const navc_epilogue_t* epi, void* stream);
 
+/* Y = epilogue(X W^T) with fp32 operands consumed by the tensor cores as TF32 (tcgen05 kind::tf32: 10-bit mantissa, two
+ * bf16-MMA time units per product against split-bf16's three): x [M, K] and w [N, K] fp32 row-major (K % 4 == 0, 16-byte
+ * aligned), generic epilogue -- bias, activation, fp32 residual, row mask; fp32 and / or bf16 hi (/ lo) outputs; a
+ * device-side row count in e->m_dev.  The "1e-3 logits" mode of the engine (precision 'tf32') uses it wherever the A
+ * operand exists in fp32 (models/bert.py:81-92 query/key/value, :227-247 FFN; Encoder.py:9-38). */
+int navc_linear_tf32(const float* x, int ldx, const float* w, int ldw, int M, int N, int K, const navc_epilogue_t* e,
+                     void* stream);
 /* Weight gradient on the tensor cores, straight from row-major operands (no transposed copies):
  *   out_f32[n, k] += sum_r dY[r, n] * X[r, k]      dY [rows, n_out] (ld_dy), X [rows, k_in] (ld_x), bf16 hi(/lo).
  * Both operands are consumed MN-major (TMA boxes of 64 rows x 64 columns).  The epilogue only honours

@@ -70,7 +70,9 @@ constexpr int kEpiWgrad = 4;
 // row-major (the data gradient dX = dY W straight from the forward's weight copies: no transposed weights).
 constexpr int kEpiDgrad = 5;
 
-template <bool kX3, int kEpi, int TBN>
+// kTf32: the operands are fp32 matrices consumed as TF32 (kind::tf32; generic epilogue only): a k-block is 32 elements =
+// the same 128-byte swizzle rows and tile sizes as 64 bf16, four k-steps of 8 elements = the same 32-byte descriptor steps.
+template <bool kX3, int kEpi, int TBN, bool kTf32 = false>
 __global__ void __launch_bounds__(tc_threads(kEpi), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -102,7 +104,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + TBM - 1) / TBM, n_blocks = (N + TBN - 1) / TBN;
-    const int k_blocks = (K + TBK - 1) / TBK;  // TMA zero-fills the K tail of the last block
+    constexpr int kKB = kTf32 ? TBK / 2 : TBK;   // K elements per k-block
+    const int k_blocks = (K + kKB - 1) / kKB;  // TMA zero-fills the K tail of the last block
     const int split = kVocab ? 1 : epi.split_k;
     const int kpb = (k_blocks + split - 1) / split;  // k-blocks per split (host guarantees every split is non-empty)
     const int n_tiles = m_blocks * n_blocks * split;
@@ -187,7 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             if (kX3) tma_load_2d(sa + kTileABytes + kTileBBytes + j * 8192, &map_a_lo, full_bar(stage), mb * TBM + j * 64, row);
                         }
                     } else {
-                        tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * TBK, mb * TBM);
+                        tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * kKB, mb * TBM);
                         if (kX3) tma_load_2d(sa + kTileABytes + kTileBBytes, &map_a_lo, full_bar(stage), kb * TBK, mb * TBM);
                     }
                     if constexpr (kMNB) {
@@ -197,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             if (kX3) tma_load_2d(sa + 2 * kTileABytes + kTileBBytes + j * 8192, &map_b_lo, full_bar(stage), nb * TBN + j * 64, row);
                         }
                     } else {
-                        tma_load_2d(sa + kTileABytes, &map_b_hi, full_bar(stage), kb * TBK, nb * TBN);
+                        tma_load_2d(sa + kTileABytes, &map_b_hi, full_bar(stage), kb * kKB, nb * TBN);
                         if (kX3) tma_load_2d(sa + 2 * kTileABytes + kTileBBytes, &map_b_lo, full_bar(stage), kb * TBK, nb * TBN);
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
@@ -207,7 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TBM, TBN) | (kMNA ? (1u << 15) : 0u) | (kMNB ? (1u << 16) : 0u);  // A / B MN-major bits
+            constexpr uint32_t idesc = kTf32 ? make_idesc_tf32(TBM, TBN)
+                                             : (make_idesc(TBM, TBN) | (kMNA ? (1u << 15) : 0u) | (kMNB ? (1u << 16) : 0u));  // A / B MN-major bits
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -236,6 +240,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             tc_mma_bf16(d_tmem, da_lo + koff_a, db_hi + koff_b, idesc, ((kb - kb0) | k) ? 1u : 0u);
                             tc_mma_bf16(d_tmem, da_hi + koff_a, db_lo + koff_b, idesc, 1u);
                             tc_mma_bf16(d_tmem, da_hi + koff_a, db_hi + koff_b, idesc, 1u);
+                        } else if (kTf32) {
+                            tc_mma_tf32(d_tmem, da_hi + koff_a, db_hi + koff_b, idesc, ((kb - kb0) | k) ? 1u : 0u);
                         } else {
                             tc_mma_bf16(d_tmem, da_hi + koff_a, db_hi + koff_b, idesc, ((kb - kb0) | k) ? 1u : 0u);
                         }
@@ -703,6 +709,8 @@ int tc_init() {
     NAVC_TC_ATTR(false, kEpiDgrad, 256); NAVC_TC_ATTR(true, kEpiDgrad, 256);
     NAVC_TC_ATTR(false, kEpiDgrad, 128); NAVC_TC_ATTR(true, kEpiDgrad, 128);
 #undef NAVC_TC_ATTR
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, kEpiGeneric, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false, 256, kEpiGeneric>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, kEpiGeneric, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false, 128, kEpiGeneric>::kSmemBytes));
     g_tc_ready = true;
     return 0;
 }
@@ -745,6 +753,23 @@ int tc_make_map_uncached(CUtensorMap* map, const uint16_t* ptr, int rows, int K,
                           estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NAVC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+    return 0;
+}
+
+// 2-D fp32 tensor map (kind::tf32 operands): box = [box_rows, 32 floats] = the same 128-byte swizzle rows
+static int tc_make_map_f32(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows) {
+    const MapKey key = {ptr, rows, K, ld, box_rows, 2};
+    MapSlot* slot;
+    if (map_cache_get(key, map, &slot)) return 0;
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)(TBK / 2), (cuuint32_t)box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estride,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NAVC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+    slot->key = key; slot->map = *map; slot->used = true;
     return 0;
 }
 
@@ -885,6 +910,21 @@ static int launch_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int l
     return launch_tc_bn<kEpi, 256>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, epi, vep, st, what);
 }
 
+// Y = epilogue(X W^T) with fp32 operands consumed as TF32 (generic epilogue: fp32 / bf16 hi / lo outputs, fp32 residual)
+template <int TBN>
+static int launch_tf32_bn(const float* x, int ldx, const float* w, int ldw, int M, int N, int K, const EpiParams& epi, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    if (tc_make_map_f32(&ma, x, M, K, ldx, TBM) || tc_make_map_f32(&mb, w, N, K, ldw, TBN)) return 1;
+    const int tiles = ((M + TBM - 1) / TBM) * ((N + TBN - 1) / TBN);
+    int sms = navc_sm_count();
+    if (sms <= 0) sms = 148;
+    const int grid = tiles < sms ? tiles : sms;
+    TcVocab v = {};
+    NAVC_CUDA(launch_pdl(gemm_tc_kernel<false, kEpiGeneric, TBN, true>, dim3(grid), dim3(tc_threads(kEpiGeneric)),
+                         TcCfg<false, TBN, kEpiGeneric>::kSmemBytes, st, ma, ma, mb, mb, ma, ma, ma, ma, M, N, K, epi, v));
+    return check_launch("navc_linear_tf32");
+}
+
 // dX[rows, k_in] = dY[rows, kred] W[n_out, k_in]: the B map is declared with its true n_out rows so that the
 // reduction tail (kred > n_out, and the k-block tail) reads zeros.
 static int launch_tc_dgrad(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld_dy, const uint16_t* w_hi,
@@ -956,6 +996,24 @@ extern "C" int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_
     }
     if (pair) return launch_tc<kEpiPair>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
     return launch_tc<kEpiGeneric>(mode, x_hi, x_lo, ldx, w_hi, w_lo, ldw, M, N, K, p, v, as_stream(stream), "navc_linear_tc");
+}
+
+extern "C" int navc_linear_tf32(const float* x, int ldx, const float* w, int ldw, int M, int N, int K, const navc_epilogue_t* e,
+                                void* stream) {
+    NAVC_REQUIRE(e && (e->out_f32 || e->out_hi), "navc_linear_tf32: no output");
+    NAVC_REQUIRE(g_tc_ready, "navc_linear_tf32: navc_init() has not been called");
+    EpiParams p = to_params(e);
+    NAVC_REQUIRE(!p.accumulate && p.split_k <= 1 && !p.res_hi, "navc_linear_tf32: no split-K / accumulate / bf16-pair residual");
+    p.split_k = 1;
+    NAVC_REQUIRE(x && w && M > 0 && N > 0 && K > 0 && K % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)w)) & 15) == 0,
+                 "navc_linear_tf32: need K %% 4 == 0, ld %% 4 == 0 and 16-byte aligned operands (M=%d N=%d K=%d)", M, N, K);
+    int sms = navc_sm_count();
+    if (sms <= 0) sms = 148;
+    const int mt = (M + TBM - 1) / TBM;
+    const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
+    const bool narrow = N <= 128 || (t256 < sms && t128 > t256) || tile_waste_pct(t256, sms) >= tile_waste_pct(t128, sms) + 8;
+    if (narrow) return launch_tf32_bn<128>(x, ldx, w, ldw, M, N, K, p, as_stream(stream));
+    return launch_tf32_bn<256>(x, ldx, w, ldw, M, N, K, p, as_stream(stream));
 }
 
 extern "C" int navc_wgrad_tc(int mode, const uint16_t* dy_hi, const uint16_t* dy_lo, int ld_dy, const uint16_t* x_hi,

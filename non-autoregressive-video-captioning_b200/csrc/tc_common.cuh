@@ -120,6 +120,15 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t da, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
+// kind::tf32: fp32 operands in shared memory (32 K-elements per 128-byte swizzle row, 8 per instruction), 10-bit mantissa
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
 // A operand from tensor memory (lane = row, one 32-bit column = two consecutive K elements), B from shared memory
 __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -176,6 +185,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+
+// kind::tf32 instruction descriptor: c = F32, a = b = TF32 (format 2), K-major both
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 // Same tile, MN-major (the 64 contiguous elements of a row are the M/N index, rows are K): what a
 // 128B-swizzled TMA load of a row-major [K rows, 64] box produces.  SBO = 1024 B between 8-row

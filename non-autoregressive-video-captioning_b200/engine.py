@@ -8,6 +8,10 @@ plumbing only; every arithmetic step of the hot path is one of our kernels.
 Precision modes (``opt['navc_precision']`` or ``$NAVC_PRECISION``):
   ``fp32``    CUDA-core fp32 GEMMs: reference-exact mode used for bit-exact token parity.
   ``bf16x3``  tcgen05 GEMMs on split-bf16 operands (3 MMAs / product): ~fp32 accuracy.
+  ``tf32``    tcgen05 ``kind::tf32`` GEMMs (2 bf16-MMA time units / product, 10-bit mantissa: ~5e-4 relative on the
+              logits) wherever the A operand exists in fp32 -- QKV / query / FFN / K|V / encoder projections; the
+              out-projections (their input comes from the attention cores as a bf16 hi/lo pair), the attention cores and
+              the vocabulary projection stay split-bf16.
   ``bf16``    tcgen05 GEMMs on bf16 operands: fastest, ~3e-3 relative logit error.
 """
 from __future__ import annotations
@@ -20,7 +24,7 @@ import torch
 from . import _lib as L
 from .config import Constants
 
-PRECISIONS = ("fp32", "bf16x3", "bf16")
+PRECISIONS = ("fp32", "bf16x3", "bf16", "tf32")
 
 
 def default_precision(opt=None) -> str:
@@ -66,7 +70,9 @@ class Engine:
         self.opt = model.opt
         self.precision = precision or default_precision(self.opt)
         self.tc = self.precision != "fp32"
-        self.tc_mode = {"bf16": L.TC_BF16, "bf16x3": L.TC_BF16X3}.get(self.precision, 0)
+        self.tc_mode = {"bf16": L.TC_BF16, "bf16x3": L.TC_BF16X3, "tf32": L.TC_BF16X3}.get(self.precision, 0)
+        self.split = self.precision in ("bf16x3", "tf32")   # bf16 operands carry a lo part
+        self.tf32 = self.precision == "tf32"
         self._sig = None
         self._members = None
         self._named = None
@@ -134,7 +140,7 @@ class Engine:
         pl = PackedLinear(w, b, src)
         if self.tc:
             pl.w_hi = torch.empty(pl.w.shape, dtype=torch.bfloat16, device=pl.w.device)
-            pl.w_lo = torch.empty_like(pl.w_hi) if self.precision == "bf16x3" else None
+            pl.w_lo = torch.empty_like(pl.w_hi) if self.split else None
             L.call("navc_split_bf16", L.ptr(pl.w), L.ptr(pl.w_hi), L.ptr(pl.w_lo), pl.w.numel(), L.stream())
         return pl
 
@@ -236,7 +242,7 @@ class Engine:
             a.f32 = torch.empty((M, N), dtype=torch.float32, device=dev)
         if bf and self.tc:
             a.hi = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
-            if self.precision == "bf16x3" or lo:
+            if self.split or lo:
                 a.lo = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
         return a
 
@@ -252,7 +258,7 @@ class Engine:
         a = Act(x2d.shape[0], x2d.shape[1], f32=x2d)
         if self.tc and need_bf:
             a.hi = torch.empty(x2d.shape, dtype=torch.bfloat16, device=x2d.device)
-            a.lo = torch.empty_like(a.hi) if self.precision == "bf16x3" else None
+            a.lo = torch.empty_like(a.hi) if self.split else None
             L.call("navc_split_bf16", L.ptr(x2d), L.ptr(a.hi), L.ptr(a.lo), x2d.numel(), L.stream())
         return a
 
@@ -280,7 +286,9 @@ class Engine:
                         L.ptr(out.f32), L.ptr(out.hi), L.ptr(out.lo), N, 0, 1, 0, L.ptr(res_hi), L.ptr(res_lo),
                         m_dev.data_ptr() if m_dev is not None else None, int(m_hint), 0)
         e0 = self._t0(tag)
-        if use_tc:
+        if self.tf32 and x.f32 is not None and K % 32 == 0 and res_hi is None:
+            L.call("navc_linear_tf32", L.ptr(x.f32), K, L.ptr(lin.w), K, M, N, K, ep, L.stream())
+        elif use_tc:
             L.call("navc_linear_tc", self.tc_mode, L.ptr(x.hi), L.ptr(x.lo), K, L.ptr(lin.w_hi), L.ptr(lin.w_lo), K,
                    M, N, K, ep, L.stream())
         else:
@@ -337,7 +345,7 @@ class Engine:
         enc = Act(B * E, D, f32=torch.empty((B, E, D), dtype=torch.float32, device=dev))
         if self.tc:
             enc.hi = torch.empty((B * E, D), dtype=torch.bfloat16, device=dev)
-            enc.lo = torch.empty_like(enc.hi) if self.precision == "bf16x3" else None
+            enc.lo = torch.empty_like(enc.hi) if self.split else None
         enc_hidden = torch.empty((B, D), dtype=torch.float32, device=dev)
         no_norm = opt.get("fusion", "temporal_concat") == "none" or opt.get("no_encoder_bn", False)
         row0 = 0
@@ -464,13 +472,13 @@ class Engine:
                 raise NotImplementedError("enhance_input=1 fails in the reference itself (SURVEY 8c)")
         # residual stream as bf16 hi/lo pairs only (no fp32 copy written / re-read) when every GEMM of the
         # layer runs on the tensor cores and no per-sublayer LayerNorm needs the fp32 rows
-        pair = self.tc and D % 64 == 0 and P["layers"][0]["f1"].N % 64 == 0 and \
+        pair = self.tc and not self.tf32 and D % 64 == 0 and P["layers"][0]["f1"].N % 64 == 0 and \
             all(lw[k] is None for lw in P["layers"] for k in ("so_ln", "co_ln", "f2_ln"))
         x = self._new(R, D, not pair, True, lo=pair)
         m_dev, mh = None, 0
         if packed is not None:
             # only the sum(len) real positions are rows (R stays the launch maximum, the count is device side)
-            assert pair and not want_attn and packed["N"] == N and packed["S"] == S
+            assert (pair or self.tf32) and not want_attn and packed["N"] == N and packed["S"] == S
             m_dev, mh = packed["count"], packed.get("hint", 0)
             tok_flat = torch.empty((R,), dtype=torch.int64, device=self.device)  # token id of every packed row
             L.call("navc_embed_ln_packed", L.ptr(tokens), L.ptr(category), L.ptr(emb["word"]), L.ptr(emb["pos"]),
@@ -547,7 +555,7 @@ class Engine:
                        L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), L.ptr(p_cross), L.stream())
             self._t1("cross" + sfx, e0)
             c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tok_flat, pair, m_dev, tag="co" + sfx, m_hint=mh)
-            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True, tag="f1" + sfx, m_dev=m_dev, m_hint=mh)
+            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc or self.tf32, bf=not self.tf32, tag="f1" + sfx, m_dev=m_dev, m_hint=mh)
             x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tok_flat, pair, m_dev, tag="f2" + sfx, m_hint=mh)
             if want_attn:
                 attns.append((p_self, p_cross))
@@ -567,7 +575,7 @@ class Engine:
         assert N == mem["B"] * group and decoding_type != "NARFormer"
         tokens = hist[:, pos].contiguous()  # this step's input token of every row
         emb = P["emb"]
-        pair = self.tc and D % 64 == 0 and P["layers"][0]["f1"].N % 64 == 0 and \
+        pair = self.tc and not self.tf32 and D % 64 == 0 and P["layers"][0]["f1"].N % 64 == 0 and \
             all(lw[k] is None for lw in P["layers"] for k in ("so_ln", "co_ln", "f2_ln"))
         x = self._new(N, D, not pair, True, lo=pair)
         # S = 1 with the position table offset to row `pos`
@@ -598,7 +606,7 @@ class Engine:
                 L.call("navc_cross_attention", L.ptr(q.f32), D, kv_l.data_ptr(), kv.N, N, 1, E, D, H, group,
                        L.ptr(ctx2.f32), L.ptr(ctx2.hi), L.ptr(ctx2.lo), None, L.stream())
             c = self._proj_res(ctx2, lw["co"], lw["co_ln"], a, tokens, pair)
-            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc, bf=True)
+            h = self.linear(c, lw["f1"], act=self.act, f32=not self.tc or self.tf32, bf=not self.tf32)
             x = self._proj_res(h, lw["f2"], lw["f2_ln"], c, tokens, pair)
         return x
 

@@ -65,7 +65,7 @@ def _alloc_operand(eng: Engine, rows, ld) -> Operand:
     dev = eng.device
     if eng.tc:
         hi = torch.empty((rows, ld), dtype=torch.bfloat16, device=dev)
-        lo = torch.empty((rows, ld), dtype=torch.bfloat16, device=dev) if eng.precision == "bf16x3" else None
+        lo = torch.empty((rows, ld), dtype=torch.bfloat16, device=dev) if eng.split else None
         return Operand(rows, ld, ld, hi=hi, lo=lo)
     return Operand(rows, ld, ld, f32=torch.empty((rows, ld), dtype=torch.float32, device=dev))
 
@@ -184,7 +184,7 @@ def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, n
     db = tb if tb is not None else (torch.zeros((N,), dtype=torch.float32, device=dev) if lin.b is not None else None)
     if eng.tc and K % 8 == 0:
         s, _ = transpose_pack(eng, dY, M, N, ld, straight=True, colsum=db)
-        if x_act is not None and x_act.hi is not None and (x_act.lo is not None or eng.precision != "bf16x3"):
+        if x_act is not None and x_act.hi is not None and (x_act.lo is not None or not eng.split):
             x_hi, x_lo = x_act.hi, x_act.lo
         else:
             xs, _ = transpose_pack(eng, x32, M, K, x32.stride(0), straight=True)
@@ -211,7 +211,7 @@ def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, n
     if not need_dx:
         return None
     dX = torch.empty((M, K), dtype=torch.float32, device=dev)
-    if eng.tc and K % 8 == 0 and lin.w_hi is not None and (lin.w_lo is not None or eng.precision != "bf16x3") and DGRAD_MN:
+    if eng.tc and K % 8 == 0 and lin.w_hi is not None and (lin.w_lo is not None or not eng.split) and DGRAD_MN:
         # dX = dY W straight from the forward's row-major bf16 weight copies (B operand consumed MN-major)
         ep = L.Epilogue(None, L.ptr(dx_residual), None, 0, K if dx_residual is not None else 0, L.ptr(dX), None, None, K, 0, 1, 0)
         L.call("navc_dgrad_tc", eng.tc_mode, L.ptr(s.hi), L.ptr(s.lo), ld, L.ptr(lin.w_hi), L.ptr(lin.w_lo), lin.K, M, N, K, ep,
@@ -292,6 +292,7 @@ class _F32Engine:
 
     def __init__(self, eng):
         self.device, self.tc, self.precision, self.tc_mode = eng.device, False, "fp32", 0
+        self.split = self.tf32 = False
 
 
 # --------------------------------------------------------------------------------------------------

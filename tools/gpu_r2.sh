@@ -28,5 +28,10 @@ gemmprof)
   NAVC_GRAPHS=0 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gemm" -s 5 -c 6 -f \
       -o gpurun_out/${TAG}_prof_gemm python tools/profile_step.py bf16x3 128 range > gpurun_out/${TAG}_ncu_gemm.log 2>&1
   python tools/ncu_metrics.py gpurun_out/${TAG}_prof_gemm.ncu-rep > gpurun_out/${TAG}_ncu_gemm_metrics.txt ;;
+trainprof)
+  # ncu table of the attention kernels of one NACF training step (forward cores + tcgen05 / CUDA-core backward)
+  timeout 900 ncu --set full --clock-control none -k regex:"attn" -s 48 -c 8 -f -o /tmp/ncu/prof_train_attn \
+      python tools/train_bench.py --method NACF --batch 256 --steps 1 --warmup 2 > gpurun_out/${TAG}_ncu_train.log 2>&1
+  python tools/ncu_table.py /tmp/ncu/prof_train_attn.ncu-rep > gpurun_out/${TAG}_ncu_table_train_attention.txt ;;
 esac; done
 ls -la gpurun_out | tail -20
