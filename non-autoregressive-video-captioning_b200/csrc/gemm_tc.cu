@@ -765,7 +765,7 @@ static int tc_make_map_f32(CUtensorMap* map, const float* ptr, int rows, int K, 
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
     cuuint32_t box[2] = {(cuuint32_t)(TBK / 2), (cuuint32_t)box_rows};
     cuuint32_t estride[2] = {1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estride,
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estride,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NAVC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);

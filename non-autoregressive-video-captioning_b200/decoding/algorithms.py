@@ -54,8 +54,7 @@ class Refiner:
                          for _ in range(2)]
         # the LAST decoder layer of a pass that only merges re-masked positions runs on those rows alone (everything behind
         # its self-attention core; include/navc.h navc_compact_rows); opt['navc_prune'] / $NAVC_PRUNE = 0: all rows + a gather
-        self.prune = str(opt.get("navc_prune", os.environ.get("NAVC_PRUNE", "1"))).lower() not in ("0", "false", "no", "off") and \
-            not getattr(self.eng, "tf32", False)   # (tf32: the compacted rows have no fp32 copy)
+        self.prune = str(opt.get("navc_prune", os.environ.get("NAVC_PRUNE", "1"))).lower() not in ("0", "false", "no", "off")
         self.rows_hint = int(rows_hint)
         self.n_steps = 0
         self.passes = 0

@@ -1,6 +1,7 @@
 """kind::tf32 GEMM (csrc/gemm_tc.cu, navc_linear_tf32) through the C ABI against a float64 torch reference, and the engine's
 'tf32' precision mode end to end.  Tolerance: TF32 keeps 10 explicit mantissa bits of each operand (2^-11 relative per
-element, random signs over the K terms): 1.5e-3 of the output magnitude."""
+element after the TMA's round-to-nearest conversion -- CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 --, random signs over the K terms):
+1e-3 of the output magnitude (measured ~3e-4; plain FLOAT32 maps let the tensor core truncate: 8x the error, biased)."""
 import math
 
 import pytest
@@ -44,7 +45,7 @@ def test_linear_tf32_matches_fp64(M, N, K, epi):
     L.call("navc_linear_tf32", L.ptr(xd), K, L.ptr(wd), K, M, N, K, ep, L.stream())
     got = out[:, :N].cpu().double()
     scale = max(y.abs().max().item(), 1e-6)
-    assert (got - y).abs().max().item() < 1.5e-3 * scale
+    assert (got - y).abs().max().item() < 1e-3 * scale
     pair = (hi.float() + lo.float())[:, :N].cpu().double()
     assert (pair - got).abs().max().item() < 1e-4 * scale   # bf16 hi + lo carries the fp32 result
 
@@ -59,7 +60,7 @@ def test_linear_tf32_device_side_row_count():
     ep = L.Epilogue(None, None, None, 0, 0, L.ptr(out), None, None, N, 0, 1, 0, None, None, cnt.data_ptr(), 0, 0)
     L.call("navc_linear_tf32", L.ptr(x), K, L.ptr(w), K, M, N, K, ep, L.stream())
     want = x[:live].double() @ w.double().t()
-    assert (out[:live].double() - want).abs().max().item() < 1.5e-3 * want.abs().max().item()
+    assert (out[:live].double() - want).abs().max().item() < 1e-3 * want.abs().max().item()
     assert torch.all(out[(live + 127) // 128 * 128:] == 7.0)   # whole tiles beyond the count are never touched
 
 
