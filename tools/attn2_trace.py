@@ -55,3 +55,13 @@ for cta in (0, 77):
             continue
         t0 = min(e[0] for r_ in range(3) for e in [((x & ((1 << 56) - 1)), 0) for x in t[cta, r_].tolist() if x])
         print("CTA %3d role %d: " % (cta, role) + " ".join("%s@%.1f" % (NAMES.get(tag, str(tag)), (c - t0) / GHZ / 1e3) for c, tag in ev[:40]))
+# distribution over CTAs of the busy span (clock64 is per SM: only differences inside a CTA are meaningful)
+spans, items = [], []
+for cta in range(148):
+    xs = [x & ((1 << 56) - 1) for x in t[cta].flatten().tolist() if x]
+    if xs:
+        spans.append((max(xs) - min(xs)) / GHZ / 1e3)
+        items.append(sum(1 for x in t[cta, 1].tolist() if x and ((x >> 56) & 0xff) == 4) - 1)
+q = lambda v, p: sorted(v)[min(len(v) - 1, int(p * len(v)))]
+print("per-CTA busy span us: min %.1f median %.1f p90 %.1f max %.1f | items per CTA: min %d max %d"
+      % (min(spans), q(spans, .5), q(spans, .9), max(spans), min(items), max(items)))
