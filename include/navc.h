@@ -271,13 +271,17 @@ int navc_cross_attention_tc_rows(int mode, const uint16_t* q_hi, const uint16_t*
 /* out[k, :] = in[rows[k], :] for k < *count (bf16 hi / lo pairs, D % 8 == 0; lo may be NULL). */
 int navc_gather_rows(const uint16_t* in_hi, const uint16_t* in_lo, int D, const int32_t* rows,
                      const int32_t* count, int max_rows, uint16_t* out_hi, uint16_t* out_lo, void* stream);
+/* Two navc_gather_rows through the same row list in one launch: oa[k] = a[rows[k]], ob[k] = b[rows[k]]. */
+int navc_gather_rows2(const uint16_t* a_hi, const uint16_t* a_lo, uint16_t* oa_hi, uint16_t* oa_lo, const uint16_t* b_hi,
+                      const uint16_t* b_lo, uint16_t* ob_hi, uint16_t* ob_lo, int D, const int32_t* rows, const int32_t* count,
+                      int max_rows, void* stream);
 /* Ordered compaction of the positions navc_refine_step selected (its flag mode: sel_rows == NULL, sel_slot = 0/1 per real
  * packed row).  In place: slot[r] := number of selected rows before r (the compact index of a selected row; slot has
  * max_rows + 1 entries); rows[k] = k-th selected packed row, ascending; seq_off_c[n] = slot[seq_off[n]], n = 0..N: the
  * packed offsets of the compacted row space -- the selected rows of a sequence (and of a video's candidates) stay
  * contiguous, so the packed cross-attention core and the GEMMs run on them unchanged; *count = seq_off_c[N].
  * Used for the LAST decoder layer of a refinement pass: only re-masked positions are read from that pass
- * (decoding/algorithms.py:155-167 assigns tokens / probabilities at mask_ind only), so everything behind the last
+ * (decoding/algorithms.py:262-268 assigns tokens / probabilities at mask_ind only), so everything behind the last
  * self-attention core runs on those rows alone. */
 int navc_compact_rows(int32_t* slot, const int32_t* seq_off, int N, int max_rows, int32_t* rows, int32_t* count,
                       int32_t* seq_off_c, void* stream);

@@ -577,6 +577,38 @@ extern "C" int navc_gather_rows(const uint16_t* in_hi, const uint16_t* in_lo, in
     return check_launch("navc_gather_rows");
 }
 
+// two row gathers through the same list in one launch (the last layer's context rows and residual rows)
+__global__ void gather_rows2_kernel(const uint16_t* __restrict__ a_hi, const uint16_t* __restrict__ a_lo, uint16_t* __restrict__ oa_hi,
+                                    uint16_t* __restrict__ oa_lo, const uint16_t* __restrict__ b_hi, const uint16_t* __restrict__ b_lo,
+                                    uint16_t* __restrict__ ob_hi, uint16_t* __restrict__ ob_lo, int D, const int32_t* __restrict__ rows,
+                                    const int32_t* __restrict__ count, int max_rows) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= max_rows || k >= __ldg(count)) return;
+    const size_t src = (size_t)rows[k] * D, dst = (size_t)k * D;
+    for (int c = lane * 8; c < D; c += 256) {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(a_hi + src + c);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(b_hi + src + c);
+        uint4 v2 = make_uint4(0u, 0u, 0u, 0u), v3 = v2;
+        if (a_lo) v2 = *reinterpret_cast<const uint4*>(a_lo + src + c);
+        if (b_lo) v3 = *reinterpret_cast<const uint4*>(b_lo + src + c);
+        *reinterpret_cast<uint4*>(oa_hi + dst + c) = v0;
+        *reinterpret_cast<uint4*>(ob_hi + dst + c) = v1;
+        if (a_lo) *reinterpret_cast<uint4*>(oa_lo + dst + c) = v2;
+        if (b_lo) *reinterpret_cast<uint4*>(ob_lo + dst + c) = v3;
+    }
+}
+
+extern "C" int navc_gather_rows2(const uint16_t* a_hi, const uint16_t* a_lo, uint16_t* oa_hi, uint16_t* oa_lo, const uint16_t* b_hi,
+                                 const uint16_t* b_lo, uint16_t* ob_hi, uint16_t* ob_lo, int D, const int32_t* rows,
+                                 const int32_t* count, int max_rows, void* stream) {
+    NAVC_REQUIRE(a_hi && b_hi && oa_hi && ob_hi && rows && count && (!a_lo || oa_lo) && (!b_lo || ob_lo) && D % 8 == 0 && max_rows > 0,
+                 "navc_gather_rows2: bad arguments");
+    gather_rows2_kernel<<<(max_rows + 7) / 8, 256, 0, as_stream(stream)>>>(a_hi, a_lo, oa_hi, oa_lo, b_hi, b_lo, ob_hi, ob_lo, D, rows, count,
+                                                                        max_rows);
+    return check_launch("navc_gather_rows2");
+}
+
 extern "C" int navc_pack_rows(const int32_t* lens, int N, int S, int32_t* seq_off, int32_t* rowmap, void* stream) {
     NAVC_REQUIRE(lens && seq_off && rowmap && N > 0 && S > 0, "navc_pack_rows: bad arguments");
     pack_rows_kernel<<<1, 1024, 0, as_stream(stream)>>>(lens, N, S, seq_off, rowmap);

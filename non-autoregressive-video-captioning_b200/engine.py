@@ -521,9 +521,8 @@ class Engine:
                 assert packed is not None and "tile_seq" in packed
                 e0 = self._t0("gather")
                 ctx_c, x_c = self._new(R, D, False, True, lo=ctx.lo is not None), self._new(R, D, False, True, lo=x.lo is not None)
-                for src, dst in ((ctx, ctx_c), (x, x_c)):
-                    L.call("navc_gather_rows", L.ptr(src.hi), L.ptr(src.lo), D, L.ptr(prune["rows"]), L.ptr(prune["count"]), R,
-                           L.ptr(dst.hi), L.ptr(dst.lo), L.stream())
+                L.call("navc_gather_rows2", L.ptr(ctx.hi), L.ptr(ctx.lo), L.ptr(ctx_c.hi), L.ptr(ctx_c.lo), L.ptr(x.hi), L.ptr(x.lo),
+                       L.ptr(x_c.hi), L.ptr(x_c.lo), D, L.ptr(prune["rows"]), L.ptr(prune["count"]), R, L.stream())
                 self._t1("gather", e0)
                 ctx, x, tok_flat = ctx_c, x_c, None          # (packed rows are never PAD: the row mask is a no-op)
                 m_dev, mh, seq_off = prune["count"], prune.get("hint", 0), prune["seq_off"]
