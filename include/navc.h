@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NAVC_VERSION 3
+#define NAVC_VERSION 4
 
 /* token ids, config/Constants.py:1-6 */
 #define NAVC_PAD 0

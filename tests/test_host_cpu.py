@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     exported = set(re.findall(r" T (navc_[a-z0-9_]+)", out))
     assert declared <= exported, declared - exported
     assert set(navc._lib.EXPORTS) == declared
-    assert lib.navc_version() == 3
+    assert lib.navc_version() == 4
 
 
 def test_ctypes_struct_layout_matches_header():
