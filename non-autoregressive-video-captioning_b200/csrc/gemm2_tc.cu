@@ -129,6 +129,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     };
 
     pdl_launch_dependents();
+    if (g2_trace_buf && threadIdx.x == 0)   // timeline: kernel entry (slot 63 of the producer's record)
+    {
+        g2_trace_buf[((size_t)blockIdx.x * 3) * 64 + 63] = (60ull << 56) | ((unsigned long long)clock64() & 0x00ffffffffffffffull);
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        g2_trace_buf[((size_t)blockIdx.x * 3 + 1) * 64 + 63] = gt;   // wall clock (ns) of the entry: comparable across SMs
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         // pair: the leader's MMA thread waits for the epilogue warps of BOTH CTAs
@@ -436,6 +443,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
         else
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (g2_trace_buf && lane == 0)      // timeline: kernel exit (slot 62)
+        {
+            g2_trace_buf[((size_t)blockIdx.x * 3) * 64 + 62] = (61ull << 56) | ((unsigned long long)clock64() & 0x00ffffffffffffffull);
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+            g2_trace_buf[((size_t)blockIdx.x * 3 + 1) * 64 + 62] = gt;
+        }
     }
 }
 

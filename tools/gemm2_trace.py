@@ -33,11 +33,28 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); run(); e1.record()
 torch.cuda.synchronize()
 fn(None)
-print("kernel %.1f us (events)" % (e0.elapsed_time(e1) * 1e3))
+print("kernel %.1f us (events, eager, traced)" % (e0.elapsed_time(e1) * 1e3))
+g = torch.cuda.CUDAGraph()
+s_ = torch.cuda.Stream()
+with torch.cuda.stream(s_):
+    run(); torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=s_):
+        for _ in range(20):
+            run()
+    g.replay(); torch.cuda.synchronize()
+    e0.record(s_); g.replay(); e1.record(s_); torch.cuda.synchronize()
+print("kernel %.1f us per launch (20 back to back in a graph, untraced)" % (e0.elapsed_time(e1) * 1e3 / 20))
 t = buf.cpu().view(148, 3, 64)
+# wall-clock (globaltimer, ns) entry / exit of every CTA: launch skew and the span of the whole grid
+gent = [int(x) for x in t[:, 1, 63].tolist() if x]; gext = [int(x) for x in t[:, 1, 62].tolist() if x]
+if gent and gext:
+    g0 = min(gent)
+    print("grid wall clock: CTA entries spread over %.2f us, last exit %.2f us after the first entry (exits: min %.2f median %.2f)"
+          % ((max(gent) - g0) / 1e3, (max(gext) - g0) / 1e3, (min(gext) - g0) / 1e3, (sorted(gext)[len(gext) // 2] - g0) / 1e3))
+t[:, 1, 62:] = 0
 NAMES = {**{20 + c: "ld%d" % c for c in range(4)}, **{30 + c: "cmp%d" % c for c in range(4)}, **{40 + c: "free%d" % c for c in range(4)},
          **{50 + c: "st%d" % c for c in range(4)}}
-NAMES.update({1: "prologue", 2: "ld0", 3: "ldN", 4: "accfree", 5: "op0", 6: "opN", 7: "accrdy", 8: "epi", 9: "drain"})
+NAMES.update({1: "prologue", 2: "ld0", 3: "ldN", 4: "accfree", 5: "op0", 6: "opN", 7: "accrdy", 8: "epi", 9: "drain", 60: "ENTRY", 61: "EXIT"})
 GHZ = float(os.environ.get("GHZ", "1.9"))
 ROLES = [int(x) for x in os.environ.get("ROLES", "0,1,2").split(",")]
 for cta in (0, 1, 75, 146):
