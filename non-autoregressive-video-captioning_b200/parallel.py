@@ -98,14 +98,34 @@ class GradientAllReduce:
             raise ValueError("model has no trainable parameters")
         dev = self.params[0].device
         # every tensor starts on a 256-byte boundary of the flat buffer (the vectorised / TMA kernels
-        # need 16-byte aligned operands); the padding stays zero and rides along in the collective
-        self.offsets, off = [], 0
+        # need 16-byte aligned operands); the padding stays zero and rides along in the collective.
+        # Parameters that the engine packs into ONE GEMM operand (query | key | value of a layer; the text -> video
+        # key | value of all layers) are laid out next to each other in that operand's row order, so that the weight /
+        # bias gradient of the packed GEMM is ONE view of the buffer and the kernels accumulate into it directly
+        # (otherwise: a zero-filled temporary + one AccumulateGrad add per parameter, ~150 tiny launches per step)
+        groups = self._packed_groups(model, dev)
+        member = {id(q): g for g in groups for q in g}
+        placed, layout = set(), []
         for p in self.params:
-            self.offsets.append(off)
+            if id(p) in placed:
+                continue
+            for q in member.get(id(p), [p]):
+                layout.append(q)
+                placed.add(id(q))
+        off_of, off = {}, 0
+        for p in layout:
+            off_of[id(p)] = off
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.offsets = [off_of[id(p)] for p in self.params]
         self.numel = off
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        self._group_views = {}
+        for g in groups:
+            o0 = off_of[id(g[0])]
+            n = sum(q.numel() for q in g)
+            tail = g[0].shape[1:]
+            self._group_views[tuple(id(q) for q in g)] = self.flat[o0:o0 + n].view((-1,) + tuple(tail))
         if broadcast:
             broadcast_model(model)
         self.attach()
@@ -113,12 +133,61 @@ class GradientAllReduce:
         eng = getattr(model, "engine", None)
         if eng is not None:
             eng.grad_sink = self.sink
+            eng.grad_sink_group = self.sink_group
             eng.grads_final_hook = self.begin_early   # called by the encoder's backward before it launches anything
         # all-reduce the finished part of the buffer under the encoder's backward ($NAVC_DP_OVERLAP=0: one collective)
         self.overlap = os.environ.get("NAVC_DP_OVERLAP", "1") not in ("0", "no", "off")
         self.weight = 1.0         # this rank's weight (unequal shards), set BEFORE backward when overlap is on
         self._early = None        # (split, work) of the collective in flight
         self._split_of = {}
+
+    def _packed_groups(self, model, dev):
+        """Parameter groups behind the engine's concatenated GEMM operands (PackedLinear.src with several entries), each as
+        two lists -- the weights and the biases -- in row order.  Only groups whose members are all trainable, distinct,
+        of ALIGN-multiple size (no padding between them) and in no other group qualify."""
+        eng = getattr(model, "engine", None)
+        if eng is None or dev.type != "cuda":
+            return []
+        from .engine import PackedLinear
+        eng.sync_weights()
+        named = eng.named_params()
+        trainable = set(id(p) for p in self.params)
+        found, seen = [], set()
+
+        def walk(o):
+            if isinstance(o, PackedLinear):
+                if len(o.src) > 1:
+                    for col in (0, 1):
+                        keys = [s_[col] for s_ in o.src]
+                        ps = [named.get(k) if k is not None else None for k in keys]
+                        ids = [id(q) for q in ps]
+                        if any(q is None for q in ps) or len(set(ids)) != len(ids) or any(i in seen or i not in trainable for i in ids):
+                            continue
+                        if any(q.numel() % ALIGN for q in ps) or any(q.shape[1:] != ps[0].shape[1:] for q in ps):
+                            continue
+                        rows = [(s_[2], s_[3]) for s_ in o.src]
+                        if rows[0][0] != 0 or any(a[1] != b[0] for a, b in zip(rows, rows[1:])) or \
+                                any(q.shape[0] != r1 - r0 for q, (r0, r1) in zip(ps, rows)):
+                            continue
+                        seen.update(ids)
+                        found.append(ps)
+            elif isinstance(o, dict):
+                for v in o.values():
+                    walk(v)
+            elif isinstance(o, (list, tuple)):
+                for v in o:
+                    walk(v)
+
+        walk(eng.P)
+        return found
+
+    def sink_group(self, ps):
+        """The ONE flat-buffer view behind the gradients of parameters ``ps`` (the members of a packed GEMM operand, in row
+        order), while every p.grad still is its own view of the buffer; else None."""
+        v = self._group_views.get(tuple(id(q) for q in ps))
+        if v is None or any(q.grad is not self._view_of.get(id(q)) for q in ps):
+            return None
+        return v
 
     def sink(self, p):
         """The flat-buffer view a backward kernel may accumulate into directly: only while p.grad IS that view

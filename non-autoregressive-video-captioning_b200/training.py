@@ -136,6 +136,7 @@ class Grads:
         # accumulate anyway (split-K weight gradients, bias column sums) add straight into p.grad and autograd gets
         # None for that parameter -- no zero-filled temporary, no AccumulateGrad add
         self.sink = getattr(eng, "grad_sink", None) if eng is not None else None
+        self.sink_group = getattr(eng, "grad_sink_group", None) if eng is not None else None
         self.named = eng.named_params() if self.sink is not None else None
 
     def target(self, key):
@@ -144,6 +145,14 @@ class Grads:
         p = self.named.get(key)
         return None if p is None else self.sink(p)
 
+    def target_group(self, keys):
+        """One gradient view for the parameters behind a concatenated GEMM operand (parallel.GradientAllReduce lays them
+        out adjacently), or None."""
+        if self.sink_group is None or any(k is None for k in keys):
+            return None
+        ps = [self.named.get(k) for k in keys]
+        return None if any(q is None for q in ps) else self.sink_group(ps)
+
     def add(self, key, t):
         if key is None:
             return
@@ -151,7 +160,8 @@ class Grads:
 
     def add_packed(self, lin: PackedLinear, dW, db):
         for wk, bk, r0, r1 in lin.src:
-            self.add(wk, dW[r0:r1] if (r0, r1) != (0, dW.shape[0]) else dW)
+            if dW is not None:
+                self.add(wk, dW[r0:r1] if (r0, r1) != (0, dW.shape[0]) else dW)
             if bk is not None and db is not None:
                 self.add(bk, db[r0:r1] if (r0, r1) != (0, db.shape[0]) else db)
 
@@ -181,6 +191,13 @@ def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, n
     if eng.tc and K % 8 == 0 and N % 8 == 0 and len(lin.src) == 1:  # one parameter behind this GEMM: accumulate in place
         tw = grads.target(lin.src[0][0])
         tb = grads.target(lin.src[0][1]) if lin.b is not None else None
+    elif eng.tc and K % 8 == 0 and N % 8 == 0:  # several parameters, adjacent in the flat gradient buffer: one view
+        tw = grads.target_group([s_[0] for s_ in lin.src])
+        tb = grads.target_group([s_[1] for s_ in lin.src]) if lin.b is not None else None
+        if tw is not None and tuple(tw.shape) != (N, K):
+            tw = None
+        if tb is not None and tb.numel() != N:
+            tb = None
     db = tb if tb is not None else (torch.zeros((N,), dtype=torch.float32, device=dev) if lin.b is not None else None)
     if eng.tc and K % 8 == 0:
         s, _ = transpose_pack(eng, dY, M, N, ld, straight=True, colsum=db)
@@ -193,14 +210,8 @@ def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, n
         dW = tw if tw is not None else torch.zeros((n_eff, K), dtype=torch.float32, device=dev)
         ep = L.Epilogue(None, None, None, 0, 0, L.ptr(dW), None, None, K, 0, _split_k(n_eff, K, M), 1)
         L.call("navc_wgrad_tc", eng.tc_mode, L.ptr(s.hi), L.ptr(s.lo), ld, L.ptr(x_hi), L.ptr(x_lo), K, M, n_eff, K, ep, L.stream())
-        if tw is None and tb is None:
-            grads.add_packed(lin, dW[:N] if n_eff != N else dW, db)
-        else:  # single source: hand over only what did not go straight into p.grad
-            wk, bk = lin.src[0][0], lin.src[0][1]
-            if tw is None:
-                grads.add(wk, dW)
-            if tb is None and db is not None:
-                grads.add(bk, db)
+        # hand over only what did not go straight into p.grad
+        grads.add_packed(lin, None if tw is not None else (dW[:N] if n_eff != N else dW), None if tb is not None else db)
     else:
         s, t = transpose_pack(eng, dY, M, N, ld, straight=need_dx, transposed=True, colsum=db)
         _, xt = transpose_pack(eng, x32, M, K, x32.stride(0), transposed=True)

@@ -728,6 +728,12 @@ def test_direct_gradient_accumulation_matches_autograd():
         model.set_precision("bf16x3")
         dp = parallel.GradientAllReduce(model, broadcast=False) if direct else None
         assert (model.engine.grad_sink is not None) == direct
+        if direct:   # query | key | value of every layer (weights and biases) and the K | V of all layers are ONE view each
+            assert len(dp._group_views) >= 2 * (2 * opt["num_hidden_layers_decoder"] + 1)
+            for ids, v in dp._group_views.items():
+                members = [p for p in dp.params if id(p) in ids]
+                assert v.numel() == sum(p.numel() for p in members)
+                assert all(p.grad.data_ptr() >= v.data_ptr() and p.grad.data_ptr() < v.data_ptr() + 4 * v.numel() for p in members)
         if dp is not None:
             dp.zero_grad()
         for mb in range(2):
