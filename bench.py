@@ -642,7 +642,7 @@ def train_block(args, world, rank, dev):
     import train_bench as tb
     out = {"config5_nacf_global1024": None, "config3": None, "cpu_reference": None}
     steps = max(4, min(args.steps, 10))
-    r = tb.measure("NACF", 1024 // world, steps, 3, args.precision, dev=dev)
+    r = tb.measure("NACF", 1024 // world, steps, 6, args.precision, dev=dev)   # 6 warm-up steps: every rotated batch twice (allocator steady state)
     r.pop("_step"), r.pop("_model")
     r["scaling"] = "strong (global batch 1024 fixed, %d per GPU)" % (1024 // world)
     out["config5_nacf_global1024"] = r

@@ -271,6 +271,10 @@ int navc_cross_attention_tc_rows(int mode, const uint16_t* q_hi, const uint16_t*
 /* out[k, :] = in[rows[k], :] for k < *count (bf16 hi / lo pairs, D % 8 == 0; lo may be NULL). */
 int navc_gather_rows(const uint16_t* in_hi, const uint16_t* in_lo, int D, const int32_t* rows,
                      const int32_t* count, int max_rows, uint16_t* out_hi, uint16_t* out_lo, void* stream);
+/* Weight refresh after an optimizer step (parameters keep their storage, values changed): one launch over a device
+ * table items[n][5] of int64 {src fp32 pointer, dst fp32 pointer or 0, bf16 hi pointer or 0, lo pointer or 0, elements}:
+ * dst[i] = src[i] (rows of a concatenated operand) and hi / lo = the split-bf16 copies of src. */
+int navc_refresh_pack(const int64_t* items, int n_items, void* stream);
 /* Two navc_gather_rows through the same row list in one launch: oa[k] = a[rows[k]], ob[k] = b[rows[k]]. */
 int navc_gather_rows2(const uint16_t* a_hi, const uint16_t* a_lo, uint16_t* oa_hi, uint16_t* oa_lo, const uint16_t* b_hi,
                       const uint16_t* b_lo, uint16_t* ob_hi, uint16_t* ob_lo, int D, const int32_t* rows, const int32_t* count,

@@ -74,6 +74,7 @@ _PROTOS = {
     "navc_gather_rows": [vp, vp, i32, vp, vp, i32, vp, vp, vp],
     "navc_compact_rows": [vp, vp, i32, i32, vp, vp, vp, vp],
     "navc_gather_rows2": [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp],
+    "navc_refresh_pack": [vp, i32, vp],
     "navc_linear_tf32": [vp, i32, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp],
     "navc_vocab_partials_tc_dyn": [i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp],
     "navc_length_beam": [vp, i32, i32, i32, i32, vp, vp, vp],

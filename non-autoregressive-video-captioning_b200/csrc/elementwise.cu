@@ -478,6 +478,49 @@ extern "C" int navc_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int64
     return check_launch("navc_split_bf16");
 }
 
+// Refresh of the packed weights after an optimizer step (same parameter storage, new values): ONE launch copies every
+// source tensor into its rows of the concatenated fp32 operand (where that is a copy) and rewrites the bf16 hi / lo copies.
+// items: [n][5] int64 = {src fp32, dst fp32 or 0, hi or 0, lo or 0, element count}; blockIdx.y = item.
+__global__ void refresh_pack_kernel(const long long* __restrict__ items) {
+    const long long* it = items + (size_t)blockIdx.y * 5;
+    const float* __restrict__ src = reinterpret_cast<const float*>(it[0]);
+    float* __restrict__ dst = reinterpret_cast<float*>(it[1]);
+    uint16_t* __restrict__ hi = reinterpret_cast<uint16_t*>(it[2]);
+    uint16_t* __restrict__ lo = reinterpret_cast<uint16_t*>(it[3]);
+    const int64_t n = it[4];
+    const bool vec = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0 && ((((uintptr_t)hi) | ((uintptr_t)lo)) & 7) == 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (vec && i + 4 <= n) {
+            const float4 v = *reinterpret_cast<const float4*>(src + i);
+            if (dst) *reinterpret_cast<float4*>(dst + i) = v;
+            if (hi) {
+                uint2 h, l;
+                split_bf16x4(v, h, l);
+                *reinterpret_cast<uint2*>(hi + i) = h;
+                if (lo) *reinterpret_cast<uint2*>(lo + i) = l;
+            }
+        } else {
+            for (int64_t j = i; j < n && j < i + 4; ++j) {
+                const float x = src[j];
+                if (dst) dst[j] = x;
+                if (hi) {
+                    uint16_t h, l;
+                    split_bf16(x, h, l);
+                    hi[j] = h;
+                    if (lo) lo[j] = l;
+                }
+            }
+        }
+    }
+}
+
+extern "C" int navc_refresh_pack(const int64_t* items, int n_items, void* stream) {
+    NAVC_REQUIRE(items && n_items > 0 && n_items <= 65535, "navc_refresh_pack: bad arguments");
+    refresh_pack_kernel<<<dim3(64, n_items), 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(items));
+    return check_launch("navc_refresh_pack");
+}
+
 extern "C" int navc_join_bf16(const uint16_t* hi, const uint16_t* lo, float* out, int64_t n, void* stream) {
     NAVC_REQUIRE(hi && out && n >= 0, "navc_join_bf16: bad arguments");
     if (n == 0) return 0;

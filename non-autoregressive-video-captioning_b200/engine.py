@@ -83,6 +83,10 @@ class Engine:
         # recorded on the launching stream around every tagged launch: prof[tag] = [(start, stop), ...]
         self.prof = None
         self.pack_id = 0
+        self._lins: List[PackedLinear] = []
+        self._copies = []
+        self._refresh_table = None
+        self._ptr_sig = None
         self.graphs: Dict[tuple, object] = {}  # CUDA graphs of the decode loop (decoding/na_generate.py)
 
     # ------------------------------------------------------------------------------------------
@@ -122,9 +126,15 @@ class Engine:
         sig = self._signature()
         if sig == self._sig and dev == self.device:
             return
+        ptrs = tuple(a[0] for a in sig)
+        same_storage = dev == self.device and self._refresh_table is not None and ptrs == self._ptr_sig
         self.device = dev
-        self._pack()
+        if same_storage and os.environ.get("NAVC_REFRESH", "1") not in ("0", "no", "off"):
+            self._refresh()   # an optimizer step: same tensors, new values -- one launch instead of a full repack
+        else:
+            self._pack()
         self._sig = sig
+        self._ptr_sig = ptrs
         self.pack_id += 1
         self.graphs.clear()  # captured graphs hold pointers into the previous packed weights
 
@@ -135,6 +145,7 @@ class Engine:
         if structure:
             self._members = None
             self._named = None
+            self._ptr_sig = None
 
     def _lin(self, w, b=None, src=()) -> PackedLinear:
         pl = PackedLinear(w, b, src)
@@ -142,10 +153,55 @@ class Engine:
             pl.w_hi = torch.empty(pl.w.shape, dtype=torch.bfloat16, device=pl.w.device)
             pl.w_lo = torch.empty_like(pl.w_hi) if self.split else None
             L.call("navc_split_bf16", L.ptr(pl.w), L.ptr(pl.w_hi), L.ptr(pl.w_lo), pl.w.numel(), L.stream())
+        self._lins.append(pl)
         return pl
+
+    def _live(self, t: torch.Tensor) -> torch.Tensor:
+        """_f32 of a parameter / buffer that the kernels read in place; a copy (dtype / alignment) is registered for refresh."""
+        v = _f32(t)
+        if v.data_ptr() != t.data_ptr():
+            self._copies.append((t, v))
+        return v
+
+    def _build_refresh_table(self):
+        """Device table for navc_refresh_pack: every source parameter -> its rows of the packed fp32 operand (if that is a
+        copy) and of the bf16 hi / lo copies."""
+        named = dict(self.members()[0])
+        rows = []
+        for pl in self._lins:
+            for wk, bk, r0, r1 in pl.src:
+                w = named.get(wk)
+                if w is None or w.dtype != torch.float32 or not w.is_contiguous():
+                    return None
+                dst = pl.w[r0:r1]
+                rows.append((w.data_ptr(), 0 if dst.data_ptr() == w.data_ptr() else dst.data_ptr(),
+                             pl.w_hi[r0:r1].data_ptr() if pl.w_hi is not None else 0,
+                             pl.w_lo[r0:r1].data_ptr() if pl.w_lo is not None else 0, w.numel()))
+                if bk is not None and pl.b is not None:
+                    b = named.get(bk)
+                    if b is None or b.dtype != torch.float32 or not b.is_contiguous():
+                        return None
+                    dstb = pl.b[r0:r1]
+                    if dstb.data_ptr() != b.data_ptr():
+                        rows.append((b.data_ptr(), dstb.data_ptr(), 0, 0, b.numel()))
+        for t, v in self._copies:
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                return None
+            rows.append((t.data_ptr(), v.data_ptr(), 0, 0, t.numel()))
+        rows = [r for r in rows if r[1] or r[2]]
+        if not rows:
+            return None
+        return torch.tensor(rows, dtype=torch.int64).to(self.device)
+
+    def _refresh(self):
+        L.call("navc_refresh_pack", L.ptr(self._refresh_table), int(self._refresh_table.shape[0]), L.stream())
+        for pl in self._lins:
+            pl.T = None
+            pl.pad = None
 
     def _pack(self):
         m, opt = self.model, self.opt
+        self._lins, self._copies, self._refresh_table = [], [], None
         params, bufs = self.members()  # what state_dict() holds (minus num_batches_tracked), without the module walk
         sd = {k: v.detach() for k, v in params}
         sd.update(bufs)
@@ -169,10 +225,10 @@ class Engine:
             jr = "joint_representation_learner."
             for i in range(len(opt["modality"])):
                 if (jr + "bn%d.weight" % i) in sd:
-                    P["norms"].append(("bn", _f32(sd[jr + "bn%d.running_mean" % i]), _f32(sd[jr + "bn%d.running_var" % i]),
-                                       _f32(sd[jr + "bn%d.weight" % i]), _f32(sd[jr + "bn%d.bias" % i])))
+                    P["norms"].append(("bn", self._live(sd[jr + "bn%d.running_mean" % i]), self._live(sd[jr + "bn%d.running_var" % i]),
+                                       self._live(sd[jr + "bn%d.weight" % i]), self._live(sd[jr + "bn%d.bias" % i])))
                 elif (jr + "ln%d.weight" % i) in sd:
-                    P["norms"].append(("ln", _f32(sd[jr + "ln%d.weight" % i]), _f32(sd[jr + "ln%d.bias" % i])))
+                    P["norms"].append(("ln", self._live(sd[jr + "ln%d.weight" % i]), self._live(sd[jr + "ln%d.bias" % i])))
                 else:
                     P["norms"].append(None)
             # length head
@@ -180,16 +236,16 @@ class Engine:
             P["len_head"] = None
             P["norm_keys"] = [jr + ("bn%d" if (jr + "bn%d.weight" % i) in sd else "ln%d") % i for i in range(len(opt["modality"]))]
             if (ap + "0.weight") in sd:
-                P["len_head"] = tuple(_f32(sd[ap + k]) for k in ("0.weight", "0.bias", "3.weight", "3.bias"))
+                P["len_head"] = tuple(self._live(sd[ap + k]) for k in ("0.weight", "0.bias", "3.weight", "3.bias"))
                 P["len_head_keys"] = tuple(ap + k for k in ("0.weight", "0.bias", "3.weight", "3.bias"))
             # decoder
             dp = "decoder.bert." if ("decoder.bert.embedding.LayerNorm.weight" in sd) else "decoder."
             e = dp + "embedding."
             P["emb_prefix"] = e
-            P["emb"] = dict(word=_f32(sd[e + "word_embeddings.weight"]),
-                            pos=_f32(sd[e + "position_embeddings.weight"]),
-                            cat=_f32(sd[e + "category_embeddings.weight"]) if (e + "category_embeddings.weight") in sd else None,
-                            ln_w=_f32(sd[e + "LayerNorm.weight"]), ln_b=_f32(sd[e + "LayerNorm.bias"]))
+            P["emb"] = dict(word=self._live(sd[e + "word_embeddings.weight"]),
+                            pos=self._live(sd[e + "position_embeddings.weight"]),
+                            cat=self._live(sd[e + "category_embeddings.weight"]) if (e + "category_embeddings.weight") in sd else None,
+                            ln_w=self._live(sd[e + "LayerNorm.weight"]), ln_b=self._live(sd[e + "LayerNorm.bias"]))
             layers, kv_w, kv_b, kv_src = [], [], [], []
             D_ = opt["dim_hidden"]
             for l in range(opt["num_hidden_layers_decoder"]):
@@ -206,7 +262,7 @@ class Engine:
 
                 def ln(prefix):
                     k = prefix + "LayerNorm.weight"
-                    return (_f32(sd[k]), _f32(sd[prefix + "LayerNorm.bias"])) if k in sd else None
+                    return (self._live(sd[k]), self._live(sd[prefix + "LayerNorm.bias"])) if k in sd else None
 
                 def one(prefix):
                     w = sd[prefix + ".weight"]
@@ -224,6 +280,7 @@ class Engine:
             P["vocab"] = self._lin(sd["tgt_word_prj.weight"], sd.get("tgt_word_prj.bias"),
                                    [("tgt_word_prj.weight", vb, 0, sd["tgt_word_prj.weight"].shape[0])])
         self.P = P
+        self._refresh_table = self._build_refresh_table() if self.device is not None and self.device.type == "cuda" else None
         self.D = opt["dim_hidden"]
         self.H = opt["num_attention_heads"]
         self.nl = opt["num_hidden_layers_decoder"]

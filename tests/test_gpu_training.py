@@ -1012,3 +1012,36 @@ def test_layernorm_encoder_norm_matches_oracle(precision):
         hyp, _ = navc_b200.Translator(model, opt, device=DEV).translate_batch(enc, category.to(DEV), None, {})
     for b in (hyp.cpu() != hyp_o).any(1).nonzero().flatten().tolist():
         assert det["video_margin"][b].item() <= 1e-4, (b, det["video_margin"][b].item())
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_weight_refresh_equals_full_repack(precision):
+    """After an in-place parameter update (an optimizer step, load_state_dict) the engine rewrites its packed operands
+    with ONE navc_refresh_pack launch instead of re-running the packing; the result must be bit-identical to a full
+    repack, for concatenated operands (q|k|v, all-layer K|V, highway w1|w2), single ones and their bf16 hi/lo copies."""
+    opt = cases.small("NACF", num_attention_heads=2)
+    torch.manual_seed(0)
+    model = navc_b200.get_model(opt)
+    model.load_state_dict(cases.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 11))
+    model.to(DEV).eval()
+    model.set_precision(precision)
+    feats, category = cases.synth_inputs(opt, 5)
+    toks = cases.synth_tokens(opt, 5, kind="nar")
+    args = dict(feats=[f.to(DEV) for f in feats], tgt_tokens=[toks["tokens_1"].to(DEV), toks["tokens"].to(DEV)], category=category.to(DEV))
+    with torch.no_grad():
+        out0 = model(**args)["tgt_word_logprobs"][1].clone()
+        eng = model.engine
+        pid = eng.pack_id
+        assert eng._refresh_table is not None and eng._refresh_table.shape[1] == 5
+        g = torch.Generator().manual_seed(3)
+        for p in model.parameters():
+            p.add_((torch.randn(p.shape, generator=g) * 0.01).to(DEV))
+        launches = L.launches
+        out1 = model(**args)["tgt_word_logprobs"][1].clone()       # refresh path
+        assert eng.pack_id == pid + 1
+        eng._refresh_table = None                                    # force the full repack of the same weights
+        eng.invalidate()
+        out2 = model(**args)["tgt_word_logprobs"][1].clone()
+        assert eng.pack_id == pid + 2
+    assert (out1 - out0).abs().max().item() > 1e-4                   # the update was seen
+    assert torch.equal(out1, out2)
