@@ -95,6 +95,14 @@ int navc_linear_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx
                    const uint16_t* w_hi, const uint16_t* w_lo, int ldw, int M, int N, int K,
                    const navc_epilogue_t* epi, void* stream);
 
+/* navc_cross_attention_bwd_tc with dK / dV leaving as the bf16 hi (/ lo) operand pair of the K|V projection's gradient
+ * GEMMs -- d_kv_hi / d_kv_lo [N * E, ld_dkv] (K at column 0, V at column D of the given pointers; the values
+ * navc_transpose_pack would make of the fp32 result) -- plus their column sums accumulated into kv_colsum [2 D] (the bias
+ * gradient; caller zeroes or passes the gradient buffer).  Saves the fp32 d_kv round trip (3 GB at 1024 videos). */
+int navc_cross_attention_bwd_tc_split(int mode, const float* q, int ldq, const float* kv, int ldkv, const int32_t* seq_off,
+                                      int N, int S, int E, int D, int H, const float* d_ctx, const float* ctx, float* d_q,
+                                      int ld_dq, uint16_t* d_kv_hi, uint16_t* d_kv_lo, int ld_dkv, float* kv_colsum,
+                                      void* stream);
 /* Y = epilogue(X W^T) with fp32 operands consumed by the tensor cores as TF32 (tcgen05 kind::tf32: 10-bit mantissa, two
  * bf16-MMA time units per product against split-bf16's three): x [M, K] and w [N, K] fp32 row-major (K % 4 == 0, 16-byte
  * aligned), generic epilogue -- bias, activation, fp32 residual, row mask; fp32 and / or bf16 hi (/ lo) outputs; a

@@ -46,6 +46,10 @@ struct AbParams {
     const float* ctx; int ld_ctx;     // forward context (or NULL): sum_j P_ij dP_ij = dO_i . O_i
     float* dq; int ld_dq;
     float* dk; float* dv; int ld_dkv;
+    // optional split output of dK / dV (what the K|V projection's gradient GEMMs consume): bf16 hi (/ lo) rows with leading
+    // dimension ld_dkv and the column sums (bias gradient) accumulated with atomicAdd; then dk / dv (fp32) are not written
+    uint16_t* dk_hi; uint16_t* dk_lo; uint16_t* dv_hi; uint16_t* dv_lo;
+    float* dk_colsum; float* dv_colsum;
     const int32_t* seq_off;
     int is_self, E, S, mask_kind, watch;
 };
@@ -132,12 +136,20 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_tc_kernel(AbParams p) 
     const int nk = p.is_self ? nq : p.E;
     float* dkb = p.dk + kv_row0 * p.ld_dkv + h * 64;
     float* dvb = p.dv + kv_row0 * p.ld_dkv + h * 64;
+    const size_t hrow0 = kv_row0 * p.ld_dkv + h * 64;   // split output: element offset of this head's first row
     if (nq <= 0) {   // no query rows: the owner's keys get zero gradient (text -> video attention only)
         if (!p.is_self)
             for (int idx = tid; idx < nk * 16; idx += AB_THREADS) {
                 const int row = idx >> 4, c = idx & 15;
-                *reinterpret_cast<float4*>(dkb + (size_t)row * p.ld_dkv + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(dvb + (size_t)row * p.ld_dkv + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.dk_hi) {
+                    const size_t o = hrow0 + (size_t)row * p.ld_dkv + c * 4;
+                    *reinterpret_cast<uint2*>(p.dk_hi + o) = make_uint2(0u, 0u);
+                    *reinterpret_cast<uint2*>(p.dv_hi + o) = make_uint2(0u, 0u);
+                    if (p.dk_lo) { *reinterpret_cast<uint2*>(p.dk_lo + o) = make_uint2(0u, 0u); *reinterpret_cast<uint2*>(p.dv_lo + o) = make_uint2(0u, 0u); }
+                } else {
+                    *reinterpret_cast<float4*>(dkb + (size_t)row * p.ld_dkv + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(dvb + (size_t)row * p.ld_dkv + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
         return;
     }
@@ -390,11 +402,36 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_tc_kernel(AbParams p) 
     tc_fence_before();
     __syncthreads();
     tr.ev();       // 6 staged
-    for (int idx = tid; idx < nk * 16; idx += AB_THREADS) {
-        const int row = idx >> 4, c = idx & 15;
-        const int off = row * 256 + (((c ^ (row & 15))) << 4);
-        *reinterpret_cast<float4*>(dvb + (size_t)row * p.ld_dkv + c * 4) = *reinterpret_cast<const float4*>(sm + AB_V + off);
-        *reinterpret_cast<float4*>(dkb + (size_t)row * p.ld_dkv + c * 4) = *reinterpret_cast<const float4*>(sm + AB_K + off);
+    if (p.dk_hi) {
+        // split output: the staged fp32 rows leave as bf16 hi (/ lo) -- exactly what navc_transpose_pack would make of them
+        for (int idx = tid; idx < nk * 16; idx += AB_THREADS) {
+            const int row = idx >> 4, c = idx & 15;
+            const int off = row * 256 + (((c ^ (row & 15))) << 4);
+            const size_t o = hrow0 + (size_t)row * p.ld_dkv + c * 4;
+            uint2 hh, ll;
+            split_bf16x4(*reinterpret_cast<const float4*>(sm + AB_V + off), hh, ll);
+            *reinterpret_cast<uint2*>(p.dv_hi + o) = hh;
+            if (p.dv_lo) *reinterpret_cast<uint2*>(p.dv_lo + o) = ll;
+            split_bf16x4(*reinterpret_cast<const float4*>(sm + AB_K + off), hh, ll);
+            *reinterpret_cast<uint2*>(p.dk_hi + o) = hh;
+            if (p.dk_lo) *reinterpret_cast<uint2*>(p.dk_lo + o) = ll;
+        }
+        // column sums of this item's rows: thread t < 64 owns column t of dK, thread 64 + t column t of dV
+        if (p.dk_colsum) {
+            const int col = tid & 63;
+            const uint8_t* base = sm + (tid < 64 ? AB_K : AB_V);
+            float acc = 0.f;
+            for (int row = 0; row < nk; ++row)
+                acc += *reinterpret_cast<const float*>(base + row * 256 + ((((col >> 2) ^ (row & 15))) << 4) + (col & 3) * 4);
+            atomicAdd((tid < 64 ? p.dk_colsum : p.dv_colsum) + h * 64 + col, acc);
+        }
+    } else {
+        for (int idx = tid; idx < nk * 16; idx += AB_THREADS) {
+            const int row = idx >> 4, c = idx & 15;
+            const int off = row * 256 + (((c ^ (row & 15))) << 4);
+            *reinterpret_cast<float4*>(dvb + (size_t)row * p.ld_dkv + c * 4) = *reinterpret_cast<const float4*>(sm + AB_V + off);
+            *reinterpret_cast<float4*>(dkb + (size_t)row * p.ld_dkv + c * 4) = *reinterpret_cast<const float4*>(sm + AB_K + off);
+        }
     }
     tr.ev();       // 7 stores issued
     if (warp == 0) {
@@ -408,7 +445,8 @@ static int ab_launch(int mode, const AbParams& p, int G, int H, cudaStream_t st,
     NAVC_REQUIRE(mode == NAVC_TC_BF16 || mode == NAVC_TC_BF16X3, "%s: bad mode %d", what, mode);
     NAVC_REQUIRE(p.ldq % 4 == 0 && p.ldkv % 4 == 0 && p.ld_dctx % 4 == 0 && p.ld_dq % 4 == 0 && p.ld_dkv % 4 == 0 &&
                      ((((uintptr_t)p.q) | ((uintptr_t)p.k) | ((uintptr_t)p.v) | ((uintptr_t)p.d_ctx) | ((uintptr_t)p.dq) |
-                       ((uintptr_t)p.dk) | ((uintptr_t)p.dv)) & 15) == 0,
+                       ((uintptr_t)p.dk) | ((uintptr_t)p.dv)) & 15) == 0 &&
+                     ((((uintptr_t)p.dk_hi) | ((uintptr_t)p.dk_lo) | ((uintptr_t)p.dv_hi) | ((uintptr_t)p.dv_lo)) & 7) == 0,
                  "%s: operands must be 16-byte aligned with leading dimensions multiple of 4", what);
     static bool ready = false;
     if (!ready) {
@@ -457,4 +495,26 @@ extern "C" int navc_cross_attention_bwd_tc(int mode, const float* q, int ldq, co
     p.dq = d_q; p.ld_dq = ld_dq; p.dk = d_kv; p.dv = d_kv + D; p.ld_dkv = ld_dkv;
     p.seq_off = seq_off; p.is_self = 0; p.E = E; p.S = S; p.mask_kind = 0; p.watch = 0;
     return ab_launch(mode, p, N, H, as_stream(stream), "navc_cross_attention_bwd_tc");
+}
+
+// Text -> video gradients with dK / dV written as the bf16 hi (/ lo) operand pair of the K|V projection's gradient GEMMs
+// (d_kv_hi / d_kv_lo [N * E, ld_dkv], K at column 0 and V at column D of the given pointers) plus their column sums
+// (kv_colsum [2 D]: the bias gradient, accumulated): the fp32 d_kv round trip (write, re-read, split) does not exist.
+extern "C" int navc_cross_attention_bwd_tc_split(int mode, const float* q, int ldq, const float* kv, int ldkv, const int32_t* seq_off,
+                                                 int N, int S, int E, int D, int H, const float* d_ctx, const float* ctx, float* d_q,
+                                                 int ld_dq, uint16_t* d_kv_hi, uint16_t* d_kv_lo, int ld_dkv, float* kv_colsum,
+                                                 void* stream) {
+    NAVC_REQUIRE(q && kv && seq_off && d_ctx && d_q && d_kv_hi, "navc_cross_attention_bwd_tc_split: null pointer");
+    NAVC_REQUIRE(mode == NAVC_TC_BF16 || d_kv_lo, "navc_cross_attention_bwd_tc_split: the split mode needs the lo output");
+    NAVC_REQUIRE(N > 0 && S > 0 && S <= 32 && E > 0 && E <= 128 && H > 0 && D == H * 64 && ld_dkv % 4 == 0,
+                 "navc_cross_attention_bwd_tc_split: needs dk == 64, S <= 32, E <= 128 and ld_dkv %% 4 == 0");
+    AbParams p = {};
+    p.q = q; p.ldq = ldq; p.k = kv; p.v = kv + D; p.ldkv = ldkv;
+    p.d_ctx = d_ctx; p.ld_dctx = D; p.ctx = ctx; p.ld_ctx = D;
+    p.dq = d_q; p.ld_dq = ld_dq; p.dk = nullptr; p.dv = nullptr; p.ld_dkv = ld_dkv;
+    p.dk_hi = d_kv_hi; p.dv_hi = d_kv_hi + D;
+    p.dk_lo = d_kv_lo; p.dv_lo = d_kv_lo ? d_kv_lo + D : nullptr;
+    p.dk_colsum = kv_colsum; p.dv_colsum = kv_colsum ? kv_colsum + D : nullptr;
+    p.seq_off = seq_off; p.is_self = 0; p.E = E; p.S = S; p.mask_kind = 0; p.watch = 0;
+    return ab_launch(mode, p, N, H, as_stream(stream), "navc_cross_attention_bwd_tc_split");
 }

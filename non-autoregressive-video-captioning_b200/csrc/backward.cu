@@ -193,6 +193,54 @@ __global__ void transpose_pack_kernel(const float* __restrict__ x, int M, int N,
     }
 }
 
+// The straight-only case (every gradient GEMM of the tensor-core path: bf16 hi / lo copy of dY + column sums = bias gradient,
+// no transposed copy), vectorised: block (32, 8) covers 64 rows x 128 columns, thread = 4 columns of every 8th row, 128-bit
+// loads / 64-bit stores, column sums in registers -> shared memory -> one atomicAdd per column and block.  (The tile kernel
+// above moves 2-byte elements: 61 us for a [16.5k, 512] gradient, 6x off the HBM time, 8 % of a training step.)
+__global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restrict__ x, int M, int N, int ld, uint16_t* __restrict__ hi,
+                                                         uint16_t* __restrict__ lo, int ld_s, float* __restrict__ colsum) {
+    __shared__ float4 csum[8][32];
+    const int c = (blockIdx.x * 32 + threadIdx.x) * 4;   // first of this thread's 4 columns
+    const int m0 = blockIdx.y * 64;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < ld_s) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int m = m0 + threadIdx.y + 8 * k;
+            if (m >= M) break;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c + 4 <= N) {
+                v = *reinterpret_cast<const float4*>(x + (size_t)m * ld + c);
+            } else if (c < N) {   // the row's last, partial group: columns >= N are pad (written as zeros)
+                const float* xr = x + (size_t)m * ld + c;
+                v.x = xr[0];
+                if (c + 1 < N) v.y = xr[1];
+                if (c + 2 < N) v.z = xr[2];
+            }
+            uint2 h, l;
+            split_bf16x4(v, h, l);
+            *reinterpret_cast<uint2*>(hi + (size_t)m * ld_s + c) = h;
+            if (lo) *reinterpret_cast<uint2*>(lo + (size_t)m * ld_s + c) = l;
+            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+        }
+    }
+    if (!colsum) return;
+    csum[threadIdx.y][threadIdx.x] = cs;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        float4 t = csum[0][threadIdx.x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            const float4 u = csum[k][threadIdx.x];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        atomicAdd(colsum + c, t.x);
+        if (c + 1 < N) atomicAdd(colsum + c + 1, t.y);
+        if (c + 2 < N) atomicAdd(colsum + c + 2, t.z);
+        if (c + 3 < N) atomicAdd(colsum + c + 3, t.w);
+    }
+}
+
 // ---- highway (train) ----------------------------------------------------------------------------------
 __global__ void highway_fwd_train_kernel(const float* __restrict__ x, const float* __restrict__ yg, int gate,
                                          int64_t n, int D, DropCfg d, float* __restrict__ o) {
@@ -949,6 +997,13 @@ extern "C" int navc_transpose_pack(const float* x, int M, int N, int ld, uint16_
     NAVC_REQUIRE(x && M > 0 && N > 0 && ld >= N, "navc_transpose_pack: bad arguments");
     NAVC_REQUIRE(!(t_f32 || t_hi) || ld_t >= M, "navc_transpose_pack: ld_t < M");
     NAVC_REQUIRE(!hi || ld_s >= N, "navc_transpose_pack: ld_s < N");
+    if (hi && !t_f32 && !t_hi && ld % 4 == 0 && ld_s % 4 == 0 && (((uintptr_t)x) & 15) == 0 &&
+        ((((uintptr_t)hi) | ((uintptr_t)lo)) & 7) == 0) {
+        dim3 g((ld_s + 127) / 128, (M + 63) / 64);
+        NAVC_REQUIRE(g.y <= 65535, "navc_transpose_pack: M too large");
+        split_colsum_kernel<<<g, dim3(32, 8), 0, as_stream(stream)>>>(x, M, N, ld, hi, lo, ld_s, colsum);
+        return check_launch("navc_transpose_pack");
+    }
     const int m_ext = (t_f32 || t_hi) && ld_t > M ? ld_t : M;  // tiles also cover the zero-filled pad columns
     const int n_ext = hi && ld_s > N ? ld_s : N;
     dim3 grid((n_ext + 31) / 32, (m_ext + 31) / 32);

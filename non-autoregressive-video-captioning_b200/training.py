@@ -167,7 +167,7 @@ class Grads:
 
 
 def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, need_dx=True,
-            dx_residual: Optional[torch.Tensor] = None, ld_dy=None):
+            dx_residual: Optional[torch.Tensor] = None, ld_dy=None, dy_split: Optional[Operand] = None, db_pre=None):
     """Backward of y = x W^T + b.  x: the forward input, an fp32 tensor [M,K] or the Act the forward GEMM
     consumed (its bf16 hi/lo copies are reused); dY [M,N] fp32 (leading dimension ld_dy, pad columns zero).
     Accumulates dW / db into ``grads``; returns dX [M,K] (+ dx_residual) or None.
@@ -179,9 +179,11 @@ def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, n
     x32 = x.f32 if x_act is not None else x
     M, K = (x_act.M, x_act.N) if x_act is not None else x.shape
     N = lin.N
-    ld = ld_dy or dY.stride(0)
     dev = eng.device
-    if ld % 16 != 0 or (need_dx and ld < _up(N, 64)) or (eng.tc and N % 8 != 0 and ld < _up(N, 64)):
+    # dy_split: the producer already wrote dY as the bf16 hi (/ lo) operand (tensor-core path only) and accumulated its
+    # column sums into db_pre = (bias-gradient tensor, whether that tensor IS the parameters' gradient view)
+    ld = dy_split.ld if dy_split is not None else (ld_dy or dY.stride(0))
+    if dy_split is None and (ld % 16 != 0 or (need_dx and ld < _up(N, 64)) or (eng.tc and N % 8 != 0 and ld < _up(N, 64))):
         # operand alignment: re-lay dY with a zero-padded leading dimension
         ldp = _up(N, 64)
         pad = torch.zeros((M, ldp), dtype=torch.float32, device=dev)
@@ -198,9 +200,15 @@ def lin_bwd(eng: Engine, x, lin: PackedLinear, dY: torch.Tensor, grads: Grads, n
             tw = None
         if tb is not None and tb.numel() != N:
             tb = None
-    db = tb if tb is not None else (torch.zeros((N,), dtype=torch.float32, device=dev) if lin.b is not None else None)
+    if db_pre is not None:
+        db, tb = db_pre[0], (db_pre[0] if db_pre[1] else None)
+    else:
+        db = tb if tb is not None else (torch.zeros((N,), dtype=torch.float32, device=dev) if lin.b is not None else None)
     if eng.tc and K % 8 == 0:
-        s, _ = transpose_pack(eng, dY, M, N, ld, straight=True, colsum=db)
+        if dy_split is not None:
+            s = dy_split
+        else:
+            s, _ = transpose_pack(eng, dY, M, N, ld, straight=True, colsum=db)
         if x_act is not None and x_act.hi is not None and (x_act.lo is not None or not eng.split):
             x_hi, x_lo = x_act.hi, x_act.lo
         else:
@@ -662,7 +670,7 @@ class DecoderFn(torch.autograd.Function):
             L.call("navc_rows_f32", L.ptr(g), L.ptr(gp), D, L.ptr(pk["rowmap"]), R, 0, L.stream())
             g = gp
         nl = len(P["layers"])
-        d_kv = torch.empty((Bv * E, nl * 2 * D), dtype=torch.float32, device=dev)
+        d_kv = None   # fp32 gradient of the all-layer K|V projection output (allocated below unless it leaves split)
         # attention gradients on the tensor cores (csrc/attention_bwd_tc.cu: dk == 64, S <= 32, E <= 128, packed rows).
         # opt['navc_attn_bwd_tc'] / $NAVC_ATTN_BWD_TC: 1 (default) text -> video attention only -- 535 vs 669 us per launch
         # at 1024 videos; the token self-attention (<= 30 keys: one 32-key chunk of a 128-wide tile) measured 302 vs 288 us
@@ -671,6 +679,20 @@ class DecoderFn(torch.autograd.Function):
         tc_ok = pk is not None and eng.tc and eng.tc_attention_ok(S, E)
         tc_bwd = tc_ok and want not in ("0", "false", "no", "off")
         tc_bwd_self = tc_ok and want in ("2", "all", "both")
+        # with the tensor-core kernel the K|V gradient leaves directly as the bf16 hi / lo operand of the projection's
+        # gradient GEMMs, its column sums (bias gradient) accumulated by the same kernel: no fp32 d_kv (3 GB at 1024 videos)
+        kv_lin = P["kv_all"]
+        kv_split = None
+        if tc_bwd and kv_lin.b is not None and kv_lin.K % 8 == 0 and os.environ.get("NAVC_KV_SPLIT", "1") not in ("0", "no", "off"):
+            kv_db = grads.target_group([s_[1] for s_ in kv_lin.src])
+            kv_db_direct = kv_db is not None and kv_db.numel() == kv_lin.N
+            if not kv_db_direct:
+                kv_db = torch.zeros((kv_lin.N,), dtype=torch.float32, device=dev)
+            kv_split = Operand(Bv * E, kv_lin.N, kv_lin.N,
+                               hi=torch.empty((Bv * E, kv_lin.N), dtype=torch.bfloat16, device=dev),
+                               lo=torch.empty((Bv * E, kv_lin.N), dtype=torch.bfloat16, device=dev) if eng.split else None)
+        else:
+            d_kv = torch.empty((Bv * E, nl * 2 * D), dtype=torch.float32, device=dev)
         for l in range(nl - 1, -1, -1):
             lw, sv = P["layers"][l], st["layers"][l]
             d_f2, d_c_res = _post_bwd(eng, g, lw["f2_ln"], lw["f2_ln_key"], sv["s_f1"], p, sv["s_f2"], p, tok_flat, sv["f2"], grads)
@@ -682,7 +704,12 @@ class DecoderFn(torch.autograd.Function):
             d_ctx2 = lin_bwd(eng, sv["ctx2"], lw["co"], d_co, grads)
             d_q = torch.empty((R, D), dtype=torch.float32, device=dev)
             off = l * 2 * D
-            if pk is not None and tc_bwd:
+            if pk is not None and kv_split is not None:
+                L.call("navc_cross_attention_bwd_tc_split", eng.tc_mode, L.ptr(sv["q"]), D, st["kv"][:, off:].data_ptr(),
+                       st["kv"].shape[1], L.ptr(pk["seq_off"]), N, S, E, D, H, L.ptr(d_ctx2), L.ptr(sv["ctx2"].f32), L.ptr(d_q), D,
+                       kv_split.hi[:, off:].data_ptr(), kv_split.lo[:, off:].data_ptr() if kv_split.lo is not None else None,
+                       kv_lin.N, kv_db[off:].data_ptr(), L.stream())
+            elif pk is not None and tc_bwd:
                 L.call("navc_cross_attention_bwd_tc", eng.tc_mode, L.ptr(sv["q"]), D, st["kv"][:, off:].data_ptr(), st["kv"].shape[1],
                        L.ptr(pk["seq_off"]), N, S, E, D, H, L.ptr(d_ctx2), L.ptr(sv["ctx2"].f32), L.ptr(d_q), D,
                        d_kv[:, off:].data_ptr(), d_kv.shape[1], L.stream())
@@ -731,7 +758,10 @@ class DecoderFn(torch.autograd.Function):
         grads.add(ep + "LayerNorm.weight", d_lw)
         grads.add(ep + "LayerNorm.bias", d_lb)
         # encoder memory: through the K|V projection of every layer and the enhance_input mean
-        d_enc = lin_bwd(eng, st["enc"], P["kv_all"], d_kv, grads)
+        if kv_split is not None:
+            d_enc = lin_bwd(eng, st["enc"], kv_lin, None, grads, dy_split=kv_split, db_pre=(kv_db, kv_db_direct))
+        else:
+            d_enc = lin_bwd(eng, st["enc"], kv_lin, d_kv, grads)
         if d_extra is not None:
             L.call("navc_mean_bwd", L.ptr(d_extra), Bv, E, D, L.ptr(d_enc), L.stream())
         return (None, None, None, None, None, d_enc.view(Bv, E, D)) + tuple(grads.g.get(k) for k in ctx.keys)

@@ -141,6 +141,28 @@ def test_transpose_pack(M, N, ld):
     close(cs, x[:, :N].sum(0), 1e-5, "colsum")
 
 
+@pytest.mark.parametrize("M,N,ld", [(70, 64, 64), (333, 520, 576), (4195, 2048, 2048), (130, 30, 64), (1, 10547, 10560), (77, 10, 16)])
+@pytest.mark.parametrize("with_lo", [True, False])
+def test_split_colsum_fast_path(M, N, ld, with_lo):
+    """navc_transpose_pack without transposed outputs (what every gradient GEMM of the tensor-core path asks for): the
+    vectorised split + column-sum kernel; pad columns N..ld-1 come out as zeros, rows beyond M are not touched."""
+    x = torch.zeros(M, ld)
+    x[:, :N] = torch.randn(M, N, generator=g(4))
+    x[:, N:] = 123.0      # garbage in the source's pad columns must not leak
+    xd = x.to(DEV)
+    hi = torch.full((M + 3, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+    lo = torch.full((M + 3, ld), 7.0, dtype=torch.bfloat16, device=DEV) if with_lo else None
+    cs = torch.zeros(N, device=DEV)
+    L.call("navc_transpose_pack", L.ptr(xd), M, N, ld, L.ptr(hi), L.ptr(lo), ld, None, None, None, 0, L.ptr(cs), L.stream())
+    want = x.clone()
+    want[:, N:] = 0.0
+    got = hi[:M].float() + (lo[:M].float() if with_lo else 0.0)
+    assert torch.allclose(got.cpu(), want, atol=1e-5 if with_lo else 4e-2)
+    assert torch.equal(hi[:M].cpu(), want.to(torch.bfloat16))
+    assert torch.all(hi[M:].float() == 7.0)
+    close(cs, x[:, :N].sum(0), 1e-5, "colsum")
+
+
 @pytest.mark.parametrize("mode", ["f32", "bf16x3"])
 def test_gemm_split_k_accumulate(mode):
     M, N, K = 300, 520, 4096 + 64
@@ -496,6 +518,41 @@ def test_cross_attention_backward_tc(mode, D, H, S, E, with_ctx):
     close(d_q[:Rp], q.grad, tol, "tc cross attn dq %s" % mode)
     close(d_kv.view(N, E, 2 * D), kv.grad, tol, "tc cross attn dkv %s" % mode)
     assert torch.all(d_q[Rp:] == 7.0)
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_cross_attention_backward_tc_split_output(mode):
+    """navc_cross_attention_bwd_tc_split: dK / dV leave as bf16 hi (/ lo) rows inside a wider [rows, L * 2D] operand, their
+    column sums accumulate into the bias-gradient slice; same numbers as the fp32 result of the plain kernel."""
+    D, H, S, E, Lw = 128, 2, 9, 12, 3     # operand of 3 "layers": this launch fills columns [2D, 4D) of it
+    lens = [S, 1, S - 3, 5, 2, 7]
+    N = len(lens)
+    seq_off, _ = _pack(lens, S)
+    Rp = int(seq_off[-1])
+    q = torch.randn(Rp, D, generator=g(63)).to(DEV)
+    kv = torch.randn(N * E, 2 * D, generator=g(64)).to(DEV)
+    d_ctx = torch.randn(Rp, D, generator=g(65)).to(DEV)
+    x3 = mode == "bf16x3"
+    md = L.TC_BF16X3 if x3 else L.TC_BF16
+    d_q0 = torch.empty(Rp, D, device=DEV); d_kv0 = torch.empty(N * E, 2 * D, device=DEV)
+    L.call("navc_cross_attention_bwd_tc", md, L.ptr(q), D, L.ptr(kv), 2 * D, P(seq_off), N, S, E, D, H, L.ptr(d_ctx), None, L.ptr(d_q0), D,
+           L.ptr(d_kv0), 2 * D, L.stream())
+    ld = Lw * 2 * D
+    hi = torch.full((N * E, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+    lo = torch.full((N * E, ld), 7.0, dtype=torch.bfloat16, device=DEV) if x3 else None
+    cs = torch.full((ld,), 0.5, device=DEV)
+    d_q1 = torch.empty(Rp, D, device=DEV)
+    off = 2 * D
+    L.call("navc_cross_attention_bwd_tc_split", md, L.ptr(q), D, L.ptr(kv), 2 * D, P(seq_off), N, S, E, D, H, L.ptr(d_ctx), None,
+           L.ptr(d_q1), D, hi[:, off:].data_ptr(), lo[:, off:].data_ptr() if x3 else None, ld, cs[off:].data_ptr(), L.stream())
+    assert torch.equal(d_q0, d_q1)
+    want_hi = d_kv0.to(torch.bfloat16)
+    assert torch.equal(hi[:, off:off + 2 * D], want_hi)
+    if x3:
+        assert torch.equal(lo[:, off:off + 2 * D], (d_kv0 - want_hi.float()).to(torch.bfloat16))
+    assert torch.all(hi[:, :off].float() == 7.0) and torch.all(hi[:, off + 2 * D:].float() == 7.0)
+    close(cs[off:off + 2 * D] - 0.5, d_kv0.sum(0), 1e-5, "kv column sums")
+    assert torch.all(cs[:off] == 0.5) and torch.all(cs[off + 2 * D:] == 0.5)
 
 
 def test_packed_row_helpers():
