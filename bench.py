@@ -210,8 +210,9 @@ def run_reference(args, opt, rank):
     _, t4, _ = cpu_run(opt, 4, 1, 0, kind)
     budget = 240.0 / max(1, args.steps + args.warmup)
     batch = 4
+    cap = int(os.environ.get("NAVC_BENCH_REF_MAXB", "128"))   # (tests bound the sample)
     for cand in (128, 64, 32, 16, 8):
-        if t4 * cand / 4.0 * 1.15 <= budget:
+        if cand <= cap and t4 * cand / 4.0 * 1.15 <= budget:
             batch = cand
             break
     value, sec, _ = cpu_run(opt, batch, args.steps, args.warmup, kind)
