@@ -425,6 +425,13 @@ int navc_act_drop(const float* u, int act, uint64_t seed, float p, int64_t n, fl
 int navc_act_drop_bwd(const float* dout, const float* u, int act, uint64_t seed, float p, int64_t n,
                       float* du, void* stream);
 
+/* navc_drop_add_bwd / navc_act_drop_bwd whose dY output leaves directly as the bf16 hi (/ lo) operand [M, ld_s] of the next
+ * linear layer's gradient GEMMs, with its column sums (that layer's bias gradient) accumulated into colsum [D] resp. [N]
+ * (or NULL) -- instead of an fp32 dY that navc_transpose_pack would re-read.  d_res (fp32, or NULL) as navc_drop_add_bwd. */
+int navc_drop_add_bwd_split(const float* dout, uint64_t seed1, float p1, uint64_t seed2, float p2, const int64_t* row_tokens,
+                            int M, int D, float* d_res, uint16_t* dy_hi, uint16_t* dy_lo, int ld_s, float* colsum, void* stream);
+int navc_act_drop_bwd_split(const float* dout, const float* u, int act, uint64_t seed, float p, int M, int N,
+                            uint16_t* dy_hi, uint16_t* dy_lo, int ld_s, float* colsum, void* stream);
 /* x [M,N] (ld) fp32 -> any of: bf16 hi/lo copy [M, ld_s]; transposed fp32 / bf16 hi/lo [N, ld_t]
  * (columns M..ld_t-1 zero-filled); colsum[n] += sum_m x[m,n] (atomic; caller zero-fills).  Feeds
  * the gradient GEMMs dX = dY W and dW = dY^T X and the bias gradients. */

@@ -241,6 +241,91 @@ __global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restri
     }
 }
 
+// Producers that write dY of the next gradient GEMM pair directly in operand form (bf16 hi / lo rows + column sums = bias
+// gradient) instead of an fp32 tensor that navc_transpose_pack would re-read: same tiling as split_colsum_kernel.
+// dropout + residual backward (models/bert.py:193-200): d_res = dout * mask2 [* rowmask], dY = d_res * mask1
+__global__ void __launch_bounds__(256) drop_add_bwd_split_kernel(const float* __restrict__ dout, DropCfg d1, DropCfg d2,
+                                                               const int64_t* __restrict__ row_tokens, int M, int D,
+                                                               float* __restrict__ d_res, uint16_t* __restrict__ hi,
+                                                               uint16_t* __restrict__ lo, int ld_s, float* __restrict__ colsum) {
+    __shared__ float4 csum[8][32];
+    const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int m0 = blockIdx.y * 64;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < D) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int m = m0 + threadIdx.y + 8 * k;
+            if (m >= M) break;
+            const int64_t e = (int64_t)m * D + c;
+            float4 g = *reinterpret_cast<const float4*>(dout + e);
+            if (row_tokens && row_tokens[m] == NAVC_PAD) g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d2.thr) g = mul4(g, drop_factor4(d2, (uint64_t)e));
+            if (d_res) *reinterpret_cast<float4*>(d_res + e) = g;
+            if (d1.thr) g = mul4(g, drop_factor4(d1, (uint64_t)e));
+            uint2 h, l;
+            split_bf16x4(g, h, l);
+            *reinterpret_cast<uint2*>(hi + (size_t)m * ld_s + c) = h;
+            if (lo) *reinterpret_cast<uint2*>(lo + (size_t)m * ld_s + c) = l;
+            cs.x += g.x; cs.y += g.y; cs.z += g.z; cs.w += g.w;
+        }
+    }
+    if (!colsum) return;
+    csum[threadIdx.y][threadIdx.x] = cs;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < D) {
+        float4 t = csum[0][threadIdx.x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            const float4 u = csum[k][threadIdx.x];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        atomicAdd(colsum + c, t.x); atomicAdd(colsum + c + 1, t.y); atomicAdd(colsum + c + 2, t.z); atomicAdd(colsum + c + 3, t.w);
+    }
+}
+
+// activation (+ dropout) backward (models/bert.py:227-230): dY = dout * mask * act'(u)
+__global__ void __launch_bounds__(256) act_drop_bwd_split_kernel(const float* __restrict__ dout, const float* __restrict__ u, int act,
+                                                               DropCfg d, int M, int N, uint16_t* __restrict__ hi,
+                                                               uint16_t* __restrict__ lo, int ld_s, float* __restrict__ colsum) {
+    __shared__ float4 csum[8][32];
+    const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int m0 = blockIdx.y * 64;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < N) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int m = m0 + threadIdx.y + 8 * k;
+            if (m >= M) break;
+            const int64_t e = (int64_t)m * N + c;
+            float4 g = *reinterpret_cast<const float4*>(dout + e);
+            if (d.thr) {
+                g.x *= drop_factor1(d, (uint64_t)e); g.y *= drop_factor1(d, (uint64_t)e + 1);
+                g.z *= drop_factor1(d, (uint64_t)e + 2); g.w *= drop_factor1(d, (uint64_t)e + 3);
+            }
+            const float4 uv = *reinterpret_cast<const float4*>(u + e);
+            g.x *= act_grad(uv.x, act); g.y *= act_grad(uv.y, act); g.z *= act_grad(uv.z, act); g.w *= act_grad(uv.w, act);
+            uint2 h, l;
+            split_bf16x4(g, h, l);
+            *reinterpret_cast<uint2*>(hi + (size_t)m * ld_s + c) = h;
+            if (lo) *reinterpret_cast<uint2*>(lo + (size_t)m * ld_s + c) = l;
+            cs.x += g.x; cs.y += g.y; cs.z += g.z; cs.w += g.w;
+        }
+    }
+    if (!colsum) return;
+    csum[threadIdx.y][threadIdx.x] = cs;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        float4 t = csum[0][threadIdx.x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            const float4 v = csum[k][threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        atomicAdd(colsum + c, t.x); atomicAdd(colsum + c + 1, t.y); atomicAdd(colsum + c + 2, t.z); atomicAdd(colsum + c + 3, t.w);
+    }
+}
+
 // ---- highway (train) ----------------------------------------------------------------------------------
 __global__ void highway_fwd_train_kernel(const float* __restrict__ x, const float* __restrict__ yg, int gate,
                                          int64_t n, int D, DropCfg d, float* __restrict__ o) {
@@ -974,6 +1059,30 @@ extern "C" int navc_drop_add_bwd(const float* dout, uint64_t seed1, float p1, ui
     drop_add_bwd_kernel<<<ew_blocks(n4, 256), 256, 0, as_stream(stream)>>>(dout, make_drop(seed1, p1), make_drop(seed2, p2),
                                                                          row_tokens, n4, D, d_y, d_res);
     return check_launch("navc_drop_add_bwd");
+}
+
+extern "C" int navc_drop_add_bwd_split(const float* dout, uint64_t seed1, float p1, uint64_t seed2, float p2,
+                                       const int64_t* row_tokens, int M, int D, float* d_res, uint16_t* dy_hi, uint16_t* dy_lo,
+                                       int ld_s, float* colsum, void* stream) {
+    NAVC_REQUIRE(dout && dy_hi && M > 0 && D > 0 && D % 4 == 0 && ld_s >= D && ld_s % 4 == 0, "navc_drop_add_bwd_split: bad arguments");
+    NAVC_REQUIRE(((((uintptr_t)dout) | ((uintptr_t)d_res)) & 15) == 0 && ((((uintptr_t)dy_hi) | ((uintptr_t)dy_lo)) & 7) == 0,
+                 "navc_drop_add_bwd_split: operands must be 16-byte (fp32) / 8-byte (bf16) aligned");
+    dim3 g((D + 127) / 128, (M + 63) / 64);
+    NAVC_REQUIRE(g.y <= 65535, "navc_drop_add_bwd_split: M too large");
+    drop_add_bwd_split_kernel<<<g, dim3(32, 8), 0, as_stream(stream)>>>(dout, make_drop(seed1, p1), make_drop(seed2, p2), row_tokens, M, D,
+                                                                       d_res, dy_hi, dy_lo, ld_s, colsum);
+    return check_launch("navc_drop_add_bwd_split");
+}
+
+extern "C" int navc_act_drop_bwd_split(const float* dout, const float* u, int act, uint64_t seed, float p, int M, int N,
+                                       uint16_t* dy_hi, uint16_t* dy_lo, int ld_s, float* colsum, void* stream) {
+    NAVC_REQUIRE(dout && u && dy_hi && M > 0 && N > 0 && N % 4 == 0 && ld_s >= N && ld_s % 4 == 0, "navc_act_drop_bwd_split: bad arguments");
+    NAVC_REQUIRE(((((uintptr_t)dout) | ((uintptr_t)u)) & 15) == 0 && ((((uintptr_t)dy_hi) | ((uintptr_t)dy_lo)) & 7) == 0,
+                 "navc_act_drop_bwd_split: operands must be 16-byte (fp32) / 8-byte (bf16) aligned");
+    dim3 g((N + 127) / 128, (M + 63) / 64);
+    NAVC_REQUIRE(g.y <= 65535, "navc_act_drop_bwd_split: M too large");
+    act_drop_bwd_split_kernel<<<g, dim3(32, 8), 0, as_stream(stream)>>>(dout, u, act, make_drop(seed, p), M, N, dy_hi, dy_lo, ld_s, colsum);
+    return check_launch("navc_act_drop_bwd_split");
 }
 
 extern "C" int navc_act_drop(const float* u, int act, uint64_t seed, float p, int64_t n, float* out_f32,

@@ -262,6 +262,38 @@ def drop_add_bwd(dout, s1, p1, s2, p2, row_tokens, want_res=True):
     return d_y, d_res
 
 
+FOLD_SPLIT = os.environ.get("NAVC_FOLD_SPLIT", "1") not in ("0", "no", "off")
+
+
+def _dy_target(eng, lin: PackedLinear, grads: Grads, M):
+    """Buffers for a producer that writes the dY of ``lin`` directly in operand form (bf16 hi / lo + column sums):
+    (Operand, bias-gradient tensor, whether that tensor is the parameter's gradient view), or None if the tensor-core
+    gradient path / the alignment rules do not apply."""
+    N = lin.N
+    if not (FOLD_SPLIT and eng.tc and lin.K % 8 == 0 and N % 64 == 0 and lin.b is not None):
+        return None
+    if len(lin.src) == 1:
+        tb = grads.target(lin.src[0][1])
+    else:
+        tb = grads.target_group([s_[1] for s_ in lin.src])
+        if tb is not None and tb.numel() != N:
+            tb = None
+    db = tb if tb is not None else torch.zeros((N,), dtype=torch.float32, device=eng.device)
+    op = _alloc_operand(eng, M, N)
+    op.K = N
+    return op, db, tb is not None
+
+
+def _post_bwd_split(eng, g, s1, p1, s2, p2, tok_flat, sp):
+    """_post_bwd without LayerNorm whose d_dense_out leaves as the operand sp (navc_drop_add_bwd_split); returns d_residual."""
+    M, D = g.shape
+    d_res = torch.empty_like(g)
+    op, db, _ = sp
+    L.call("navc_drop_add_bwd_split", L.ptr(g), s1, p1, s2, p2, L.ptr(tok_flat), M, D, L.ptr(d_res), L.ptr(op.hi), L.ptr(op.lo), op.ld,
+           L.ptr(db), L.stream())
+    return d_res
+
+
 def _post(eng, y, res, ln, s1, p1, s2, p2, tok_flat, saved):
     """dense output -> dropout -> +residual -> [LayerNorm] -> [dropout] -> * non_pad_mask
     (models/bert.py:193-200 with p2 == 0; bert.py:241-247 with the second dropout)."""
@@ -695,13 +727,31 @@ class DecoderFn(torch.autograd.Function):
             d_kv = torch.empty((Bv * E, nl * 2 * D), dtype=torch.float32, device=dev)
         for l in range(nl - 1, -1, -1):
             lw, sv = P["layers"][l], st["layers"][l]
-            d_f2, d_c_res = _post_bwd(eng, g, lw["f2_ln"], lw["f2_ln_key"], sv["s_f1"], p, sv["s_f2"], p, tok_flat, sv["f2"], grads)
-            d_h = lin_bwd(eng, sv["h"], lw["f2"], d_f2, grads)
-            d_u = torch.empty_like(d_h)
-            L.call("navc_act_drop_bwd", L.ptr(d_h), L.ptr(sv["u"]), eng.act, 0, 0.0, d_h.numel(), L.ptr(d_u), L.stream())
-            d_c = lin_bwd(eng, sv["c"], lw["f1"], d_u, grads, dx_residual=d_c_res)
-            d_co, d_a_res = _post_bwd(eng, d_c, lw["co_ln"], lw["co_ln_key"], sv["s_co"], p, 0, 0.0, tok_flat, sv["co"], grads)
-            d_ctx2 = lin_bwd(eng, sv["ctx2"], lw["co"], d_co, grads)
+            # (the dY of every GEMM below leaves its producer directly as the bf16 hi / lo operand + bias column sums where
+            # the layer has no LayerNorm in between: no fp32 dY, no separate split pass)
+            sp = _dy_target(eng, lw["f2"], grads, g.shape[0]) if lw["f2_ln"] is None else None
+            if sp is not None:
+                d_c_res = _post_bwd_split(eng, g, sv["s_f1"], p, sv["s_f2"], p, tok_flat, sp)
+                d_h = lin_bwd(eng, sv["h"], lw["f2"], None, grads, dy_split=sp[0], db_pre=(sp[1], sp[2]))
+            else:
+                d_f2, d_c_res = _post_bwd(eng, g, lw["f2_ln"], lw["f2_ln_key"], sv["s_f1"], p, sv["s_f2"], p, tok_flat, sv["f2"], grads)
+                d_h = lin_bwd(eng, sv["h"], lw["f2"], d_f2, grads)
+            sp = _dy_target(eng, lw["f1"], grads, d_h.shape[0])
+            if sp is not None:
+                L.call("navc_act_drop_bwd_split", L.ptr(d_h), L.ptr(sv["u"]), eng.act, 0, 0.0, d_h.shape[0], d_h.shape[1],
+                       L.ptr(sp[0].hi), L.ptr(sp[0].lo), sp[0].ld, L.ptr(sp[1]), L.stream())
+                d_c = lin_bwd(eng, sv["c"], lw["f1"], None, grads, dx_residual=d_c_res, dy_split=sp[0], db_pre=(sp[1], sp[2]))
+            else:
+                d_u = torch.empty_like(d_h)
+                L.call("navc_act_drop_bwd", L.ptr(d_h), L.ptr(sv["u"]), eng.act, 0, 0.0, d_h.numel(), L.ptr(d_u), L.stream())
+                d_c = lin_bwd(eng, sv["c"], lw["f1"], d_u, grads, dx_residual=d_c_res)
+            sp = _dy_target(eng, lw["co"], grads, d_c.shape[0]) if lw["co_ln"] is None else None
+            if sp is not None:
+                d_a_res = _post_bwd_split(eng, d_c, sv["s_co"], p, 0, 0.0, tok_flat, sp)
+                d_ctx2 = lin_bwd(eng, sv["ctx2"], lw["co"], None, grads, dy_split=sp[0], db_pre=(sp[1], sp[2]))
+            else:
+                d_co, d_a_res = _post_bwd(eng, d_c, lw["co_ln"], lw["co_ln_key"], sv["s_co"], p, 0, 0.0, tok_flat, sv["co"], grads)
+                d_ctx2 = lin_bwd(eng, sv["ctx2"], lw["co"], d_co, grads)
             d_q = torch.empty((R, D), dtype=torch.float32, device=dev)
             off = l * 2 * D
             if pk is not None and kv_split is not None:
@@ -721,8 +771,13 @@ class DecoderFn(torch.autograd.Function):
                 L.call("navc_cross_attention_bwd", L.ptr(sv["q"]), D, st["kv"][:, off:].data_ptr(), st["kv"].shape[1], N, S, E, D, H, 1,
                        L.ptr(d_ctx2), L.ptr(d_q), D, d_kv[:, off:].data_ptr(), d_kv.shape[1], L.stream())
             d_a = lin_bwd(eng, sv["a"], lw["cq"], d_q, grads, dx_residual=d_a_res)
-            d_so, d_x_res = _post_bwd(eng, d_a, lw["so_ln"], lw["so_ln_key"], sv["s_so"], p, 0, 0.0, tok_flat, sv["so"], grads)
-            d_ctx1 = lin_bwd(eng, sv["ctx1"], lw["so"], d_so, grads)
+            sp = _dy_target(eng, lw["so"], grads, d_a.shape[0]) if lw["so_ln"] is None else None
+            if sp is not None:
+                d_x_res = _post_bwd_split(eng, d_a, sv["s_so"], p, 0, 0.0, tok_flat, sp)
+                d_ctx1 = lin_bwd(eng, sv["ctx1"], lw["so"], None, grads, dy_split=sp[0], db_pre=(sp[1], sp[2]))
+            else:
+                d_so, d_x_res = _post_bwd(eng, d_a, lw["so_ln"], lw["so_ln_key"], sv["s_so"], p, 0, 0.0, tok_flat, sv["so"], grads)
+                d_ctx1 = lin_bwd(eng, sv["ctx1"], lw["so"], d_so, grads)
             d_qkv = torch.empty((R, 3 * D), dtype=torch.float32, device=dev)
             if pk is not None and tc_bwd_self:
                 L.call("navc_self_attention_bwd_tc", eng.tc_mode, L.ptr(sv["qkv"]), 3 * D, L.ptr(pk["seq_off"]), N, S, D, H,
