@@ -301,7 +301,70 @@ extern "C" int navc_refine_step(const navc_step_t* p, int N, int S, void* stream
 // thread t owns a contiguous chunk of rows.  slot[r] becomes the number of selected rows before r (for a selected row: its
 // index in `rows`), rows[] the selected rows in ascending order, seq_off_c[n] = slot[seq_off[n]] the packed offsets of the
 // compacted row space (a sequence's / video's selected rows stay contiguous), count = seq_off_c[N].
-__global__ void compact_rows_kernel(int32_t* __restrict__ slot, const int32_t* __restrict__ seq_off, int N, int max_rows,
+__global__ void __launch_bounds__(1024) compact_rows_kernel(int32_t* __restrict__ slot, const int32_t* __restrict__ seq_off, int N, int max_rows,
+                                    int32_t* __restrict__ rows, int32_t* __restrict__ count, int32_t* __restrict__ seq_off_c) {
+    // warp w owns a contiguous segment of 32-row groups; lane = row inside a group (coalesced, independent loads; the first
+    // version walked 21 dependent loads per thread: 12 us).  Flags of a warp's groups stay in registers between the passes.
+    constexpr int kMaxGroups = 32;                 // groups per warp: 32 warps x 32 groups x 32 rows = 32768 rows
+    __shared__ int wsum[32];
+    __shared__ int total_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int R = seq_off[N];
+    if (R > max_rows) R = max_rows;
+    const int groups = (max_rows + 31) >> 5;
+    const int gpw = (groups + 31) >> 5;            // groups per warp (<= kMaxGroups, checked by the host)
+    const int g0 = warp * gpw;
+    uint32_t bits[kMaxGroups];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+        bits[k] = 0u;
+        if (k < gpw) {
+            const int r = (g0 + k) * 32 + lane;
+            const int f = (r < R) ? (slot[r] != 0) : 0;
+            bits[k] = __ballot_sync(0xffffffffu, f);
+            c += __popc(bits[k]);                  // (warp-uniform)
+        }
+    }
+    if (lane == 0) wsum[warp] = c;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = wsum[lane];
+        int wi = w;
+#pragma unroll
+        for (int sh = 1; sh < 32; sh <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, sh);
+            if (lane >= sh) wi += v;
+        }
+        wsum[lane] = wi - w;                       // exclusive prefix of the warp totals
+        if (lane == 31) total_s = wi;
+    }
+    __syncthreads();
+    int base = wsum[warp];
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+        if (k < gpw) {
+            const int r = (g0 + k) * 32 + lane;
+            const uint32_t b = bits[k];
+            const int pre = base + __popc(b & ((1u << lane) - 1u));
+            if (r < R) {
+                slot[r] = pre;
+                if ((b >> lane) & 1u) rows[pre] = r;
+            }
+            base += __popc(b);
+        }
+    }
+    const int total = total_s;
+    if (tid == 0) { count[0] = total; slot[R] = total; }
+    __syncthreads();
+    for (int n = tid; n <= N; n += blockDim.x) {
+        const int r = seq_off[n];
+        seq_off_c[n] = r >= R ? total : slot[r];
+    }
+}
+
+// any row count: thread t walks a contiguous chunk of rows (used beyond 32768 rows)
+__global__ void compact_rows_serial_kernel(int32_t* __restrict__ slot, const int32_t* __restrict__ seq_off, int N, int max_rows,
                                     int32_t* __restrict__ rows, int32_t* __restrict__ count, int32_t* __restrict__ seq_off_c) {
     __shared__ int wsum[32];
     __shared__ int total_s;
@@ -352,7 +415,10 @@ __global__ void compact_rows_kernel(int32_t* __restrict__ slot, const int32_t* _
 extern "C" int navc_compact_rows(int32_t* slot, const int32_t* seq_off, int N, int max_rows, int32_t* rows, int32_t* count,
                                  int32_t* seq_off_c, void* stream) {
     NAVC_REQUIRE(slot && seq_off && rows && count && seq_off_c && N > 0 && max_rows > 0, "navc_compact_rows: bad arguments");
-    compact_rows_kernel<<<1, 1024, 0, as_stream(stream)>>>(slot, seq_off, N, max_rows, rows, count, seq_off_c);
+    if (max_rows > 32768)
+        compact_rows_serial_kernel<<<1, 1024, 0, as_stream(stream)>>>(slot, seq_off, N, max_rows, rows, count, seq_off_c);
+    else
+        compact_rows_kernel<<<1, 1024, 0, as_stream(stream)>>>(slot, seq_off, N, max_rows, rows, count, seq_off_c);
     return check_launch("navc_compact_rows");
 }
 

@@ -464,7 +464,7 @@ def test_compact_rows_orders_the_selected_positions():
     """navc_compact_rows (include/navc.h): ordered compaction of refine_step's selection flags -- ascending row list,
     packed row -> compact index, per-sequence offsets of the compacted row space, device-side count."""
     g = torch.Generator().manual_seed(5)
-    for N, S in ((1, 7), (37, 28), (768, 28)):
+    for N, S in ((1, 7), (37, 28), (768, 28), (1170, 28), (3072, 30)):   # the last one: beyond 32768 rows (serial kernel)
         lens = torch.randint(1, S + 1, (N,), generator=g, dtype=torch.int32)
         seq_off = torch.zeros(N + 1, dtype=torch.int32)
         seq_off[1:] = torch.cumsum(lens, 0)
