@@ -103,6 +103,15 @@ int navc_cross_attention_bwd_tc_split(int mode, const float* q, int ldq, const f
                                       int N, int S, int E, int D, int H, const float* d_ctx, const float* ctx, float* d_q,
                                       int ld_dq, uint16_t* d_kv_hi, uint16_t* d_kv_lo, int ld_dkv, float* kv_colsum,
                                       void* stream);
+/* Two chained linear layers in ONE persistent launch (csrc/gemm2_tc.cu, G2Chain): y0 = epilogue0(x w0^T), then
+ * y1 = epilogue1(y0 w1^T) -- e.g. the attention out-projection (+ residual) followed by the text -> video query projection
+ * (models/bert.py:192-200 then :81-92 of the next block).  N == K (square layers), bf16 hi (/ lo) outputs in e0->out_hi/lo
+ * and e1->out_hi/lo (y0 is also problem 1's A operand), the same device-side row count in both epilogues.  A tile of
+ * problem 1 waits for the row block of y0 through per-row-block completion counters; one pipeline fill / drain and one
+ * tile quantisation instead of two. */
+int navc_linear_chain_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w0_hi,
+                         const uint16_t* w0_lo, int ldw0, const navc_epilogue_t* e0, const uint16_t* w1_hi,
+                         const uint16_t* w1_lo, int ldw1, const navc_epilogue_t* e1, int M, int N, int K, void* stream);
 /* Y = epilogue(X W^T) with fp32 operands consumed by the tensor cores as TF32 (tcgen05 kind::tf32: 10-bit mantissa, two
  * bf16-MMA time units per product against split-bf16's three): x [M, K] and w [N, K] fp32 row-major (K % 4 == 0, 16-byte
  * aligned), generic epilogue -- bias, activation, fp32 residual, row mask; fp32 and / or bf16 hi (/ lo) outputs; a

@@ -75,6 +75,7 @@ _PROTOS = {
     "navc_compact_rows": [vp, vp, i32, i32, vp, vp, vp, vp],
     "navc_gather_rows2": [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp],
     "navc_refresh_pack": [vp, i32, vp],
+    "navc_linear_chain_tc": [i32, vp, vp, i32, vp, vp, i32, C.POINTER(Epilogue), vp, vp, i32, C.POINTER(Epilogue), i32, i32, i32, vp],
     "navc_drop_add_bwd_split": [vp, u64, f32, u64, f32, vp, i32, i32, vp, vp, vp, i32, vp, vp],
     "navc_act_drop_bwd_split": [vp, vp, i32, u64, f32, i32, i32, vp, vp, i32, vp, vp],
     "navc_cross_attention_bwd_tc_split": [i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp],

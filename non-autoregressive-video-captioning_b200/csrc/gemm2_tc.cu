@@ -51,7 +51,18 @@ template <bool kX3, int TBN, int kCl = 1> struct G2Cfg {
     static_assert(kStages >= 2, "operand ring needs at least two stages");
 };
 
-struct G2Unit { int mb, n0, w; bool valid; };
+struct G2Unit { int mb, n0, w; bool valid; int prob; };
+
+// Second problem of a CHAINED launch (kChain): Y1 = epilogue1(Y0 W1^T) right behind Y0 = epilogue0(X W0^T) in ONE
+// persistent grid.  Both problems have the same M (device side), N, K and tile configuration; a tile of problem 1 needs
+// the whole row block of Y0, so the epilogue warps of problem 0 publish per-row-block completion counts (after their TMA
+// stores have completed) and the producer of a problem-1 tile acquires them before its first A load.  cnt: [m_blocks]
+// int32, zero at launch (the host clears it).
+struct G2Chain {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo, p_hi, p_lo, o_hi, o_lo;
+    EpiParams epi;
+    int* cnt;
+};
 
 // Optional in-kernel timeline (tools/gemm2_trace.py): when navc_debug_trace() has installed a buffer, the producer
 // lane, the MMA lane and lane 0 of epilogue warp 2 of every CTA record (tag, clock64) pairs -- 3 roles x 64 events.
@@ -67,13 +78,12 @@ struct G2Trace {
     }
 };
 
-template <bool kX3, int TBN, int kCl, bool kRes>
-__global__ void __launch_bounds__(G2_THREADS, 1)
-gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                const __grid_constant__ CUtensorMap map_p_hi, const __grid_constant__ CUtensorMap map_p_lo,
-                const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
-                int M_max, int N, int K, EpiParams epi) {
+template <bool kX3, int TBN, int kCl, bool kRes, bool kChain>
+__device__ __forceinline__ void gemm2_tc_body(const CUtensorMap& map_a_hi, const CUtensorMap& map_a_lo,
+                const CUtensorMap& map_b_hi, const CUtensorMap& map_b_lo,
+                const CUtensorMap& map_p_hi, const CUtensorMap& map_p_lo,
+                const CUtensorMap& map_o_hi, const CUtensorMap& map_o_lo,
+                int M_max, int N, int K, const EpiParams& epi, const G2Chain* chain) {
     using Cfg = G2Cfg<kX3, TBN, kCl>;
     constexpr int kTileB = Cfg::kTileB;
     constexpr bool kPair = kCl == 2;
@@ -90,6 +100,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + G2_ACC + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + bar_off + 8 * (2 * Cfg::kStages + 2 * G2_ACC));
+    auto pub_bar = [&](int i) { return bar_base + 256u + 8u * (uint32_t)(i & 7); };   // chained launches: "tile i of problem 0 stored"
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int crank = kPair ? (int)cluster_ctarank() : 0;
@@ -99,7 +110,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     //      partly filled wave are cut into `parts` column parts of TBN / parts columns ----
     const int m_blocks = (M + G2_BM - 1) / G2_BM, n_blocks = (N + TBN - 1) / TBN;
     const int k_blocks = (K + G2_BK - 1) / G2_BK;   // TMA zero-fills the K tail
-    const int n_units = ((m_blocks + kCl - 1) / kCl) * n_blocks;
+    const int n_units1 = ((m_blocks + kCl - 1) / kCl) * n_blocks;   // units of one problem
+    const int n_units = kChain ? 2 * n_units1 : n_units1;            // chained: problem 0's units, then problem 1's
     const int full = (n_units / G) * G, rem = n_units - full;
     int parts = 1;
     if (rem > 0 && epi.dbg != 7) {
@@ -107,6 +119,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         parts = q >= 4 ? 4 : (q >= 2 ? 2 : 1);
         if (parts > TBN / 64) parts = TBN / 64;     // parts keep >= 64 columns
     }
+    if (kChain && full < n_units1) parts = 1;   // chained: problem 0's tiles are always whole (their completion is counted per tile)
     const int total = full + rem * parts;
     auto get_unit = [&](int it, G2Unit& u) -> bool {
         const int t = cid + it * G;
@@ -121,6 +134,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             part = x - (x / parts) * parts;
             u.w = TBN / parts;
         }
+        u.prob = 0;
+        if (kChain && ui >= n_units1) { ui -= n_units1; u.prob = 1; }
         const int mg = ui / n_blocks, nb = ui - mg * n_blocks;   // column block fastest: concurrent clusters share the A rows in L2
         u.mb = mg * kCl + crank;
         u.n0 = nb * TBN + part * u.w;
@@ -140,6 +155,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         // pair: the leader's MMA thread waits for the epilogue warps of BOTH CTAs
         for (int s = 0; s < G2_ACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kCl * G2_EPI_WARPS); }
+        if (kChain) for (int i = 0; i < 8; ++i) mbar_init(pub_bar(i), G2_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (kPair) {
@@ -175,6 +191,21 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const int brows = u.w / kCl;                         // B rows this CTA stages
                 const uint32_t bytes = (uint32_t)(kParts * (G2_TILE_A + brows * 128));
                 const int brow0 = u.n0 + crank * brows;
+                const bool p1 = kChain && u.prob;
+                const CUtensorMap* ma_hi = p1 ? &chain->a_hi : &map_a_hi; const CUtensorMap* ma_lo = p1 ? &chain->a_lo : &map_a_lo;
+                const CUtensorMap* mb_hi = p1 ? &chain->b_hi : &map_b_hi; const CUtensorMap* mb_lo = p1 ? &chain->b_lo : &map_b_lo;
+                const CUtensorMap* mp_hi = p1 ? &chain->p_hi : &map_p_hi; const CUtensorMap* mp_lo = p1 ? &chain->p_lo : &map_p_lo;
+                if (p1 && u.valid) {
+                    // every column tile of this row block of problem 0 has been published
+                    const int need = n_blocks;   // one count per column tile of the row block (the publisher warp below)
+                    const int* c = chain->cnt + u.mb;
+                    int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory");
+                        if (seen < need) __nanosleep(100);
+                    } while (seen < need);
+                    asm volatile("fence.proxy.async;" ::: "memory");   // the TMA loads below read what other SMs' TMA stores wrote
+                }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);   // the MMAs reading this slot (of this CTA) have retired
                     if (kb == 0) tr.ev(2);                     // first load of a unit issued
@@ -190,15 +221,15 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
                         if constexpr (kPair) tma_load_2d_2cta(dst, map, fb, c0, c1); else tma_load_2d(dst, map, fb, c0, c1);
                     };
-                    load(sa, &map_a_hi, kb * G2_BK, u.mb * G2_BM);
-                    if (kX3) load(sa + G2_TILE_A + kTileB, &map_a_lo, kb * G2_BK, u.mb * G2_BM);
+                    load(sa, ma_hi, kb * G2_BK, u.mb * G2_BM);
+                    if (kX3) load(sa + G2_TILE_A + kTileB, ma_lo, kb * G2_BK, u.mb * G2_BM);
                     if (!part) {
-                        load(sa + G2_TILE_A, &map_b_hi, kb * G2_BK, brow0);
-                        if (kX3) load(sa + 2 * G2_TILE_A + kTileB, &map_b_lo, kb * G2_BK, brow0);
+                        load(sa + G2_TILE_A, mb_hi, kb * G2_BK, brow0);
+                        if (kX3) load(sa + 2 * G2_TILE_A + kTileB, mb_lo, kb * G2_BK, brow0);
                     } else {
                         for (int j = 0; j < brows / G2_PBOX; ++j) {
-                            load(sa + G2_TILE_A + j * (G2_PBOX * 128), &map_p_hi, kb * G2_BK, brow0 + j * G2_PBOX);
-                            if (kX3) load(sa + 2 * G2_TILE_A + kTileB + j * (G2_PBOX * 128), &map_p_lo, kb * G2_BK, brow0 + j * G2_PBOX);
+                            load(sa + G2_TILE_A + j * (G2_PBOX * 128), mp_hi, kb * G2_BK, brow0 + j * G2_PBOX);
+                            if (kX3) load(sa + 2 * G2_TILE_A + kTileB + j * (G2_PBOX * 128), mp_lo, kb * G2_BK, brow0 + j * G2_PBOX);
                         }
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
@@ -262,6 +293,22 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
             }
         }
+    } else if (kChain && warp == 2 + G2_EPI_WARPS) {
+        // ===================== publisher (chained launches only) =====================
+        // Making a tile's stores visible to the other SMs costs a gpu-scope fence of ~5 us (measured: in the epilogue warps it
+        // doubled their time per tile).  So the epilogue warps only arrive on a CTA-local barrier; this otherwise idle warp
+        // fences (cumulative over what the arrivals released) and moves the row block's count.
+        if (lane == 0) {
+            G2Unit u;
+            int i0 = 0;
+            for (int it = 0; get_unit(it, u); ++it) {
+                if (u.prob || !u.valid) continue;
+                mbar_wait_relaxed(pub_bar(i0), (uint32_t)((i0 >> 3) & 1));
+                __threadfence();
+                asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(chain->cnt + u.mb) : "memory");
+                ++i0;
+            }
+        }
     } else {
         // ===================== epilogue (warps 2..17) =====================
         constexpr int GW = TBN / 4, STEPS = GW / 16;
@@ -286,32 +333,36 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         G2Unit u;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int chain_i0 = 0;   // problem-0 tiles of this CTA so far (index of the publisher's barrier ring)
         for (int it = 0; get_unit(it, u); ++it) {
+            const EpiParams& eu = (kChain && u.prob) ? chain->epi : epi;
+            const CUtensorMap* mo_hi_u = (kChain && u.prob) ? &chain->o_hi : &map_o_hi;
+            const CUtensorMap* mo_lo_u = (kChain && u.prob) ? &chain->o_lo : &map_o_lo;
             const int row0 = u.mb * G2_BM + quarter * 32;
             const int rowp = row0 + lane;
             const bool row_ok = u.valid && rowp < M;
-            const bool rz = (row_ok && epi.row_tokens) ? (epi.row_tokens[rowp] == NAVC_PAD) : false;
+            const bool rz = (row_ok && eu.row_tokens) ? (eu.row_tokens[rowp] == NAVC_PAD) : false;
             const bool active = u.valid && cl0 < u.w && u.n0 + cl0 < N && row0 < M && epi.dbg != 11;   // warp-uniform
             // residual of one 16-column step: 32 bytes of hi (+ lo) per row
-            const bool res_wide = (epi.ld_res % 16 == 0) && ((((uintptr_t)epi.res_hi) | ((uintptr_t)epi.res_lo)) & 31) == 0;
+            const bool res_wide = (eu.ld_res % 16 == 0) && ((((uintptr_t)eu.res_hi) | ((uintptr_t)eu.res_lo)) & 31) == 0;
             uint32_t rh[kRes ? 2 : 1][8], rl[kRes ? 2 : 1][8];
             auto load_res = [&](int c, uint32_t (&h)[8], uint32_t (&l)[8]) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { h[j] = 0u; l[j] = 0u; }
                 const int col = u.n0 + cl0 + c * 16;
-                if (row_ok && cl0 + c * 16 < u.w && col < N) {
-                    const size_t ro = (size_t)rowp * epi.ld_res + col;
+                if (row_ok && eu.res_hi && cl0 + c * 16 < u.w && col < N) {
+                    const size_t ro = (size_t)rowp * eu.ld_res + col;
                     if (res_wide && col + 16 <= N) {
-                        ld_global_nc_256(epi.res_hi + ro, h);
-                        if (epi.res_lo) ld_global_nc_256(epi.res_lo + ro, l);
+                        ld_global_nc_256(eu.res_hi + ro, h);
+                        if (eu.res_lo) ld_global_nc_256(eu.res_lo + ro, l);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 2; ++i)
                             if (col + i * 8 < N) {
-                                const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(epi.res_hi + ro + i * 8));
+                                const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(eu.res_hi + ro + i * 8));
                                 h[i * 4] = a4.x; h[i * 4 + 1] = a4.y; h[i * 4 + 2] = a4.z; h[i * 4 + 3] = a4.w;
-                                if (epi.res_lo) {
-                                    const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(epi.res_lo + ro + i * 8));
+                                if (eu.res_lo) {
+                                    const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(eu.res_lo + ro + i * 8));
                                     l[i * 4] = b4.x; l[i * 4 + 1] = b4.y; l[i * 4 + 2] = b4.z; l[i * 4 + 3] = b4.w;
                                 }
                             }
@@ -321,13 +372,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (kRes && active) {
                 // the unit's whole row segment -> L2 now (the layer input was written several launches ago and has
                 // mostly left L2): the later steps' loads, issued only one step ahead, then miss no further than L2
-                if (row_ok && epi.dbg != 13) {
-                    const size_t ro = (size_t)rowp * epi.ld_res + u.n0 + cl0;
+                if (row_ok && eu.res_hi && epi.dbg != 13) {
+                    const size_t ro = (size_t)rowp * eu.ld_res + u.n0 + cl0;
                     int wcols = u.w - cl0 < GW ? u.w - cl0 : GW;
                     if (u.n0 + cl0 + wcols > N) wcols = N - u.n0 - cl0;
-                    prefetch_l2(epi.res_hi + ro);
-                    prefetch_l2(epi.res_hi + ro + wcols - 1);
-                    if (epi.res_lo) { prefetch_l2(epi.res_lo + ro); prefetch_l2(epi.res_lo + ro + wcols - 1); }
+                    prefetch_l2(eu.res_hi + ro);
+                    prefetch_l2(eu.res_hi + ro + wcols - 1);
+                    if (eu.res_lo) { prefetch_l2(eu.res_lo + ro); prefetch_l2(eu.res_lo + ro + wcols - 1); }
                 }
                 load_res(0, rh[0], rl[0]);   // overlaps the main loop of this tile
             }
@@ -350,7 +401,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (epi.bias && col0 + i * 4 < N) bv[i] = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + i * 4));
+                        if (eu.bias && col0 + i * 4 < N) bv[i] = __ldg(reinterpret_cast<const float4*>(eu.bias + col0 + i * 4));
                     }
                     tc_wait_ld();
                     const bool more = c + 1 < STEPS && cl + 16 < u.w && col0 + 16 < N;
@@ -366,12 +417,12 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         v[i * 4 + 3] = __uint_as_float(r[c % RB][i * 4 + 3]) + bv[i].w;
                     }
                     if (kRes && more) tc_ld16(t_row + (uint32_t)((c + 1) * 16), r[0]);   // r[0] is free again
-                    if (epi.act == NAVC_ACT_GELU_NEW) {
+                    if (eu.act == NAVC_ACT_GELU_NEW) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], NAVC_ACT_GELU_NEW);
-                    } else if (epi.act != NAVC_ACT_NONE) {
+                    } else if (eu.act != NAVC_ACT_NONE) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], epi.act);
+                        for (int j = 0; j < 16; ++j) v[j] = act_apply_fast(v[j], eu.act);
                     }
                     if constexpr (kRes) {
 #pragma unroll
@@ -385,7 +436,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         for (int j = 0; j < 16; ++j) v[j] = 0.f;
                     }
                     uint32_t hw[8], lw[8];
-                    if (epi.out_lo) {
+                    if (eu.out_lo) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
                     } else {
@@ -397,9 +448,19 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                     tr.ev(30 + c);
                     if (epi.dbg == 12) continue;   // profiling aid: no stores
+                    if (kChain && !u.prob) {
+                        // chained, problem 0: generic-proxy stores (32 bytes of hi and of lo per row), see the publication below
+                        if (row_ok) {
+                            const size_t oo = (size_t)rowp * eu.ld_out + col0;
+                            st_global_256(eu.out_hi + oo, hw);
+                            if (eu.out_lo) st_global_256(eu.out_lo + oo, lw);
+                        }
+                        tr.ev(50 + c);
+                        continue;
+                    }
                     // hi box: its previous store (one bulk group before the most recent one) must have read the staging box
                     if (lane == 0) {
-                        if (epi.out_lo) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (eu.out_lo) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
                     __syncwarp();
@@ -408,10 +469,10 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&map_o_hi, stg_s, col0, row0);
+                        tma_store_2d(mo_hi_u, stg_s, col0, row0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    if (epi.out_lo) {
+                    if (eu.out_lo) {
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the previous lo box
                         __syncwarp();
                         *reinterpret_cast<uint4*>(stg + 1024 + lane * 32) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -419,7 +480,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&map_o_lo, stg_s + 1024u, col0, row0);
+                            tma_store_2d(mo_lo_u, stg_s + 1024u, col0, row0);
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                     }
@@ -427,7 +488,14 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 }
             }
             tr.ev(8);   // epilogue of the unit issued
-            arrive_drained(acc);
+            arrive_drained(acc);   // (before the publication below: the accumulator stage is free once it has been read)
+            if (kChain && !u.prob && u.valid) {
+                // problem 0's tiles leave through ordinary 256-bit stores (above), not TMA boxes (only the issuing thread can wait
+                // for a bulk store to COMPLETE): all lanes' stores -> warp barrier -> arrival (release) on the publisher's barrier
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pub_bar(chain_i0));
+                ++chain_i0;
+            }
             if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging stays valid until read
@@ -453,6 +521,29 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     }
 }
 
+template <bool kX3, int TBN, int kCl, bool kRes>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const __grid_constant__ CUtensorMap map_p_hi, const __grid_constant__ CUtensorMap map_p_lo,
+                const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+                int M_max, int N, int K, EpiParams epi) {
+    gemm2_tc_body<kX3, TBN, kCl, kRes, false>(map_a_hi, map_a_lo, map_b_hi, map_b_lo, map_p_hi, map_p_lo, map_o_hi, map_o_lo, M_max, N, K,
+                                              epi, nullptr);
+}
+
+// two chained problems (G2Chain above): single CTAs, 128-wide tiles, the residual-capable epilogue for both
+template <bool kX3>
+__global__ void __launch_bounds__(G2_THREADS + 32, 1)
+gemm2_chain_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   const __grid_constant__ CUtensorMap map_p_hi, const __grid_constant__ CUtensorMap map_p_lo,
+                   const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+                   int M_max, int N, int K, EpiParams epi, const __grid_constant__ G2Chain chain) {
+    gemm2_tc_body<kX3, 128, 1, true, true>(map_a_hi, map_a_lo, map_b_hi, map_b_lo, map_p_hi, map_p_lo, map_o_hi, map_o_lo, M_max, N, K,
+                                           epi, &chain);
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 int tc_make_store_map16(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld);   // gemm_tc.cu
 
@@ -465,6 +556,8 @@ extern "C" int navc_debug_trace(void* buf) {
 namespace navc {
 
 static bool g_g2_ready = false;
+static int* g_chain_cnt = nullptr;           // per-row-block completion counts of a chained launch (cleared per launch)
+constexpr int kChainCntInts = 8192;          // row blocks: up to 1M rows
 static int g2_init() {
     if (g_g2_ready) return 0;
 #define NAVC_G2_ATTR(X3, BN, CL) \
@@ -473,6 +566,9 @@ static int g2_init() {
     NAVC_G2_ATTR(false, 128, 1); NAVC_G2_ATTR(false, 256, 1); NAVC_G2_ATTR(true, 128, 1); NAVC_G2_ATTR(true, 256, 1);
     NAVC_G2_ATTR(false, 128, 2); NAVC_G2_ATTR(false, 256, 2); NAVC_G2_ATTR(true, 128, 2); NAVC_G2_ATTR(true, 256, 2);
 #undef NAVC_G2_ATTR
+    NAVC_CUDA(cudaFuncSetAttribute(gemm2_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<true, 128, 1>::kSmemBytes));
+    NAVC_CUDA(cudaFuncSetAttribute(gemm2_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<false, 128, 1>::kSmemBytes));
+    NAVC_CUDA(cudaMalloc(&g_chain_cnt, kChainCntInts * sizeof(int)));
     g_g2_ready = true;
     return 0;
 }
@@ -583,4 +679,67 @@ int g2_linear(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, con
 #undef NAVC_G2_GO
 }
 
+// Y0 = epi0(X W0^T) then Y1 = epi1(Y0 W1^T) in one launch (gemm2_chain_kernel): N == K (square layers), 128-wide tiles.
+int g2_chain(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w0_hi, const uint16_t* w0_lo, int ldw0,
+             const EpiParams& e0, const uint16_t* w1_hi, const uint16_t* w1_lo, int ldw1, const EpiParams& e1, int M, int N, int K,
+             cudaStream_t st) {
+    NAVC_REQUIRE(tc_ready(), "navc_linear_chain_tc: navc_init() has not been called");
+    if (g2_init()) return 2;
+    const bool x3 = mode == NAVC_TC_BF16X3;
+    NAVC_REQUIRE(N == K && N % 128 == 0 && M > 0, "navc_linear_chain_tc: needs N == K, N %% 128 == 0 (N=%d K=%d)", N, K);
+    NAVC_REQUIRE(e0.out_hi && e1.out_hi && (!x3 || (e0.out_lo && e1.out_lo)) && !e0.out_f32 && !e1.out_f32 && !e0.residual && !e1.residual &&
+                     e0.m_dev == e1.m_dev, "navc_linear_chain_tc: bf16 hi/lo outputs only, same device-side row count");
+    NAVC_REQUIRE(e0.ld_out % 16 == 0 && ((((uintptr_t)e0.out_hi) | ((uintptr_t)e0.out_lo)) & 31) == 0,
+                 "navc_linear_chain_tc: y0 needs 32-byte aligned rows (256-bit stores)");
+    int sms = navc_sm_count();
+    if (sms <= 0) sms = 148;
+    const int m_blocks = (M + G2_BM - 1) / G2_BM, n_blocks = N / 128;
+    NAVC_REQUIRE(m_blocks <= kChainCntInts, "navc_linear_chain_tc: too many rows");
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mp_hi, mp_lo, mo_hi, mo_lo;
+    G2Chain ch;
+    if (tc_make_map(&ma_hi, x_hi, M, K, ldx, G2_BM) || tc_make_map(&mb_hi, w0_hi, N, K, ldw0, 128) || tc_make_map(&mp_hi, w0_hi, N, K, ldw0, G2_PBOX) ||
+        tc_make_map(&ch.a_hi, e0.out_hi, M, N, e0.ld_out, G2_BM) || tc_make_map(&ch.b_hi, w1_hi, N, K, ldw1, 128) ||
+        tc_make_map(&ch.p_hi, w1_hi, N, K, ldw1, G2_PBOX)) return 1;
+    ma_lo = ma_hi; mb_lo = mb_hi; mp_lo = mp_hi; ch.a_lo = ch.a_hi; ch.b_lo = ch.b_hi; ch.p_lo = ch.p_hi;
+    if (x3) {
+        if (tc_make_map(&ma_lo, x_lo, M, K, ldx, G2_BM) || tc_make_map(&mb_lo, w0_lo, N, K, ldw0, 128) || tc_make_map(&mp_lo, w0_lo, N, K, ldw0, G2_PBOX) ||
+            tc_make_map(&ch.a_lo, e0.out_lo, M, N, e0.ld_out, G2_BM) || tc_make_map(&ch.b_lo, w1_lo, N, K, ldw1, 128) ||
+            tc_make_map(&ch.p_lo, w1_lo, N, K, ldw1, G2_PBOX)) return 1;
+    }
+    if (tc_make_store_map16(&mo_hi, e0.out_hi, M, N, e0.ld_out) || tc_make_store_map16(&ch.o_hi, e1.out_hi, M, N, e1.ld_out)) return 1;
+    mo_lo = mo_hi; ch.o_lo = ch.o_hi;
+    if (e0.out_lo && tc_make_store_map16(&mo_lo, e0.out_lo, M, N, e0.ld_out)) return 1;
+    if (e1.out_lo && tc_make_store_map16(&ch.o_lo, e1.out_lo, M, N, e1.ld_out)) return 1;
+    ch.epi = e1;
+    ch.cnt = g_chain_cnt;
+    NAVC_CUDA(cudaMemsetAsync(g_chain_cnt, 0, (size_t)m_blocks * sizeof(int), st));
+    const int units = 2 * m_blocks * n_blocks;
+    int grid = sms;
+    if (grid > units) grid = units;   // (all CTAs co-resident: one per SM)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(G2_THREADS + 32);   // + the publisher warp
+    cfg.dynamicSmemBytes = x3 ? G2Cfg<true, 128, 1>::kSmemBytes : G2Cfg<false, 128, 1>::kSmemBytes;
+    cfg.stream = st;
+    if (x3)
+        NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_chain_kernel<true>, ma_hi, ma_lo, mb_hi, mb_lo, mp_hi, mp_lo, mo_hi, mo_lo, M, N, K, e0, ch));
+    else
+        NAVC_CUDA(cudaLaunchKernelEx(&cfg, gemm2_chain_kernel<false>, ma_hi, ma_lo, mb_hi, mb_lo, mp_hi, mp_lo, mo_hi, mo_lo, M, N, K, e0, ch));
+    return check_launch("navc_linear_chain_tc");
+}
+
 }  // namespace navc
+
+// Two chained linear layers in one launch: y0 = epilogue0(x w0^T) (bias, activation, bf16 hi/lo residual, row mask), then
+// y1 = epilogue1(y0 w1^T), bf16 hi (/ lo) outputs; N == K (square layers).  See G2Chain in this file.
+extern "C" int navc_linear_chain_tc(int mode, const uint16_t* x_hi, const uint16_t* x_lo, int ldx, const uint16_t* w0_hi,
+                                    const uint16_t* w0_lo, int ldw0, const navc_epilogue_t* e0, const uint16_t* w1_hi,
+                                    const uint16_t* w1_lo, int ldw1, const navc_epilogue_t* e1, int M, int N, int K, void* stream) {
+    using namespace navc;
+    NAVC_REQUIRE(e0 && e1 && x_hi && w0_hi && w1_hi, "navc_linear_chain_tc: null pointer");
+    NAVC_REQUIRE(mode == NAVC_TC_BF16 || (mode == NAVC_TC_BF16X3 && x_lo && w0_lo && w1_lo), "navc_linear_chain_tc: bad mode / missing lo operands");
+    NAVC_REQUIRE(ldx % 8 == 0 && ldw0 % 8 == 0 && ldw1 % 8 == 0 && e0->ld_out % 8 == 0 && e1->ld_out % 8 == 0,
+                 "navc_linear_chain_tc: leading dimensions must be multiples of 8");
+    const EpiParams p0 = to_params(e0), p1 = to_params(e1);
+    return g2_chain(mode, x_hi, x_lo, ldx, w0_hi, w0_lo, ldw0, p0, w1_hi, w1_lo, ldw1, p1, M, N, K, as_stream(stream));
+}

@@ -129,3 +129,39 @@ def test_gemm2_device_row_count(mode, cluster, cnt):
     CTA of the last cluster without a tile)."""
     run(mode, 21504, 512, 512, cluster, cnt=cnt)
     run(mode, 21504, 2048, 512, cluster, cnt=cnt, epilogue=False)
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("M,live", [(21504, 10553), (21504, 3285), (700, 700), (130, 77), (21504, 21504)])
+def test_chained_linears_equal_two_launches(mode, M, live):
+    """navc_linear_chain_tc (out-projection + residual, then the next projection, in one persistent launch with per-row-block
+    completion counters) against the same two layers as separate launches: equal outputs, over repeated launches with fresh
+    inputs (the second problem's tiles must never read a row block of y0 before it is complete)."""
+    D = 512
+    x3 = mode == "bf16x3"
+    md = L.TC_BF16X3 if x3 else L.TC_BF16
+    cnt = torch.tensor([live], dtype=torch.int32, device=DEV)
+    w0 = torch.randn(D, D, generator=g(1)) / math.sqrt(D); w1 = torch.randn(D, D, generator=g(2)) / math.sqrt(D)
+    b0 = torch.randn(D, generator=g(3)).to(DEV); b1 = torch.randn(D, generator=g(4)).to(DEV)
+    w0h, w0l = [t.to(DEV) for t in split(w0)]; w1h, w1l = [t.to(DEV) for t in split(w1)]
+    for rep in range(6):
+        x = torch.randn(M, D, generator=g(10 + rep)); res = torch.randn(M, D, generator=g(40 + rep))
+        xh, xl = [t.to(DEV) for t in split(x)]; rh, rl = [t.to(DEV) for t in split(res)]
+        outs = []
+        for chained in (False, True):
+            a_h = torch.full((M, D), float("nan"), dtype=torch.bfloat16, device=DEV); a_l = torch.full_like(a_h, float("nan"))
+            q_h = torch.full((M, D), float("nan"), dtype=torch.bfloat16, device=DEV); q_l = torch.full_like(q_h, float("nan"))
+            e0 = L.Epilogue(L.ptr(b0), None, None, 0, D, None, L.ptr(a_h), L.ptr(a_l) if x3 else None, D, 0, 1, 0, L.ptr(rh), L.ptr(rl) if x3 else None,
+                            cnt.data_ptr(), live, 0)
+            e1 = L.Epilogue(L.ptr(b1), None, None, 0, 0, None, L.ptr(q_h), L.ptr(q_l) if x3 else None, D, 0, 1, 0, None, None, cnt.data_ptr(), live, 0)
+            if chained:
+                L.call("navc_linear_chain_tc", md, L.ptr(xh), L.ptr(xl) if x3 else None, D, L.ptr(w0h), L.ptr(w0l) if x3 else None, D, e0,
+                       L.ptr(w1h), L.ptr(w1l) if x3 else None, D, e1, M, D, D, L.stream())
+            else:
+                L.call("navc_linear_tc", md, L.ptr(xh), L.ptr(xl) if x3 else None, D, L.ptr(w0h), L.ptr(w0l) if x3 else None, D, M, D, D, e0, L.stream())
+                L.call("navc_linear_tc", md, L.ptr(a_h), L.ptr(a_l) if x3 else None, D, L.ptr(w1h), L.ptr(w1l) if x3 else None, D, M, D, D, e1, L.stream())
+            torch.cuda.synchronize()
+            outs.append([t[:live].float().cpu() for t in ((a_h, a_l, q_h, q_l) if x3 else (a_h, q_h))])
+        for u, v in zip(*outs):
+            assert not torch.isnan(v).any()
+            assert torch.equal(u, v)
